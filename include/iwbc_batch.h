@@ -1,0 +1,140 @@
+/* iwbc_batch.h -- C ABI of the B200-native batched whole-body-control cycle (libiwbc_b200.so).
+ *
+ * Drop-in boundary for ONE path of resibots/inria_wbc: `Controller::update` -> `_solve`
+ * (pinocchio kinematics/dynamics -> TSID task/contact stacking -> eiquadprog QP -> decode ->
+ * integrate), for thousands to millions of independent robot states per call.  Plain pointers
+ * and sizes only; every entry point names the reference interface it replaces.  Errors: functions
+ * return 0 on success and a negative code otherwise; `iwbc_last_error()` gives the message (the
+ * reference throws `inria_wbc::Exception`, include/inria_wbc/exceptions.hpp:52-94).  A QP that is
+ * not solved to optimality is *data* (`status[i]`), not an error: the reference throws there
+ * (src/controllers/controller.cpp:284-308), a batch cannot.
+ *
+ * There is no CPU fallback: the compute entry points fail with IWBC_ERR_CUDA when no sm_100 device
+ * is usable.
+ */
+#ifndef IWBC_BATCH_H
+#define IWBC_BATCH_H
+
+#include "iwbc_problem.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IWBC_OK 0
+#define IWBC_ERR_CONFIG -1   /* YAML / URDF / SRDF problem (IWBC_CHECK / IWBC_ASSERT in the reference) */
+#define IWBC_ERR_ARG -2      /* bad argument (size asserts of Controller::update, controller.cpp:163-205) */
+#define IWBC_ERR_CUDA -3     /* CUDA runtime error or no usable device */
+#define IWBC_ERR_UNSUPPORTED -4
+
+#define IWBC_ACTIVE_WORDS 12 /* 32-bit words of the per-instance active-set bitmask (>= mi bits) */
+
+typedef struct iwbc_problem iwbc_problem; /* compiled controller: model + task stack (host) */
+typedef struct iwbc_batch iwbc_batch;     /* one GPU's batch workspace bound to a problem   */
+
+const char* iwbc_last_error(void);
+int iwbc_abi_version(void);
+
+/* ------------------------------------------------------------------ construction (host only)
+ * Replaces `controllers::Factory::instance().create(name, YAML::LoadFile(path))`
+ * (include/inria_wbc/utils/factory.hpp:51-63, include/inria_wbc/controllers/controller.hpp:235-237)
+ * and everything the constructors chain does (src/controllers/controller.cpp:65-130,
+ * src/controllers/pos_tracker.cpp:40-159, src/controllers/humanoid_pos_tracker.cpp:37-79,
+ * src/controllers/talos_pos_tracker.cpp:37-60).  The controller name is read from CONTROLLER.name
+ * ("pos-tracker", "humanoid-pos-tracker", "talos-pos-tracker").
+ *   controller_yaml : path of the controller file (e.g. etc/talos/talos_pos_tracker.yaml)
+ *   robots_path     : directory `CONTROLLER.urdf` is resolved against (utheque's role)
+ *   etc_path        : replaces a leading "@ETC@" of CONTROLLER.base_path (NULL: dirname/.. of the yaml)
+ *   overrides_yaml  : optional YAML text of CONTROLLER keys to override, the way the reference's
+ *                     tests mutate the loaded node (tests/test_determinism.cpp:66-70)
+ */
+iwbc_problem* iwbc_problem_load(const char* controller_yaml, const char* robots_path, const char* etc_path,
+    const char* overrides_yaml);
+void iwbc_problem_free(iwbc_problem* p);
+
+/* flat description shared with the device (and with the CPU oracle in tests) */
+const iwbc_problem_t* iwbc_problem_data(const iwbc_problem* p);
+
+/* sizes: nq nv na ncontacts nref, and the QP shape (n, me, mi) for a given contact mask
+ * (PosTracker prints these: src/controllers/pos_tracker.cpp:150-158) */
+int iwbc_problem_dims(const iwbc_problem* p, int* nq, int* nv, int* na, int* ncontacts, int* nref);
+int iwbc_problem_qp_shape(const iwbc_problem* p, unsigned contact_mask, int* n, int* me, int* mi, int* cost_rows);
+unsigned iwbc_problem_default_contact_mask(const iwbc_problem* p);
+
+/* construction-time references: what make_se3 / make_com / make_posture / make_contact_task store
+ * (src/controllers/tasks.cpp:74-77,108,217,361-362) + init_com.  out has nref doubles. */
+int iwbc_problem_default_refs(const iwbc_problem* p, double* out);
+/* offset/length of a task's or contact's block inside the reference vector: the batched form of
+ * PosTracker::set_se3_ref / set_com_ref / set_momentum_ref / set_contact_se3_ref / set_posture_ref
+ * (include/inria_wbc/controllers/pos_tracker.hpp:52-58) is "write into refs[i][offset..]" */
+int iwbc_problem_ref_slot(const iwbc_problem* p, const char* task_or_contact, int* offset, int* length);
+/* PosTracker::set_task_weight / Behavior::_customize_tasks (pos_tracker.hpp:67, src/behaviors/behavior.cpp:7-22) */
+int iwbc_problem_set_task_weight(iwbc_problem* p, const char* task, double weight);
+int iwbc_problem_contact_index(const iwbc_problem* p, const char* contact);
+/* names: kind 0 = actuated dofs (Controller::controllable_dofs), 1 = tasks, 2 = contacts, 3 = mimic dofs.
+ * Returns the count; name i is copied to buf (if buf != NULL). */
+int iwbc_problem_name(const iwbc_problem* p, int kind, int i, char* buf, int buflen);
+/* reference configuration q0 (nq doubles, pinocchio layout, quaternion normalised: pos_tracker.cpp:62-77) */
+int iwbc_problem_q0(const iwbc_problem* p, double* out);
+
+/* ------------------------------------------------------------------ batched update (GPU)
+ * Instance-major arrays: q[B][nq], v[B][nv], refs[B][nref] (refs_stride = nref) or one shared
+ * reference vector (refs_stride = 0); contact_mask[B] or NULL (all default-active contacts).
+ * Instances with different masks are bucketed inside the call.
+ */
+typedef struct {
+    double* tau;       /* [B][na]   getActuatorForces            (controller.cpp:250)          */
+    double* dv;        /* [B][nv]   getAccelerations             (controller.cpp:251)          */
+    double* f;         /* [B][12*ncontacts] getContactForces, 0 for inactive (controller.cpp:258-261) */
+    double* q_next;    /* [B][nq]   pinocchio::integrate(q, dt * v_next)  (controller.cpp:255) */
+    double* v_next;    /* [B][nv]   dq + dt * dv                 (controller.cpp:254)          */
+    double* q_cmd;     /* [B][nv]   "DART" layout q_: base angle-axis (controller.cpp:263-276) */
+    double* momentum;  /* [B][3]    Ag.bottomRows(3) * dq        (controller.cpp:245)          */
+    int* status;       /* [B]       iwbc_status (HQP status)     (controller.cpp:249,287-304)  */
+    int* iters;        /* [B]       active-set iterations                                      */
+    unsigned* active;  /* [B][IWBC_ACTIVE_WORDS] bitmask over the instance's CI rows           */
+} iwbc_results_t;      /* any pointer may be NULL */
+
+iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch);
+void iwbc_batch_free(iwbc_batch* b);
+
+/* `Controller::update(sensor_data)` for B states held in HOST memory (closed-loop form: q, v are
+ * the sensor-side state, controller.cpp:163-205).  Copies in, runs the cycle, copies the requested
+ * results out and synchronises.  Pinned host buffers make the copies asynchronous. */
+int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, const double* refs, long refs_stride,
+    const unsigned* contact_mask, const iwbc_results_t* out);
+
+/* Same, all pointers are DEVICE pointers on the batch's device; enqueued on `stream`
+ * (a cudaStream_t passed as void*), no synchronisation.  Uniform contact mask per call. */
+int iwbc_batch_update_device(iwbc_batch* b, int B, const double* q, const double* v, const double* refs, long refs_stride,
+    unsigned contact_mask, const iwbc_results_t* out, void* stream);
+
+/* Open-loop ticks (closed_loop: false, Controller::_solve() on the integrated state): advances
+ * the device-resident state (q, v) `ticks` times in place with constant references. */
+int iwbc_batch_rollout_device(iwbc_batch* b, int B, double* q, double* v, const double* refs, long refs_stride,
+    unsigned contact_mask, int ticks, const iwbc_results_t* out_last, void* stream);
+
+/* number of kernel launches issued by this batch so far (bench.py's gpu_launches) */
+long iwbc_batch_launch_count(const iwbc_batch* b);
+/* average device time (ms) of the cycle kernel over the launches since the last reset, measured
+ * with CUDA events on the launching stream; reset = 1 clears the accumulators */
+double iwbc_batch_kernel_ms(iwbc_batch* b, int reset);
+int iwbc_batch_enable_timing(iwbc_batch* b, int on);
+
+/* stage dump of ONE instance for parity tests (device results copied to host; any pointer may be NULL):
+ * M[nv*nv] nle[nv] H[n*n] g[n] x[n], all row-major */
+int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, const double* ref, unsigned contact_mask,
+    double* M, double* nle, double* H, double* g, double* x);
+
+/* ------------------------------------------------------------------ solver interface
+ * Batched form of `tsid::solvers::SolverHQPBase::solve` for the EiquadprogFast backend
+ * (src/controllers/pos_tracker.cpp:96,102; src/controllers/controller.cpp:247): B dense QPs of one
+ * shape, HOST pointers, row-major:  min 1/2 x'Hx + g'x  s.t. CE x + ce0 = 0, CI x + ci0 >= 0.
+ * status[i]: iwbc_status.  active[i][IWBC_ACTIVE_WORDS]: final active inequality set. */
+int iwbc_qp_solve_batch(int device, int B, int n, int me, int mi, const double* H, const double* g, const double* CE,
+    const double* ce0, const double* CI, const double* ci0, double* x, int* status, int* iters, unsigned* active);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IWBC_BATCH_H */

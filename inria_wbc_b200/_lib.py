@@ -1,0 +1,277 @@
+"""ctypes binding of include/iwbc_batch.h (libiwbc_b200.so)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ETC_PATH = os.path.join(_HERE, "etc")
+ROBOTS_PATH = os.path.join(_HERE, "robots")
+STATUS_OPTIMAL = 0
+ACTIVE_WORDS = 12
+
+
+class IwbcError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "libiwbc_b200.so")
+
+
+_lib = None
+
+
+class _Results(C.Structure):
+    _fields_ = [("tau", C.c_void_p), ("dv", C.c_void_p), ("f", C.c_void_p), ("q_next", C.c_void_p),
+                ("v_next", C.c_void_p), ("q_cmd", C.c_void_p), ("momentum", C.c_void_p), ("status", C.c_void_p),
+                ("iters", C.c_void_p), ("active", C.c_void_p)]
+
+
+def lib():
+    """Load the product library; fails loudly if it has not been built (python __graft_entry__.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise IwbcError("libiwbc_b200.so is not built: run `python __graft_entry__.py` (or make -C inria_wbc_b200/csrc)")
+    L = C.CDLL(p)
+    vp, cp, ci, cu, cd, cl = C.c_void_p, C.c_char_p, C.c_int, C.c_uint, C.c_double, C.c_long
+    pi = C.POINTER(C.c_int)
+    sig = {
+        "iwbc_last_error": (cp, []),
+        "iwbc_abi_version": (ci, []),
+        "iwbc_problem_load": (vp, [cp, cp, cp, cp]),
+        "iwbc_problem_free": (None, [vp]),
+        "iwbc_problem_data": (vp, [vp]),
+        "iwbc_problem_dims": (ci, [vp, pi, pi, pi, pi, pi]),
+        "iwbc_problem_qp_shape": (ci, [vp, cu, pi, pi, pi, pi]),
+        "iwbc_problem_default_contact_mask": (cu, [vp]),
+        "iwbc_problem_default_refs": (ci, [vp, vp]),
+        "iwbc_problem_ref_slot": (ci, [vp, cp, pi, pi]),
+        "iwbc_problem_set_task_weight": (ci, [vp, cp, cd]),
+        "iwbc_problem_contact_index": (ci, [vp, cp]),
+        "iwbc_problem_name": (ci, [vp, ci, ci, cp, ci]),
+        "iwbc_problem_q0": (ci, [vp, vp]),
+        "iwbc_batch_create": (vp, [vp, ci, ci]),
+        "iwbc_batch_free": (None, [vp]),
+        "iwbc_batch_update": (ci, [vp, ci, vp, vp, vp, cl, vp, C.POINTER(_Results)]),
+        "iwbc_batch_update_device": (ci, [vp, ci, vp, vp, vp, cl, cu, C.POINTER(_Results), vp]),
+        "iwbc_batch_rollout_device": (ci, [vp, ci, vp, vp, vp, cl, cu, ci, C.POINTER(_Results), vp]),
+        "iwbc_batch_launch_count": (cl, [vp]),
+        "iwbc_batch_kernel_ms": (cd, [vp, ci]),
+        "iwbc_batch_enable_timing": (ci, [vp, ci]),
+        "iwbc_batch_debug_instance": (ci, [vp, vp, vp, vp, cu, vp, vp, vp, vp, vp]),
+        "iwbc_qp_solve_batch": (ci, [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    L._declared = sorted(sig)
+    _lib = L
+    return L
+
+
+def _err(L):
+    return (L.iwbc_last_error() or b"").decode()
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Problem:
+    """A compiled controller (model + task stack): what `controllers::Factory::create(name, yaml)` builds."""
+
+    def __init__(self, controller_yaml, robots_path=ROBOTS_PATH, etc_path=ETC_PATH, overrides=None):
+        L = lib()
+        if not os.path.isabs(controller_yaml) and not os.path.exists(controller_yaml):
+            controller_yaml = os.path.join(ETC_PATH, controller_yaml)
+        ov = None
+        if overrides:
+            ov = overrides if isinstance(overrides, str) else "\n".join("%s: %s" % (k, _yaml_scalar(v)) for k, v in overrides.items())
+        self._h = L.iwbc_problem_load(controller_yaml.encode(), robots_path.encode(), etc_path.encode() if etc_path else None,
+                                      ov.encode() if ov else None)
+        if not self._h:
+            raise IwbcError(_err(L))
+        d = [C.c_int() for _ in range(5)]
+        L.iwbc_problem_dims(self._h, *[C.byref(x) for x in d])
+        self.nq, self.nv, self.na, self.ncontacts, self.nref = [x.value for x in d]
+        self.default_contact_mask = L.iwbc_problem_default_contact_mask(self._h)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.iwbc_problem_free(self._h)
+            self._h = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def data_ptr(self):
+        """const iwbc_problem_t* (handed to the CPU oracle by the tests)"""
+        return lib().iwbc_problem_data(self._h)
+
+    def qp_shape(self, contact_mask=None):
+        m = self.default_contact_mask if contact_mask is None else contact_mask
+        d = [C.c_int() for _ in range(4)]
+        lib().iwbc_problem_qp_shape(self._h, m, *[C.byref(x) for x in d])
+        return tuple(x.value for x in d)  # n, me, mi, cost rows
+
+    def default_refs(self):
+        out = np.zeros(self.nref)
+        lib().iwbc_problem_default_refs(self._h, out.ctypes.data)
+        return out
+
+    def q0(self):
+        out = np.zeros(self.nq)
+        lib().iwbc_problem_q0(self._h, out.ctypes.data)
+        return out
+
+    def ref_slot(self, name):
+        o, n = C.c_int(), C.c_int()
+        if lib().iwbc_problem_ref_slot(self._h, name.encode(), C.byref(o), C.byref(n)) != 0:
+            raise IwbcError(_err(lib()))
+        return o.value, n.value
+
+    def set_task_weight(self, name, w):
+        if lib().iwbc_problem_set_task_weight(self._h, name.encode(), float(w)) != 0:
+            raise IwbcError(_err(lib()))
+
+    def contact_index(self, name):
+        r = lib().iwbc_problem_contact_index(self._h, name.encode())
+        if r < 0:
+            raise IwbcError(_err(lib()))
+        return r
+
+    def names(self, kind):
+        k = {"dofs": 0, "tasks": 1, "contacts": 2, "mimics": 3}[kind]
+        n = lib().iwbc_problem_name(self._h, k, -1, None, 0)
+        out = []
+        buf = C.create_string_buffer(256)
+        for i in range(n):
+            lib().iwbc_problem_name(self._h, k, i, buf, 256)
+            out.append(buf.value.decode())
+        return out
+
+
+def _yaml_scalar(v):
+    if isinstance(v, bool):
+        return "true" if v else "false"
+    if isinstance(v, dict):
+        return "{" + ", ".join("%s: %s" % (k, _yaml_scalar(x)) for k, x in v.items()) + "}"
+    return str(v)
+
+
+class Results:
+    """Host-side result arrays of one batched update (numpy, instance-major)."""
+
+    FIELDS = ("tau", "dv", "f", "q_next", "v_next", "q_cmd", "momentum", "status", "iters", "active")
+
+    def __init__(self, problem, B, fields=FIELDS):
+        P = problem
+        shapes = {"tau": (B, P.na), "dv": (B, P.nv), "f": (B, 12 * P.ncontacts), "q_next": (B, P.nq), "v_next": (B, P.nv),
+                  "q_cmd": (B, P.nv), "momentum": (B, 3), "status": (B,), "iters": (B,), "active": (B, ACTIVE_WORDS)}
+        dt = {"status": np.int32, "iters": np.int32, "active": np.uint32}
+        for f in self.FIELDS:
+            setattr(self, f, np.zeros(shapes[f], dtype=dt.get(f, np.float64)) if f in fields else None)
+
+    def as_struct(self):
+        return _Results(*[_ptr(getattr(self, f)) for f in self.FIELDS])
+
+
+class Batch:
+    """One GPU's batch workspace: `update(states[])` (BASELINE.json north_star)."""
+
+    def __init__(self, problem, device=0, max_batch=65536):
+        self.problem = problem
+        self._h = lib().iwbc_batch_create(problem.handle, device, max_batch)
+        if not self._h:
+            raise IwbcError(_err(lib()))
+        self.max_batch = max_batch
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.iwbc_batch_free(self._h)
+            self._h = None
+
+    def update(self, q, v, refs=None, contact_mask=None, out=None, fields=Results.FIELDS):
+        """Host arrays in, host arrays out (the reference-facing call: H2D + kernels + D2H)."""
+        P = self.problem
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, P.nq)
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, P.nv)
+        B = q.shape[0]
+        if refs is None:
+            refs = P.default_refs()
+        refs = np.ascontiguousarray(refs, dtype=np.float64)
+        stride = 0 if refs.ndim == 1 else P.nref
+        cm = None if contact_mask is None else np.ascontiguousarray(np.broadcast_to(np.asarray(contact_mask, dtype=np.uint32), (B,)))
+        if out is None:
+            out = Results(P, B, fields)
+        st = out.as_struct()
+        rc = lib().iwbc_batch_update(self._h, B, q.ctypes.data, v.ctypes.data, refs.ctypes.data, stride, _ptr(cm), C.byref(st))
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+        return out
+
+    def update_device(self, B, q_ptr, v_ptr, refs_ptr, refs_stride, contact_mask, out_ptrs, stream=0):
+        """All pointers are device addresses (ints); asynchronous on `stream`."""
+        st = _Results(*[out_ptrs.get(f) for f in Results.FIELDS])
+        rc = lib().iwbc_batch_update_device(self._h, B, q_ptr, v_ptr, refs_ptr, refs_stride, contact_mask, C.byref(st), stream)
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+
+    def rollout_device(self, B, q_ptr, v_ptr, refs_ptr, refs_stride, contact_mask, ticks, out_ptrs=None, stream=0):
+        st = _Results(*[(out_ptrs or {}).get(f) for f in Results.FIELDS])
+        rc = lib().iwbc_batch_rollout_device(self._h, B, q_ptr, v_ptr, refs_ptr, refs_stride, contact_mask, ticks, C.byref(st), stream)
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+
+    def debug_instance(self, q, v, ref=None, contact_mask=None):
+        P = self.problem
+        n = P.qp_shape(contact_mask)[0]
+        ref = P.default_refs() if ref is None else np.ascontiguousarray(ref, dtype=np.float64)
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        M, nle, H, g, x = np.zeros((P.nv, P.nv)), np.zeros(P.nv), np.zeros((n, n)), np.zeros(n), np.zeros(n)
+        m = P.default_contact_mask if contact_mask is None else contact_mask
+        rc = lib().iwbc_batch_debug_instance(self._h, q.ctypes.data, v.ctypes.data, ref.ctypes.data, m, M.ctypes.data,
+                                             nle.ctypes.data, H.ctypes.data, g.ctypes.data, x.ctypes.data)
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+        return dict(M=M, nle=nle, H=H, g=g, x=x)
+
+    @property
+    def launch_count(self):
+        return lib().iwbc_batch_launch_count(self._h)
+
+    def enable_timing(self, on=True):
+        lib().iwbc_batch_enable_timing(self._h, 1 if on else 0)
+
+    def kernel_ms(self, reset=False):
+        return lib().iwbc_batch_kernel_ms(self._h, 1 if reset else 0)
+
+
+def qp_solve_batch(H, g, CE, ce0, CI, ci0, device=0):
+    """Batched SolverHQPBase::solve (EiquadprogFast conventions). Arrays: H[B,n,n] g[B,n] CE[B,me,n] ce0[B,me] CI[B,mi,n] ci0[B,mi]."""
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    B, n, _ = H.shape
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    me = 0 if CE is None else CE.shape[1]
+    mi = 0 if CI is None else CI.shape[1]
+    CE = None if me == 0 else np.ascontiguousarray(CE, dtype=np.float64)
+    ce0 = None if me == 0 else np.ascontiguousarray(ce0, dtype=np.float64)
+    CI = None if mi == 0 else np.ascontiguousarray(CI, dtype=np.float64)
+    ci0 = None if mi == 0 else np.ascontiguousarray(ci0, dtype=np.float64)
+    x = np.zeros((B, n))
+    status = np.zeros(B, dtype=np.int32)
+    iters = np.zeros(B, dtype=np.int32)
+    active = np.zeros((B, ACTIVE_WORDS), dtype=np.uint32)
+    rc = lib().iwbc_qp_solve_batch(device, B, n, me, mi, H.ctypes.data, g.ctypes.data, _ptr(CE), _ptr(ce0), _ptr(CI), _ptr(ci0),
+                                   x.ctypes.data, status.ctypes.data, iters.ctypes.data, active.ctypes.data)
+    if rc != 0:
+        raise IwbcError(_err(lib()))
+    return x, status, iters, active

@@ -1,0 +1,895 @@
+// batch.cu -- GPU half of the C ABI (include/iwbc_batch.h): kernel entry points, launch logic,
+// device workspaces, host<->device staging.  sm_100a only; no CPU fallback.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/iwbc_batch.h"
+#include "cycle_kernel.cuh"
+#include "host_state.hpp"
+
+namespace iwbc {
+namespace dev {
+
+    // ------------------------------------------------------------------------------ the kernel
+    // One group of G threads per instance, IPC instances per CTA, persistent over the batch.
+    template <int G, int IPC>
+    __global__ void __launch_bounds__(G* IPC) k_cycle(const iwbc_problem_t* __restrict__ gP, IO io)
+    {
+        extern __shared__ double smem[];
+        const int grp = threadIdx.x / G;
+        const int tid = threadIdx.x - grp * G;
+        Sizes z;
+        z.nv = c_P.nv;
+        z.nq = c_P.nq;
+        z.nj = c_P.nj;
+        z.nf = c_P.nframes;
+        z.nc = c_P.ncontacts;
+        z.n = c_S.n;
+        z.mi = c_S.mi;
+        z.rows_dense = c_S.rows_dense;
+        z.nref = c_P.nref;
+        z.ldJ = c_S.ldJ;
+        z.ldM = c_S.ldM;
+        const Sm sm = make_sm(smem + (size_t)grp * c_S.total, z);
+        const int nv = z.nv, nq = z.nq, n = z.n, na = c_P.na, nu = nv - na;
+        int flip = 0;
+
+        // dof -> joint table
+        for (int j = tid; j < z.nj; j += G) {
+            const int c0 = gP->idx_v[j], cn = gP->jtype[j] == IWBC_J_FREEFLYER ? 6 : 1;
+            for (int k = 0; k < cn; ++k)
+                sm.dofj[c0 + k] = j;
+        }
+        const int ngroups = gridDim.x * IPC;
+        for (int inst = blockIdx.x * IPC + grp; inst < io.B; inst += ngroups) {
+            // ---- load state and references (coalesced: the instance's q / v / refs are contiguous)
+            const double* gq = io.q + (size_t)inst * nq;
+            const double* gv = io.v + (size_t)inst * nv;
+            const double* gr = io.refs + (size_t)inst * io.refs_stride;
+            for (int k = tid; k < nq; k += G)
+                sm.qs[k] = gq[k];
+            for (int k = tid; k < nv; k += G)
+                sm.vs[k] = gv[k];
+            for (int k = tid; k < z.nref; k += G)
+                sm.ref[k] = gr[k];
+            Grp<G>::sync();
+
+            k_dyn<G>(gP, sm, z, tid, flip);
+            k_asm<G>(gP, sm, z, tid, flip);
+
+            if (io.dbg_M && inst == 0) {
+                for (int e = tid; e < nv * nv; e += G)
+                    io.dbg_M[e] = sm.M[(e / nv) * z.ldM + (e % nv)];
+                for (int k = tid; k < nv; k += G)
+                    io.dbg_nle[k] = sm.nle[k];
+                for (int e = tid; e < n * n; e += G) {
+                    const int i = e / n, j = e % n;
+                    io.dbg_H[e] = i >= j ? sm.J[i + j * z.ldJ] : sm.J[j + i * z.ldJ];
+                }
+                for (int k = tid; k < n; k += G)
+                    io.dbg_g[k] = sm.g[k];
+                Grp<G>::sync();
+            }
+
+            int iters = 0, iq = 0;
+            const int status = gi_solve<G, FusedRows>(gP, sm, z, (const FusedRows*)nullptr, c_S.me, c_S.mi, tid, flip, iters, iq);
+
+            // ---- decode (controller.cpp:250-260) + integrate (:254-256) + command repack (:263-282)
+            FusedRows::wrenches<G>(sm, z, tid);
+            Grp<G>::sync();
+            if (io.dbg_x && inst == 0)
+                for (int k = tid; k < n; k += G)
+                    io.dbg_x[k] = sm.x[k];
+            const double dt = c_P.dt;
+            if (io.tau)
+                for (int i = tid; i < na; i += G)
+                    io.tau[(size_t)inst * na + i] = sm.nle[nu + i] + FusedRows::act_row_value(sm, z, i);
+            if (io.dv)
+                for (int k = tid; k < nv; k += G)
+                    io.dv[(size_t)inst * nv + k] = sm.x[k];
+            if (io.f)
+                for (int k = tid; k < 12 * z.nc; k += G) {
+                    const int c = k / 12;
+                    io.f[(size_t)inst * 12 * z.nc + k] = c_S.cidx[c] >= 0 ? sm.x[nv + c_S.cidx[c] + (k - 12 * c)] : 0.0;
+                }
+            // v+ -> sm.d (nv <= n), q+ -> sm.z region is too small for nq = nv + 1 when nk = 0: use sm.np / sm.gc
+            for (int k = tid; k < nv; k += G)
+                sm.d[k] = sm.vs[k] + dt * sm.x[k];
+            Grp<G>::sync();
+            double* qn = sm.x_old; // n + 2 >= nq
+            for (int j = tid; j < z.nj; j += G) {
+                const int iqx = gP->idx_q[j], iv = gP->idx_v[j];
+                if (gP->jtype[j] != IWBC_J_FREEFLYER) {
+                    qn[iqx] = sm.qs[iqx] + dt * sm.d[iv];
+                    continue;
+                }
+                // SE(3) exponential of dt * v+ composed on the right (pinocchio JointModelFreeFlyer::integrate)
+                const double* qq = sm.qs + iqx;
+                V3 vl = dt * ld3(sm.d + iv), w = dt * ld3(sm.d + iv + 3);
+                const double t2 = dot(w, w), t = sqrt(t2);
+                double bb, cc, s2, c2;
+                if (t < 1e-8) {
+                    bb = 0.5 - t2 / 24;
+                    cc = 1.0 / 6 - t2 / 120;
+                    s2 = 0.5 - t2 / 48;
+                    c2 = 1 - t2 / 8;
+                }
+                else {
+                    double st, ct;
+                    sincos(t, &st, &ct);
+                    bb = (1 - ct) / t2;
+                    cc = (t - st) / (t2 * t);
+                    double sh, ch;
+                    sincos(0.5 * t, &sh, &ch);
+                    s2 = sh / t;
+                    c2 = ch;
+                }
+                V3 wv = cross(w, vl);
+                V3 pe = vl + bb * wv + cc * cross(w, wv);
+                double R0[9];
+                quat_R(qq[3], qq[4], qq[5], qq[6], R0);
+                V3 pn = rmul(R0, pe) + ld3(qq);
+                const double ex = s2 * w.x, ey = s2 * w.y, ez = s2 * w.z, ew = c2;
+                const double x0 = qq[3], y0 = qq[4], z0 = qq[5], w0 = qq[6];
+                double rx = w0 * ex + x0 * ew + y0 * ez - z0 * ey;
+                double ry = w0 * ey - x0 * ez + y0 * ew + z0 * ex;
+                double rz = w0 * ez + x0 * ey - y0 * ex + z0 * ew;
+                double rw = w0 * ew - x0 * ex - y0 * ey - z0 * ez;
+                if (rx * x0 + ry * y0 + rz * z0 + rw * w0 < 0) {
+                    rx = -rx, ry = -ry, rz = -rz, rw = -rw;
+                }
+                const double nn = sqrt(rx * rx + ry * ry + rz * rz + rw * rw);
+                st3(qn + iqx, pn);
+                qn[iqx + 3] = rx / nn;
+                qn[iqx + 4] = ry / nn;
+                qn[iqx + 5] = rz / nn;
+                qn[iqx + 6] = rw / nn;
+            }
+            Grp<G>::sync();
+            if (io.v_next)
+                for (int k = tid; k < nv; k += G)
+                    io.v_next[(size_t)inst * nv + k] = sm.d[k];
+            if (io.q_next)
+                for (int k = tid; k < nq; k += G)
+                    io.q_next[(size_t)inst * nq + k] = qn[k];
+            if (io.q_cmd) {
+                double* o = io.q_cmd + (size_t)inst * nv;
+                if (c_P.floating_base) {
+                    if (tid == 0) {
+                        const double vx = qn[3], vy = qn[4], vz = qn[5], ww = qn[6];
+                        double nrm = sqrt(vx * vx + vy * vy + vz * vz);
+                        double ax = 1, ay = 0, az = 0, ang = 0;
+                        if (nrm != 0) {
+                            ang = 2 * atan2(nrm, fabs(ww));
+                            if (ww < 0)
+                                nrm = -nrm;
+                            ax = vx / nrm, ay = vy / nrm, az = vz / nrm;
+                        }
+                        o[0] = qn[0], o[1] = qn[1], o[2] = qn[2];
+                        o[3] = ang * ax, o[4] = ang * ay, o[5] = ang * az;
+                    }
+                    for (int k = tid; k < na; k += G)
+                        o[6 + k] = qn[7 + k];
+                }
+                else
+                    for (int k = tid; k < nv; k += G)
+                        o[k] = qn[k];
+            }
+            if (io.momentum && tid < 3)
+                io.momentum[(size_t)inst * 3 + tid] = sm.sc[34 + tid]; // Ag.bottomRows(3) * v = angular part of hg
+            if (tid == 0) {
+                if (io.status)
+                    io.status[inst] = status;
+                if (io.iters)
+                    io.iters[inst] = iters;
+                if (io.active) {
+                    unsigned* a = io.active + (size_t)inst * IWBC_ACTIVE_WORDS;
+                    unsigned words[IWBC_ACTIVE_WORDS];
+                    for (int k = 0; k < IWBC_ACTIVE_WORDS; ++k)
+                        words[k] = 0;
+                    for (int k = c_S.me; k < iq; ++k) {
+                        const int r = sm.act[k];
+                        if (r >= 0 && r < 32 * IWBC_ACTIVE_WORDS)
+                            words[r >> 5] |= 1u << (r & 31);
+                    }
+                    for (int k = 0; k < IWBC_ACTIVE_WORDS; ++k)
+                        a[k] = words[k];
+                }
+            }
+            if (io.q_rw) { // open-loop roll-out: the integrated state becomes the next tick's state
+                for (int k = tid; k < nq; k += G)
+                    io.q_rw[(size_t)inst * nq + k] = qn[k];
+                for (int k = tid; k < nv; k += G)
+                    io.v_rw[(size_t)inst * nv + k] = sm.d[k];
+            }
+            Grp<G>::sync();
+        }
+    }
+
+    // ---- dense QP kernel: the SolverHQPBase-shaped entry point.  H[B][n][n] etc. in global memory.
+    struct QpIO {
+        int B, n, me, mi;
+        const double *H, *g, *CE, *ce0, *CI, *ci0;
+        double* x;
+        int* status;
+        int* iters;
+        unsigned* active;
+    };
+    template <int G, int IPC>
+    __global__ void __launch_bounds__(G* IPC) k_qp_dense(QpIO io)
+    {
+        extern __shared__ double smem[];
+        const int grp = threadIdx.x / G;
+        const int tid = threadIdx.x - grp * G;
+        Sizes z;
+        z.nv = 0, z.nq = 0, z.nj = 0, z.nf = 0, z.nc = 0, z.nref = 0, z.rows_dense = 0;
+        z.n = io.n;
+        z.mi = io.mi;
+        z.ldJ = c_S.ldJ;
+        z.ldM = 1;
+        const Sm sm = make_sm(smem + (size_t)grp * c_S.total, z);
+        const int n = io.n;
+        int flip = 0;
+        const int ngroups = gridDim.x * IPC;
+        for (int inst = blockIdx.x * IPC + grp; inst < io.B; inst += ngroups) {
+            const double* H = io.H + (size_t)inst * n * n;
+            for (int e = tid; e < n * n; e += G) {
+                const int i = e / n, j = e - i * n;
+                if (i >= j)
+                    sm.J[i + j * z.ldJ] = H[e];
+            }
+            for (int k = tid; k < n; k += G)
+                sm.g[k] = io.g[(size_t)inst * n + k];
+            Grp<G>::sync();
+            DenseRows rows;
+            rows.CE = io.CE + (size_t)inst * io.me * n;
+            rows.ce0 = io.ce0 + (size_t)inst * io.me;
+            rows.CI = io.CI + (size_t)inst * io.mi * n;
+            rows.ci0 = io.ci0 + (size_t)inst * io.mi;
+            rows.n = n, rows.me = io.me, rows.mi = io.mi;
+            int iters = 0, iq = 0;
+            const int status = gi_solve<G, DenseRows>(nullptr, sm, z, &rows, io.me, io.mi, tid, flip, iters, iq);
+            Grp<G>::sync();
+            for (int k = tid; k < n; k += G)
+                io.x[(size_t)inst * n + k] = sm.x[k];
+            if (tid == 0) {
+                io.status[inst] = status;
+                io.iters[inst] = iters;
+                unsigned* a = io.active + (size_t)inst * IWBC_ACTIVE_WORDS;
+                for (int k = 0; k < IWBC_ACTIVE_WORDS; ++k)
+                    a[k] = 0;
+                for (int k = io.me; k < iq; ++k) {
+                    const int r = sm.act[k];
+                    if (r >= 0 && r < 32 * IWBC_ACTIVE_WORDS)
+                        a[r >> 5] |= 1u << (r & 31);
+                }
+            }
+            Grp<G>::sync();
+        }
+    }
+
+} // namespace dev
+} // namespace iwbc
+
+using namespace iwbc;
+
+#define CUDA_TRY(expr)                                                                                        \
+    do {                                                                                                      \
+        cudaError_t e_ = (expr);                                                                              \
+        if (e_ != cudaSuccess) {                                                                              \
+            set_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+            return IWBC_ERR_CUDA;                                                                             \
+        }                                                                                                     \
+    } while (0)
+
+struct iwbc_batch {
+    const iwbc_problem* prob = nullptr;
+    unsigned long revision = ~0ul;
+    int device = 0;
+    int max_batch = 0;
+    int sm_count = 0;
+    iwbc_problem_t* d_prob = nullptr;
+    cudaStream_t stream = nullptr;
+    // staging buffers (device)
+    double *d_q = nullptr, *d_v = nullptr, *d_refs = nullptr;
+    double *d_tau = nullptr, *d_dv = nullptr, *d_f = nullptr, *d_qn = nullptr, *d_vn = nullptr, *d_qc = nullptr, *d_mom = nullptr;
+    int *d_status = nullptr, *d_iters = nullptr;
+    unsigned* d_active = nullptr;
+    // bucketing scratch (host)
+    std::vector<int> perm;
+    std::vector<double> hq, hv, hr;
+    // launch bookkeeping
+    long launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double ms_sum = 0;
+    long ms_n = 0;
+    unsigned shape_mask = ~0u;
+    dev::Shape shape;
+    int G = 0, IPC = 0;
+    size_t smem_bytes = 0;
+    int grid = 0;
+};
+
+namespace {
+
+// which (device, problem revision, mask) the __constant__ copies currently hold
+struct ConstOwner {
+    const void* batch = nullptr;
+    unsigned long revision = 0;
+    unsigned mask = ~0u;
+} g_const_owner[16];
+
+template <int G, int IPC>
+int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
+{
+    auto kern = dev::k_cycle<G, IPC>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
+    if (b->grid == 0) {
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G * IPC, b->smem_bytes));
+        if (per_sm < 1) {
+            set_error("cycle kernel does not fit on an SM (shared memory " + std::to_string(b->smem_bytes) + " B)");
+            return IWBC_ERR_CUDA;
+        }
+        b->grid = b->sm_count * per_sm;
+    }
+    int grid = std::min(b->grid, (io.B + IPC - 1) / IPC);
+    if (b->timing)
+        cudaEventRecord(b->ev0, st);
+    kern<<<grid, G * IPC, b->smem_bytes, st>>>(b->d_prob, io);
+    if (b->timing) {
+        cudaEventRecord(b->ev1, st);
+        cudaEventSynchronize(b->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+        b->ms_sum += ms;
+        b->ms_n++;
+    }
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IWBC_OK;
+}
+
+// choose the thread-group width for this problem shape
+void choose_group(const iwbc_problem_t& P, int n, int& G, int& IPC)
+{
+    if (n <= 32 && P.nj * 16 <= 8 * 32) {
+        G = 32;
+        IPC = 4;
+    }
+    else if (n <= 64 && P.nj * 16 <= 8 * 64) {
+        G = 64;
+        IPC = 1;
+    }
+    else if (n <= 96 && P.nj * 16 <= 8 * 96) {
+        G = 96;
+        IPC = 1;
+    }
+    else {
+        G = 128;
+        IPC = 1;
+    }
+}
+
+int prepare_shape(iwbc_batch* b, unsigned mask)
+{
+    const iwbc_problem_t& P = b->prob->cs.prob;
+    if (b->shape_mask == mask && b->revision == b->prob->revision)
+        return IWBC_OK;
+    dev::Shape& S = b->shape;
+    std::memset(&S, 0, sizeof(S));
+    host::QPShape qs = host::qp_shape(P, mask);
+    S.n = qs.n;
+    S.nk = qs.nk;
+    S.me = qs.me;
+    S.mi = qs.mi;
+    int nk = 0;
+    for (int c = 0; c < IWBC_MAXC; ++c)
+        S.cidx[c] = -1;
+    for (int c = 0; c < P.ncontacts; ++c)
+        if (mask & (1u << c)) {
+            S.cidx[c] = nk;
+            nk += 12;
+        }
+    int ie = 0, ii = 0;
+    for (int k = 0; k < P.nl0; ++k) {
+        const iwbc_block_t& B = P.l0[k];
+        if (B.kind == IWBC_B_BASEDYN) {
+            S.ce[S.nce++] = {0, 0, ie, P.nv - P.na};
+            ie += P.nv - P.na;
+        }
+        else if (B.kind == IWBC_B_CONTACT_MOTION) {
+            if (S.cidx[B.index] < 0)
+                continue;
+            S.ce[S.nce++] = {1, B.index, ie, 6};
+            ie += 6;
+        }
+        else if (B.kind == IWBC_B_CONTACT_FORCE) {
+            if (S.cidx[B.index] < 0)
+                continue;
+            S.ci[S.nci++] = {2, B.index, ii, 17};
+            ii += 34;
+        }
+        else {
+            const iwbc_task_t& T = P.tasks[B.index];
+            S.ci[S.nci++] = {T.type == IWBC_T_BOUNDS ? 0 : 1, B.index, ii, T.nrows};
+            ii += 2 * T.nrows;
+        }
+    }
+    S.rows_dense = 0;
+    for (int k = 0; k < P.nl1; ++k)
+        if (P.l1[k].kind == IWBC_B_TASK && P.tasks[P.l1[k].index].type != IWBC_T_POSTURE)
+            S.rows_dense += P.tasks[P.l1[k].index].nrows;
+    S.maxdepth = 0;
+    for (int j = 0; j < P.nj; ++j)
+        S.maxdepth = std::max(S.maxdepth, P.depth[j]);
+    S.ldJ = S.n | 1;
+    S.ldM = P.nv | 1;
+    dev::Sizes z;
+    z.nv = P.nv, z.nq = P.nq, z.nj = P.nj, z.nf = P.nframes, z.nc = P.ncontacts, z.n = S.n, z.mi = S.mi;
+    z.rows_dense = S.rows_dense, z.nref = P.nref, z.ldJ = S.ldJ, z.ldM = S.ldM;
+    dev::make_layout(z, S);
+    choose_group(P, S.n, b->G, b->IPC);
+    b->smem_bytes = (size_t)S.total * sizeof(double) * b->IPC;
+    b->grid = 0;
+    b->shape_mask = mask;
+    return IWBC_OK;
+}
+
+int upload_constants(iwbc_batch* b, cudaStream_t st)
+{
+    ConstOwner& o = g_const_owner[b->device & 15];
+    if (b->revision != b->prob->revision) {
+        CUDA_TRY(cudaMemcpyAsync(b->d_prob, &b->prob->cs.prob, sizeof(iwbc_problem_t), cudaMemcpyHostToDevice, st));
+        b->revision = b->prob->revision;
+        o.batch = nullptr;
+    }
+    if (o.batch != b || o.revision != b->revision || o.mask != b->shape_mask) {
+        // other streams may still be running a kernel that reads the old constants
+        if (o.batch != nullptr && o.batch != b)
+            CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_P, &b->prob->cs.prob, sizeof(iwbc_problem_t), 0, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_S, &b->shape, sizeof(dev::Shape), 0, cudaMemcpyHostToDevice, st));
+        o.batch = b;
+        o.revision = b->revision;
+        o.mask = b->shape_mask;
+    }
+    return IWBC_OK;
+}
+
+int run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t st)
+{
+    int rc = prepare_shape(b, mask);
+    if (rc)
+        return rc;
+    rc = upload_constants(b, st);
+    if (rc)
+        return rc;
+    if (b->G == 32)
+        return launch_cycle<32, 4>(b, io, st);
+    if (b->G == 64)
+        return launch_cycle<64, 1>(b, io, st);
+    if (b->G == 96)
+        return launch_cycle<96, 1>(b, io, st);
+    return launch_cycle<128, 1>(b, io, st);
+}
+
+template <class T>
+int dalloc(T** p, size_t count)
+{
+    CUDA_TRY(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    return IWBC_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch)
+{
+    if (!p || max_batch <= 0) {
+        set_error("iwbc_batch_create: bad argument");
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        set_error(std::string("no usable CUDA device ") + std::to_string(device) + " (" + (e != cudaSuccess ? cudaGetErrorString(e) : "out of range")
+            + "): the batched cycle has no CPU fallback");
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major < 10) {
+        set_error("device " + std::to_string(device) + " is sm_" + std::to_string(prop.major * 10 + prop.minor) + "; this library is built for sm_100a only");
+        return nullptr;
+    }
+    cudaSetDevice(device);
+    auto* b = new iwbc_batch;
+    b->prob = p;
+    b->device = device;
+    b->max_batch = max_batch;
+    b->sm_count = prop.multiProcessorCount;
+    const iwbc_problem_t& P = p->cs.prob;
+    const size_t B = (size_t)max_batch;
+    bool ok = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreate(&b->ev0) == cudaSuccess && cudaEventCreate(&b->ev1) == cudaSuccess;
+    ok = ok && dalloc(&b->d_prob, 1) == 0 && dalloc(&b->d_q, B * P.nq) == 0 && dalloc(&b->d_v, B * P.nv) == 0
+        && dalloc(&b->d_refs, B * P.nref) == 0 && dalloc(&b->d_tau, B * P.na) == 0 && dalloc(&b->d_dv, B * P.nv) == 0
+        && dalloc(&b->d_f, B * 12 * P.ncontacts) == 0 && dalloc(&b->d_qn, B * P.nq) == 0 && dalloc(&b->d_vn, B * P.nv) == 0
+        && dalloc(&b->d_qc, B * P.nv) == 0 && dalloc(&b->d_mom, B * 3) == 0 && dalloc(&b->d_status, B) == 0 && dalloc(&b->d_iters, B) == 0
+        && dalloc(&b->d_active, B * IWBC_ACTIVE_WORDS) == 0;
+    if (!ok) {
+        if (std::string(iwbc_last_error()).empty())
+            set_error("iwbc_batch_create: CUDA allocation failed");
+        iwbc_batch_free(b);
+        return nullptr;
+    }
+    return b;
+}
+
+void iwbc_batch_free(iwbc_batch* b)
+{
+    if (!b)
+        return;
+    cudaSetDevice(b->device);
+    ConstOwner& o = g_const_owner[b->device & 15];
+    if (o.batch == b)
+        o.batch = nullptr;
+    if (b->stream)
+        cudaStreamSynchronize(b->stream);
+    void* ptrs[] = {b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
+    for (void* p : ptrs)
+        if (p)
+            cudaFree(p);
+    if (b->ev0)
+        cudaEventDestroy(b->ev0);
+    if (b->ev1)
+        cudaEventDestroy(b->ev1);
+    if (b->stream)
+        cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+int iwbc_batch_update_device(iwbc_batch* b, int B, const double* q, const double* v, const double* refs, long refs_stride, unsigned contact_mask,
+    const iwbc_results_t* out, void* stream)
+{
+    if (!b || !q || !v || !refs || !out || B < 0) {
+        set_error("iwbc_batch_update_device: bad argument");
+        return IWBC_ERR_ARG;
+    }
+    if (B == 0)
+        return IWBC_OK;
+    CUDA_TRY(cudaSetDevice(b->device));
+    dev::IO io;
+    std::memset(&io, 0, sizeof(io));
+    io.B = B;
+    io.q = q, io.v = v, io.refs = refs, io.refs_stride = refs_stride;
+    io.tau = out->tau, io.dv = out->dv, io.f = out->f, io.q_next = out->q_next, io.v_next = out->v_next, io.q_cmd = out->q_cmd;
+    io.momentum = out->momentum, io.status = out->status, io.iters = out->iters, io.active = out->active;
+    return run_cycle(b, io, contact_mask, stream ? (cudaStream_t)stream : b->stream);
+}
+
+int iwbc_batch_rollout_device(iwbc_batch* b, int B, double* q, double* v, const double* refs, long refs_stride, unsigned contact_mask, int ticks,
+    const iwbc_results_t* out_last, void* stream)
+{
+    if (!b || !q || !v || !refs || B < 0 || ticks < 0) {
+        set_error("iwbc_batch_rollout_device: bad argument");
+        return IWBC_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->stream;
+    for (int t = 0; t < ticks; ++t) {
+        dev::IO io;
+        std::memset(&io, 0, sizeof(io));
+        io.B = B;
+        io.q = q, io.v = v, io.refs = refs, io.refs_stride = refs_stride;
+        io.q_rw = q, io.v_rw = v;
+        if (out_last) { // status is OR-ed over ticks by the caller reading it after the last tick
+            io.status = out_last->status, io.iters = out_last->iters;
+            if (t == ticks - 1) {
+                io.tau = out_last->tau, io.dv = out_last->dv, io.f = out_last->f, io.q_cmd = out_last->q_cmd;
+                io.momentum = out_last->momentum, io.active = out_last->active;
+            }
+        }
+        int rc = run_cycle(b, io, contact_mask, st);
+        if (rc)
+            return rc;
+    }
+    return IWBC_OK;
+}
+
+int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, const double* refs, long refs_stride, const unsigned* contact_mask,
+    const iwbc_results_t* out)
+{
+    if (!b || !q || !v || !refs || !out || B < 0) {
+        set_error("iwbc_batch_update: bad argument");
+        return IWBC_ERR_ARG;
+    }
+    if (B > b->max_batch) {
+        set_error("iwbc_batch_update: B = " + std::to_string(B) + " exceeds max_batch = " + std::to_string(b->max_batch));
+        return IWBC_ERR_ARG;
+    }
+    if (refs_stride != 0 && refs_stride != b->prob->cs.prob.nref) {
+        set_error("iwbc_batch_update: refs_stride must be 0 (shared) or nref");
+        return IWBC_ERR_ARG;
+    }
+    if (B == 0)
+        return IWBC_OK;
+    CUDA_TRY(cudaSetDevice(b->device));
+    const iwbc_problem_t& P = b->prob->cs.prob;
+    cudaStream_t st = b->stream;
+    const unsigned dflt = iwbc_problem_default_contact_mask(b->prob);
+    // ---- bucket by contact mask (every launch is shape-uniform): instance order is restored on the way out
+    bool uniform = true;
+    if (contact_mask)
+        for (int i = 1; i < B; ++i)
+            if (contact_mask[i] != contact_mask[0]) {
+                uniform = false;
+                break;
+            }
+    const size_t nq = P.nq, nv = P.nv, na = P.na, nf = 12 * P.ncontacts, nref = P.nref;
+    auto copy_out = [&](int first, int count, const int* perm) -> int {
+        // device slot s in [first, first+count) holds instance perm[s] (or s when perm == nullptr)
+        auto back = [&](void* host, const void* devp, size_t elem_bytes, size_t per) -> int {
+            if (!host)
+                return IWBC_OK;
+            if (!perm) {
+                CUDA_TRY(cudaMemcpyAsync((char*)host + first * per * elem_bytes, (const char*)devp + first * per * elem_bytes, count * per * elem_bytes,
+                    cudaMemcpyDeviceToHost, st));
+            }
+            else {
+                for (int s = first; s < first + count; ++s)
+                    CUDA_TRY(cudaMemcpyAsync((char*)host + (size_t)perm[s] * per * elem_bytes, (const char*)devp + (size_t)s * per * elem_bytes,
+                        per * elem_bytes, cudaMemcpyDeviceToHost, st));
+            }
+            return IWBC_OK;
+        };
+        int rc = 0;
+        rc |= back(out->tau, b->d_tau, 8, na);
+        rc |= back(out->dv, b->d_dv, 8, nv);
+        rc |= back(out->f, b->d_f, 8, nf);
+        rc |= back(out->q_next, b->d_qn, 8, nq);
+        rc |= back(out->v_next, b->d_vn, 8, nv);
+        rc |= back(out->q_cmd, b->d_qc, 8, nv);
+        rc |= back(out->momentum, b->d_mom, 8, 3);
+        rc |= back(out->status, b->d_status, 4, 1);
+        rc |= back(out->iters, b->d_iters, 4, 1);
+        rc |= back(out->active, b->d_active, 4, IWBC_ACTIVE_WORDS);
+        return rc ? IWBC_ERR_CUDA : IWBC_OK;
+    };
+    auto dev_results = [&](size_t first) {
+        iwbc_results_t r;
+        r.tau = out->tau ? b->d_tau + first * na : nullptr;
+        r.dv = out->dv ? b->d_dv + first * nv : nullptr;
+        r.f = out->f ? b->d_f + first * nf : nullptr;
+        r.q_next = out->q_next ? b->d_qn + first * nq : nullptr;
+        r.v_next = out->v_next ? b->d_vn + first * nv : nullptr;
+        r.q_cmd = out->q_cmd ? b->d_qc + first * nv : nullptr;
+        r.momentum = out->momentum ? b->d_mom + first * 3 : nullptr;
+        r.status = out->status ? b->d_status + first : nullptr;
+        r.iters = out->iters ? b->d_iters + first : nullptr;
+        r.active = out->active ? b->d_active + first * IWBC_ACTIVE_WORDS : nullptr;
+        return r;
+    };
+    if (uniform) {
+        CUDA_TRY(cudaMemcpyAsync(b->d_q, q, B * nq * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->d_v, v, B * nv * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->d_refs, refs, (refs_stride ? (size_t)B : 1) * nref * 8, cudaMemcpyHostToDevice, st));
+        iwbc_results_t r = dev_results(0);
+        int rc = iwbc_batch_update_device(b, B, b->d_q, b->d_v, b->d_refs, refs_stride, contact_mask ? contact_mask[0] : dflt, &r, st);
+        if (rc)
+            return rc;
+        rc = copy_out(0, B, nullptr);
+        if (rc)
+            return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return IWBC_OK;
+    }
+    // mixed masks: stable sort of instance indices by mask, gather on the host, one launch per mask
+    b->perm.resize(B);
+    for (int i = 0; i < B; ++i)
+        b->perm[i] = i;
+    std::stable_sort(b->perm.begin(), b->perm.end(), [&](int a, int c) { return contact_mask[a] < contact_mask[c]; });
+    b->hq.resize(B * nq);
+    b->hv.resize(B * nv);
+    if (refs_stride)
+        b->hr.resize(B * nref);
+    for (int s = 0; s < B; ++s) {
+        const int i = b->perm[s];
+        std::memcpy(&b->hq[s * nq], q + i * nq, nq * 8);
+        std::memcpy(&b->hv[s * nv], v + i * nv, nv * 8);
+        if (refs_stride)
+            std::memcpy(&b->hr[s * nref], refs + (size_t)i * nref, nref * 8);
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->d_q, b->hq.data(), B * nq * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->d_v, b->hv.data(), B * nv * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->d_refs, refs_stride ? b->hr.data() : refs, (refs_stride ? (size_t)B : 1) * nref * 8, cudaMemcpyHostToDevice, st));
+    int first = 0;
+    while (first < B) {
+        const unsigned m = contact_mask[b->perm[first]];
+        int last = first;
+        while (last < B && contact_mask[b->perm[last]] == m)
+            ++last;
+        iwbc_results_t r = dev_results(first);
+        int rc = iwbc_batch_update_device(b, last - first, b->d_q + first * nq, b->d_v + first * nv, b->d_refs + (refs_stride ? first * nref : 0),
+            refs_stride, m, &r, st);
+        if (rc)
+            return rc;
+        first = last;
+    }
+    int rc = copy_out(0, B, b->perm.data());
+    if (rc)
+        return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return IWBC_OK;
+}
+
+long iwbc_batch_launch_count(const iwbc_batch* b) { return b ? b->launches : 0; }
+
+int iwbc_batch_enable_timing(iwbc_batch* b, int on)
+{
+    if (!b)
+        return IWBC_ERR_ARG;
+    b->timing = on != 0;
+    return IWBC_OK;
+}
+
+double iwbc_batch_kernel_ms(iwbc_batch* b, int reset)
+{
+    if (!b)
+        return 0;
+    double r = b->ms_n ? b->ms_sum / b->ms_n : 0.0;
+    if (reset) {
+        b->ms_sum = 0;
+        b->ms_n = 0;
+    }
+    return r;
+}
+
+int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, const double* ref, unsigned contact_mask, double* M, double* nle,
+    double* H, double* g, double* x)
+{
+    if (!b || !q || !v || !ref) {
+        set_error("iwbc_batch_debug_instance: bad argument");
+        return IWBC_ERR_ARG;
+    }
+    CUDA_TRY(cudaSetDevice(b->device));
+    const iwbc_problem_t& P = b->prob->cs.prob;
+    host::QPShape qs = host::qp_shape(P, contact_mask);
+    const size_t nv = P.nv, n = qs.n;
+    double *dM, *dn, *dH, *dg, *dx;
+    CUDA_TRY(cudaMalloc(&dM, nv * nv * 8));
+    CUDA_TRY(cudaMalloc(&dn, nv * 8));
+    CUDA_TRY(cudaMalloc(&dH, n * n * 8));
+    CUDA_TRY(cudaMalloc(&dg, n * 8));
+    CUDA_TRY(cudaMalloc(&dx, n * 8));
+    cudaStream_t st = b->stream;
+    CUDA_TRY(cudaMemcpyAsync(b->d_q, q, P.nq * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->d_v, v, nv * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->d_refs, ref, P.nref * 8, cudaMemcpyHostToDevice, st));
+    dev::IO io;
+    std::memset(&io, 0, sizeof(io));
+    io.B = 1;
+    io.q = b->d_q, io.v = b->d_v, io.refs = b->d_refs, io.refs_stride = 0;
+    io.dbg_M = dM, io.dbg_nle = dn, io.dbg_H = dH, io.dbg_g = dg, io.dbg_x = dx;
+    int rc = run_cycle(b, io, contact_mask, st);
+    if (rc == 0) {
+        if (M)
+            cudaMemcpyAsync(M, dM, nv * nv * 8, cudaMemcpyDeviceToHost, st);
+        if (nle)
+            cudaMemcpyAsync(nle, dn, nv * 8, cudaMemcpyDeviceToHost, st);
+        if (H)
+            cudaMemcpyAsync(H, dH, n * n * 8, cudaMemcpyDeviceToHost, st);
+        if (g)
+            cudaMemcpyAsync(g, dg, n * 8, cudaMemcpyDeviceToHost, st);
+        if (x)
+            cudaMemcpyAsync(x, dx, n * 8, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_error(std::string("CUDA error: ") + cudaGetErrorString(e));
+            rc = IWBC_ERR_CUDA;
+        }
+    }
+    cudaFree(dM), cudaFree(dn), cudaFree(dH), cudaFree(dg), cudaFree(dx);
+    return rc;
+}
+
+int iwbc_qp_solve_batch(int device, int B, int n, int me, int mi, const double* H, const double* g, const double* CE, const double* ce0,
+    const double* CI, const double* ci0, double* x, int* status, int* iters, unsigned* active)
+{
+    if (B <= 0 || n <= 0 || me < 0 || mi < 0 || !H || !g || !x || !status || (me && (!CE || !ce0)) || (mi && (!CI || !ci0))) {
+        set_error("iwbc_qp_solve_batch: bad argument");
+        return IWBC_ERR_ARG;
+    }
+    if (mi > 32 * IWBC_ACTIVE_WORDS || n > 128) {
+        set_error("iwbc_qp_solve_batch: n <= 128 and mi <= 384 supported");
+        return IWBC_ERR_UNSUPPORTED;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        set_error("no usable CUDA device: the batched QP has no CPU fallback");
+        return IWBC_ERR_CUDA;
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    dev::Shape S;
+    std::memset(&S, 0, sizeof(S));
+    S.n = n, S.me = me, S.mi = mi, S.ldJ = n | 1, S.ldM = 1;
+    dev::Sizes z;
+    std::memset(&z, 0, sizeof(z));
+    z.n = n, z.mi = mi, z.ldJ = S.ldJ, z.ldM = 1;
+    dev::make_layout(z, S);
+    const size_t Bz = B;
+    double *dH, *dg, *dCE, *dce, *dCI, *dci, *dx;
+    int *dst, *dit;
+    unsigned* dact;
+    CUDA_TRY(cudaMalloc(&dH, Bz * n * n * 8));
+    CUDA_TRY(cudaMalloc(&dg, Bz * n * 8));
+    CUDA_TRY(cudaMalloc(&dCE, std::max<size_t>(Bz * me * n, 1) * 8));
+    CUDA_TRY(cudaMalloc(&dce, std::max<size_t>(Bz * me, 1) * 8));
+    CUDA_TRY(cudaMalloc(&dCI, std::max<size_t>(Bz * mi * n, 1) * 8));
+    CUDA_TRY(cudaMalloc(&dci, std::max<size_t>(Bz * mi, 1) * 8));
+    CUDA_TRY(cudaMalloc(&dx, Bz * n * 8));
+    CUDA_TRY(cudaMalloc(&dst, Bz * 4));
+    CUDA_TRY(cudaMalloc(&dit, Bz * 4));
+    CUDA_TRY(cudaMalloc(&dact, Bz * IWBC_ACTIVE_WORDS * 4));
+    CUDA_TRY(cudaMemcpy(dH, H, Bz * n * n * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dg, g, Bz * n * 8, cudaMemcpyHostToDevice));
+    if (me) {
+        CUDA_TRY(cudaMemcpy(dCE, CE, Bz * me * n * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dce, ce0, Bz * me * 8, cudaMemcpyHostToDevice));
+    }
+    if (mi) {
+        CUDA_TRY(cudaMemcpy(dCI, CI, Bz * mi * n * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dci, ci0, Bz * mi * 8, cudaMemcpyHostToDevice));
+    }
+    ConstOwner& o = g_const_owner[device & 15];
+    CUDA_TRY(cudaDeviceSynchronize());
+    o.batch = nullptr;
+    CUDA_TRY(cudaMemcpyToSymbol(dev::c_S, &S, sizeof(S)));
+    dev::QpIO io = {B, n, me, mi, dH, dg, dCE, dce, dCI, dci, dx, dst, dit, dact};
+    int rc = IWBC_OK;
+    auto launch = [&](auto kern, int G, int IPC) -> int {
+        size_t smem = (size_t)S.total * 8 * IPC;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G * IPC, smem));
+        if (per_sm < 1) {
+            set_error("QP kernel does not fit in shared memory");
+            return IWBC_ERR_CUDA;
+        }
+        int grid = std::min(prop.multiProcessorCount * per_sm, (B + IPC - 1) / IPC);
+        kern<<<grid, G * IPC, smem>>>(io);
+        CUDA_TRY(cudaGetLastError());
+        return IWBC_OK;
+    };
+    if (n <= 32)
+        rc = launch(dev::k_qp_dense<32, 4>, 32, 4);
+    else if (n <= 64)
+        rc = launch(dev::k_qp_dense<64, 1>, 64, 1);
+    else if (n <= 96)
+        rc = launch(dev::k_qp_dense<96, 1>, 96, 1);
+    else
+        rc = launch(dev::k_qp_dense<128, 1>, 128, 1);
+    if (rc == IWBC_OK) {
+        CUDA_TRY(cudaMemcpy(x, dx, Bz * n * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(status, dst, Bz * 4, cudaMemcpyDeviceToHost));
+        if (iters)
+            CUDA_TRY(cudaMemcpy(iters, dit, Bz * 4, cudaMemcpyDeviceToHost));
+        if (active)
+            CUDA_TRY(cudaMemcpy(active, dact, Bz * IWBC_ACTIVE_WORDS * 4, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(dH), cudaFree(dg), cudaFree(dCE), cudaFree(dce), cudaFree(dCI), cudaFree(dci), cudaFree(dx), cudaFree(dst), cudaFree(dit), cudaFree(dact);
+    return rc;
+}
+
+} // extern "C"
