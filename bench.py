@@ -1,0 +1,379 @@
+#!/usr/bin/env python3
+"""bench.py -- batched TSID control updates ("QP solves") per second on N B200s of one node.
+
+  python bench.py --gpus 1 --steps 20 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+         bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...      # the CPU path (oracle, one instance per thread) on the same workload
+
+A "step" is one pass of the whole control cycle (k_dyn + k_asm + k_qp + k_dec, one fused kernel
+launch) over one batch of synthetic randomized robot states (SURVEY.md 8(d) recipes).  Weak scaling:
+every GPU steps its own batch of the same size, no collective on the data path.
+
+Printed JSON (one line, rank 0):
+  value      whole-job updates/s with inputs resident in HBM, CUDA events on the launching stream,
+             max over ranks, L2 flushed between timed steps
+  e2e        the same metric through the reference-facing call `Batch.update` (C ABI
+             iwbc_batch_update): pinned HOST buffers in, HOST results out, copies inside the timed region
+  roofline   FP64 FMA roofline of the fused kernel (this path is FP64 CUDA-core bound, not HBM or
+             tensor bound: SURVEY.md 8(d)); peak measured live with a dependent-FMA probe; the HBM
+             figure for the state/result traffic is given as a secondary number
+  cpu_baseline  the CPU oracle (port of the reference path) on this box's host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (controller yaml, overrides, per-GPU batch, recipe)
+    "talos_ds_16384": ("talos/talos_pos_tracker.yaml", None, 16384, "talos"),
+    "franka_65536": ("franka/pos_tracker.yaml", None, 65536, "franka"),
+    "tiago_65536": ("tiago/pos_tracker.yaml", {"urdf": "tiago/tiago_steel_no_wheel.urdf"}, 65536, "arm"),
+}
+DEFAULT_WORKLOAD = "talos_ds_16384"
+
+
+# ----------------------------------------------------------------------------- synthetic inputs
+def make_inputs(P, B, recipe, seed):
+    """config 2 (Franka) / config 3 (Talos double support) randomized states and targets."""
+    rng = np.random.default_rng(seed)
+    q = np.tile(P.q0(), (B, 1))
+    v = np.zeros((B, P.nv))
+    refs = np.tile(P.default_refs(), (B, 1))
+    na = P.na
+    if recipe == "talos":
+        dofs = P.names("dofs")
+        mimics = set(P.names("mimics"))
+        free = np.array([d not in mimics for d in dofs])
+        q[:, P.nq - na:][:, free] += rng.normal(0, 0.02, (B, int(free.sum())))
+        v[:, P.nv - na:] = rng.normal(0, 0.05, (B, na))
+        off, _ = P.ref_slot("com")
+        refs[:, off + 2] += rng.uniform(-0.2, 0.0, B)
+    else:
+        from inria_wbc_b200 import trajs
+        S = P.struct()
+        lo, hi = np.array(S.q_lo[:na]), np.array(S.q_hi[:na])
+        narm = 7 if recipe == "franka" else na
+        qa = rng.uniform(lo[:narm] + 0.1, hi[:narm] - 0.1, (B, narm))
+        q[:, P.nq - na:P.nq - na + narm] = qa
+        v[:, P.nv - na:P.nv - na + narm] = rng.normal(0, 0.1, (B, narm))
+        # ee reference = construction-time pose composed with a random offset (cheap stand-in for FK(q) o delta)
+        off, _ = P.ref_slot("ee")
+        p0, R0 = trajs.sample_se3(refs[0, off:off + 24])
+        dp = rng.uniform(-0.2, 0.2, (B, 3))
+        ang = rng.uniform(0, 0.5, B)
+        ax = rng.normal(size=(B, 3))
+        ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+        for i in range(B):
+            R = R0 @ trajs._rot(ax[i], ang[i])
+            refs[i, off:off + 24] = trajs.se3_sample(p0 + dp[i], R)
+    return q, v, refs
+
+
+# ----------------------------------------------------------------------------- flop model
+def algorithmic_flops(nv, na, n, me, mi, rows, adds, nj, nframes_jac, nsc_pairs):
+    """Reference-algorithm FLOPs per update (FMA = 2): SURVEY.md 8(d) F = F_dyn + F_asm + F_qp."""
+    f_qp = rows * n * (n + 1) + 2 * rows * n + n ** 3 / 3 + n ** 3 / 3 + 2 * n * n
+    for iq in range(me):
+        f_qp += 2 * n * n + 2 * n * (n - iq) + iq * iq + 6 * n * (n - iq - 1) + 4 * n
+    iq = me
+    f_qp += adds * (2 * mi * n + 2 * n * n + 2 * n * (n - iq) + iq * iq + 6 * n * (n - iq - 1) + 6 * n)
+    f_qp += 2 * mi * n
+    # textbook counts: per joint forward pass (placement, velocity, 2 accelerations, force) ~ 330, backward (RNEA + CRBA
+    # force-set propagation over the subtree) ~ 60 per (joint, supported dof) pair ~ nv*depth, Jacobian columns 30/dof,
+    # CoM / centroidal 120/joint
+    f_dyn = nj * (330 + 120) + nv * 30 + nv * 8 * 60
+    # task assembly: one 6 x nv local frame Jacobian per SE3 task / contact (66 flops per column), 3 x nv world Jacobians for
+    # the self-collision pairs (2 per pair, 15 flops per column), actuation-bounds mapping C*[M_a | -J_a'] as the reference
+    # does it (dense na x na x n), Jc = T' J per contact (12 x 6 x nv)
+    f_asm = nframes_jac * nv * 66 + nsc_pairs * 2 * nv * 15 + (2 * na * na * n if mi > 2 * na else 0) + (n - nv) // 12 * (2 * 12 * 6 * nv)
+    return dict(f_qp=float(f_qp), f_dyn=float(f_dyn), f_asm=float(f_asm), total=float(f_qp + f_dyn + f_asm))
+
+
+def problem_counts(P):
+    S = P.struct()
+    nfr = 0
+    nsc = 0
+    for k in range(S.ntasks):
+        t = S.tasks[k]
+        if t.type == 0:
+            nfr += 1
+        if t.type == 4:
+            nsc += t.nav
+    nfr += P.ncontacts
+    return S.nj, nfr, nsc
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if p[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def oracle_rate(P, q, v, refs, seconds, threads):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    n = q.shape[0]
+    ol.cycle_batch(P, q[:min(n, 256)], v[:min(n, 256)], refs[:min(n, 256)], nthreads=threads)  # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        ol.cycle_batch(P, q, v, refs, nthreads=threads)
+        done += n
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return done / el, done, el
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port; the reference itself cannot be built here:
+    SURVEY.md 8(c)), one independent controller instance per thread over all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import inria_wbc_b200 as iw
+    yaml, ov, B, recipe = WORKLOADS[args.workload]
+    P = iw.Problem(yaml, overrides=ov)
+    threads = os.cpu_count() or 1
+    sample = min(B, 2048)
+    q, v, refs = make_inputs(P, sample, recipe, 0xB200 + 3)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as ol
+    for _ in range(max(args.warmup, 1)):
+        ol.cycle_batch(P, q, v, refs, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ol.cycle_batch(P, q, v, refs, nthreads=threads)
+    el = time.perf_counter() - t0
+    val = sample * args.steps / el
+    line = {"impl": "reference", "metric": "batched TSID control updates (QP solves) per second", "value": val, "unit": "updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "per_step_sample": sample, "note": "CPU oracle port of the reference path; one instance per thread"},
+            "cpu_baseline": {"value": val, "unit": "updates/s", "cores": threads, "kind": "port", "sample": "%d instances x %d steps" % (sample, args.steps)},
+            "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import inria_wbc_b200 as iw
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the batched cycle has no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    yaml, ov, B, recipe = WORKLOADS[args.workload]
+    if args.batch:
+        B = args.batch
+    P = iw.Problem(yaml, overrides=ov)
+    q, v, refs = make_inputs(P, B, recipe, 0xB200 + 3 + 1000 * rank)
+    bt = iw.Batch(P, local, B)
+    n, me, mi, rows = P.qp_shape()
+    mask = P.default_contact_mask
+
+    # ---- device-resident arm
+    dq, dv_, dr = (torch.from_numpy(x).to(dev) for x in (q, v, refs))
+    out = {"tau": torch.empty(B, P.na, dtype=torch.float64, device=dev), "dv": torch.empty(B, P.nv, dtype=torch.float64, device=dev),
+           "f": torch.empty(B, max(12 * P.ncontacts, 1), dtype=torch.float64, device=dev),
+           "q_next": torch.empty(B, P.nq, dtype=torch.float64, device=dev), "v_next": torch.empty(B, P.nv, dtype=torch.float64, device=dev),
+           "status": torch.empty(B, dtype=torch.int32, device=dev), "iters": torch.empty(B, dtype=torch.int32, device=dev)}
+    ptrs = {k: t.data_ptr() for k, t in out.items()}
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    stream = torch.cuda.Stream(device=dev)  # an explicit stream: the events below must see the kernel
+    torch.cuda.synchronize()
+
+    def step():
+        bt.update_device(B, dq.data_ptr(), dv_.data_ptr(), dr.data_ptr(), P.nref, mask, ptrs, stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = bt.launch_count
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        with torch.cuda.stream(stream):
+            flush.fill_(float(k))  # L2 flush, outside the timed events
+            ev[k][0].record(stream)
+            step()
+            ev[k][1].record(stream)
+    barrier()
+    launches = bt.launch_count - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    clocks = sampler.stop() if rank == 0 else None
+    status = out["status"].cpu().numpy()
+    iters = out["iters"].cpu().numpy()
+    n_opt = int((status == 0).sum())
+
+    # ---- end-to-end arm: pinned host buffers through the reference-facing call
+    hq, hv, hr = (torch.from_numpy(x).pin_memory() for x in (q, v, refs))
+    res = iw.Results(P, B, fields=("tau", "dv", "f", "q_next", "v_next", "status"))
+    pinned = {}
+    for fld in ("tau", "dv", "f", "q_next", "v_next", "status"):
+        t = torch.from_numpy(getattr(res, fld)).pin_memory()
+        pinned[fld] = t
+        setattr(res, fld, t.numpy())
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        bt.update(hq.numpy(), hv.numpy(), hr.numpy(), out=res)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        bt.update(hq.numpy(), hv.numpy(), hr.numpy(), out=res)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = q.nbytes + v.nbytes + refs.nbytes
+    d2h = sum(getattr(res, f).nbytes for f in ("tau", "dv", "f", "q_next", "v_next", "status"))
+
+    # ---- max over ranks
+    tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    agg = torch.tensor([float(n_opt), float(iters.sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    total_ms, e2e_s = tt.tolist()
+    n_opt_all, iters_all = agg.tolist()
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = B * world / (ms_per_step * 1e-3)
+        e2e_val = B * world / (e2e_s / e2e_steps)
+        adds = max(iters_all / (B * world) - 1.0, 0.0)
+        nj, nfr, nsc = problem_counts(P)
+        fl = algorithmic_flops(P.nv, P.na, n, me, mi, rows, adds, nj, nfr, nsc)
+        kern_ms = float(np.mean(step_ms))
+        peak = iw.measure_fp64_tflops(local)
+        achieved = fl["total"] * B / (kern_ms * 1e-3) / 1e12
+        io_bytes = 8 * (P.nq + P.nv + P.nref) + 8 * (P.na + 2 * P.nv + 12 * P.ncontacts + P.nq) + 8
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+        except Exception:
+            pass
+        line = {
+            "metric": "batched TSID control updates (QP solves) per second", "value": value, "unit": "updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "controller": yaml, "per_gpu_batch": B, "qp": {"n": n, "me": me, "mi": mi, "cost_rows": rows},
+                       "l2": "flushed (256 MB write) between timed steps", "optimal_fraction": n_opt_all / (B * world),
+                       "mean_active_set_iterations": iters_all / (B * world), "p50_cycle_latency_ms_per_batch": float(np.median(step_ms)),
+                       "parallelism": "dp%d (independent shards, no collective)" % world},
+            "e2e": {"value": e2e_val, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64-fma (CUDA cores); not hbm / tensor bound", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak > 0 else None, "peak_source": "measured live (dependent-FMA probe, iwbc_measure_fp64_tflops)",
+                         "flops_per_update": fl, "kernel_ms": kern_ms, "traffic": traffic,
+                         "hbm": {"achieved": io_bytes * B / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": io_bytes * B / (kern_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_update": io_bytes,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            ns = min(B, 4096)
+            rate, done, el = oracle_rate(P, q[:ns], v[:ns], refs[:ns], 2.5, threads)
+            rate1, done1, el1 = oracle_rate(P, q[:256], v[:256], refs[:256], 1.0, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "updates/s", "cores": threads, "kind": "port",
+                                    "sample": "%d updates of the same workload in %.2f s on %d threads (oracle port)" % (done, el, threads),
+                                    "single_thread": rate1,
+                                    "reference_recorded": "0.0126 ms/cycle Franka, different unknown hardware (tests/ref_test_franka.yaml:11)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

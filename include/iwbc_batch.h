@@ -121,6 +121,16 @@ long iwbc_batch_launch_count(const iwbc_batch* b);
 double iwbc_batch_kernel_ms(iwbc_batch* b, int reset);
 int iwbc_batch_enable_timing(iwbc_batch* b, int on);
 
+/* clock64() timestamps of the phases of the last iwbc_batch_debug_instance call (instance 0):
+ * start, after k_dyn, after k_asm, after factor+inverse, after equalities, after the active-set loop, after decode */
+int iwbc_batch_debug_cycles(const iwbc_batch* b, long long* out7);
+/* launch shape of the cycle kernel for the last contact mask: threads per instance, instances per CTA, grid, dynamic smem */
+int iwbc_batch_launch_info(const iwbc_batch* b, int* G, int* ipc, int* grid, long* smem_bytes);
+
+/* measured FP64 FMA throughput of the device in TFLOP/s (dependent-FMA chains, 8-way ILP): the roofline
+ * denominator of this FP64 CUDA-core-bound path; < 0 on error */
+double iwbc_measure_fp64_tflops(int device);
+
 /* stage dump of ONE instance for parity tests (device results copied to host; any pointer may be NULL):
  * M[nv*nv] nle[nv] H[n*n] g[n] x[n], all row-major */
 int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, const double* ref, unsigned contact_mask,

@@ -6,4 +6,4 @@ a Python mirror of the reference's controller surface (`controllers.py`).  There
 the compute calls raise if the CUDA library or a GPU is missing.
 """
 from ._lib import (Problem, Batch, Results, qp_solve_batch, lib, lib_path, IwbcError,  # noqa: F401
-                   ETC_PATH, ROBOTS_PATH, STATUS_OPTIMAL, ACTIVE_WORDS)
+                   ETC_PATH, ROBOTS_PATH, STATUS_OPTIMAL, ACTIVE_WORDS, measure_fp64_tflops)

@@ -63,6 +63,9 @@ def lib():
         "iwbc_batch_kernel_ms": (cd, [vp, ci]),
         "iwbc_batch_enable_timing": (ci, [vp, ci]),
         "iwbc_batch_debug_instance": (ci, [vp, vp, vp, vp, cu, vp, vp, vp, vp, vp]),
+        "iwbc_measure_fp64_tflops": (cd, [ci]),
+        "iwbc_batch_debug_cycles": (ci, [vp, vp]),
+        "iwbc_batch_launch_info": (ci, [vp, pi, pi, pi, C.POINTER(C.c_long)]),
         "iwbc_qp_solve_batch": (ci, [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
@@ -114,6 +117,11 @@ class Problem:
     def data_ptr(self):
         """const iwbc_problem_t* (handed to the CPU oracle by the tests)"""
         return lib().iwbc_problem_data(self._h)
+
+    def struct(self):
+        """ctypes view of the flat iwbc_problem_t (read-only)."""
+        from ._problem_struct import view
+        return view(self.data_ptr)
 
     def qp_shape(self, contact_mask=None):
         m = self.default_contact_mask if contact_mask is None else contact_mask
@@ -244,6 +252,17 @@ class Batch:
             raise IwbcError(_err(lib()))
         return dict(M=M, nle=nle, H=H, g=g, x=x)
 
+    def debug_cycles(self):
+        """Phase durations (SM cycles) of the last debug_instance call: dyn, asm, factor, equalities, active-set loop, decode."""
+        t = np.zeros(7, dtype=np.int64)
+        lib().iwbc_batch_debug_cycles(self._h, t.ctypes.data)
+        return dict(zip(("dyn", "asm", "factor", "eq", "ineq", "decode"), np.diff(t).tolist()))
+
+    def launch_info(self):
+        g, i, gr, sm = C.c_int(), C.c_int(), C.c_int(), C.c_long()
+        lib().iwbc_batch_launch_info(self._h, C.byref(g), C.byref(i), C.byref(gr), C.byref(sm))
+        return dict(threads_per_instance=g.value, instances_per_cta=i.value, grid=gr.value, smem_bytes=sm.value)
+
     @property
     def launch_count(self):
         return lib().iwbc_batch_launch_count(self._h)
@@ -253,6 +272,13 @@ class Batch:
 
     def kernel_ms(self, reset=False):
         return lib().iwbc_batch_kernel_ms(self._h, 1 if reset else 0)
+
+
+def measure_fp64_tflops(device=0):
+    r = lib().iwbc_measure_fp64_tflops(device)
+    if r < 0:
+        raise IwbcError(_err(lib()))
+    return r
 
 
 def qp_solve_batch(H, g, CE, ce0, CI, ci0, device=0):

@@ -37,7 +37,6 @@ namespace dev {
         z.ldJ = c_S.ldJ;
         z.ldM = c_S.ldM;
         const Sm sm = make_sm(smem + (size_t)grp * c_S.total, z);
-        const int nv = z.nv, nq = z.nq, n = z.n, na = c_P.na, nu = nv - na;
         int flip = 0;
 
         // dof -> joint table
@@ -48,166 +47,7 @@ namespace dev {
         }
         const int ngroups = gridDim.x * IPC;
         for (int inst = blockIdx.x * IPC + grp; inst < io.B; inst += ngroups) {
-            // ---- load state and references (coalesced: the instance's q / v / refs are contiguous)
-            const double* gq = io.q + (size_t)inst * nq;
-            const double* gv = io.v + (size_t)inst * nv;
-            const double* gr = io.refs + (size_t)inst * io.refs_stride;
-            for (int k = tid; k < nq; k += G)
-                sm.qs[k] = gq[k];
-            for (int k = tid; k < nv; k += G)
-                sm.vs[k] = gv[k];
-            for (int k = tid; k < z.nref; k += G)
-                sm.ref[k] = gr[k];
-            Grp<G>::sync();
-
-            k_dyn<G>(gP, sm, z, tid, flip);
-            k_asm<G>(gP, sm, z, tid, flip);
-
-            if (io.dbg_M && inst == 0) {
-                for (int e = tid; e < nv * nv; e += G)
-                    io.dbg_M[e] = sm.M[(e / nv) * z.ldM + (e % nv)];
-                for (int k = tid; k < nv; k += G)
-                    io.dbg_nle[k] = sm.nle[k];
-                for (int e = tid; e < n * n; e += G) {
-                    const int i = e / n, j = e % n;
-                    io.dbg_H[e] = i >= j ? sm.J[i + j * z.ldJ] : sm.J[j + i * z.ldJ];
-                }
-                for (int k = tid; k < n; k += G)
-                    io.dbg_g[k] = sm.g[k];
-                Grp<G>::sync();
-            }
-
-            int iters = 0, iq = 0;
-            const int status = gi_solve<G, FusedRows>(gP, sm, z, (const FusedRows*)nullptr, c_S.me, c_S.mi, tid, flip, iters, iq);
-
-            // ---- decode (controller.cpp:250-260) + integrate (:254-256) + command repack (:263-282)
-            FusedRows::wrenches<G>(sm, z, tid);
-            Grp<G>::sync();
-            if (io.dbg_x && inst == 0)
-                for (int k = tid; k < n; k += G)
-                    io.dbg_x[k] = sm.x[k];
-            const double dt = c_P.dt;
-            if (io.tau)
-                for (int i = tid; i < na; i += G)
-                    io.tau[(size_t)inst * na + i] = sm.nle[nu + i] + FusedRows::act_row_value(sm, z, i);
-            if (io.dv)
-                for (int k = tid; k < nv; k += G)
-                    io.dv[(size_t)inst * nv + k] = sm.x[k];
-            if (io.f)
-                for (int k = tid; k < 12 * z.nc; k += G) {
-                    const int c = k / 12;
-                    io.f[(size_t)inst * 12 * z.nc + k] = c_S.cidx[c] >= 0 ? sm.x[nv + c_S.cidx[c] + (k - 12 * c)] : 0.0;
-                }
-            // v+ -> sm.d (nv <= n), q+ -> sm.z region is too small for nq = nv + 1 when nk = 0: use sm.np / sm.gc
-            for (int k = tid; k < nv; k += G)
-                sm.d[k] = sm.vs[k] + dt * sm.x[k];
-            Grp<G>::sync();
-            double* qn = sm.x_old; // n + 2 >= nq
-            for (int j = tid; j < z.nj; j += G) {
-                const int iqx = gP->idx_q[j], iv = gP->idx_v[j];
-                if (gP->jtype[j] != IWBC_J_FREEFLYER) {
-                    qn[iqx] = sm.qs[iqx] + dt * sm.d[iv];
-                    continue;
-                }
-                // SE(3) exponential of dt * v+ composed on the right (pinocchio JointModelFreeFlyer::integrate)
-                const double* qq = sm.qs + iqx;
-                V3 vl = dt * ld3(sm.d + iv), w = dt * ld3(sm.d + iv + 3);
-                const double t2 = dot(w, w), t = sqrt(t2);
-                double bb, cc, s2, c2;
-                if (t < 1e-8) {
-                    bb = 0.5 - t2 / 24;
-                    cc = 1.0 / 6 - t2 / 120;
-                    s2 = 0.5 - t2 / 48;
-                    c2 = 1 - t2 / 8;
-                }
-                else {
-                    double st, ct;
-                    sincos(t, &st, &ct);
-                    bb = (1 - ct) / t2;
-                    cc = (t - st) / (t2 * t);
-                    double sh, ch;
-                    sincos(0.5 * t, &sh, &ch);
-                    s2 = sh / t;
-                    c2 = ch;
-                }
-                V3 wv = cross(w, vl);
-                V3 pe = vl + bb * wv + cc * cross(w, wv);
-                double R0[9];
-                quat_R(qq[3], qq[4], qq[5], qq[6], R0);
-                V3 pn = rmul(R0, pe) + ld3(qq);
-                const double ex = s2 * w.x, ey = s2 * w.y, ez = s2 * w.z, ew = c2;
-                const double x0 = qq[3], y0 = qq[4], z0 = qq[5], w0 = qq[6];
-                double rx = w0 * ex + x0 * ew + y0 * ez - z0 * ey;
-                double ry = w0 * ey - x0 * ez + y0 * ew + z0 * ex;
-                double rz = w0 * ez + x0 * ey - y0 * ex + z0 * ew;
-                double rw = w0 * ew - x0 * ex - y0 * ey - z0 * ez;
-                if (rx * x0 + ry * y0 + rz * z0 + rw * w0 < 0) {
-                    rx = -rx, ry = -ry, rz = -rz, rw = -rw;
-                }
-                const double nn = sqrt(rx * rx + ry * ry + rz * rz + rw * rw);
-                st3(qn + iqx, pn);
-                qn[iqx + 3] = rx / nn;
-                qn[iqx + 4] = ry / nn;
-                qn[iqx + 5] = rz / nn;
-                qn[iqx + 6] = rw / nn;
-            }
-            Grp<G>::sync();
-            if (io.v_next)
-                for (int k = tid; k < nv; k += G)
-                    io.v_next[(size_t)inst * nv + k] = sm.d[k];
-            if (io.q_next)
-                for (int k = tid; k < nq; k += G)
-                    io.q_next[(size_t)inst * nq + k] = qn[k];
-            if (io.q_cmd) {
-                double* o = io.q_cmd + (size_t)inst * nv;
-                if (c_P.floating_base) {
-                    if (tid == 0) {
-                        const double vx = qn[3], vy = qn[4], vz = qn[5], ww = qn[6];
-                        double nrm = sqrt(vx * vx + vy * vy + vz * vz);
-                        double ax = 1, ay = 0, az = 0, ang = 0;
-                        if (nrm != 0) {
-                            ang = 2 * atan2(nrm, fabs(ww));
-                            if (ww < 0)
-                                nrm = -nrm;
-                            ax = vx / nrm, ay = vy / nrm, az = vz / nrm;
-                        }
-                        o[0] = qn[0], o[1] = qn[1], o[2] = qn[2];
-                        o[3] = ang * ax, o[4] = ang * ay, o[5] = ang * az;
-                    }
-                    for (int k = tid; k < na; k += G)
-                        o[6 + k] = qn[7 + k];
-                }
-                else
-                    for (int k = tid; k < nv; k += G)
-                        o[k] = qn[k];
-            }
-            if (io.momentum && tid < 3)
-                io.momentum[(size_t)inst * 3 + tid] = sm.sc[34 + tid]; // Ag.bottomRows(3) * v = angular part of hg
-            if (tid == 0) {
-                if (io.status)
-                    io.status[inst] = status;
-                if (io.iters)
-                    io.iters[inst] = iters;
-                if (io.active) {
-                    unsigned* a = io.active + (size_t)inst * IWBC_ACTIVE_WORDS;
-                    unsigned words[IWBC_ACTIVE_WORDS];
-                    for (int k = 0; k < IWBC_ACTIVE_WORDS; ++k)
-                        words[k] = 0;
-                    for (int k = c_S.me; k < iq; ++k) {
-                        const int r = sm.act[k];
-                        if (r >= 0 && r < 32 * IWBC_ACTIVE_WORDS)
-                            words[r >> 5] |= 1u << (r & 31);
-                    }
-                    for (int k = 0; k < IWBC_ACTIVE_WORDS; ++k)
-                        a[k] = words[k];
-                }
-            }
-            if (io.q_rw) { // open-loop roll-out: the integrated state becomes the next tick's state
-                for (int k = tid; k < nq; k += G)
-                    io.q_rw[(size_t)inst * nq + k] = qn[k];
-                for (int k = tid; k < nv; k += G)
-                    io.v_rw[(size_t)inst * nv + k] = sm.d[k];
-            }
+            cycle_instance<G>(gP, sm, z, io, inst, tid, flip);
             Grp<G>::sync();
         }
     }
@@ -274,6 +114,19 @@ namespace dev {
         }
     }
 
+    // FP64 FMA peak probe: 8 independent dependent-FMA chains per thread (the roofline denominator of this
+    // path is FP64 CUDA-core throughput, which MEASURED_PEAKS.json does not hold: SURVEY.md 8(d))
+    __global__ void k_fp64_peak(double* out, int iters, double a, double b)
+    {
+        double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+        for (int i = 0; i < iters; ++i) {
+            x0 = fma(x0, a, b), x1 = fma(x1, a, b), x2 = fma(x2, a, b), x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b), x5 = fma(x5, a, b), x6 = fma(x6, a, b), x7 = fma(x7, a, b);
+        }
+        if (x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 == 123.456)
+            out[0] = x0;
+    }
+
 } // namespace dev
 } // namespace iwbc
 
@@ -313,6 +166,7 @@ struct iwbc_batch {
     unsigned shape_mask = ~0u;
     dev::Shape shape;
     int G = 0, IPC = 0;
+    long long last_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t smem_bytes = 0;
     int grid = 0;
 };
@@ -732,6 +586,62 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
     return IWBC_OK;
 }
 
+int iwbc_batch_debug_cycles(const iwbc_batch* b, long long* out7)
+{
+    if (!b || !out7)
+        return IWBC_ERR_ARG;
+    for (int k = 0; k < 7; ++k)
+        out7[k] = b->last_cycles[k];
+    return IWBC_OK;
+}
+
+int iwbc_batch_launch_info(const iwbc_batch* b, int* G, int* ipc, int* grid, long* smem_bytes)
+{
+    if (!b)
+        return IWBC_ERR_ARG;
+    if (G)
+        *G = b->G;
+    if (ipc)
+        *ipc = b->IPC;
+    if (grid)
+        *grid = b->grid;
+    if (smem_bytes)
+        *smem_bytes = (long)b->smem_bytes;
+    return IWBC_OK;
+}
+
+double iwbc_measure_fp64_tflops(int device)
+{
+    if (cudaSetDevice(device) != cudaSuccess) {
+        set_error("iwbc_measure_fp64_tflops: no usable CUDA device");
+        return -1.0;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    double* d = nullptr;
+    cudaMalloc(&d, 8);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 1 << 14, blocks = prop.multiProcessorCount * 8, threads = 256;
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        dev::k_fp64_peak<<<blocks, threads>>>(d, iters, 0.999999, 1e-7);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best)
+            best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return best;
+}
+
 long iwbc_batch_launch_count(const iwbc_batch* b) { return b ? b->launches : 0; }
 
 int iwbc_batch_enable_timing(iwbc_batch* b, int on)
@@ -780,6 +690,10 @@ int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, c
     io.B = 1;
     io.q = b->d_q, io.v = b->d_v, io.refs = b->d_refs, io.refs_stride = 0;
     io.dbg_M = dM, io.dbg_nle = dn, io.dbg_H = dH, io.dbg_g = dg, io.dbg_x = dx;
+    long long* dcyc = nullptr;
+    CUDA_TRY(cudaMalloc(&dcyc, 8 * sizeof(long long)));
+    CUDA_TRY(cudaMemsetAsync(dcyc, 0, 8 * sizeof(long long), st));
+    io.dbg_cycles = dcyc;
     int rc = run_cycle(b, io, contact_mask, st);
     if (rc == 0) {
         if (M)
@@ -792,13 +706,14 @@ int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, c
             cudaMemcpyAsync(g, dg, n * 8, cudaMemcpyDeviceToHost, st);
         if (x)
             cudaMemcpyAsync(x, dx, n * 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(b->last_cycles, dcyc, 8 * sizeof(long long), cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) {
             set_error(std::string("CUDA error: ") + cudaGetErrorString(e));
             rc = IWBC_ERR_CUDA;
         }
     }
-    cudaFree(dM), cudaFree(dn), cudaFree(dH), cudaFree(dg), cudaFree(dx);
+    cudaFree(dM), cudaFree(dn), cudaFree(dH), cudaFree(dg), cudaFree(dx), cudaFree(dcyc);
     return rc;
 }
 

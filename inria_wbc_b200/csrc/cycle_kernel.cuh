@@ -26,7 +26,33 @@
 //   * multipliers of *equality* constraints are not tracked (they never feed back into x, the
 //     active set or the status).
 #pragma once
+#ifdef IWBC_CPU_SIM
+// Debug build of this very source for a host compiler: a "group" of ONE thread executes the kernel
+// body serially (tests/cpu_sim.cpp).  It exercises the control flow and arithmetic of the device
+// code without a GPU; it is test tooling, not a product path (the shipped library never defines
+// IWBC_CPU_SIM).
+#include <cmath>
+#include <cstring>
+#include <type_traits>
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __constant__
+#define __restrict__
+namespace iwbc { namespace dev {
+struct SimIdx { int x; };
+static SimIdx threadIdx = {0};
+inline void __syncwarp(unsigned) {}
+inline void __syncthreads() {}
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
+inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
+inline long long clock64() { return 0; }
+inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
+using std::sqrt; using std::fabs; using std::fmin; using std::fmax; using std::exp; using std::log1p; using std::acos; using std::sin; using std::atan2; using std::fma;
+} }
+#else
 #include <cuda_runtime.h>
+#endif
 
 #include "../../include/iwbc_batch.h"
 
@@ -83,6 +109,7 @@ namespace dev {
         double* dbg_H;
         double* dbg_g;
         double* dbg_x;
+        long long* dbg_cycles; // phase timestamps (clock64) of instance 0: load, dyn, asm, factor, eq, ineq, decode
     };
 
     __constant__ iwbc_problem_t c_P; // uniform-access copy (task tables, sizes)
@@ -156,8 +183,8 @@ namespace dev {
         double c = fmin(1.0, fmax(-1.0, 0.5 * (tr - 1)));
         double theta = acos(c);
         V3 v = mk(R[7] - R[5], R[2] - R[6], R[3] - R[1]);
-        if (theta < 1e-8)
-            return (0.5 * (1 + theta * theta / 6)) * v;
+        if (theta < 1.220703125e-4) // TaylorSeriesExpansion<double>::precision<3>() = eps^(1/4)
+            return 0.5 * v;
         if (theta > M_PI - 1e-2) {
             double cphi = -(tr - 1) / 2;
             double beta = theta * theta / (1 + cphi);
@@ -172,7 +199,7 @@ namespace dev {
         V3 w = log3(R);
         double t2 = dot(w, w), t = sqrt(t2);
         double alpha, beta;
-        if (t < 1e-8) {
+        if (t < 1.220703125e-4) {
             alpha = 1 - t2 / 12 - t2 * t2 / 720;
             beta = 1.0 / 12 + t2 / 720;
         }
@@ -406,34 +433,35 @@ namespace dev {
     __device__ void k_dyn(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, int tid, int& flip)
     {
         const int nj = z.nj, nv = z.nv;
-        // ---- joint transforms in the parent frame (registers), then oMi level by level
-        double li[12]; // liMi of joint `tid`
-        const int j0 = tid;
-        if (j0 < nj) {
-            const double* jp = gP->jplace[j0];
-            const int ty = gP->jtype[j0];
-            double jm[9];
-            V3 jt = mk(0, 0, 0);
-            if (ty == IWBC_J_FREEFLYER) {
-                const double* qq = sm.qs + gP->idx_q[j0];
-                quat_R(qq[3], qq[4], qq[5], qq[6], jm);
-                jt = mk(qq[0], qq[1], qq[2]);
-            }
-            else if (ty == IWBC_J_REVOLUTE) {
-                axis_angle_R(ld3(gP->axis[j0]), sm.qs[gP->idx_q[j0]], jm);
-            }
-            else {
-                jm[0] = jm[4] = jm[8] = 1;
-                jm[1] = jm[2] = jm[3] = jm[5] = jm[6] = jm[7] = 0;
-                jt = sm.qs[gP->idx_q[j0]] * ld3(gP->axis[j0]);
-            }
-            mm3(jp, jm, li);
-            st3(li + 9, rmul(jp, jt) + ld3(jp + 9));
-        }
-        const int my_depth = j0 < nj ? gP->depth[j0] : -1;
-        const int my_parent = j0 < nj ? gP->parent[j0] : -1;
+        // ---- placements, world motion subspaces, velocities and drift accelerations, level by level
+        // (a joint is handled by thread j % G when its depth comes up; parents are one level above)
         for (int dpt = 0; dpt <= c_S.maxdepth; ++dpt) {
-            if (my_depth == dpt) {
+            for (int j0 = tid; j0 < nj; j0 += G) {
+                if (gP->depth[j0] != dpt)
+                    continue;
+                double li[12]; // liMi: placement in the parent joint frame times the joint transform
+                {
+                    const double* jp = gP->jplace[j0];
+                    const int ty = gP->jtype[j0];
+                    double jm[9];
+                    V3 jt = mk(0, 0, 0);
+                    if (ty == IWBC_J_FREEFLYER) {
+                        const double* qq = sm.qs + gP->idx_q[j0];
+                        quat_R(qq[3], qq[4], qq[5], qq[6], jm);
+                        jt = mk(qq[0], qq[1], qq[2]);
+                    }
+                    else if (ty == IWBC_J_REVOLUTE) {
+                        axis_angle_R(ld3(gP->axis[j0]), sm.qs[gP->idx_q[j0]], jm);
+                    }
+                    else {
+                        jm[0] = jm[4] = jm[8] = 1;
+                        jm[1] = jm[2] = jm[3] = jm[5] = jm[6] = jm[7] = 0;
+                        jt = sm.qs[gP->idx_q[j0]] * ld3(gP->axis[j0]);
+                    }
+                    mm3(jp, jm, li);
+                    st3(li + 9, rmul(jp, jt) + ld3(jp + 9));
+                }
+                const int my_parent = gP->parent[j0];
                 double* o = sm.oMi + 12 * j0;
                 V3 vp = mk(0, 0, 0), wp = mk(0, 0, 0), alp = mk(0, 0, 0), aap = mk(0, 0, 0);
                 if (my_parent >= 0) {
@@ -536,31 +564,41 @@ namespace dev {
             sm.sc[k] = s;
         }
         Grp<G>::sync();
-        // ---- subtree sums (composite inertia, subtree force): joint j sums its DFS range, into registers first
+        // ---- subtree sums (composite inertia, subtree force): joint j sums its DFS range.  In place, so the sums
+        // are staged in registers (chunks of 8 items per thread) and written back after a barrier.
         {
-            // work item = (joint, quantity), 16 quantities per joint; results written after a barrier (in place)
-            const int items = nj * 16;
-            double acc[8];
-            int cnt = 0;
-            for (int it = tid; it < items; it += G, ++cnt) {
-                const int j = it >> 4, k = it & 15;
-                const int last = gP->last_desc[j];
-                double s = 0;
-                for (int jj = j; jj <= last; ++jj)
-                    s += k < 10 ? sm.Yw[10 * jj + k] : sm.fw[6 * jj + (k - 10)];
-                acc[cnt & 7] = s;
-            }
-            Grp<G>::sync();
-            cnt = 0;
-            for (int it = tid; it < items; it += G, ++cnt) {
-                const int j = it >> 4, k = it & 15;
-                if (k < 10)
-                    sm.Yw[10 * j + k] = acc[cnt & 7];
-                else
-                    sm.fw[6 * j + (k - 10)] = acc[cnt & 7];
+            const int items = nj * 16; // (joint, quantity), 16 quantities per joint
+            for (int base = 0; base < items; base += 8 * G) {
+                double acc[8];
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    const int it = base + c8 * G + tid;
+                    double s = 0;
+                    if (it < items) {
+                        const int j = it >> 4, k = it & 15;
+                        const int last = gP->last_desc[j];
+                        for (int jj = j; jj <= last; ++jj)
+                            s += k < 10 ? sm.Yw[10 * jj + k] : sm.fw[6 * jj + (k - 10)];
+                    }
+                    acc[c8] = s;
+                }
+                // a later chunk still has to read the un-summed values of joints >= its own, and the DFS ranges only
+                // extend forward: chunks are processed in increasing joint order, so writing back chunk c is safe
+                Grp<G>::sync();
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    const int it = base + c8 * G + tid;
+                    if (it < items) {
+                        const int j = it >> 4, k = it & 15;
+                        if (k < 10)
+                            sm.Yw[10 * j + k] = acc[c8];
+                        else
+                            sm.fw[6 * j + (k - 10)] = acc[c8];
+                    }
+                }
+                Grp<G>::sync();
             }
         }
-        Grp<G>::sync();
         // ---- per dof: nle = S . f_subtree, F = Yc S
         for (int c = tid; c < nv; c += G) {
             const int j = sm.dofj[c];
@@ -1474,7 +1512,7 @@ namespace dev {
     // Returns the eiquadprog status mapped to iwbc_status; iq_out = final active-set size.
     template <int G, class ROWS>
     __device__ int gi_solve(const iwbc_problem_t* gP, const Sm& sm, const Sizes& z, const ROWS* dense, int me, int mi, int tid, int& flip,
-        int& iter_out, int& iq_out)
+        int& iter_out, int& iq_out, long long* cyc = nullptr)
     {
         const int n = z.n, ld = z.ldJ;
         const double eps = 2.220446049250313e-16;
@@ -1487,6 +1525,8 @@ namespace dev {
         }
         unconstrained_min<G>(sm, n, ld, tid);
         c2 = finish_J<G>(sm, n, ld, tid, flip);
+        if (cyc && tid == 0)
+            cyc[3] = clock64();
         double R_norm = 1.0;
         int iq = 0, iter = 0;
 
@@ -1525,6 +1565,8 @@ namespace dev {
                 return IWBC_STATUS_ERROR; // REDUNDANT_EQUALITIES
             }
         }
+        if (cyc && tid == 0)
+            cyc[4] = clock64();
         // iai = K \ A ; all constraints eligible
         for (int k = tid; k < mi; k += G)
             sm.iai[k] = k;
@@ -1715,6 +1757,186 @@ namespace dev {
         iter_out = iter;
         iq_out = iq;
         return status;
+    }
+
+    // =================================================================================== one instance
+    // load -> k_dyn -> k_asm -> k_qp -> k_dec for instance `inst`, executed by one group of G threads
+    template <int G>
+    __device__ void cycle_instance(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, const IO& io, int inst, int tid, int& flip)
+    {
+        const int nv = z.nv, nq = z.nq, n = z.n, na = c_P.na, nu = nv - na;
+        // ---- load state and references (coalesced: the instance's q / v / refs are contiguous)
+        const double* gq = io.q + (size_t)inst * nq;
+        const double* gv = io.v + (size_t)inst * nv;
+        const double* gr = io.refs + (size_t)inst * io.refs_stride;
+        for (int k = tid; k < nq; k += G)
+            sm.qs[k] = gq[k];
+        for (int k = tid; k < nv; k += G)
+            sm.vs[k] = gv[k];
+        for (int k = tid; k < z.nref; k += G)
+            sm.ref[k] = gr[k];
+        Grp<G>::sync();
+        long long* cyc = (io.dbg_cycles && inst == 0) ? io.dbg_cycles : nullptr;
+        if (cyc && tid == 0)
+            cyc[0] = clock64();
+
+        k_dyn<G>(gP, sm, z, tid, flip);
+        if (cyc && tid == 0)
+            cyc[1] = clock64();
+        k_asm<G>(gP, sm, z, tid, flip);
+        if (cyc && tid == 0)
+            cyc[2] = clock64();
+
+        if (io.dbg_M && inst == 0) {
+            for (int e = tid; e < nv * nv; e += G)
+                io.dbg_M[e] = sm.M[(e / nv) * z.ldM + (e % nv)];
+            for (int k = tid; k < nv; k += G)
+                io.dbg_nle[k] = sm.nle[k];
+            for (int e = tid; e < n * n; e += G) {
+                const int i = e / n, j = e % n;
+                io.dbg_H[e] = i >= j ? sm.J[i + j * z.ldJ] : sm.J[j + i * z.ldJ];
+            }
+            for (int k = tid; k < n; k += G)
+                io.dbg_g[k] = sm.g[k];
+            Grp<G>::sync();
+        }
+
+        int iters = 0, iq = 0;
+        const int status = gi_solve<G, FusedRows>(gP, sm, z, (const FusedRows*)nullptr, c_S.me, c_S.mi, tid, flip, iters, iq, cyc);
+        if (cyc && tid == 0)
+            cyc[5] = clock64();
+
+        // ---- decode (controller.cpp:250-260) + integrate (:254-256) + command repack (:263-282)
+        FusedRows::wrenches<G>(sm, z, tid);
+        Grp<G>::sync();
+        if (io.dbg_x && inst == 0)
+            for (int k = tid; k < n; k += G)
+                io.dbg_x[k] = sm.x[k];
+        const double dt = c_P.dt;
+        if (io.tau)
+            for (int i = tid; i < na; i += G)
+                io.tau[(size_t)inst * na + i] = sm.nle[nu + i] + FusedRows::act_row_value(sm, z, i);
+        if (io.dv)
+            for (int k = tid; k < nv; k += G)
+                io.dv[(size_t)inst * nv + k] = sm.x[k];
+        if (io.f)
+            for (int k = tid; k < 12 * z.nc; k += G) {
+                const int c = k / 12;
+                io.f[(size_t)inst * 12 * z.nc + k] = c_S.cidx[c] >= 0 ? sm.x[nv + c_S.cidx[c] + (k - 12 * c)] : 0.0;
+            }
+        // v+ -> sm.d (nv <= n), q+ -> sm.z region is too small for nq = nv + 1 when nk = 0: use sm.np / sm.gc
+        for (int k = tid; k < nv; k += G)
+            sm.d[k] = sm.vs[k] + dt * sm.x[k];
+        Grp<G>::sync();
+        double* qn = sm.x_old; // n + 2 >= nq
+        for (int j = tid; j < z.nj; j += G) {
+            const int iqx = gP->idx_q[j], iv = gP->idx_v[j];
+            if (gP->jtype[j] != IWBC_J_FREEFLYER) {
+                qn[iqx] = sm.qs[iqx] + dt * sm.d[iv];
+                continue;
+            }
+            // SE(3) exponential of dt * v+ composed on the right (pinocchio JointModelFreeFlyer::integrate)
+            const double* qq = sm.qs + iqx;
+            V3 vl = dt * ld3(sm.d + iv), w = dt * ld3(sm.d + iv + 3);
+            const double t2 = dot(w, w), t = sqrt(t2);
+            double bb, cc, s2, c2;
+            if (t < 1.220703125e-4) {
+                bb = 0.5 - t2 / 24;
+                cc = 1.0 / 6 - t2 / 120;
+                s2 = 0.5 - t2 / 48;
+                c2 = 1 - t2 / 8;
+            }
+            else {
+                double st, ct;
+                sincos(t, &st, &ct);
+                bb = (1 - ct) / t2;
+                cc = (t - st) / (t2 * t);
+                double sh, ch;
+                sincos(0.5 * t, &sh, &ch);
+                s2 = sh / t;
+                c2 = ch;
+            }
+            V3 wv = cross(w, vl);
+            V3 pe = vl + bb * wv + cc * cross(w, wv);
+            double R0[9];
+            quat_R(qq[3], qq[4], qq[5], qq[6], R0);
+            V3 pn = rmul(R0, pe) + ld3(qq);
+            const double ex = s2 * w.x, ey = s2 * w.y, ez = s2 * w.z, ew = c2;
+            const double x0 = qq[3], y0 = qq[4], z0 = qq[5], w0 = qq[6];
+            double rx = w0 * ex + x0 * ew + y0 * ez - z0 * ey;
+            double ry = w0 * ey - x0 * ez + y0 * ew + z0 * ex;
+            double rz = w0 * ez + x0 * ey - y0 * ex + z0 * ew;
+            double rw = w0 * ew - x0 * ex - y0 * ey - z0 * ez;
+            if (rx * x0 + ry * y0 + rz * z0 + rw * w0 < 0) {
+                rx = -rx, ry = -ry, rz = -rz, rw = -rw;
+            }
+            const double nn = sqrt(rx * rx + ry * ry + rz * rz + rw * rw);
+            st3(qn + iqx, pn);
+            qn[iqx + 3] = rx / nn;
+            qn[iqx + 4] = ry / nn;
+            qn[iqx + 5] = rz / nn;
+            qn[iqx + 6] = rw / nn;
+        }
+        Grp<G>::sync();
+        if (io.v_next)
+            for (int k = tid; k < nv; k += G)
+                io.v_next[(size_t)inst * nv + k] = sm.d[k];
+        if (io.q_next)
+            for (int k = tid; k < nq; k += G)
+                io.q_next[(size_t)inst * nq + k] = qn[k];
+        if (io.q_cmd) {
+            double* o = io.q_cmd + (size_t)inst * nv;
+            if (c_P.floating_base) {
+                if (tid == 0) {
+                    const double vx = qn[3], vy = qn[4], vz = qn[5], ww = qn[6];
+                    double nrm = sqrt(vx * vx + vy * vy + vz * vz);
+                    double ax = 1, ay = 0, az = 0, ang = 0;
+                    if (nrm != 0) {
+                        ang = 2 * atan2(nrm, fabs(ww));
+                        if (ww < 0)
+                            nrm = -nrm;
+                        ax = vx / nrm, ay = vy / nrm, az = vz / nrm;
+                    }
+                    o[0] = qn[0], o[1] = qn[1], o[2] = qn[2];
+                    o[3] = ang * ax, o[4] = ang * ay, o[5] = ang * az;
+                }
+                for (int k = tid; k < na; k += G)
+                    o[6 + k] = qn[7 + k];
+            }
+            else
+                for (int k = tid; k < nv; k += G)
+                    o[k] = qn[k];
+        }
+        if (io.momentum)
+            for (int k = tid; k < 3; k += G)
+                io.momentum[(size_t)inst * 3 + k] = sm.sc[34 + k]; // Ag.bottomRows(3) * v = angular part of hg
+        if (tid == 0) {
+            if (io.status)
+                io.status[inst] = status;
+            if (io.iters)
+                io.iters[inst] = iters;
+            if (io.active) {
+                unsigned* a = io.active + (size_t)inst * IWBC_ACTIVE_WORDS;
+                unsigned words[IWBC_ACTIVE_WORDS];
+                for (int k = 0; k < IWBC_ACTIVE_WORDS; ++k)
+                    words[k] = 0;
+                for (int k = c_S.me; k < iq; ++k) {
+                    const int r = sm.act[k];
+                    if (r >= 0 && r < 32 * IWBC_ACTIVE_WORDS)
+                        words[r >> 5] |= 1u << (r & 31);
+                }
+                for (int k = 0; k < IWBC_ACTIVE_WORDS; ++k)
+                    a[k] = words[k];
+            }
+        }
+        if (cyc && tid == 0)
+            cyc[6] = clock64();
+        if (io.q_rw) { // open-loop roll-out: the integrated state becomes the next tick's state
+            for (int k = tid; k < nq; k += G)
+                io.q_rw[(size_t)inst * nq + k] = qn[k];
+            for (int k = tid; k < nv; k += G)
+                io.v_rw[(size_t)inst * nv + k] = sm.d[k];
+        }
     }
 
 } // namespace dev

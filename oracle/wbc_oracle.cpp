@@ -149,7 +149,7 @@ inline M3 exp3(V3 w)
 {
     double t2 = dot(w, w), t = std::sqrt(t2);
     double a, b; // R = I + a [w] + b [w]^2
-    if (t < 1e-8) {
+    if (t < 1.220703125e-4) {
         a = 1 - t2 / 6;
         b = 0.5 - t2 / 24;
     }
@@ -171,9 +171,8 @@ inline V3 log3(const M3& R)
     double c = std::min(1.0, std::max(-1.0, 0.5 * (tr - 1)));
     double theta = std::acos(c);
     V3 v = {R.m[7] - R.m[5], R.m[2] - R.m[6], R.m[3] - R.m[1]};
-    if (theta < 1e-8) {
-        return 0.5 * (1 + theta * theta / 6) * v;
-    }
+    if (theta < 1.220703125e-4) // TaylorSeriesExpansion<double>::precision<3>() = eps^(1/4)
+        return 0.5 * v;
     if (theta > M_PI - 1e-2) {
         // near pi: use the diagonal
         double cphi = -(tr - 1) / 2; // = -cos(theta)
@@ -193,7 +192,7 @@ inline Motion log6(const SE3& M)
     V3 w = log3(M.R);
     double t2 = dot(w, w), t = std::sqrt(t2);
     double alpha, beta;
-    if (t < 1e-8) {
+    if (t < 1.220703125e-4) {
         alpha = 1 - t2 / 12 - t2 * t2 / 720;
         beta = 1.0 / 12 + t2 / 720;
     }
@@ -211,7 +210,7 @@ inline SE3 exp6(Motion nu)
     V3 w = nu.ang, v = nu.lin;
     double t2 = dot(w, w), t = std::sqrt(t2);
     double a, b, c; // R = I + a W + b W^2 ; p = (I + b W + c W^2) v
-    if (t < 1e-8) {
+    if (t < 1.220703125e-4) {
         a = 1 - t2 / 6;
         b = 0.5 - t2 / 24;
         c = 1.0 / 6 - t2 / 120;
@@ -1309,7 +1308,7 @@ void cycle(const iwbc_problem_t& P, const double* q, const double* v, const doub
             // quaternion of the increment, composed on the right
             V3 w3 = nu6.ang;
             double t = norm(w3), s2, c2;
-            if (t < 1e-8) {
+            if (t < 1.220703125e-4) {
                 s2 = 0.5 - t * t / 48;
                 c2 = 1 - t * t / 8;
             }

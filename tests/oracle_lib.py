@@ -119,3 +119,55 @@ def frame(problem, q, v, frame_id):
     lib().oracle_frame(C.c_void_p(problem.data_ptr), _p(np.ascontiguousarray(q, dtype=np.float64)),
                        _p(np.ascontiguousarray(v, dtype=np.float64)), C.c_int(frame_id), _p(oMf), _p(vel), _p(acc), _p(J))
     return dict(oMf=oMf, vel=vel, acc=acc, J=J)
+
+
+# ----------------------------------------------------------------- CPU simulation of the device source (test tooling)
+_sim = None
+
+
+def sim_lib():
+    global _sim
+    if _sim is None:
+        so = os.path.join(ROOT, "tests", "libcpusim.so")
+        srcs = [os.path.join(ROOT, "tests", "cpu_sim.cpp"), os.path.join(ROOT, "inria_wbc_b200", "csrc", "cycle_kernel.cuh")]
+        if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused", "-o", so, srcs[0]])
+        _sim = C.CDLL(so)
+    return _sim
+
+
+def sim_cycle_batch(problem, q, v, refs=None, contact_mask=None):
+    P = problem
+    q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, P.nq)
+    v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, P.nv)
+    B = q.shape[0]
+    refs = P.default_refs() if refs is None else np.ascontiguousarray(refs, dtype=np.float64)
+    stride = 0 if refs.ndim == 1 else P.nref
+    m = P.default_contact_mask if contact_mask is None else contact_mask
+    out = dict(tau=np.zeros((B, P.na)), dv=np.zeros((B, P.nv)), f=np.zeros((B, 12 * P.ncontacts)), q_next=np.zeros((B, P.nq)),
+               v_next=np.zeros((B, P.nv)), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32),
+               active=np.zeros((B, ORACLE_ACTIVE_WORDS), np.uint32), q_cmd=np.zeros((B, P.nv)), momentum=np.zeros((B, 3)))
+    rc = sim_lib().sim_cycle_batch(C.c_void_p(P.data_ptr), C.c_int(B), _p(q), _p(v), _p(refs), C.c_long(stride), C.c_uint(m),
+                                   _p(out["tau"]), _p(out["dv"]), _p(out["f"]), _p(out["q_next"]), _p(out["v_next"]), _p(out["status"]),
+                                   _p(out["iters"]), _p(out["active"]), _p(out["q_cmd"]), _p(out["momentum"]))
+    assert rc == 0
+    return out
+
+
+def sim_qp_solve(H, g, CE, ce0, CI, ci0):
+    n = len(g)
+    me = 0 if CE is None else len(ce0)
+    mi = 0 if CI is None else len(ci0)
+    H = np.ascontiguousarray(H, dtype=np.float64)
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    CE = np.zeros((1, n)) if me == 0 else np.ascontiguousarray(CE, dtype=np.float64)
+    ce0 = np.zeros(1) if me == 0 else np.ascontiguousarray(ce0, dtype=np.float64)
+    CI = np.zeros((1, n)) if mi == 0 else np.ascontiguousarray(CI, dtype=np.float64)
+    ci0 = np.zeros(1) if mi == 0 else np.ascontiguousarray(ci0, dtype=np.float64)
+    x = np.zeros(n)
+    status = np.zeros(1, np.int32)
+    iters = np.zeros(1, np.int32)
+    active = np.zeros(ORACLE_ACTIVE_WORDS, np.uint32)
+    sim_lib().sim_qp_solve(C.c_int(n), C.c_int(me), C.c_int(mi), _p(H), _p(g), _p(CE), _p(ce0), _p(CI), _p(ci0), _p(x), _p(status),
+                           _p(iters), _p(active))
+    return dict(status=int(status[0]), x=x, iters=int(iters[0]), active=active)

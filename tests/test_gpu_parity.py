@@ -1,0 +1,197 @@
+"""Parity tests proper: the CUDA path through the C ABI against the CPU oracle (run on a B200 with -m gpu).
+Bar (BASELINE.json north_star): tau, dv, f within 1e-8 relative, same final active set (modulo weakly active
+rows at degenerate friction vertices, see test_cpu_sim.active_sets_equivalent), same status."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import inria_wbc_b200 as iw
+import oracle_lib as ol
+from conftest import random_states
+from test_cpu_sim import active_sets_equivalent
+from test_oracle_qp import random_qp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+TOL = 1e-8
+
+
+def _rel(a, b):
+    return (np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), 1e-9)).max() if b.size else 0.0
+
+
+def _check(P, bt, q, v, refs=None, mask=None, tol=TOL):
+    r = bt.update(q, v, refs, contact_mask=mask)
+    o = ol.cycle_batch(P, q, v, refs, contact_mask=mask, nthreads=os.cpu_count())
+    assert np.array_equal(r.status, o["status"])
+    ok = o["status"] == 0
+    assert ok.mean() > 0.9
+    for k in ("tau", "dv", "f", "q_next", "v_next", "q_cmd", "momentum"):
+        assert _rel(getattr(r, k)[ok], o[k][ok]) < tol, k
+    bad = np.where(ok & ~np.all(r.active == o["active"], axis=1))[0]
+    for i in bad[:50]:
+        rr = None if refs is None else (refs if refs.ndim == 1 else refs[i])
+        m = None if mask is None else int(np.broadcast_to(mask, (len(q),))[i])
+        assert active_sets_equivalent(P, q[i], v[i], rr, o["active"][i], r.active[i], m), i
+    return r, o
+
+
+def test_library_is_the_cuda_one():
+    assert os.path.exists(iw.lib_path())
+    assert iw.measure_fp64_tflops(0) > 5.0
+
+
+def test_franka_batch(franka):
+    import bench
+    q, v, refs = bench.make_inputs(franka, 4096, "franka", 0xB200)
+    bt = iw.Batch(franka, 0, 4096)
+    r, o = _check(franka, bt, q, v, refs)
+    assert (r.iters == 1).all() and bt.launch_count == 1
+
+
+def test_tiago_active_bounds(tiago):
+    q, v = random_states(tiago, 2048, 2, qn=0.2, vn=0.3)
+    bt = iw.Batch(tiago, 0, 2048)
+    r, o = _check(tiago, bt, q, v)
+    assert np.array_equal(r.iters, o["iters"]) and r.iters.max() > 3
+
+
+def test_talos_double_support_config3(talos):
+    import bench
+    B = 2048
+    q, v, refs = bench.make_inputs(talos, B, "talos", 0xB200 + 3)
+    bt = iw.Batch(talos, 0, B)
+    r, o = _check(talos, bt, q, v, refs)
+    assert np.array_equal(r.active, o["active"])  # non-degenerate workload: identical active sets
+    assert np.array_equal(r.iters, o["iters"])
+
+
+def test_talos_stage_dump(talos):
+    q, v = random_states(talos, 1, 9, base=True)
+    bt = iw.Batch(talos, 0, 8)
+    d = bt.debug_instance(q[0], v[0])
+    o = ol.cycle_debug(talos, q[0], v[0])
+    for k, tol in (("M", 1e-12), ("nle", 1e-12), ("H", 1e-11), ("g", 1e-11), ("x", 1e-8)):
+        assert np.abs(d[k] - o[k]).max() <= tol * np.abs(o[k]).max(), k
+
+
+def test_talos_mixed_contact_masks_are_bucketed(talos):
+    B = 600
+    q, v = random_states(talos, B, 12)
+    mask = np.random.default_rng(1).choice(np.array([3, 1, 2], dtype=np.uint32), B)
+    bt = iw.Batch(talos, 0, B)
+    r, o = _check(talos, bt, q, v, mask=mask)
+    assert bt.launch_count == 3  # one shape-uniform launch per contact mask
+    f = r.f.reshape(B, 2, 12)
+    assert np.all(f[mask == 1, 1] == 0) and np.all(f[mask == 2, 0] == 0)
+
+
+def test_full_size_properties(talos):
+    """BASELINE config 3 at full size (16 384): size-independent properties instead of the oracle."""
+    import bench
+    B = 16384
+    q, v, refs = bench.make_inputs(talos, B, "talos", 0xB200 + 3)
+    bt = iw.Batch(talos, 0, B)
+    r = bt.update(q, v, refs)
+    assert (r.status == 0).all()
+    S = talos.struct()
+    # semi-implicit Euler identity and joint-space integration
+    np.testing.assert_allclose(r.v_next, v + S.dt * r.dv, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(r.q_next[:, 7:], q[:, 7:] + S.dt * r.v_next[:, 6:], rtol=0, atol=1e-15)
+    assert np.abs(np.linalg.norm(r.q_next[:, 3:7], axis=1) - 1).max() < 1e-15
+    # constraints hold: torque limits, friction cone, unilateral normal force
+    tmax = np.array(S.tau_max[:talos.na])
+    assert (np.abs(r.tau) <= tmax * (1 + 1e-9) + 1e-9).all()
+    f = r.f.reshape(B, 2, 4, 3)
+    fz = f[..., 2].sum(axis=2)
+    assert (fz >= 5.0 - 1e-6).all() and (fz <= 1500 + 1e-6).all()
+    assert (np.abs(f[..., 0]) <= 0.3 * f[..., 2] + 1e-6).all() and (np.abs(f[..., 1]) <= 0.3 * f[..., 2] + 1e-6).all()
+    # bitwise run-to-run determinism (the reference's test_determinism contract, on the GPU)
+    r2 = bt.update(q, v, refs)
+    for k in ("tau", "dv", "f", "q_next", "status", "iters", "active"):
+        assert np.array_equal(getattr(r, k), getattr(r2, k)), k
+    # a random subset against the oracle
+    idx = np.random.default_rng(0).choice(B, 256, replace=False)
+    o = ol.cycle_batch(talos, q[idx], v[idx], refs[idx], nthreads=os.cpu_count())
+    for k in ("tau", "dv", "f"):
+        assert _rel(getattr(r, k)[idx], o[k]) < TOL, k
+    assert np.array_equal(r.active[idx], o["active"])
+
+
+def test_franka_full_size_linearity(franka):
+    """Franka 65 536 (config 2): the stack is an unconstrained least squares, so dv is affine in the posture reference."""
+    import bench
+    B = 65536
+    q, v, refs = bench.make_inputs(franka, B, "franka", 0xB200)
+    bt = iw.Batch(franka, 0, B)
+    r0 = bt.update(q, v, refs, fields=("dv", "status"))
+    off, _ = franka.ref_slot("posture")
+    d1, d2 = np.zeros_like(refs), np.zeros_like(refs)
+    rng = np.random.default_rng(3)
+    d1[:, off:off + 9] = rng.normal(0, 0.1, (B, 9))
+    d2[:, off:off + 9] = rng.normal(0, 0.1, (B, 9))
+    r1 = bt.update(q, v, refs + d1, fields=("dv", "status"))
+    r2 = bt.update(q, v, refs + d2, fields=("dv", "status"))
+    r12 = bt.update(q, v, refs + d1 + d2, fields=("dv", "status"))
+    assert (r0.status == 0).all()
+    lhs, rhs = r12.dv - r0.dv, (r1.dv - r0.dv) + (r2.dv - r0.dv)
+    assert np.abs(lhs - rhs).max() < 1e-7 * np.abs(r0.dv).max()
+
+
+def test_rollout_device_matches_oracle(talos):
+    import torch
+    from inria_wbc_b200 import behaviors, ETC_PATH
+    B, T = 8, 40
+    q, v = random_states(talos, B, 21, qn=0.01, vn=0.02)
+    refs = talos.default_refs()
+    dq, dv_, dr = (torch.from_numpy(x).cuda() for x in (q.copy(), v.copy(), refs))
+    bt = iw.Batch(talos, 0, B)
+    st = torch.empty(B, dtype=torch.int32, device="cuda")
+    bt.rollout_device(B, dq.data_ptr(), dv_.data_ptr(), dr.data_ptr(), 0, talos.default_contact_mask, T, {"status": st.data_ptr()})
+    torch.cuda.synchronize()
+    assert (st.cpu().numpy() == 0).all() and bt.launch_count == T
+    for i in range(B):
+        o = ol.rollout(talos, q[i], v[i], refs, T)
+        assert o["rc"] == 0
+        assert np.abs(dq[i].cpu().numpy() - o["q"]).max() < 1e-8   # test_determinism's tolerance on q, GPU vs oracle
+        assert np.abs(dv_[i].cpu().numpy() - o["v"]).max() < 1e-7
+
+
+def test_dense_qp_solver_interface():
+    rng = np.random.default_rng(7)
+    for n, me, mi in ((9, 0, 6), (20, 5, 30), (74, 18, 244)):
+        B = 64
+        qs = [random_qp(rng, n, me, mi) for _ in range(B)]
+        H, g, CE, ce0, CI, ci0 = (np.stack([p[k] for p in qs]) for k in range(6))
+        x, status, iters, active = iw.qp_solve_batch(H, g, CE if me else None, ce0 if me else None, CI, ci0)
+        for i in range(B):
+            o = ol.qp_solve(*qs[i][:2], qs[i][2] if me else None, qs[i][3] if me else None, *qs[i][4:])
+            assert status[i] == o["status"] == 0
+            np.testing.assert_allclose(x[i], o["x"], rtol=0, atol=1e-9 * np.abs(o["x"]).max())
+            bits = np.zeros(iw.ACTIVE_WORDS, np.uint32)
+            for r in o["active"]:
+                bits[r >> 5] |= np.uint32(1 << (r & 31))
+            assert np.array_equal(bits, active[i]) and iters[i] == o["iters"]
+
+
+def test_infeasible_instances_are_data_not_errors(talos):
+    # absurd velocities make the bound constraints inconsistent: status 1 per instance, no exception, others unaffected
+    q, v = random_states(talos, 64, 30)
+    v[::2, 10] = 500.0
+    bt = iw.Batch(talos, 0, 64)
+    r = bt.update(q, v)
+    o = ol.cycle_batch(talos, q, v, nthreads=8)
+    assert np.array_equal(r.status, o["status"])
+    assert (r.status[1::2] == 0).all() and (r.status[::2] != 0).any()
+
+
+def test_argument_errors(franka):
+    bt = iw.Batch(franka, 0, 16)
+    q, v = random_states(franka, 32, 1)
+    with pytest.raises(iw.IwbcError, match="max_batch"):
+        bt.update(q, v)
+    with pytest.raises(iw.IwbcError):
+        iw.Batch(franka, 99, 16)
