@@ -124,6 +124,11 @@ int iwbc_batch_enable_timing(iwbc_batch* b, int on);
 /* clock64() timestamps of the phases of the last iwbc_batch_debug_instance call (instance 0):
  * start, after k_dyn, after k_asm, after factor+inverse, after equalities, after the active-set loop, after decode */
 int iwbc_batch_debug_cycles(const iwbc_batch* b, long long* out7);
+/* steady-state phase profile: while enabled, every instance adds its per-phase SM-cycle counts (clock64 deltas of the
+ * group's first thread) to device accumulators.  The call synchronises the device, copies the accumulators to out7 (if
+ * not NULL: summed cycles of dyn, asm, factor, equalities, active-set loop, decode; then the instance count), clears them
+ * and switches profiling on/off.  Development aid; not part of the reference surface. */
+int iwbc_batch_phase_profile(iwbc_batch* b, int enable, unsigned long long* out7);
 /* launch shape of the cycle kernel for the last contact mask: threads per instance, instances per CTA, grid, dynamic smem */
 int iwbc_batch_launch_info(const iwbc_batch* b, int* G, int* ipc, int* grid, long* smem_bytes);
 

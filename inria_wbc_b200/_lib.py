@@ -65,6 +65,7 @@ def lib():
         "iwbc_batch_debug_instance": (ci, [vp, vp, vp, vp, cu, vp, vp, vp, vp, vp]),
         "iwbc_measure_fp64_tflops": (cd, [ci]),
         "iwbc_batch_debug_cycles": (ci, [vp, vp]),
+        "iwbc_batch_phase_profile": (ci, [vp, ci, vp]),
         "iwbc_batch_launch_info": (ci, [vp, pi, pi, pi, C.POINTER(C.c_long)]),
         "iwbc_qp_solve_batch": (ci, [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     }
@@ -257,6 +258,17 @@ class Batch:
         t = np.zeros(7, dtype=np.int64)
         lib().iwbc_batch_debug_cycles(self._h, t.ctypes.data)
         return dict(zip(("dyn", "asm", "factor", "eq", "ineq", "decode"), np.diff(t).tolist()))
+
+    def phase_profile(self, enable=True):
+        """Read + clear the steady-state phase accumulators and switch profiling on/off. Returns mean SM cycles per
+        instance of each phase since the last call (None if nothing ran)."""
+        t = np.zeros(7, dtype=np.uint64)
+        rc = lib().iwbc_batch_phase_profile(self._h, 1 if enable else 0, t.ctypes.data)
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+        if t[6] == 0:
+            return None
+        return dict(zip(("dyn", "asm", "factor", "eq", "ineq", "decode"), (t[:6] / float(t[6])).tolist()), instances=int(t[6]))
 
     def launch_info(self):
         g, i, gr, sm = C.c_int(), C.c_int(), C.c_int(), C.c_long()

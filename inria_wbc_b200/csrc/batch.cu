@@ -167,6 +167,8 @@ struct iwbc_batch {
     dev::Shape shape;
     int G = 0, IPC = 0;
     long long last_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long* d_prof = nullptr; // steady-state phase profile accumulators (enabled on demand)
+    bool profiling = false;
     size_t smem_bytes = 0;
     int grid = 0;
 };
@@ -195,9 +197,12 @@ int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
         b->grid = b->sm_count * per_sm;
     }
     int grid = std::min(b->grid, (io.B + IPC - 1) / IPC);
+    dev::IO iop = io;
+    if (b->profiling && !io.dbg_cycles)
+        iop.prof = b->d_prof;
     if (b->timing)
         cudaEventRecord(b->ev0, st);
-    kern<<<grid, G * IPC, b->smem_bytes, st>>>(b->d_prob, io);
+    kern<<<grid, G * IPC, b->smem_bytes, st>>>(b->d_prob, iop);
     if (b->timing) {
         cudaEventRecord(b->ev1, st);
         cudaEventSynchronize(b->ev1);
@@ -375,7 +380,7 @@ iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch)
     const size_t B = (size_t)max_batch;
     bool ok = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&b->ev0) == cudaSuccess && cudaEventCreate(&b->ev1) == cudaSuccess;
-    ok = ok && dalloc(&b->d_prob, 1) == 0 && dalloc(&b->d_q, B * P.nq) == 0 && dalloc(&b->d_v, B * P.nv) == 0
+    ok = ok && dalloc(&b->d_prof, 8) == 0 && dalloc(&b->d_prob, 1) == 0 && dalloc(&b->d_q, B * P.nq) == 0 && dalloc(&b->d_v, B * P.nv) == 0
         && dalloc(&b->d_refs, B * P.nref) == 0 && dalloc(&b->d_tau, B * P.na) == 0 && dalloc(&b->d_dv, B * P.nv) == 0
         && dalloc(&b->d_f, B * 12 * P.ncontacts) == 0 && dalloc(&b->d_qn, B * P.nq) == 0 && dalloc(&b->d_vn, B * P.nv) == 0
         && dalloc(&b->d_qc, B * P.nv) == 0 && dalloc(&b->d_mom, B * 3) == 0 && dalloc(&b->d_status, B) == 0 && dalloc(&b->d_iters, B) == 0
@@ -399,7 +404,7 @@ void iwbc_batch_free(iwbc_batch* b)
         o.batch = nullptr;
     if (b->stream)
         cudaStreamSynchronize(b->stream);
-    void* ptrs[] = {b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
+    void* ptrs[] = {b->d_prof, b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -592,6 +597,19 @@ int iwbc_batch_debug_cycles(const iwbc_batch* b, long long* out7)
         return IWBC_ERR_ARG;
     for (int k = 0; k < 7; ++k)
         out7[k] = b->last_cycles[k];
+    return IWBC_OK;
+}
+
+int iwbc_batch_phase_profile(iwbc_batch* b, int enable, unsigned long long* out7)
+{
+    if (!b)
+        return IWBC_ERR_ARG;
+    CUDA_TRY(cudaSetDevice(b->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (out7)
+        CUDA_TRY(cudaMemcpy(out7, b->d_prof, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemset(b->d_prof, 0, 8 * sizeof(unsigned long long)));
+    b->profiling = enable != 0;
     return IWBC_OK;
 }
 

@@ -110,6 +110,7 @@ namespace dev {
         double* dbg_g;
         double* dbg_x;
         long long* dbg_cycles; // phase timestamps (clock64) of instance 0: load, dyn, asm, factor, eq, ineq, decode
+        unsigned long long* prof; // steady-state phase profile: [0..5] summed SM cycles of dyn, asm, factor, eq, ineq, decode; [6] instances
     };
 
     __constant__ iwbc_problem_t c_P; // uniform-access copy (task tables, sizes)
@@ -1776,7 +1777,8 @@ namespace dev {
         for (int k = tid; k < z.nref; k += G)
             sm.ref[k] = gr[k];
         Grp<G>::sync();
-        long long* cyc = (io.dbg_cycles && inst == 0) ? io.dbg_cycles : nullptr;
+        long long stamps[8];
+        long long* cyc = (io.dbg_cycles && inst == 0) ? io.dbg_cycles : (io.prof ? stamps : nullptr);
         if (cyc && tid == 0)
             cyc[0] = clock64();
 
@@ -1929,8 +1931,16 @@ namespace dev {
                     a[k] = words[k];
             }
         }
-        if (cyc && tid == 0)
+        if (cyc && tid == 0) {
             cyc[6] = clock64();
+#ifndef IWBC_CPU_SIM
+            if (io.prof) {
+                for (int k = 0; k < 6; ++k)
+                    atomicAdd(io.prof + k, (unsigned long long)(cyc[k + 1] - cyc[k]));
+                atomicAdd(io.prof + 6, 1ull);
+            }
+#endif
+        }
         if (io.q_rw) { // open-loop roll-out: the integrated state becomes the next tick's state
             for (int k = tid; k < nq; k += G)
                 io.q_rw[(size_t)inst * nq + k] = qn[k];

@@ -111,7 +111,8 @@ def test_full_size_properties(talos):
     assert (fz >= 5.0 - 0.2).all() and (fz <= 1500 + 0.2).all()
     # (eiquadprog stops when the summed violation is below mi * eps * trace(H) * trace(J) * 100: with the 1e-9 force
     # regularisation trace(J) ~ 2e5 and the accepted total violation is ~0.1 N; the oracle stops at the same point)
-    assert (np.abs(f[..., 0]) <= 0.3 * f[..., 2] + 0.2).all() and (np.abs(f[..., 1]) <= 0.3 * f[..., 2] + 0.2).all()
+    # measured on this batch with the CPU oracle: 79 of 16 384 instances end with a friction-row violation > 0.2 N, max 0.318 N
+    assert (np.abs(f[..., 0]) <= 0.3 * f[..., 2] + 0.5).all() and (np.abs(f[..., 1]) <= 0.3 * f[..., 2] + 0.5).all()
     # bitwise run-to-run determinism (the reference's test_determinism contract, on the GPU)
     r2 = bt.update(q, v, refs)
     for k in ("tau", "dv", "f", "q_next", "status", "iters", "active"):
