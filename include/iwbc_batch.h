@@ -126,9 +126,10 @@ int iwbc_batch_enable_timing(iwbc_batch* b, int on);
 int iwbc_batch_debug_cycles(const iwbc_batch* b, long long* out7);
 /* steady-state phase profile: while enabled, every instance adds its per-phase SM-cycle counts (clock64 deltas of the
  * group's first thread) to device accumulators.  The call synchronises the device, copies the accumulators to out7 (if
- * not NULL: summed cycles of dyn, asm, factor, equalities, active-set loop, decode; then the instance count), clears them
- * and switches profiling on/off.  Development aid; not part of the reference surface. */
-int iwbc_batch_phase_profile(iwbc_batch* b, int enable, unsigned long long* out7);
+ * not NULL, 16 entries: [0..5] summed cycles of dyn, asm, factor, equalities, active-set loop, decode of the
+ * active-set kernel and [6] its instance count; [8..13] dyn, rows, H + Cholesky, QR + solve, termination test, decode of
+ * the fast kernel and [14] the instances it finished), clears them and switches profiling on/off.  Development aid; not part of the reference surface. */
+int iwbc_batch_phase_profile(iwbc_batch* b, int enable, unsigned long long* out16);
 /* launch shape of the cycle kernel for the last contact mask: threads per instance, instances per CTA, grid, dynamic smem */
 int iwbc_batch_launch_info(const iwbc_batch* b, int* G, int* ipc, int* grid, long* smem_bytes);
 

@@ -261,14 +261,17 @@ class Batch:
 
     def phase_profile(self, enable=True):
         """Read + clear the steady-state phase accumulators and switch profiling on/off. Returns mean SM cycles per
-        instance of each phase since the last call (None if nothing ran)."""
-        t = np.zeros(7, dtype=np.uint64)
+        instance of each phase since the last call, for the active-set kernel and for the fast kernel."""
+        t = np.zeros(16, dtype=np.uint64)
         rc = lib().iwbc_batch_phase_profile(self._h, 1 if enable else 0, t.ctypes.data)
         if rc != 0:
             raise IwbcError(_err(lib()))
-        if t[6] == 0:
-            return None
-        return dict(zip(("dyn", "asm", "factor", "eq", "ineq", "decode"), (t[:6] / float(t[6])).tolist()), instances=int(t[6]))
+        out = {}
+        if t[6]:
+            out["active_set"] = dict(zip(("dyn", "asm", "factor", "eq", "ineq", "decode"), (t[:6] / float(t[6])).tolist()), instances=int(t[6]))
+        if t[14]:
+            out["fast"] = dict(zip(("dyn", "rows", "H_chol", "qr_solve", "check", "decode"), (t[8:14] / float(t[14])).tolist()), instances=int(t[14]))
+        return out or None
 
     def launch_info(self):
         g, i, gr, sm = C.c_int(), C.c_int(), C.c_int(), C.c_long()

@@ -2,6 +2,7 @@
 // device workspaces, host<->device staging.  sm_100a only; no CPU fallback.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -11,6 +12,7 @@
 
 #include "../../include/iwbc_batch.h"
 #include "cycle_kernel.cuh"
+#include "fast_kernel.cuh"
 #include "host_state.hpp"
 
 namespace iwbc {
@@ -46,7 +48,9 @@ namespace dev {
                 sm.dofj[c0 + k] = j;
         }
         const int ngroups = gridDim.x * IPC;
-        for (int inst = blockIdx.x * IPC + grp; inst < io.B; inst += ngroups) {
+        const int count = io.list ? *io.list_count : io.B;
+        for (int idx = blockIdx.x * IPC + grp; idx < count; idx += ngroups) {
+            const int inst = io.list ? io.list[idx] : idx;
             cycle_instance<G>(gP, sm, z, io, inst, tid, flip);
             Grp<G>::sync();
         }
@@ -167,8 +171,17 @@ struct iwbc_batch {
     dev::Shape shape;
     int G = 0, IPC = 0;
     long long last_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    unsigned long long* d_prof = nullptr; // steady-state phase profile accumulators (enabled on demand)
+    unsigned long long* d_prof = nullptr; // steady-state phase profile accumulators (enabled on demand): [0..6] active-set kernel, [8..14] fast kernel
     bool profiling = false;
+    // fast path (fast_kernel.cuh): equality-constrained first pass, 3 CTAs / SM; the active-set kernel continues the rest
+    bool fast_ok = false, fast_enabled = true;
+    dev::FShape fshape;
+    dev::FPlan fplan;
+    dev::FPlan* d_fplan = nullptr;
+    int *d_slow_list = nullptr, *d_slow_count = nullptr;
+    int fast_grid = 0;
+    size_t fast_smem = 0;
+    bool plan_dirty = true;
     size_t smem_bytes = 0;
     int grid = 0;
 };
@@ -198,9 +211,36 @@ int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
     }
     int grid = std::min(b->grid, (io.B + IPC - 1) / IPC);
     dev::IO iop = io;
+    constexpr int FT_ = 128;
+    const bool use_fast = b->fast_ok && b->fast_enabled && G > 32 && !io.dbg_M && !io.dbg_cycles;
+    if (use_fast) {
+        auto fk = dev::k_fast<FT_>;
+        if (b->fast_grid == 0) {
+            CUDA_TRY(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->fast_smem));
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, FT_, b->fast_smem));
+            if (per_sm < 1) {
+                set_error("fast kernel does not fit on an SM");
+                return IWBC_ERR_CUDA;
+            }
+            b->fast_grid = b->sm_count * per_sm;
+        }
+        iop.slow_list = b->d_slow_list;
+        iop.slow_count = b->d_slow_count;
+        if (b->profiling)
+            iop.prof = b->d_prof;
+        CUDA_TRY(cudaMemsetAsync(b->d_slow_count, 0, sizeof(int), st));
+        if (b->timing)
+            cudaEventRecord(b->ev0, st);
+        fk<<<std::min(b->fast_grid, io.B), FT_, b->fast_smem, st>>>(b->d_prob, b->d_fplan, iop);
+        b->launches++;
+        iop.list = b->d_slow_list;
+        iop.list_count = b->d_slow_count;
+        grid = std::min(b->grid, (io.B + IPC - 1) / IPC);
+    }
     if (b->profiling && !io.dbg_cycles)
         iop.prof = b->d_prof;
-    if (b->timing)
+    if (b->timing && !use_fast)
         cudaEventRecord(b->ev0, st);
     kern<<<grid, G * IPC, b->smem_bytes, st>>>(b->d_prob, iop);
     if (b->timing) {
@@ -299,6 +339,10 @@ int prepare_shape(iwbc_batch* b, unsigned mask)
     b->smem_bytes = (size_t)S.total * sizeof(double) * b->IPC;
     b->grid = 0;
     b->shape_mask = mask;
+    b->fast_ok = b->G > 32 && dev::build_fast_plan(P, S, 128, b->fshape, b->fplan);
+    b->fast_smem = (size_t)b->fshape.total * sizeof(double);
+    b->fast_grid = 0;
+    b->plan_dirty = true;
     return IWBC_OK;
 }
 
@@ -310,12 +354,18 @@ int upload_constants(iwbc_batch* b, cudaStream_t st)
         b->revision = b->prob->revision;
         o.batch = nullptr;
     }
+    if (b->plan_dirty) {
+        // (the stream may still run a kernel reading the previous plan: the copy is stream-ordered behind it)
+        CUDA_TRY(cudaMemcpyAsync(b->d_fplan, &b->fplan, sizeof(dev::FPlan), cudaMemcpyHostToDevice, st));
+        b->plan_dirty = false;
+    }
     if (o.batch != b || o.revision != b->revision || o.mask != b->shape_mask) {
         // other streams may still be running a kernel that reads the old constants
         if (o.batch != nullptr && o.batch != b)
             CUDA_TRY(cudaDeviceSynchronize());
         CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_P, &b->prob->cs.prob, sizeof(iwbc_problem_t), 0, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_S, &b->shape, sizeof(dev::Shape), 0, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_F, &b->fshape, sizeof(dev::FShape), 0, cudaMemcpyHostToDevice, st));
         o.batch = b;
         o.revision = b->revision;
         o.mask = b->shape_mask;
@@ -380,7 +430,12 @@ iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch)
     const size_t B = (size_t)max_batch;
     bool ok = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&b->ev0) == cudaSuccess && cudaEventCreate(&b->ev1) == cudaSuccess;
-    ok = ok && dalloc(&b->d_prof, 8) == 0 && dalloc(&b->d_prob, 1) == 0 && dalloc(&b->d_q, B * P.nq) == 0 && dalloc(&b->d_v, B * P.nv) == 0
+    ok = ok && dalloc(&b->d_fplan, 1) == 0 && dalloc(&b->d_slow_list, B) == 0 && dalloc(&b->d_slow_count, 1) == 0;
+    {
+        const char* e = getenv("IWBC_NO_FAST");
+        b->fast_enabled = !(e && e[0] == '1');
+    }
+    ok = ok && dalloc(&b->d_prof, 16) == 0 && dalloc(&b->d_prob, 1) == 0 && dalloc(&b->d_q, B * P.nq) == 0 && dalloc(&b->d_v, B * P.nv) == 0
         && dalloc(&b->d_refs, B * P.nref) == 0 && dalloc(&b->d_tau, B * P.na) == 0 && dalloc(&b->d_dv, B * P.nv) == 0
         && dalloc(&b->d_f, B * 12 * P.ncontacts) == 0 && dalloc(&b->d_qn, B * P.nq) == 0 && dalloc(&b->d_vn, B * P.nv) == 0
         && dalloc(&b->d_qc, B * P.nv) == 0 && dalloc(&b->d_mom, B * 3) == 0 && dalloc(&b->d_status, B) == 0 && dalloc(&b->d_iters, B) == 0
@@ -404,7 +459,7 @@ void iwbc_batch_free(iwbc_batch* b)
         o.batch = nullptr;
     if (b->stream)
         cudaStreamSynchronize(b->stream);
-    void* ptrs[] = {b->d_prof, b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
+    void* ptrs[] = {b->d_fplan, b->d_slow_list, b->d_slow_count, b->d_prof, b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -607,8 +662,8 @@ int iwbc_batch_phase_profile(iwbc_batch* b, int enable, unsigned long long* out7
     CUDA_TRY(cudaSetDevice(b->device));
     CUDA_TRY(cudaDeviceSynchronize());
     if (out7)
-        CUDA_TRY(cudaMemcpy(out7, b->d_prof, 7 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemset(b->d_prof, 0, 8 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemcpy(out7, b->d_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemset(b->d_prof, 0, 16 * sizeof(unsigned long long)));
     b->profiling = enable != 0;
     return IWBC_OK;
 }

@@ -45,6 +45,8 @@ static SimIdx threadIdx = {0};
 inline void __syncwarp(unsigned) {}
 inline void __syncthreads() {}
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
+template <class T> inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 inline long long clock64() { return 0; }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }
@@ -110,6 +112,10 @@ namespace dev {
         double* dbg_g;
         double* dbg_x;
         long long* dbg_cycles; // phase timestamps (clock64) of instance 0: load, dyn, asm, factor, eq, ineq, decode
+        const int* list;       // optional: instance indices to process (active-set continuation of the fast path)
+        const int* list_count; // device-side length of `list`
+        int* slow_list;        // fast path: instances that need the active-set iteration are appended here
+        int* slow_count;
         unsigned long long* prof; // steady-state phase profile: [0..5] summed SM cycles of dyn, asm, factor, eq, ineq, decode; [6] instances
     };
 
@@ -1760,64 +1766,26 @@ namespace dev {
         return status;
     }
 
-    // =================================================================================== one instance
-    // load -> k_dyn -> k_asm -> k_qp -> k_dec for instance `inst`, executed by one group of G threads
+    // =================================================================================== k_dec
+    // decode (controller.cpp:250-260) + integrate (:254-256) + command repack (:263-282) + result stores.
+    // Scratch: sm.d (v+), sm.x_old (q+).  taut: precomputed M_a dv - J_a' f (or nullptr: evaluated here).
     template <int G>
-    __device__ void cycle_instance(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, const IO& io, int inst, int tid, int& flip)
+    __device__ void k_dec(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, const IO& io, int inst, int tid, int status, int iters,
+        int iq, const double* taut)
     {
         const int nv = z.nv, nq = z.nq, n = z.n, na = c_P.na, nu = nv - na;
-        // ---- load state and references (coalesced: the instance's q / v / refs are contiguous)
-        const double* gq = io.q + (size_t)inst * nq;
-        const double* gv = io.v + (size_t)inst * nv;
-        const double* gr = io.refs + (size_t)inst * io.refs_stride;
-        for (int k = tid; k < nq; k += G)
-            sm.qs[k] = gq[k];
-        for (int k = tid; k < nv; k += G)
-            sm.vs[k] = gv[k];
-        for (int k = tid; k < z.nref; k += G)
-            sm.ref[k] = gr[k];
-        Grp<G>::sync();
-        long long stamps[8];
-        long long* cyc = (io.dbg_cycles && inst == 0) ? io.dbg_cycles : (io.prof ? stamps : nullptr);
-        if (cyc && tid == 0)
-            cyc[0] = clock64();
-
-        k_dyn<G>(gP, sm, z, tid, flip);
-        if (cyc && tid == 0)
-            cyc[1] = clock64();
-        k_asm<G>(gP, sm, z, tid, flip);
-        if (cyc && tid == 0)
-            cyc[2] = clock64();
-
-        if (io.dbg_M && inst == 0) {
-            for (int e = tid; e < nv * nv; e += G)
-                io.dbg_M[e] = sm.M[(e / nv) * z.ldM + (e % nv)];
-            for (int k = tid; k < nv; k += G)
-                io.dbg_nle[k] = sm.nle[k];
-            for (int e = tid; e < n * n; e += G) {
-                const int i = e / n, j = e % n;
-                io.dbg_H[e] = i >= j ? sm.J[i + j * z.ldJ] : sm.J[j + i * z.ldJ];
-            }
-            for (int k = tid; k < n; k += G)
-                io.dbg_g[k] = sm.g[k];
+        // ---- decode (controller.cpp:250-260) + integrate (:254-256) + command repack (:263-282)
+        if (!taut) {
+            FusedRows::wrenches<G>(sm, z, tid);
             Grp<G>::sync();
         }
-
-        int iters = 0, iq = 0;
-        const int status = gi_solve<G, FusedRows>(gP, sm, z, (const FusedRows*)nullptr, c_S.me, c_S.mi, tid, flip, iters, iq, cyc);
-        if (cyc && tid == 0)
-            cyc[5] = clock64();
-
-        // ---- decode (controller.cpp:250-260) + integrate (:254-256) + command repack (:263-282)
-        FusedRows::wrenches<G>(sm, z, tid);
-        Grp<G>::sync();
         if (io.dbg_x && inst == 0)
             for (int k = tid; k < n; k += G)
                 io.dbg_x[k] = sm.x[k];
         const double dt = c_P.dt;
         if (io.tau)
             for (int i = tid; i < na; i += G)
-                io.tau[(size_t)inst * na + i] = sm.nle[nu + i] + FusedRows::act_row_value(sm, z, i);
+                io.tau[(size_t)inst * na + i] = sm.nle[nu + i] + (taut ? taut[i] : FusedRows::act_row_value(sm, z, i));
         if (io.dv)
             for (int k = tid; k < nv; k += G)
                 io.dv[(size_t)inst * nv + k] = sm.x[k];
@@ -1931,6 +1899,64 @@ namespace dev {
                     a[k] = words[k];
             }
         }
+        if (io.q_rw) { // open-loop roll-out: the integrated state becomes the next tick's state
+            double* qn2 = sm.x_old;
+            for (int k = tid; k < nq; k += G)
+                io.q_rw[(size_t)inst * nq + k] = qn2[k];
+            for (int k = tid; k < nv; k += G)
+                io.v_rw[(size_t)inst * nv + k] = sm.d[k];
+        }
+    }
+
+    // =================================================================================== one instance
+    // load -> k_dyn -> k_asm -> k_qp -> k_dec for instance `inst`, executed by one group of G threads
+    template <int G>
+    __device__ void cycle_instance(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, const IO& io, int inst, int tid, int& flip)
+    {
+        const int nv = z.nv, nq = z.nq, n = z.n, na = c_P.na, nu = nv - na;
+        // ---- load state and references (coalesced: the instance's q / v / refs are contiguous)
+        const double* gq = io.q + (size_t)inst * nq;
+        const double* gv = io.v + (size_t)inst * nv;
+        const double* gr = io.refs + (size_t)inst * io.refs_stride;
+        for (int k = tid; k < nq; k += G)
+            sm.qs[k] = gq[k];
+        for (int k = tid; k < nv; k += G)
+            sm.vs[k] = gv[k];
+        for (int k = tid; k < z.nref; k += G)
+            sm.ref[k] = gr[k];
+        Grp<G>::sync();
+        long long stamps[8];
+        long long* cyc = (io.dbg_cycles && inst == 0) ? io.dbg_cycles : (io.prof ? stamps : nullptr);
+        if (cyc && tid == 0)
+            cyc[0] = clock64();
+
+        k_dyn<G>(gP, sm, z, tid, flip);
+        if (cyc && tid == 0)
+            cyc[1] = clock64();
+        k_asm<G>(gP, sm, z, tid, flip);
+        if (cyc && tid == 0)
+            cyc[2] = clock64();
+
+        if (io.dbg_M && inst == 0) {
+            for (int e = tid; e < nv * nv; e += G)
+                io.dbg_M[e] = sm.M[(e / nv) * z.ldM + (e % nv)];
+            for (int k = tid; k < nv; k += G)
+                io.dbg_nle[k] = sm.nle[k];
+            for (int e = tid; e < n * n; e += G) {
+                const int i = e / n, j = e % n;
+                io.dbg_H[e] = i >= j ? sm.J[i + j * z.ldJ] : sm.J[j + i * z.ldJ];
+            }
+            for (int k = tid; k < n; k += G)
+                io.dbg_g[k] = sm.g[k];
+            Grp<G>::sync();
+        }
+
+        int iters = 0, iq = 0;
+        const int status = gi_solve<G, FusedRows>(gP, sm, z, (const FusedRows*)nullptr, c_S.me, c_S.mi, tid, flip, iters, iq, cyc);
+        if (cyc && tid == 0)
+            cyc[5] = clock64();
+
+        k_dec<G>(gP, sm, z, io, inst, tid, status, iters, iq, (const double*)nullptr);
         if (cyc && tid == 0) {
             cyc[6] = clock64();
 #ifndef IWBC_CPU_SIM
@@ -1940,12 +1966,6 @@ namespace dev {
                 atomicAdd(io.prof + 6, 1ull);
             }
 #endif
-        }
-        if (io.q_rw) { // open-loop roll-out: the integrated state becomes the next tick's state
-            for (int k = tid; k < nq; k += G)
-                io.q_rw[(size_t)inst * nq + k] = qn[k];
-            for (int k = tid; k < nv; k += G)
-                io.v_rw[(size_t)inst * nv + k] = sm.d[k];
         }
     }
 

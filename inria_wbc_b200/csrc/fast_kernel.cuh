@@ -1,0 +1,1238 @@
+// fast_kernel.cuh -- the "first pass" of the batched control cycle for floating-base robots with contacts.
+//
+// eiquadprog's Goldfarb-Idnani loop starts from the minimiser of the cost on the
+// EQUALITY constraints and only then looks at the inequalities.  On the reference's own workloads most
+// states end there (Talos double-support squat: 91 % of instances finish with an empty active set), so
+// this kernel computes exactly that point -- dynamics, task/contact rows, H, the equality-constrained
+// minimiser x_eq, s = CI x_eq + ci0 -- and
+//   * if eiquadprog's termination test passes at x_eq (same formula: |sum min(0, s)| <= mi eps c1 c2 100),
+//     decodes and writes the results (status OPTIMAL, 1 iteration, empty active set);
+//   * otherwise appends the instance to a list that the active-set kernel (cycle_kernel.cuh) then steps
+//     through the full Goldfarb-Idnani iteration.
+// The point of the split is occupancy: without the n x n matrix J and the triangular factor R of the
+// active-set method an instance needs ~63 kB of shared memory instead of 134 kB, so three CTAs fit on an
+// SM instead of one, and the equality phase collapses from 18 sequential Givens sweeps over J to
+//   1. a left-looking Cholesky of the dv-block of H (H is block diagonal: the contact-force blocks are
+//      constants of the problem and are factorised once on the host) whose matrix is AUGMENTED with the
+//      constraint normals and the gradient as extra rows, so that B = L^-1 N and y = L^-1 g fall out of
+//      the same sweep,
+//   2. a Householder QR of B (n x me),
+//   3. x_eq = L^-T w,  w = -Q [R^-T ce0 ; (Q' y)_2]   (compact-WY application of Q via the Gram matrix
+//      of the reflectors, then one back-substitution).
+// x_eq, the multipliers and s are the same quantities the reference computes (they do not depend on how
+// Q is built); parity is checked against the oracle in tests/.
+//
+// Kinematics / dynamics are evaluated in world coordinates without level-by-level recursion: every joint
+// composes the transforms along its own root path (the path table is static), velocities and drift
+// accelerations are prefix sums of per-joint terms along the same path.
+#pragma once
+#include "cycle_kernel.cuh"
+
+namespace iwbc {
+namespace dev {
+
+#define IWBC_FMAXD 20   /* max tree depth + 1 handled by the fast path */
+#define IWBC_FMAXJOBS 96
+#define IWBC_FMAXBLK 40
+#define IWBC_FMAXROWS 96
+#define IWBC_FMAXME 24
+#define IWBC_FMAXPAIRS ((IWBC_FMAXME + 1) * (IWBC_FMAXME + 2) / 2)
+
+    enum { FJ_SE3 = 0, FJ_CONTACT = 1, FJ_SELFCOL = 2, FJ_COM = 3, FJ_MOM = 4 };
+    enum { FB_SE3 = 0, FB_COM = 1, FB_MOM = 2, FB_SELFCOL = 3, FB_CONTACT = 4 };
+
+    struct FJob {
+        short kind, task, a, slot; // slot: rhs slot (SE3 / COM / MOM) or pair slot (SELFCOL)
+    };
+    struct FBlock {
+        short kind, index, row0, nrows, slot0, pad;
+    };
+    struct FRow {
+        short kind, task, comp, slot; // kind: FB_*; comp: component of the 6-/3-vector; slot: rhs slot (or first pair slot)
+    };
+
+    // static tables of one (problem, contact mask): global memory, read through L1
+    struct FPlan {
+        unsigned char path[IWBC_MAXJ][IWBC_FMAXD]; // joints from the root to j (path[j][depth[j]] = j)
+        unsigned char dofj[IWBC_MAXNV];
+        unsigned char tile_i[136], tile_j[136];
+        unsigned char pair_i[IWBC_FMAXPAIRS], pair_k[IWBC_FMAXPAIRS];
+        FJob jobs[IWBC_FMAXJOBS];
+        FBlock blocks[IWBC_FMAXBLK];
+        FRow rows[IWBC_FMAXROWS];
+        double hdiag[IWBC_MAXNV];   // posture weights on the diagonal of H + the 1e-8 regularisation
+        double Uff[IWBC_MAXC][144]; // per active-contact slot: L_ff^-T (upper triangular, row-major) of the constant force block of H
+        double ygf[IWBC_MAXC][12];  // L_ff^-1 g_f
+    };
+
+    struct FShape {
+        int ok;    // the fast path applies
+        int nca;   // active contacts
+        int cact[IWBC_MAXC];
+        int me, cb0, nf, NC; // equalities; first base-dynamics column (= 6 nca); force-block columns (= nu + 1); QR columns (= me + 1)
+        int ldh, nrh;        // leading dimension / rows of the augmented matrix (nv + me + 1)
+        int nvp;             // row stride of A (nv rounded up to 4)
+        int njobs, nblocks, nrows, ntiles, npairs, nposture, nslots;
+        int ci_bounds, ci_act; // index of the bounds / actuation-bounds block in Shape::ci (-1: none)
+        int posture[4];
+        double c1f, c2f;     // trace(H_ff), trace(L_ff^-T)
+        // shared-memory offsets (doubles)
+        int o_qs, o_vs, o_X, o_Y, o_Z, o_Jft, o_cb, o_nle, o_lb, o_ub, o_g, o_x, o_w, o_sc, o_rhs, o_sc4, o_P, o_Rm, o_tv, o_hd, o_il, o_tau, o_int, total;
+        int d_liMi, d_oMi, d_Sw, d_vw, d_aw, d_Yw, d_fw, d_Fc, d_oMf, d_vf, d_af;
+        int z_Bf, z_G;
+    };
+
+    __constant__ FShape c_F;
+
+    // ------------------------------------------------------------------------------------------ host: plan
+    inline bool build_fast_plan(const iwbc_problem_t& P, const Shape& S, int T, FShape& F, FPlan& pl)
+    {
+        std::memset(&F, 0, sizeof(F));
+        std::memset(&pl, 0, sizeof(pl));
+        const int nv = P.nv, nj = P.nj, na = P.na, nu = nv - na;
+        if (!P.floating_base || nu != 6 || S.me == 0 || S.me > IWBC_FMAXME)
+            return false;
+        for (int c = 0; c < P.ncontacts; ++c)
+            if (S.cidx[c] >= 0)
+                F.cact[F.nca++] = c;
+        if (F.nca == 0 || S.me != 6 * F.nca + nu)
+            return false;
+        for (int j = 0; j < nj; ++j) {
+            if (P.depth[j] + 1 > IWBC_FMAXD)
+                return false;
+            int a = j;
+            for (int d = P.depth[j]; d >= 0; --d) {
+                pl.path[j][d] = (unsigned char)a;
+                a = P.parent[a];
+            }
+            const int c0 = P.idx_v[j], cn = P.jtype[j] == IWBC_J_FREEFLYER ? 6 : 1;
+            for (int k = 0; k < cn; ++k)
+                pl.dofj[c0 + k] = (unsigned char)j;
+        }
+        F.me = S.me;
+        F.cb0 = 6 * F.nca;
+        F.nf = nu + 1;
+        F.NC = S.me + 1;
+        F.nrh = nv + S.me + 1;
+        F.ldh = F.nrh | 1;
+        F.nvp = (nv + 3) & ~3;
+        // ---- jobs, row blocks, rows (level-1 order = Hessian summation order)
+        int nslots = 0, npairslots = 0, row = 0;
+        for (int k = 0; k < nv; ++k)
+            pl.hdiag[k] = P.hess_reg;
+        for (int bl = 0; bl < P.nl1; ++bl) {
+            if (P.l1[bl].kind != IWBC_B_TASK)
+                continue;
+            const int t = P.l1[bl].index;
+            const iwbc_task_t& Tk = P.tasks[t];
+            if (Tk.type == IWBC_T_POSTURE) {
+                if (F.nposture >= 4)
+                    return false;
+                F.posture[F.nposture++] = t;
+                for (int i = 0; i < na; ++i)
+                    if (Tk.mask[i])
+                        pl.hdiag[nu + i] += Tk.weight;
+                continue;
+            }
+            if (F.nblocks >= IWBC_FMAXBLK || row + Tk.nrows > IWBC_FMAXROWS)
+                return false;
+            FBlock& B = pl.blocks[F.nblocks++];
+            B.index = (short)t, B.row0 = (short)row, B.nrows = (short)Tk.nrows;
+            if (Tk.type == IWBC_T_SE3 || Tk.type == IWBC_T_COM || Tk.type == IWBC_T_MOMENTUM) {
+                if (F.njobs >= IWBC_FMAXJOBS)
+                    return false;
+                const int ncomp = Tk.type == IWBC_T_COM ? 3 : 6;
+                B.kind = Tk.type == IWBC_T_SE3 ? FB_SE3 : Tk.type == IWBC_T_COM ? FB_COM : FB_MOM;
+                B.slot0 = (short)nslots;
+                pl.jobs[F.njobs++] = {(short)(Tk.type == IWBC_T_SE3 ? FJ_SE3 : Tk.type == IWBC_T_COM ? FJ_COM : FJ_MOM), (short)t, 0, (short)nslots};
+                int idx = 0;
+                for (int i = 0; i < ncomp; ++i)
+                    if (Tk.mask[i])
+                        pl.rows[row + idx++] = {B.kind, (short)t, (short)i, (short)nslots};
+                if (idx != Tk.nrows)
+                    return false;
+                nslots++;
+            }
+            else if (Tk.type == IWBC_T_SELFCOL) {
+                B.kind = FB_SELFCOL;
+                B.slot0 = (short)npairslots;
+                for (int a = 0; a < Tk.nav; ++a) {
+                    if (F.njobs >= IWBC_FMAXJOBS)
+                        return false;
+                    pl.jobs[F.njobs++] = {(short)FJ_SELFCOL, (short)t, (short)a, (short)(npairslots + a)};
+                }
+                pl.rows[row] = {FB_SELFCOL, (short)t, 0, (short)npairslots};
+                npairslots += Tk.nav;
+            }
+            else
+                return false;
+            row += Tk.nrows;
+        }
+        if (row != S.rows_dense)
+            return false;
+        F.nrows = row;
+        for (int s = 0; s < F.nca; ++s) {
+            if (F.njobs >= IWBC_FMAXJOBS || F.nblocks >= IWBC_FMAXBLK)
+                return false;
+            pl.jobs[F.njobs++] = {(short)FJ_CONTACT, (short)F.cact[s], 0, 0};
+            FBlock& B = pl.blocks[F.nblocks++];
+            B.kind = FB_CONTACT, B.index = (short)F.cact[s], B.row0 = 0, B.nrows = 6, B.slot0 = 0;
+        }
+        F.nslots = nslots;
+        F.ci_bounds = F.ci_act = -1;
+        for (int b = 0; b < S.nci; ++b) {
+            if (S.ci[b].kind == 0) {
+                if (F.ci_bounds >= 0 || S.ci[b].rows != na)
+                    return false;
+                F.ci_bounds = b;
+            }
+            else if (S.ci[b].kind == 1) {
+                if (F.ci_act >= 0 || S.ci[b].rows != na)
+                    return false;
+                F.ci_act = b;
+            }
+        }
+        // ---- H tiles (4 x 4, lower triangle) and reflector pairs
+        const int ntb = F.nvp / 4;
+        for (int ti = 0; ti < ntb; ++ti)
+            for (int tj = 0; tj <= ti; ++tj) {
+                if (F.ntiles >= 136)
+                    return false;
+                pl.tile_i[F.ntiles] = (unsigned char)ti, pl.tile_j[F.ntiles] = (unsigned char)tj;
+                F.ntiles++;
+            }
+        if (T > 1 && F.ntiles > T)
+            return false;
+        for (int k = 0; k <= F.me; ++k) // k == me: the transformed right-hand side t
+            for (int i = 0; i < k && i < F.me; ++i) {
+                pl.pair_i[F.npairs] = (unsigned char)i, pl.pair_k[F.npairs] = (unsigned char)k;
+                F.npairs++;
+            }
+        // ---- constant force blocks: H_ff = w T' W^2 T + reg I, per active contact
+        F.c1f = 0, F.c2f = 0;
+        for (int s = 0; s < F.nca; ++s) {
+            const iwbc_contact_t& C = P.contacts[F.cact[s]];
+            double H[144], L[144], gf[12];
+            for (int i = 0; i < 12; ++i) {
+                for (int j = 0; j < 12; ++j) {
+                    double a = 0;
+                    for (int r = 0; r < 6; ++r)
+                        a += (C.wreg[r] * C.T[r * 12 + i]) * (C.wreg[r] * C.T[r * 12 + j]);
+                    H[i * 12 + j] = C.w_forcereg * a + (i == j ? P.hess_reg : 0.0);
+                }
+                double a = 0;
+                for (int r = 0; r < 6; ++r)
+                    a += (C.wreg[r] * C.T[r * 12 + i]) * (C.wreg[r] * C.fref[r]);
+                gf[i] = -C.w_forcereg * a;
+                F.c1f += H[i * 12 + i];
+            }
+            std::memset(L, 0, sizeof(L));
+            for (int k = 0; k < 12; ++k) {
+                double d = H[k * 12 + k];
+                for (int j = 0; j < k; ++j)
+                    d -= L[k * 12 + j] * L[k * 12 + j];
+                if (!(d > 0))
+                    return false;
+                L[k * 12 + k] = std::sqrt(d);
+                for (int i = k + 1; i < 12; ++i) {
+                    double a = H[i * 12 + k];
+                    for (int j = 0; j < k; ++j)
+                        a -= L[i * 12 + j] * L[k * 12 + j];
+                    L[i * 12 + k] = a / L[k * 12 + k];
+                }
+            }
+            // Linv (lower) by forward substitution, U = Linv^T
+            double Li[144];
+            std::memset(Li, 0, sizeof(Li));
+            for (int c = 0; c < 12; ++c)
+                for (int i = c; i < 12; ++i) {
+                    double a = (i == c) ? 1.0 : 0.0;
+                    for (int j = c; j < i; ++j)
+                        a -= L[i * 12 + j] * Li[j * 12 + c];
+                    Li[i * 12 + c] = a / L[i * 12 + i];
+                }
+            for (int i = 0; i < 12; ++i) {
+                for (int j = 0; j < 12; ++j)
+                    pl.Uff[s][i * 12 + j] = Li[j * 12 + i];
+                F.c2f += Li[i * 12 + i];
+                double a = 0;
+                for (int j = 0; j <= i; ++j)
+                    a += Li[i * 12 + j] * gf[j];
+                pl.ygf[s][i] = a;
+            }
+        }
+        // ---- shared-memory layout
+        const int nq = P.nq, nf = P.nframes, n = S.n;
+        int o = 0;
+        auto take = [&](int cnt) {
+            int r = o;
+            o += align2(cnt);
+            return r;
+        };
+        F.o_qs = take(nq);
+        F.o_vs = take(nv);
+        const int xa = S.rows_dense * F.nvp + align2(S.rows_dense), xm = nv * S.ldM;
+        F.o_X = take(xa > xm ? xa : xm);
+        int d = 0;
+        auto dt = [&](int cnt) {
+            int r = d;
+            d += align2(cnt);
+            return r;
+        };
+        F.d_liMi = dt(12 * nj), F.d_oMi = dt(12 * nj), F.d_Sw = dt(6 * nv), F.d_vw = dt(6 * nj), F.d_aw = dt(6 * nj), F.d_Yw = dt(10 * nj);
+        F.d_fw = dt(6 * nj), F.d_Fc = dt(6 * nv);
+        F.d_oMf = dt(12 * nf), F.d_vf = dt(6 * nf), F.d_af = dt(6 * nf);
+        if (12 * nf + 6 * nf < 6 * nj) // vJ scratch lives in [oMf, vf]
+            d += 6 * nj;
+        const int hs = nv * F.ldh;
+        F.o_Y = take(d > hs ? d : hs);
+        F.z_Bf = 0;
+        F.z_G = align2(12 * F.nca * F.nf);
+        const int zq = F.z_G + align2((F.me + 1) * (F.me + 1));
+        F.o_Z = take(P.nref > zq ? P.nref : zq);
+        F.o_Jft = take(P.ncontacts * 6 * nv);
+        F.o_cb = take(12 * P.ncontacts);
+        F.o_nle = take(nv);
+        F.o_lb = take(nv);
+        F.o_ub = take(nv);
+        F.o_g = take(n + 2);
+        F.o_x = take(n + 2);
+        F.o_w = take(n + 2);
+        F.o_sc = take(48);
+        F.o_rhs = take(6 * (nslots > 0 ? nslots : 1));
+        F.o_sc4 = take(4 * (npairslots > 0 ? npairslots : 1));
+        F.o_P = take(8 * F.NC);
+        F.o_Rm = take(F.me * F.NC + 3 * F.me + 8); // R (me x NC), tau, scale, invbeta
+        F.o_tv = take(3 * (F.me + 2));
+        F.o_hd = take(nv);
+        F.o_il = take(nv);
+        F.o_tau = take(nv);
+        F.o_int = take((nv + 16) / 2 + 1);
+        F.total = o;
+        F.ok = 1;
+        return true;
+    }
+
+    // ------------------------------------------------------------------------------------------ device
+    template <int T>
+    struct FT {
+        static constexpr int PAIR = T >= 64 ? 2 : 1;                   // threads per row in the Cholesky
+        static constexpr int SEG = T >= 128 ? 6 : (T >= 64 ? 3 : 1);   // row segments in the QR
+        static constexpr int NTPT = T > 1 ? 1 : 136;                   // H tiles per thread
+        static constexpr int NCH = (IWBC_MAXJ * 16 + T - 1) / T;       // subtree-sum items per thread
+    };
+
+    template <int T>
+    __device__ __forceinline__ void fsync()
+    {
+        if (T > 1)
+            __syncthreads();
+    }
+
+    // block-wide sum of one value (T > 32: via shared scratch red[T/32]); result broadcast
+    template <int T>
+    __device__ __forceinline__ double fblock_sum(double v, double* red, int tid)
+    {
+        if (T == 1)
+            return v;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1)
+            v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((tid & 31) == 0)
+            red[tid >> 5] = v;
+        fsync<T>();
+        double s = red[0];
+        for (int w = 1; w < (T + 31) / 32; ++w)
+            s += red[w];
+        fsync<T>();
+        return s;
+    }
+
+    // One instance.  Returns true when the instance is finished here (results written), false when it has to go through
+    // the active-set kernel.
+    template <int T>
+    __device__ bool fast_instance(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, double* smem, const IO& io, int inst, int tid,
+        long long* cyc)
+    {
+        const FShape& F = c_F;
+        const Shape& S = c_S;
+        const int nv = c_P.nv, nq = c_P.nq, nj = c_P.nj, na = c_P.na, nu = nv - na, nfr = c_P.nframes, n = S.n, me = F.me, NC = F.NC;
+        const int ld = F.ldh, nvp = F.nvp, ldM = S.ldM;
+        double* const qs = smem + F.o_qs;
+        double* const vs = smem + F.o_vs;
+        double* const X = smem + F.o_X;
+        double* const Y = smem + F.o_Y;
+        double* const Z = smem + F.o_Z;
+        double* const A = X;
+        double* const bvec = X + F.nrows * nvp;
+        double* const M = X;
+        double* const Hs = Y;
+        double* const liMi = Y + F.d_liMi;
+        double* const vJ = Y + F.d_oMf; // scratch until the frames are computed
+        double* const gvec = smem + F.o_g;
+        double* const xv = smem + F.o_x;
+        double* const wv = smem + F.o_w;
+        double* const sc = smem + F.o_sc;
+        double* const rhs = smem + F.o_rhs;
+        double* const sc4 = smem + F.o_sc4;
+        double* const Pp = smem + F.o_P;
+        double* const Rm = smem + F.o_Rm;
+        double* const tauv = Rm + me * NC;
+        double* const scalev = tauv + me;
+        double* const invb = scalev + me;
+        double* const tv = smem + F.o_tv;
+        double* const hd = smem + F.o_hd;
+        double* const il = smem + F.o_il;
+        double* const taut = smem + F.o_tau;
+        double* const Bf = Z + F.z_Bf;
+        double* const Gm = Z + F.z_G;
+        Sm sm;
+        sm.qs = qs, sm.vs = vs, sm.ref = Z;
+        sm.oMi = Y + F.d_oMi, sm.Sw = Y + F.d_Sw, sm.vw = Y + F.d_vw, sm.aw = Y + F.d_aw, sm.Yw = Y + F.d_Yw, sm.fw = Y + F.d_fw, sm.Fc = Y + F.d_Fc;
+        sm.oMf = Y + F.d_oMf, sm.vf = Y + F.d_vf, sm.af = Y + F.d_af;
+        sm.M = M, sm.Jft = smem + F.o_Jft, sm.cb = smem + F.o_cb, sm.nle = smem + F.o_nle, sm.lb = smem + F.o_lb, sm.ub = smem + F.o_ub;
+        sm.x = xv, sm.g = gvec, sm.sc = sc;
+        sm.dofj = reinterpret_cast<int*>(smem + F.o_int);
+
+        // ---------------------------------------------------------------- load
+        {
+            const double* gq = io.q + (size_t)inst * nq;
+            const double* gv = io.v + (size_t)inst * nv;
+            const double* gr = io.refs + (size_t)inst * io.refs_stride;
+            for (int k = tid; k < nq; k += T)
+                qs[k] = gq[k];
+            for (int k = tid; k < nv; k += T)
+                vs[k] = gv[k];
+            for (int k = tid; k < c_P.nref; k += T)
+                Z[k] = gr[k];
+        }
+        fsync<T>();
+        if (cyc && tid == 0)
+            cyc[0] = clock64();
+
+        // ---------------------------------------------------------------- joint transforms (one joint per thread) + acceleration bounds
+        for (int j = tid; j < nj + na; j += T) {
+            if (j >= nj) {
+                const int i = j - nj;
+                acc_bounds(gP, i, qs[nq - na + i], vs[nv - na + i], sm.lb[i], sm.ub[i]);
+                continue;
+            }
+            const double* jp = gP->jplace[j];
+            const int ty = gP->jtype[j];
+            double jm[9];
+            V3 jt = mk(0, 0, 0);
+            if (ty == IWBC_J_FREEFLYER) {
+                const double* qq = qs + gP->idx_q[j];
+                quat_R(qq[3], qq[4], qq[5], qq[6], jm);
+                jt = mk(qq[0], qq[1], qq[2]);
+            }
+            else if (ty == IWBC_J_REVOLUTE)
+                axis_angle_R(ld3(gP->axis[j]), qs[gP->idx_q[j]], jm);
+            else {
+                jm[0] = jm[4] = jm[8] = 1;
+                jm[1] = jm[2] = jm[3] = jm[5] = jm[6] = jm[7] = 0;
+                jt = qs[gP->idx_q[j]] * ld3(gP->axis[j]);
+            }
+            double* li = liMi + 12 * j;
+            mm3(jp, jm, li);
+            st3(li + 9, rmul(jp, jt) + ld3(jp + 9));
+        }
+        fsync<T>();
+        // ---------------------------------------------------------------- world placements along the root path, motion subspaces, joint velocities
+        for (int j = tid; j < nj; j += T) {
+            const unsigned char* path = gF->path[j];
+            const int dep = gP->depth[j];
+            double o[12];
+            {
+                const double* l0 = liMi + 12 * path[0];
+#pragma unroll
+                for (int k = 0; k < 12; ++k)
+                    o[k] = l0[k];
+            }
+            for (int d = 1; d <= dep; ++d) {
+                const double* li = liMi + 12 * path[d];
+                double t[9];
+                mm3(o, li, t);
+                V3 p = rmul(o, ld3(li + 9)) + ld3(o + 9);
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+                    o[k] = t[k];
+                o[9] = p.x, o[10] = p.y, o[11] = p.z;
+            }
+            double* oo = sm.oMi + 12 * j;
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+                oo[k] = o[k];
+            const V3 p = ld3(o + 9);
+            const int ty = gP->jtype[j], c0 = gP->idx_v[j];
+            V3 vJl = mk(0, 0, 0), vJa = mk(0, 0, 0);
+            if (ty == IWBC_J_FREEFLYER) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    V3 col = mk(o[k], o[3 + k], o[6 + k]);
+                    st3(sm.Sw + 6 * (c0 + k), col);
+                    st3(sm.Sw + 6 * (c0 + k) + 3, mk(0, 0, 0));
+                    V3 lin = cross(p, col);
+                    st3(sm.Sw + 6 * (c0 + 3 + k), lin);
+                    st3(sm.Sw + 6 * (c0 + 3 + k) + 3, col);
+                    vJl = vJl + vs[c0 + k] * col + vs[c0 + 3 + k] * lin;
+                    vJa = vJa + vs[c0 + 3 + k] * col;
+                }
+            }
+            else {
+                V3 aw = rmul(o, ld3(gP->axis[j]));
+                V3 lin, ang;
+                if (ty == IWBC_J_REVOLUTE) {
+                    ang = aw;
+                    lin = cross(p, aw);
+                }
+                else {
+                    ang = mk(0, 0, 0);
+                    lin = aw;
+                }
+                st3(sm.Sw + 6 * c0, lin);
+                st3(sm.Sw + 6 * c0 + 3, ang);
+                vJl = vs[c0] * lin;
+                vJa = vs[c0] * ang;
+            }
+            st3(vJ + 6 * j, vJl);
+            st3(vJ + 6 * j + 3, vJa);
+        }
+        fsync<T>();
+        // ---------------------------------------------------------------- velocities / drift accelerations (prefix sums along the path), inertias, momenta, forces
+        for (int j = tid; j < nj; j += T) {
+            const unsigned char* path = gF->path[j];
+            const int dep = gP->depth[j];
+            V3 vl = mk(0, 0, 0), w = mk(0, 0, 0), al = mk(0, 0, 0), aa = mk(0, 0, 0);
+            for (int d = 0; d <= dep; ++d) {
+                const double* pj = vJ + 6 * path[d];
+                const V3 jl = ld3(pj), ja = ld3(pj + 3);
+                al = al + cross(vl, ja) + cross(w, jl);
+                aa = aa + cross(w, ja);
+                vl = vl + jl;
+                w = w + ja;
+            }
+            st3(sm.vw + 6 * j, vl);
+            st3(sm.vw + 6 * j + 3, w);
+            st3(sm.aw + 6 * j, al);
+            st3(sm.aw + 6 * j + 3, aa);
+            const double* o = sm.oMi + 12 * j;
+            const double m = gP->mass[j];
+            V3 c = rmul(o, ld3(gP->com[j])) + ld3(o + 9);
+            const double* I = gP->inertia[j];
+            double Il[9] = {I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]};
+            double t[9], Iw[9];
+            mm3(o, Il, t);
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int bb = 0; bb < 3; ++bb)
+                    Iw[3 * a + bb] = t[3 * a] * o[3 * bb] + t[3 * a + 1] * o[3 * bb + 1] + t[3 * a + 2] * o[3 * bb + 2];
+            const double cc = dot(c, c);
+            const double Ixx = Iw[0] + m * (cc - c.x * c.x), Ixy = Iw[1] - m * c.x * c.y, Ixz = Iw[2] - m * c.x * c.z;
+            const double Iyy = Iw[4] + m * (cc - c.y * c.y), Iyz = Iw[5] - m * c.y * c.z, Izz = Iw[8] + m * (cc - c.z * c.z);
+            V3 h = m * c;
+            double* Yj = sm.Yw + 10 * j;
+            Yj[0] = m;
+            st3(Yj + 1, h);
+            Yj[4] = Ixx, Yj[5] = Ixy, Yj[6] = Ixz, Yj[7] = Iyy, Yj[8] = Iyz, Yj[9] = Izz;
+            V3 alg = al - ld3(c_P.gravity);
+            auto Iapply = [&](V3 x) { return mk(Ixx * x.x + Ixy * x.y + Ixz * x.z, Ixy * x.x + Iyy * x.y + Iyz * x.z, Ixz * x.x + Iyz * x.y + Izz * x.z); };
+            V3 hl = m * vl - cross(h, w), ha = Iapply(w) + cross(h, vl);
+            V3 fl = m * alg - cross(h, aa) + cross(w, hl);
+            V3 fa = Iapply(aa) + cross(h, alg) + cross(w, ha) + cross(vl, hl);
+            st3(sm.fw + 6 * j, fl);
+            st3(sm.fw + 6 * j + 3, fa);
+            st3(sm.Fc + 6 * j, hl); // body momenta (only their total is needed): Fc is free until the dof pass
+            st3(sm.Fc + 6 * j + 3, ha);
+        }
+        fsync<T>();
+        // ---------------------------------------------------------------- subtree sums (composite inertia, subtree force) + momentum total
+        {
+            double acc[FT<T>::NCH];
+            const int items = nj * 16;
+#pragma unroll
+            for (int c8 = 0; c8 < FT<T>::NCH; ++c8) {
+                const int it = c8 * T + tid;
+                double s = 0;
+                if (it < items) {
+                    const int j = it >> 4, k = it & 15;
+                    const int last = gP->last_desc[j];
+                    if (k < 10)
+                        for (int jj = j; jj <= last; ++jj)
+                            s += sm.Yw[10 * jj + k];
+                    else
+                        for (int jj = j; jj <= last; ++jj)
+                            s += sm.fw[6 * jj + (k - 10)];
+                }
+                acc[c8] = s;
+            }
+            for (int k = tid; k < 6; k += T) { // total momentum -> sc[10..15]
+                double s = 0;
+                for (int j = 0; j < nj; ++j)
+                    s += sm.Fc[6 * j + k];
+                sc[10 + k] = s;
+            }
+            fsync<T>();
+#pragma unroll
+            for (int c8 = 0; c8 < FT<T>::NCH; ++c8) {
+                const int it = c8 * T + tid;
+                if (it < items) {
+                    const int j = it >> 4, k = it & 15;
+                    if (k < 10)
+                        sm.Yw[10 * j + k] = acc[c8];
+                    else
+                        sm.fw[6 * j + (k - 10)] = acc[c8];
+                }
+            }
+            fsync<T>();
+        }
+        // ---------------------------------------------------------------- per dof: nle, F = Yc S ; frames ; centroidal totals
+        for (int it = tid; it < nv + nfr + 1; it += T) {
+            if (it < nv) {
+                const int c = it, j = gF->dofj[c];
+                V3 sl = ld3(sm.Sw + 6 * c), sa = ld3(sm.Sw + 6 * c + 3);
+                sm.nle[c] = dot(sl, ld3(sm.fw + 6 * j)) + dot(sa, ld3(sm.fw + 6 * j + 3));
+                const double* Yj = sm.Yw + 10 * j;
+                V3 h = ld3(Yj + 1);
+                V3 Fl = Yj[0] * sl - cross(h, sa);
+                V3 Fa = mk(Yj[4] * sa.x + Yj[5] * sa.y + Yj[6] * sa.z, Yj[5] * sa.x + Yj[7] * sa.y + Yj[8] * sa.z, Yj[6] * sa.x + Yj[8] * sa.y + Yj[9] * sa.z)
+                    + cross(h, sl);
+                st3(sm.Fc + 6 * c, Fl);
+                st3(sm.Fc + 6 * c + 3, Fa);
+            }
+            else if (it < nv + nfr) {
+                const int f = it - nv;
+                const int pj = gP->fparent[f];
+                const double* fp = gP->fplace[f];
+                double o[12];
+                V3 vl = mk(0, 0, 0), w = mk(0, 0, 0), al = mk(0, 0, 0), aa = mk(0, 0, 0);
+                if (pj >= 0) {
+                    const double* pm = sm.oMi + 12 * pj;
+                    mm3(pm, fp, o);
+                    st3(o + 9, rmul(pm, ld3(fp + 9)) + ld3(pm + 9));
+                    vl = ld3(sm.vw + 6 * pj);
+                    w = ld3(sm.vw + 6 * pj + 3);
+                    al = ld3(sm.aw + 6 * pj);
+                    aa = ld3(sm.aw + 6 * pj + 3);
+                }
+                else {
+                    for (int k = 0; k < 12; ++k)
+                        o[k] = fp[k];
+                }
+                V3 p = ld3(o + 9);
+                V3 wl = rtmul(o, w), vll = rtmul(o, vl - cross(p, w));
+                V3 aal = rtmul(o, aa), all = rtmul(o, al - cross(p, aa)) + cross(wl, vll);
+                // (vJ aliases [oMf, vf]: it is dead since the previous barrier)
+                double* of = sm.oMf + 12 * f;
+                for (int k = 0; k < 12; ++k)
+                    of[k] = o[k];
+                st3(sm.vf + 6 * f, vll);
+                st3(sm.vf + 6 * f + 3, wl);
+                st3(sm.af + 6 * f, all);
+                st3(sm.af + 6 * f + 3, aal);
+            }
+            else {
+                // totals = subtree sums of the roots; sc: [0..9] mass h I, [10..15] momentum, [16..21] force,
+                // [22..24] com, [25..27] vcom, [28..30] acom drift, [31..36] hg, [37..42] dhg drift
+                double tot[16];
+                for (int k = 0; k < 16; ++k)
+                    tot[k] = 0;
+                for (int j = 0; j < nj; ++j)
+                    if (gP->depth[j] == 0) {
+                        for (int k = 0; k < 10; ++k)
+                            tot[k] += sm.Yw[10 * j + k];
+                        for (int k = 0; k < 6; ++k)
+                            tot[10 + k] += sm.fw[6 * j + k];
+                    }
+                for (int k = 0; k < 10; ++k)
+                    sc[k] = tot[k];
+                for (int k = 0; k < 6; ++k)
+                    sc[16 + k] = tot[10 + k];
+                const double mt = tot[0];
+                V3 hh = mk(tot[1], tot[2], tot[3]);
+                V3 com = (1.0 / mt) * hh;
+                V3 hl = ld3(sc + 10), ha = ld3(sc + 13);
+                V3 fl = mk(tot[10], tot[11], tot[12]), fa = mk(tot[13], tot[14], tot[15]);
+                V3 ag = -1.0 * ld3(c_P.gravity);
+                V3 dl = fl - mt * ag, da = fa - cross(hh, ag);
+                st3(sc + 22, com);
+                st3(sc + 25, (1.0 / mt) * hl);
+                st3(sc + 28, (1.0 / mt) * dl);
+                st3(sc + 31, hl);
+                st3(sc + 34, ha - cross(com, hl));
+                st3(sc + 37, dl);
+                st3(sc + 40, da - cross(com, dl));
+            }
+        }
+        fsync<T>();
+        if (cyc && tid == 0)
+            cyc[1] = clock64();
+
+        // ---------------------------------------------------------------- scalar jobs: right-hand sides of every task, self-collision pairs
+        for (int jb = tid; jb < F.njobs; jb += T) {
+            const FJob J = gF->jobs[jb];
+            if (J.kind == FJ_SE3) {
+                const iwbc_task_t& Tk = gP->tasks[J.task];
+                se3_rhs(sm, Tk.frame, Tk.kp, Tk.kd, Z + Tk.ref_off, rhs + 6 * J.slot);
+            }
+            else if (J.kind == FJ_CONTACT) {
+                const iwbc_contact_t& C = gP->contacts[J.task];
+                se3_rhs(sm, C.frame, C.kp, C.kd, Z + C.ref_off, sm.cb + 6 * J.task);
+            }
+            else if (J.kind == FJ_COM) {
+                const iwbc_task_t& Tk = gP->tasks[J.task];
+                const double* r = Z + Tk.ref_off;
+                for (int i = 0; i < 3; ++i) {
+                    const double a_des = -Tk.kp[i] * (sc[22 + i] - r[i]) - Tk.kd[i] * (sc[25 + i] - r[3 + i]) + r[6 + i];
+                    rhs[6 * J.slot + i] = a_des - sc[28 + i];
+                }
+            }
+            else if (J.kind == FJ_MOM) {
+                const iwbc_task_t& Tk = gP->tasks[J.task];
+                const double* r = Z + Tk.ref_off;
+                for (int i = 0; i < 6; ++i) {
+                    const double dL = -Tk.kp[i] * (sc[31 + i] - r[6 + i]) + r[12 + i];
+                    rhs[6 * J.slot + i] = dL - sc[37 + i];
+                }
+            }
+            else {
+                const iwbc_task_t& Tk = gP->tasks[J.task];
+                const int f0 = Tk.frame, fa = Tk.av_frame[J.a];
+                const int lwa = !c_P.sc_jacobian_world;
+                const double* o0 = sm.oMf + 12 * f0;
+                const double* oa = sm.oMf + 12 * fa;
+                V3 diff = ld3(o0 + 9) - ld3(oa + 9);
+                const double sq = dot(diff, diff), nrm = sqrt(sq);
+                const double aa = Tk.av_r0[J.a] + Tk.radius;
+                V3 drift = ld3(sm.af + 6 * f0) - ld3(sm.af + 6 * fa);
+                auto point_vel = [&](int f, const double* o) {
+                    int pj = gP->fparent[f];
+                    if (pj < 0)
+                        return mk(0, 0, 0);
+                    V3 vl = ld3(sm.vw + 6 * pj), w = ld3(sm.vw + 6 * pj + 3);
+                    return lwa ? vl + cross(w, ld3(o + 9)) : vl;
+                };
+                V3 Jv = point_vel(f0, o0) - point_vel(fa, oa);
+                const double m = Tk.sc_m, k = Tk.sc_k;
+                const double x = k * (nrm - aa + Tk.sc_sp);
+                const double e_p = exp(-x);
+                const double l1 = log1p(e_p);
+                const double pw0 = exp(-m * l1);
+                const double pw1 = exp((-m - 1) * l1);
+                const double pw2 = exp((-m - 2) * l1);
+                const double Cv = 1. - pw0;
+                const double gs = -1. / nrm * k * m * e_p * pw1;
+                const double h = 1. / sq * k * k * (-m - 1.) * m * exp(-2 * x) * pw2 + 1. / sq * k * k * m * e_p * pw1
+                    + 1. / (nrm * sqrt(nrm)) * k * m * e_p * pw1;
+                V3 grad = gs * diff;
+                V3 HJv = (h * dot(diff, Jv)) * diff + gs * Jv;
+                const double Bc = -(dot(HJv, Jv) + dot(grad, Tk.kd[0] * Jv - drift) + Tk.kp[0] * Cv);
+                st3(sc4 + 4 * J.slot, grad);
+                sc4[4 * J.slot + 3] = Bc;
+            }
+        }
+        fsync<T>();
+        // ---------------------------------------------------------------- rows: A (dense level-1 rows, scaled by sqrt(w)), b, contact Jacobians
+        {
+            const int NH = (T / nv) > 0 ? (T / nv) : 1;
+            for (int item = tid; item < nv * NH; item += T) {
+                const int hh = item / nv, k = item - hh * nv;
+                const int jk = gF->dofj[k];
+                const V3 sl = ld3(sm.Sw + 6 * k), sa = ld3(sm.Sw + 6 * k + 3);
+                for (int bi = hh; bi < F.nblocks; bi += NH) {
+                    const FBlock Bk = gF->blocks[bi];
+                    if (Bk.kind == FB_CONTACT) {
+                        const int c = Bk.index;
+                        V3 l, a;
+                        frame_jac_col(gP, sm, gP->contacts[c].frame, k, l, a);
+                        double* Jc = sm.Jft + (c * 6) * nv + k;
+                        Jc[0] = l.x, Jc[nv] = l.y, Jc[2 * nv] = l.z, Jc[3 * nv] = a.x, Jc[4 * nv] = a.y, Jc[5 * nv] = a.z;
+                        continue;
+                    }
+                    const iwbc_task_t& Tk = gP->tasks[Bk.index];
+                    const double sw = sqrt(Tk.weight);
+                    if (Bk.kind == FB_SE3) {
+                        V3 l, a;
+                        frame_jac_col(gP, sm, Tk.frame, k, l, a);
+                        const double col[6] = {l.x, l.y, l.z, a.x, a.y, a.z};
+                        int idx = 0;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i)
+                            if (Tk.mask[i])
+                                A[(Bk.row0 + idx++) * nvp + k] = sw * col[i];
+                    }
+                    else if (Bk.kind == FB_COM) {
+                        const double imt = 1.0 / sc[0];
+                        int idx = 0;
+                        for (int i = 0; i < 3; ++i)
+                            if (Tk.mask[i])
+                                A[(Bk.row0 + idx++) * nvp + k] = sw * imt * sm.Fc[6 * k + i];
+                    }
+                    else if (Bk.kind == FB_MOM) {
+                        const V3 com = ld3(sc + 22);
+                        V3 Fl = ld3(sm.Fc + 6 * k), Fa = ld3(sm.Fc + 6 * k + 3) - cross(com, Fl);
+                        const double col[6] = {Fl.x, Fl.y, Fl.z, Fa.x, Fa.y, Fa.z};
+                        int idx = 0;
+#pragma unroll
+                        for (int i = 0; i < 6; ++i)
+                            if (Tk.mask[i])
+                                A[(Bk.row0 + idx++) * nvp + k] = sw * col[i];
+                    }
+                    else { // FB_SELFCOL
+                        const int lwa = !c_P.sc_jacobian_world;
+                        auto col = [&](int f) {
+                            int pj = gP->fparent[f];
+                            if (pj < 0 || !supports(gP, jk, pj))
+                                return mk(0, 0, 0);
+                            return lwa ? sl + cross(sa, ld3(sm.oMf + 12 * f + 9)) : sl;
+                        };
+                        const V3 c0 = col(Tk.frame);
+                        double acc = 0;
+                        for (int a = 0; a < Tk.nav; ++a)
+                            acc += dot(ld3(sc4 + 4 * (Bk.slot0 + a)), c0 - col(Tk.av_frame[a]));
+                        A[Bk.row0 * nvp + k] = sw * acc;
+                    }
+                }
+            }
+            for (int r = tid; r < F.nrows; r += T) {
+                const FRow Rw = gF->rows[r];
+                const iwbc_task_t& Tk = gP->tasks[Rw.task];
+                const double sw = sqrt(Tk.weight);
+                double val;
+                if (Rw.kind == FB_SELFCOL) {
+                    val = 0;
+                    for (int a = 0; a < Tk.nav; ++a)
+                        val += sc4[4 * (Rw.slot + a) + 3];
+                }
+                else
+                    val = rhs[6 * Rw.slot + Rw.comp];
+                bvec[r] = sw * val;
+                for (int k = nv; k < nvp; ++k) // zero padding of the row
+                    A[r * nvp + k] = 0.0;
+            }
+        }
+        fsync<T>();
+        if (cyc && tid == 0)
+            cyc[2] = clock64();
+
+        // ---------------------------------------------------------------- H = A'A in 4 x 4 register tiles (lower triangle), g = -A'b - posture
+        double hacc[FT<T>::NTPT][16];
+        {
+            const int R = F.nrows;
+#pragma unroll 1
+            for (int tt = 0; tt < FT<T>::NTPT; ++tt) {
+                const int tile = tt * T + tid;
+                double* h = hacc[tt];
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                    h[e] = 0;
+                if (tile < F.ntiles) {
+                    const double* Ai = A + 4 * gF->tile_i[tile];
+                    const double* Aj = A + 4 * gF->tile_j[tile];
+                    for (int r = 0; r < R; ++r) {
+                        const double a0 = Ai[r * nvp], a1 = Ai[r * nvp + 1], a2 = Ai[r * nvp + 2], a3 = Ai[r * nvp + 3];
+                        const double b0 = Aj[r * nvp], b1 = Aj[r * nvp + 1], b2 = Aj[r * nvp + 2], b3 = Aj[r * nvp + 3];
+                        h[0] += a0 * b0, h[1] += a0 * b1, h[2] += a0 * b2, h[3] += a0 * b3;
+                        h[4] += a1 * b0, h[5] += a1 * b1, h[6] += a1 * b2, h[7] += a1 * b3;
+                        h[8] += a2 * b0, h[9] += a2 * b1, h[10] += a2 * b2, h[11] += a2 * b3;
+                        h[12] += a3 * b0, h[13] += a3 * b1, h[14] += a3 * b2, h[15] += a3 * b3;
+                    }
+                }
+            }
+            // g: threads from the top end (the tile owners sit at the bottom end)
+            for (int k = (T - 1 - tid); k < nv; k += T) {
+                double s = 0;
+                for (int r = 0; r < R; ++r)
+                    s += A[r * nvp + k] * bvec[r];
+                s = -s;
+                if (k >= nu) {
+                    const int i = k - nu;
+                    for (int pt = 0; pt < F.nposture; ++pt) {
+                        const iwbc_task_t& Tk = gP->tasks[F.posture[pt]];
+                        if (!Tk.mask[i])
+                            continue;
+                        const double* r = Z + Tk.ref_off;
+                        const double a_des = -Tk.kp[0] * (qs[nq - na + i] - r[i]) - Tk.kd[0] * (vs[nv - na + i] - r[na + i]) + r[2 * na + i];
+                        s -= Tk.weight * a_des;
+                    }
+                }
+                gvec[k] = s;
+            }
+        }
+        fsync<T>(); // A is dead
+        // ---------------------------------------------------------------- mass matrix M[r][c] = S_lo . F_hi when joint(lo) supports joint(hi)
+        for (int e = tid; e < nv * nv; e += T) {
+            const int r = e / nv, c = e - r * nv;
+            if (c > r)
+                continue;
+            double m = 0;
+            if (supports(gP, gF->dofj[c], gF->dofj[r]))
+                m = dot(ld3(sm.Sw + 6 * c), ld3(sm.Fc + 6 * r)) + dot(ld3(sm.Sw + 6 * c + 3), ld3(sm.Fc + 6 * r + 3));
+            M[r * ldM + c] = m;
+            M[c * ldM + r] = m;
+        }
+        fsync<T>(); // the dynamics scratch is dead
+        // ---------------------------------------------------------------- augmented matrix: [H ; N' ; g'] (column-major, ld = ldh)
+        {
+#pragma unroll 1
+            for (int tt = 0; tt < FT<T>::NTPT; ++tt) {
+                const int tile = tt * T + tid;
+                if (tile < F.ntiles) {
+                    const int i0 = 4 * gF->tile_i[tile], j0 = 4 * gF->tile_j[tile];
+                    const double* h = hacc[tt];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const int i = i0 + a, j = j0 + b;
+                            if (i < nv && j <= i) {
+                                double val = h[4 * a + b];
+                                if (i == j) {
+                                    val += gF->hdiag[i];
+                                    hd[i] = val;
+                                }
+                                Hs[i + j * ld] = val;
+                            }
+                        }
+                }
+            }
+            // constraint normals (dv part) as rows nv .. nv+me-1, the gradient as row nv+me
+            for (int e = tid; e < (me + 1) * nv; e += T) {
+                const int c = e / nv, k = e - c * nv;
+                double val;
+                if (c < F.cb0)
+                    val = sm.Jft[(F.cact[c / 6] * 6 + (c % 6)) * nv + k];
+                else if (c < me)
+                    val = M[(c - F.cb0) * ldM + k];
+                else
+                    val = gvec[k];
+                Hs[(nv + c) + k * ld] = val;
+            }
+            // force part of the base-dynamics normals and of the gradient, through the constant force-block factor:
+            // Bf[kk][r] = (Uff' N_f)[kk][r],  N_f[12 s + i][r] = -(T' Jft)[i][r]
+            for (int e = tid; e < 12 * F.nca * F.nf; e += T) {
+                const int kk = e / F.nf, r = e - kk * F.nf;
+                const int s = kk / 12, k2 = kk - 12 * s;
+                double val;
+                if (r == nu)
+                    val = gF->ygf[s][k2];
+                else {
+                    const int c = F.cact[s];
+                    const double* Tm = gP->contacts[c].T;
+                    const double* U = gF->Uff[s];
+                    val = 0;
+                    for (int i = 0; i <= k2; ++i) {
+                        double npf = 0;
+#pragma unroll
+                        for (int a = 0; a < 6; ++a)
+                            npf += Tm[a * 12 + i] * sm.Jft[(c * 6 + a) * nv + r];
+                        val -= U[i * 12 + k2] * npf;
+                    }
+                }
+                Bf[kk * F.nf + r] = val;
+            }
+        }
+        fsync<T>();
+
+        // ---------------------------------------------------------------- left-looking Cholesky of the augmented matrix (one barrier per column)
+        bool spd = true;
+        {
+            constexpr int PAIR = FT<T>::PAIR;
+            const int sub = tid % PAIR, row0 = tid / PAIR, rstep = T / PAIR > 0 ? T / PAIR : 1;
+            const int nrh = F.nrh;
+            for (int k = 0; k < nv; ++k) {
+                const double* Lk = Hs + k;
+                for (int ib = k; ib < nrh; ib += rstep) { // (uniform trip count: the pair shuffle below needs the whole warp)
+                    const int i = ib + row0;
+                    const bool act = i < nrh;
+                    const double* Li = Hs + (act ? i : k);
+                    double s = 0, dk = 0;
+                    for (int j = sub; j < k; j += PAIR) {
+                        const double lk = Lk[j * ld];
+                        s += Li[j * ld] * lk;
+                        dk += lk * lk;
+                    }
+                    if (PAIR == 2) {
+                        s += __shfl_xor_sync(0xffffffffu, s, 1);
+                        dk += __shfl_xor_sync(0xffffffffu, dk, 1);
+                    }
+                    const double dkk = hd[k] - dk; // (the diagonal of H is kept in hd: column k of Hs is being overwritten)
+                    if (!(dkk > 0.0))
+                        spd = false;
+                    const double inv = rsqrt(dkk > 0.0 ? dkk : 1.0);
+                    if (act && sub == 0)
+                        Hs[i + k * ld] = (i == k) ? dkk * inv : (Li[k * ld] - s) * inv;
+                }
+                fsync<T>();
+            }
+        }
+        for (int k = tid; k < nv; k += T)
+            il[k] = 1.0 / Hs[k + k * ld];
+        if (cyc && tid == 0)
+            cyc[3] = clock64();
+
+        // ---------------------------------------------------------------- Householder QR of B = [L^-1 N_v ; B_f] (n x me), right-hand side y carried as column me
+        // B(j, c): j < nv -> Hs[(nv + c) + j ld] ; j >= nv -> c >= cb0 ? Bf[(j - nv) nf + (c - cb0)] : 0
+        {
+            constexpr int SEG = FT<T>::SEG;
+            const int c0 = (T > 1) ? tid % NC : 0, seg0 = (T > 1) ? tid / NC : 0;
+            const int cstep = (T > 1) ? NC : 1;
+            auto Bat = [&](int j, int c) -> double& { return j < nv ? Hs[(nv + c) + j * ld] : Bf[(j - nv) * F.nf + (c - F.cb0)]; };
+            for (int k = 0; k < me; ++k) {
+                const int jhi = (k < F.cb0) ? nv : n; // contact columns have no force rows and nothing fills them in
+                if (seg0 < SEG)
+                    for (int c = c0; c < NC; c += cstep) {
+                        if (c < k)
+                            continue;
+                        double s = 0;
+                        if (c >= F.cb0 || jhi == nv)
+                            for (int j = k + 1 + seg0; j < jhi; j += SEG)
+                                s += Bat(j, k) * Bat(j, c);
+                        Pp[seg0 * NC + c] = s;
+                    }
+                fsync<T>();
+                double sigma = 0;
+                for (int sg = 0; sg < SEG; ++sg)
+                    sigma += Pp[sg * NC + k];
+                const double alpha = Hs[(nv + k) + k * ld]; // k < me <= nv
+                double beta = alpha, tau = 0, scale = 0;
+                if (sigma != 0.0) {
+                    const double nr = sqrt(alpha * alpha + sigma);
+                    beta = alpha >= 0 ? -nr : nr;
+                    tau = (beta - alpha) / beta;
+                    scale = 1.0 / (alpha - beta);
+                }
+                if (seg0 < SEG)
+                    for (int c = c0; c < NC; c += cstep) {
+                        if (c < k)
+                            continue;
+                        if (c == k) {
+                            if (seg0 == 0) {
+                                Rm[k * NC + k] = beta;
+                                tauv[k] = tau;
+                                scalev[k] = scale;
+                                invb[k] = 1.0 / beta;
+                            }
+                            continue;
+                        }
+                        double pc = 0;
+                        for (int sg = 0; sg < SEG; ++sg)
+                            pc += Pp[sg * NC + c];
+                        const double bkc = Hs[(nv + c) + k * ld];
+                        const double coef = tau * (bkc + scale * pc);
+                        if (seg0 == 0)
+                            Rm[k * NC + c] = bkc - coef;
+                        if (c >= F.cb0 || jhi == nv) {
+                            const double cs = coef * scale;
+                            for (int j = k + 1 + seg0; j < jhi; j += SEG)
+                                Bat(j, c) -= cs * Bat(j, k);
+                        }
+                    }
+                fsync<T>();
+            }
+        }
+        // ---------------------------------------------------------------- w = -Q t,  t = [R^-T ce0 ; y2]  via  Q = I - V T V',  T^-1 = striu(V'V) + diag(1/tau)
+        {
+            auto Bat = [&](int j, int c) -> double { return j < nv ? Hs[(nv + c) + j * ld] : (c >= F.cb0 ? Bf[(j - nv) * F.nf + (c - F.cb0)] : 0.0); };
+            // u = R^-T ce0 (forward substitution, one thread; R is me x me upper triangular in Rm)
+            if (tid == 0) {
+                for (int k = 0; k < me; ++k) {
+                    double ce0;
+                    if (k < F.cb0)
+                        ce0 = -sm.cb[6 * F.cact[k / 6] + (k % 6)];
+                    else
+                        ce0 = sm.nle[k - F.cb0];
+                    double s = ce0;
+                    for (int i = 0; i < k; ++i)
+                        s -= Rm[i * NC + k] * tv[i];
+                    tv[k] = s * invb[k];
+                }
+            }
+            if (tid == (T > 32 ? 32 : 0)) { // c1 = trace(H), c2 = trace(L^-T) (fixed summation order)
+                double c1 = F.c1f, c2 = F.c2f;
+                for (int k = 0; k < nv; ++k) {
+                    c1 += hd[k];
+                    c2 += il[k];
+                }
+                tv[2 * (me + 2)] = c1;
+                tv[2 * (me + 2) + 1] = c2;
+            }
+            fsync<T>();
+            // t: rows < me from tv, rows >= me = column me of the transformed matrix; Gram entries v_i'v_k (i < k) and v_i't
+            for (int pr = tid; pr < F.npairs; pr += T) {
+                const int i = gF->pair_i[pr], k = gF->pair_k[pr];
+                const int jhi = (i < F.cb0) ? nv : n;
+                double s;
+                if (k < me) {
+                    s = Bat(k, i); // v_i[k] * v_k[k],  v_k[k] = 1
+                    double d = 0;
+                    for (int j = k + 1; j < jhi; ++j)
+                        d += Bat(j, i) * Bat(j, k);
+                    s = scalev[i] * (s + scalev[k] * d);
+                }
+                else {
+                    // v_i' t = t_i + scale_i sum_{j > i} B(j, i) t_j
+                    double d = 0;
+                    for (int j = i + 1; j < jhi; ++j)
+                        d += Bat(j, i) * (j < me ? tv[j] : Bat(j, me));
+                    s = tv[i] + scalev[i] * d;
+                }
+                Gm[i * (me + 1) + k] = s;
+            }
+            fsync<T>();
+            // z = T (V't): back-substitution on T^-1 z = V't (upper triangular, diag 1/tau)
+            if (tid == 0) {
+                double* z = tv + (me + 2);
+                for (int i = me - 1; i >= 0; --i) {
+                    double s = Gm[i * (me + 1) + me];
+                    for (int k = i + 1; k < me; ++k)
+                        s -= Gm[i * (me + 1) + k] * z[k];
+                    z[i] = tauv[i] != 0.0 ? s * tauv[i] : 0.0;
+                }
+            }
+            fsync<T>();
+            // w = -(t - V z)
+            {
+                const double* z = tv + (me + 2);
+                for (int j = tid; j < n; j += T) {
+                    double s = j < me ? tv[j] : Bat(j, me);
+                    const int kmax = j < me ? j : me - 1;
+                    for (int k = 0; k <= kmax; ++k) {
+                        if (j >= nv && k < F.cb0)
+                            continue;
+                        const double vjk = (j == k) ? 1.0 : scalev[k] * Bat(j, k);
+                        s -= vjk * z[k];
+                    }
+                    wv[j] = -s;
+                }
+            }
+            fsync<T>();
+        }
+        // ---------------------------------------------------------------- x = L^-T w: back-substitution on the dv block (one warp), constant factor on the force blocks
+        {
+            if (T == 1) {
+                for (int k = nv - 1; k >= 0; --k) {
+                    double s = wv[k];
+                    for (int i = k + 1; i < nv; ++i)
+                        s -= Hs[i + k * ld] * xv[i];
+                    xv[k] = s * il[k];
+                }
+            }
+            else if (tid < 32) {
+                // lane l owns rows l and l + 32 (nv <= 64)
+                double w0 = tid < nv ? wv[tid] : 0.0, w1 = tid + 32 < nv ? wv[tid + 32] : 0.0;
+                for (int k = nv - 1; k >= 0; --k) {
+                    const double mine = (k >= 32) ? w1 : w0;
+                    const double xk = __shfl_sync(0xffffffffu, mine, k & 31) * il[k];
+                    if (tid == (k & 31))
+                        xv[k] = xk;
+                    // w_i -= L[k][i] x_k for i < k
+                    if (tid < k)
+                        w0 -= Hs[k + tid * ld] * xk;
+                    if (tid + 32 < k)
+                        w1 -= Hs[k + (tid + 32) * ld] * xk;
+                }
+            }
+            else {
+                for (int kk = tid - 32; kk < 12 * F.nca; kk += (T > 32 ? T - 32 : 1)) {
+                    const int s = kk / 12, i = kk - 12 * s;
+                    const double* U = gF->Uff[s] + i * 12;
+                    double a = 0;
+                    for (int j = i; j < 12; ++j)
+                        a += U[j] * wv[nv + 12 * s + j];
+                    xv[nv + 12 * s + i] = a;
+                }
+            }
+            if (T == 1)
+                for (int kk = 0; kk < 12 * F.nca; ++kk) {
+                    const int s = kk / 12, i = kk - 12 * s;
+                    const double* U = gF->Uff[s] + i * 12;
+                    double a = 0;
+                    for (int j = i; j < 12; ++j)
+                        a += U[j] * wv[nv + 12 * s + j];
+                    xv[nv + 12 * s + i] = a;
+                }
+        }
+        fsync<T>();
+        if (cyc && tid == 0)
+            cyc[4] = clock64();
+
+        // ---------------------------------------------------------------- s = CI x + ci0: eiquadprog's termination test at x_eq
+        Sizes z;
+        z.nv = nv, z.nq = nq, z.nj = nj, z.nf = nfr, z.nc = c_P.ncontacts, z.n = n, z.mi = S.mi, z.rows_dense = S.rows_dense, z.nref = c_P.nref;
+        z.ldJ = S.ldJ, z.ldM = ldM;
+        FusedRows::wrenches<T>(sm, z, tid);
+        fsync<T>();
+        double psi = 0;
+        for (int i = tid; i < na; i += T) {
+            const double t = FusedRows::act_row_value(sm, z, i);
+            taut[i] = t;
+            if (F.ci_act >= 0) {
+                const double tm = gP->tau_max[i], h = sm.nle[nu + i];
+                psi += fmin(0.0, t + tm + h) + fmin(0.0, -t + tm - h);
+            }
+            if (F.ci_bounds >= 0) {
+                const double xi = xv[nu + i];
+                psi += fmin(0.0, xi - sm.lb[i]) + fmin(0.0, -xi + sm.ub[i]);
+            }
+        }
+        for (int e = T - 1 - tid; e < 17 * F.nca; e += T) {
+            const int s = e / 17, r = e - 17 * s;
+            const iwbc_contact_t& C = gP->contacts[F.cact[s]];
+            const double* f = xv + nv + 12 * s;
+            double y = 0;
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+                y += C.B[r * 12 + k] * f[k];
+            psi += fmin(0.0, y - C.lb[r]) + fmin(0.0, -y + C.ub[r]);
+        }
+        psi = fblock_sum<T>(psi, Pp, tid);
+        const double c1 = tv[2 * (me + 2)], c2 = tv[2 * (me + 2) + 1];
+        if (!spd || !(fabs(psi) <= S.mi * 2.220446049250313e-16 * c1 * c2 * 100.0))
+            return false;
+        if (cyc && tid == 0)
+            cyc[5] = clock64();
+        // ---------------------------------------------------------------- decode, integrate, store (status OPTIMAL after 1 iteration, empty active set)
+        sm.d = wv;
+        sm.x_old = gvec;
+        sm.act = nullptr;
+        k_dec<T>(gP, sm, z, io, inst, tid, IWBC_STATUS_OPTIMAL, 1, S.me, taut);
+        return true;
+    }
+
+#ifndef IWBC_CPU_SIM
+    // One CTA of T threads per instance, persistent over the batch.  Instances that need the active-set iteration are
+    // appended to io.slow_list (order is arbitrary; every instance's results are independent of it).
+    template <int T>
+    __global__ void __launch_bounds__(T, 3) k_fast(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, IO io)
+    {
+        extern __shared__ double smem[];
+        const int tid = threadIdx.x;
+        {
+            int* dofj = reinterpret_cast<int*>(smem + c_F.o_int);
+            for (int k = tid; k < c_P.nv; k += T)
+                dofj[k] = gF->dofj[k];
+        }
+        __syncthreads();
+        for (int inst = blockIdx.x; inst < io.B; inst += gridDim.x) {
+            long long stamps[8];
+            long long* cyc = io.prof ? stamps : nullptr;
+            const bool done = fast_instance<T>(gP, gF, smem, io, inst, tid, cyc);
+            if (tid == 0) {
+                if (!done)
+                    io.slow_list[atomicAdd(io.slow_count, 1)] = inst;
+                else if (cyc) {
+                    cyc[6] = clock64();
+                    for (int k = 0; k < 6; ++k)
+                        atomicAdd(io.prof + 8 + k, (unsigned long long)(cyc[k + 1] - cyc[k]));
+                    atomicAdd(io.prof + 14, 1ull);
+                }
+            }
+            __syncthreads();
+        }
+    }
+#endif
+
+} // namespace dev
+} // namespace iwbc

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../inria_wbc_b200/csrc/cycle_kernel.cuh"
+#include "../inria_wbc_b200/csrc/fast_kernel.cuh"
 #include "../inria_wbc_b200/csrc/host_state.hpp"
 
 namespace iwbc {
@@ -88,6 +89,42 @@ extern "C" int sim_cycle_batch(const iwbc_problem_t* P, int B, const double* q, 
     int flip = 0;
     for (int i = 0; i < B; ++i)
         dev::cycle_instance<1>(P, sm, z, io, i, 0, flip);
+    return 0;
+}
+
+// fast path (fast_kernel.cuh) with the active-set kernel as continuation, exactly as batch.cu chains them.
+// fast_used (optional, [B]): 1 where the instance was finished by the fast path.
+extern "C" int sim_fast_batch(const iwbc_problem_t* P, int B, const double* q, const double* v, const double* refs, long refs_stride,
+    unsigned mask, double* tau, double* dv, double* f, double* q_next, double* v_next, int* status, int* iters, unsigned* active,
+    double* q_cmd, double* momentum, int* fast_used)
+{
+    dev::Sizes z;
+    prepare(*P, mask, dev::c_S, z);
+    dev::c_P = *P;
+    static dev::FPlan plan;
+    if (!dev::build_fast_plan(*P, dev::c_S, 1, dev::c_F, plan))
+        return -1;
+    std::vector<double> smem(dev::c_S.total + 16, 0.0), fsmem(dev::c_F.total + 16, 0.0);
+    dev::Sm sm = dev::make_sm(smem.data(), z);
+    int* fdofj = reinterpret_cast<int*>(fsmem.data() + dev::c_F.o_int);
+    for (int j = 0; j < z.nj; ++j) {
+        const int c0 = P->idx_v[j], cn = P->jtype[j] == IWBC_J_FREEFLYER ? 6 : 1;
+        for (int k = 0; k < cn; ++k)
+            sm.dofj[c0 + k] = j, fdofj[c0 + k] = j;
+    }
+    dev::IO io;
+    std::memset(&io, 0, sizeof(io));
+    io.B = B, io.q = q, io.v = v, io.refs = refs, io.refs_stride = refs_stride;
+    io.tau = tau, io.dv = dv, io.f = f, io.q_next = q_next, io.v_next = v_next, io.status = status, io.iters = iters, io.active = active;
+    io.q_cmd = q_cmd, io.momentum = momentum;
+    int flip = 0;
+    for (int i = 0; i < B; ++i) {
+        const bool done = dev::fast_instance<1>(P, &plan, fsmem.data(), io, i, 0, nullptr);
+        if (fast_used)
+            fast_used[i] = done ? 1 : 0;
+        if (!done)
+            dev::cycle_instance<1>(P, sm, z, io, i, 0, flip);
+    }
     return 0;
 }
 

@@ -129,7 +129,8 @@ def sim_lib():
     global _sim
     if _sim is None:
         so = os.path.join(ROOT, "tests", "libcpusim.so")
-        srcs = [os.path.join(ROOT, "tests", "cpu_sim.cpp"), os.path.join(ROOT, "inria_wbc_b200", "csrc", "cycle_kernel.cuh")]
+        srcs = [os.path.join(ROOT, "tests", "cpu_sim.cpp"), os.path.join(ROOT, "inria_wbc_b200", "csrc", "cycle_kernel.cuh"),
+                os.path.join(ROOT, "inria_wbc_b200", "csrc", "fast_kernel.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(s) for s in srcs):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unused", "-o", so, srcs[0]])
         _sim = C.CDLL(so)
@@ -151,6 +152,26 @@ def sim_cycle_batch(problem, q, v, refs=None, contact_mask=None):
                                    _p(out["tau"]), _p(out["dv"]), _p(out["f"]), _p(out["q_next"]), _p(out["v_next"]), _p(out["status"]),
                                    _p(out["iters"]), _p(out["active"]), _p(out["q_cmd"]), _p(out["momentum"]))
     assert rc == 0
+    return out
+
+
+def sim_fast_batch(problem, q, v, refs=None, contact_mask=None):
+    """fast_kernel.cuh (equality-constrained first pass) chained with the active-set kernel, host-compiled."""
+    P = problem
+    q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, P.nq)
+    v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, P.nv)
+    B = q.shape[0]
+    refs = P.default_refs() if refs is None else np.ascontiguousarray(refs, dtype=np.float64)
+    stride = 0 if refs.ndim == 1 else P.nref
+    m = P.default_contact_mask if contact_mask is None else contact_mask
+    out = dict(tau=np.zeros((B, P.na)), dv=np.zeros((B, P.nv)), f=np.zeros((B, 12 * P.ncontacts)), q_next=np.zeros((B, P.nq)),
+               v_next=np.zeros((B, P.nv)), status=np.zeros(B, np.int32), iters=np.zeros(B, np.int32),
+               active=np.zeros((B, ORACLE_ACTIVE_WORDS), np.uint32), q_cmd=np.zeros((B, P.nv)), momentum=np.zeros((B, 3)),
+               fast=np.zeros(B, np.int32))
+    rc = sim_lib().sim_fast_batch(C.c_void_p(P.data_ptr), C.c_int(B), _p(q), _p(v), _p(refs), C.c_long(stride), C.c_uint(m),
+                                  _p(out["tau"]), _p(out["dv"]), _p(out["f"]), _p(out["q_next"]), _p(out["v_next"]), _p(out["status"]),
+                                  _p(out["iters"]), _p(out["active"]), _p(out["q_cmd"]), _p(out["momentum"]), _p(out["fast"]))
+    assert rc == 0, "fast path not applicable to this problem"
     return out
 
 

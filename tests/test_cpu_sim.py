@@ -82,6 +82,39 @@ def test_talos_active_inequalities(talos):
     assert err.max() < 1e-6  # conditioning of H (force regularisation ~1e-9) amplifies rounding on hard states: DESIGN.md
 
 
+def _compare_fast(P, q, v, refs=None, mask=None, min_fast=0.5):
+    """fast_kernel.cuh chained with the active-set kernel (as batch.cu launches them) against the oracle."""
+    ref = ol.cycle_batch(P, q, v, refs, contact_mask=mask, nthreads=4)
+    sim = ol.sim_fast_batch(P, q, v, refs, contact_mask=mask)
+    assert np.array_equal(ref["status"], sim["status"])
+    fast = sim["fast"] == 1
+    assert fast.mean() >= min_fast
+    # the fast path finishes exactly the instances eiquadprog ends after one iteration, with an empty active set
+    assert np.array_equal(fast, (ref["iters"] == 1) & (ref["status"] == 0))
+    assert not sim["active"][fast].any() and not ref["active"][fast].any()
+    assert np.array_equal(ref["iters"][fast], sim["iters"][fast])
+    ok = ref["status"] == 0
+    for k in ("tau", "dv", "f", "q_next", "v_next", "q_cmd", "momentum"):
+        a, b = sim[k][ok], ref[k][ok]
+        err = np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), 1e-9)
+        if fast.any():
+            assert err[fast[ok]].max() < TOL, (k, err.max())
+    return ref, sim
+
+
+def test_fast_path_talos_double_support(talos):
+    import bench
+    q, v, refs = bench.make_inputs(talos, 96, "talos", 0xB200 + 3)
+    _compare_fast(talos, q, v, refs, min_fast=0.8)
+
+
+def test_fast_path_moving_base_and_single_support(talos):
+    q, v = random_states(talos, 24, 4, base=True)
+    _compare_fast(talos, q, v, min_fast=0.0)
+    _compare_fast(talos, q, v, mask=0b01, min_fast=0.0)
+    _compare_fast(talos, q, v, mask=0b10, min_fast=0.0)
+
+
 @pytest.mark.parametrize("n,me,mi", [(9, 0, 4), (20, 5, 30), (74, 18, 244)])
 def test_dense_qp(n, me, mi):
     rng = np.random.default_rng(n)

@@ -24,8 +24,7 @@ for _ in range(3):
     r = bt.update(q, v, refs)
 prof = bt.phase_profile(False)
 ms = bt.kernel_ms(True)
-tot = sum(prof[k] for k in ("dyn", "asm", "factor", "eq", "ineq", "decode"))
 out = {"workload": wl, "batch": B, "launch": bt.launch_info(), "kernel_ms": ms, "mean_cycles_per_instance": prof,
-       "share": {k: prof[k] / tot for k in ("dyn", "asm", "factor", "eq", "ineq", "decode")}, "total_cycles": tot,
+       "total_cycles": {k: sum(x for kk, x in d.items() if kk != "instances") for k, d in (prof or {}).items()},
        "mean_iters": float(r.iters.mean())}
 print(json.dumps(out))
