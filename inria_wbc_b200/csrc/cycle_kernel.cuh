@@ -47,6 +47,7 @@ inline void __syncthreads() {}
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
 template <class T> inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+struct double2 { double x, y; };
 inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 inline long long clock64() { return 0; }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }

@@ -114,7 +114,7 @@ namespace dev {
         F.nf = nu + 1;
         F.NC = S.me + 1;
         F.nrh = nv + S.me + 1;
-        F.ldh = F.nrh | 1;
+        F.ldh = (F.nrh + 1) & ~1; // even: the Cholesky panel reads pairs of rows as double2
         F.nvp = (nv + 3) & ~3;
         // ---- jobs, row blocks, rows (level-1 order = Hessian summation order)
         int nslots = 0, npairslots = 0, row = 0;
@@ -303,7 +303,7 @@ namespace dev {
         F.o_sc4 = take(4 * (npairslots > 0 ? npairslots : 1));
         F.o_P = take(8 * F.NC);
         F.o_Rm = take(F.me * F.NC + 3 * F.me + 8); // R (me x NC), tau, scale, invbeta
-        F.o_tv = take(3 * (F.me + 2));
+        F.o_tv = take(3 * (F.me + 2) + 4);
         F.o_hd = take(nv);
         F.o_il = take(nv);
         F.o_tau = take(nv);
@@ -935,98 +935,179 @@ namespace dev {
         }
         fsync<T>();
 
-        // ---------------------------------------------------------------- left-looking Cholesky of the augmented matrix (one barrier per column)
+        // ---------------------------------------------------------------- blocked left-looking Cholesky of the augmented matrix (panels of 4 columns, 2 barriers each)
         bool spd = true;
         {
             constexpr int PAIR = FT<T>::PAIR;
-            const int sub = tid % PAIR, row0 = tid / PAIR, rstep = T / PAIR > 0 ? T / PAIR : 1;
+            const int sub = tid % PAIR, row0 = tid / PAIR, rstep = (T / PAIR) > 0 ? (T / PAIR) : 1;
             const int nrh = F.nrh;
-            for (int k = 0; k < nv; ++k) {
-                const double* Lk = Hs + k;
-                for (int ib = k; ib < nrh; ib += rstep) { // (uniform trip count: the pair shuffle below needs the whole warp)
+            double* const Db = Pp; // copy of the updated diagonal block (16 doubles)
+            for (int cb = 0; cb < nv; cb += 4) {
+                const int pw = nv - cb < 4 ? nv - cb : 4;
+                // (1) panel update: rows i >= cb of columns cb .. cb+3 minus the contribution of all previous columns
+                const double* Lp = Hs + cb;
+                for (int ib = cb; ib < nrh; ib += rstep) { // (uniform trip count: the pair shuffles need the whole warp)
                     const int i = ib + row0;
                     const bool act = i < nrh;
-                    const double* Li = Hs + (act ? i : k);
-                    double s = 0, dk = 0;
-                    for (int j = sub; j < k; j += PAIR) {
-                        const double lk = Lk[j * ld];
-                        s += Li[j * ld] * lk;
-                        dk += lk * lk;
+                    const double* Li = Hs + (act ? i : cb);
+                    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+                    for (int j = sub; j < cb; j += PAIR) {
+                        const double li = Li[j * ld];
+                        const double2 p01 = *reinterpret_cast<const double2*>(Lp + j * ld); // 16-byte aligned: cb % 4 == 0, ld even
+                        const double2 p23 = *reinterpret_cast<const double2*>(Lp + j * ld + 2);
+                        a0 += li * p01.x, a1 += li * p01.y, a2 += li * p23.x, a3 += li * p23.y;
                     }
                     if (PAIR == 2) {
-                        s += __shfl_xor_sync(0xffffffffu, s, 1);
-                        dk += __shfl_xor_sync(0xffffffffu, dk, 1);
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+                        a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+                        a3 += __shfl_xor_sync(0xffffffffu, a3, 1);
                     }
-                    const double dkk = hd[k] - dk; // (the diagonal of H is kept in hd: column k of Hs is being overwritten)
-                    if (!(dkk > 0.0))
+                    if (act && sub == 0) {
+                        double* Ri = Hs + i + cb * ld;
+                        const double v0 = Ri[0] - a0, v1 = pw > 1 ? Ri[ld] - a1 : 0.0, v2 = pw > 2 ? Ri[2 * ld] - a2 : 0.0, v3 = pw > 3 ? Ri[3 * ld] - a3 : 0.0;
+                        Ri[0] = v0;
+                        if (pw > 1)
+                            Ri[ld] = v1;
+                        if (pw > 2)
+                            Ri[2 * ld] = v2;
+                        if (pw > 3)
+                            Ri[3 * ld] = v3;
+                        if (i < cb + 4) {
+                            double* dr = Db + 4 * (i - cb);
+                            dr[0] = v0, dr[1] = v1, dr[2] = v2, dr[3] = v3;
+                        }
+                    }
+                }
+                fsync<T>();
+                // (2) factor the diagonal block (every thread, redundantly, from the copy) and solve the panel rows
+                {
+                    const double d00 = Db[0], d10 = Db[4], d20 = pw > 2 ? Db[8] : 0.0, d30 = pw > 3 ? Db[12] : 0.0;
+                    const double d11 = pw > 1 ? Db[5] : 1.0, d21 = pw > 2 ? Db[9] : 0.0, d31 = pw > 3 ? Db[13] : 0.0;
+                    const double d22 = pw > 2 ? Db[10] : 1.0, d32 = pw > 3 ? Db[14] : 0.0, d33 = pw > 3 ? Db[15] : 1.0;
+                    const double d10u = pw > 1 ? d10 : 0.0;
+                    if (!(d00 > 0.0))
                         spd = false;
-                    const double inv = rsqrt(dkk > 0.0 ? dkk : 1.0);
-                    if (act && sub == 0)
-                        Hs[i + k * ld] = (i == k) ? dkk * inv : (Li[k * ld] - s) * inv;
+                    const double i0 = rsqrt(d00 > 0.0 ? d00 : 1.0);
+                    const double l10 = d10u * i0, l20 = d20 * i0, l30 = d30 * i0;
+                    const double t1 = d11 - l10 * l10;
+                    if (!(t1 > 0.0))
+                        spd = false;
+                    const double i1 = rsqrt(t1 > 0.0 ? t1 : 1.0);
+                    const double l21 = (d21 - l20 * l10) * i1, l31 = (d31 - l30 * l10) * i1;
+                    const double t2 = d22 - l20 * l20 - l21 * l21;
+                    if (!(t2 > 0.0))
+                        spd = false;
+                    const double i2 = rsqrt(t2 > 0.0 ? t2 : 1.0);
+                    const double l32 = (d32 - l30 * l20 - l31 * l21) * i2;
+                    const double t3 = d33 - l30 * l30 - l31 * l31 - l32 * l32;
+                    if (!(t3 > 0.0))
+                        spd = false;
+                    const double i3 = rsqrt(t3 > 0.0 ? t3 : 1.0);
+                    if (tid == 0) {
+                        il[cb] = i0;
+                        if (pw > 1)
+                            il[cb + 1] = i1;
+                        if (pw > 2)
+                            il[cb + 2] = i2;
+                        if (pw > 3)
+                            il[cb + 3] = i3;
+                    }
+                    for (int i = cb + tid; i < nrh; i += T) {
+                        double* Ri = Hs + i + cb * ld;
+                        const int r = i - cb;
+                        const double x0 = Ri[0] * i0;
+                        Ri[0] = x0;
+                        if (pw > 1 && r >= 1) {
+                            const double x1 = (Ri[ld] - x0 * l10) * i1;
+                            Ri[ld] = x1;
+                            if (pw > 2 && r >= 2) {
+                                const double x2 = (Ri[2 * ld] - x0 * l20 - x1 * l21) * i2;
+                                Ri[2 * ld] = x2;
+                                if (pw > 3 && r >= 3)
+                                    Ri[3 * ld] = (Ri[3 * ld] - x0 * l30 - x1 * l31 - x2 * l32) * i3;
+                            }
+                        }
+                    }
                 }
                 fsync<T>();
             }
         }
-        for (int k = tid; k < nv; k += T)
-            il[k] = 1.0 / Hs[k + k * ld];
         if (cyc && tid == 0)
             cyc[3] = clock64();
 
         // ---------------------------------------------------------------- Householder QR of B = [L^-1 N_v ; B_f] (n x me), right-hand side y carried as column me
-        // B(j, c): j < nv -> Hs[(nv + c) + j ld] ; j >= nv -> c >= cb0 ? Bf[(j - nv) nf + (c - cb0)] : 0
+        // B(j, c): j < nv -> Hs[(nv + c) + j ld] ; j >= nv -> c >= cb0 ? Bf[(j - nv) nf + (c - cb0)] : 0.  Column k keeps its
+        // sub-diagonal part unscaled (v_k = e_k + scale_k B(k+1:, k)).  Threads whose column is already factorised (c < k)
+        // accumulate the Gram entries v_c'v_k needed to apply Q afterwards.
+        const int nfrc = 12 * F.nca, nfc = F.nf, cb0 = F.cb0;
+        constexpr int SEG = FT<T>::SEG;
+        const int qc0 = (T > 1) ? tid % NC : 0, seg0 = (T > 1) ? tid / NC : 0;
+        const int cstep = (T > 1) ? NC : 1;
         {
-            constexpr int SEG = FT<T>::SEG;
-            const int c0 = (T > 1) ? tid % NC : 0, seg0 = (T > 1) ? tid / NC : 0;
-            const int cstep = (T > 1) ? NC : 1;
-            auto Bat = [&](int j, int c) -> double& { return j < nv ? Hs[(nv + c) + j * ld] : Bf[(j - nv) * F.nf + (c - F.cb0)]; };
             for (int k = 0; k < me; ++k) {
-                const int jhi = (k < F.cb0) ? nv : n; // contact columns have no force rows and nothing fills them in
+                const double* colk = Hs + (nv + k);
+                const bool frc = k >= cb0; // column k has force rows (contact columns have none and nothing fills them in)
                 if (seg0 < SEG)
-                    for (int c = c0; c < NC; c += cstep) {
-                        if (c < k)
-                            continue;
+                    for (int c = qc0; c < NC; c += cstep) {
+                        const double* colc = Hs + (nv + c);
                         double s = 0;
-                        if (c >= F.cb0 || jhi == nv)
-                            for (int j = k + 1 + seg0; j < jhi; j += SEG)
-                                s += Bat(j, k) * Bat(j, c);
+                        for (int j = k + 1 + seg0; j < nv; j += SEG)
+                            s += colk[j * ld] * colc[j * ld];
+                        if (frc && c >= cb0) {
+                            const double* fk = Bf + (k - cb0);
+                            const double* fc = Bf + (c - cb0);
+                            for (int jj = seg0; jj < nfrc; jj += SEG)
+                                s += fk[jj * nfc] * fc[jj * nfc];
+                        }
                         Pp[seg0 * NC + c] = s;
                     }
                 fsync<T>();
                 double sigma = 0;
                 for (int sg = 0; sg < SEG; ++sg)
                     sigma += Pp[sg * NC + k];
-                const double alpha = Hs[(nv + k) + k * ld]; // k < me <= nv
-                double beta = alpha, tau = 0, scale = 0;
+                const double alpha = colk[k * ld]; // k < me <= nv
+                double beta = alpha, tau = 0, scale = 0, ibeta = 1.0 / alpha;
                 if (sigma != 0.0) {
-                    const double nr = sqrt(alpha * alpha + sigma);
+                    const double nn = alpha * alpha + sigma;
+                    const double inr = rsqrt(nn), nr = nn * inr;
                     beta = alpha >= 0 ? -nr : nr;
-                    tau = (beta - alpha) / beta;
+                    ibeta = alpha >= 0 ? -inr : inr;
+                    tau = 1.0 + fabs(alpha) * inr;          // (beta - alpha) / beta
                     scale = 1.0 / (alpha - beta);
                 }
                 if (seg0 < SEG)
-                    for (int c = c0; c < NC; c += cstep) {
-                        if (c < k)
-                            continue;
+                    for (int c = qc0; c < NC; c += cstep) {
                         if (c == k) {
                             if (seg0 == 0) {
                                 Rm[k * NC + k] = beta;
                                 tauv[k] = tau;
                                 scalev[k] = scale;
-                                invb[k] = 1.0 / beta;
+                                invb[k] = ibeta;
                             }
                             continue;
                         }
                         double pc = 0;
                         for (int sg = 0; sg < SEG; ++sg)
                             pc += Pp[sg * NC + c];
-                        const double bkc = Hs[(nv + c) + k * ld];
+                        double* colc = Hs + (nv + c);
+                        const double bkc = colc[k * ld];
+                        if (c < k) { // Gram entry v_c'v_k = scale_c (B(k, c) + scale_k sum_{j > k} B(j, c) B(j, k))
+                            if (seg0 == 0)
+                                Gm[c * (me + 1) + k] = scalev[c] * (bkc + scale * pc);
+                            continue;
+                        }
                         const double coef = tau * (bkc + scale * pc);
                         if (seg0 == 0)
                             Rm[k * NC + c] = bkc - coef;
-                        if (c >= F.cb0 || jhi == nv) {
-                            const double cs = coef * scale;
-                            for (int j = k + 1 + seg0; j < jhi; j += SEG)
-                                Bat(j, c) -= cs * Bat(j, k);
+                        const double cs = coef * scale;
+                        for (int j = k + 1 + seg0; j < nv; j += SEG)
+                            colc[j * ld] -= cs * colk[j * ld];
+                        if (frc) {
+                            const double* fk = Bf + (k - cb0);
+                            double* fc = Bf + (c - cb0);
+                            for (int jj = seg0; jj < nfrc; jj += SEG)
+                                fc[jj * nfc] -= cs * fk[jj * nfc];
                         }
                     }
                 fsync<T>();
@@ -1034,22 +1115,29 @@ namespace dev {
         }
         // ---------------------------------------------------------------- w = -Q t,  t = [R^-T ce0 ; y2]  via  Q = I - V T V',  T^-1 = striu(V'V) + diag(1/tau)
         {
-            auto Bat = [&](int j, int c) -> double { return j < nv ? Hs[(nv + c) + j * ld] : (c >= F.cb0 ? Bf[(j - nv) * F.nf + (c - F.cb0)] : 0.0); };
-            // u = R^-T ce0 (forward substitution, one thread; R is me x me upper triangular in Rm)
-            if (tid == 0) {
+            double* const zv = tv + (me + 2);
+            double* const zs = tv + 2 * (me + 2) + 2;
+            auto ce0_of = [&](int k) { return k < cb0 ? -sm.cb[6 * F.cact[k / 6] + (k % 6)] : sm.nle[k - cb0]; };
+            // u = R^-T ce0: column-oriented forward substitution by the first warp; c1 = trace(H), c2 = trace(L^-T) by another thread
+            if (T == 1) {
                 for (int k = 0; k < me; ++k) {
-                    double ce0;
-                    if (k < F.cb0)
-                        ce0 = -sm.cb[6 * F.cact[k / 6] + (k % 6)];
-                    else
-                        ce0 = sm.nle[k - F.cb0];
-                    double s = ce0;
+                    double sacc = ce0_of(k);
                     for (int i = 0; i < k; ++i)
-                        s -= Rm[i * NC + k] * tv[i];
-                    tv[k] = s * invb[k];
+                        sacc -= Rm[i * NC + k] * tv[i];
+                    tv[k] = sacc * invb[k];
                 }
             }
-            if (tid == (T > 32 ? 32 : 0)) { // c1 = trace(H), c2 = trace(L^-T) (fixed summation order)
+            else if (tid < 32) {
+                double rk = tid < me ? ce0_of(tid) : 0.0;
+                for (int i = 0; i < me; ++i) {
+                    const double ui = __shfl_sync(0xffffffffu, rk, i) * invb[i];
+                    if (tid == i)
+                        tv[i] = ui;
+                    if (tid > i && tid < me)
+                        rk -= Rm[i * NC + tid] * ui;
+                }
+            }
+            if (tid == (T > 32 ? 32 : 0)) { // fixed summation order
                 double c1 = F.c1f, c2 = F.c2f;
                 for (int k = 0; k < nv; ++k) {
                     c1 += hd[k];
@@ -1059,53 +1147,69 @@ namespace dev {
                 tv[2 * (me + 2) + 1] = c2;
             }
             fsync<T>();
-            // t: rows < me from tv, rows >= me = column me of the transformed matrix; Gram entries v_i'v_k (i < k) and v_i't
-            for (int pr = tid; pr < F.npairs; pr += T) {
-                const int i = gF->pair_i[pr], k = gF->pair_k[pr];
-                const int jhi = (i < F.cb0) ? nv : n;
-                double s;
-                if (k < me) {
-                    s = Bat(k, i); // v_i[k] * v_k[k],  v_k[k] = 1
-                    double d = 0;
-                    for (int j = k + 1; j < jhi; ++j)
-                        d += Bat(j, i) * Bat(j, k);
-                    s = scalev[i] * (s + scalev[k] * d);
+            // v_i't = t_i + scale_i sum_{j > i} B(j, i) t_j  (partial sums per row segment)
+            if (seg0 < SEG)
+                for (int i = qc0; i < me; i += cstep) {
+                    const double* coli = Hs + (nv + i);
+                    const double* colt = Hs + (nv + me);
+                    double sacc = 0;
+                    for (int j = i + 1 + seg0; j < nv; j += SEG)
+                        sacc += coli[j * ld] * (j < me ? tv[j] : colt[j * ld]);
+                    if (i >= cb0) {
+                        const double* fi = Bf + (i - cb0);
+                        const double* ft = Bf + (me - cb0);
+                        for (int jj = seg0; jj < nfrc; jj += SEG)
+                            sacc += fi[jj * nfc] * ft[jj * nfc];
+                    }
+                    Pp[seg0 * NC + i] = sacc;
                 }
-                else {
-                    // v_i' t = t_i + scale_i sum_{j > i} B(j, i) t_j
-                    double d = 0;
-                    for (int j = i + 1; j < jhi; ++j)
-                        d += Bat(j, i) * (j < me ? tv[j] : Bat(j, me));
-                    s = tv[i] + scalev[i] * d;
-                }
-                Gm[i * (me + 1) + k] = s;
-            }
             fsync<T>();
-            // z = T (V't): back-substitution on T^-1 z = V't (upper triangular, diag 1/tau)
-            if (tid == 0) {
-                double* z = tv + (me + 2);
+            // z = T (V't): back-substitution on T^-1 z = V't (upper triangular, diagonal 1/tau); zs = z * scale
+            if (T == 1) {
                 for (int i = me - 1; i >= 0; --i) {
-                    double s = Gm[i * (me + 1) + me];
+                    double sacc = tv[i] + scalev[i] * Pp[i];
                     for (int k = i + 1; k < me; ++k)
-                        s -= Gm[i * (me + 1) + k] * z[k];
-                    z[i] = tauv[i] != 0.0 ? s * tauv[i] : 0.0;
+                        sacc -= Gm[i * (me + 1) + k] * zv[k];
+                    zv[i] = sacc * tauv[i];
+                    zs[i] = zv[i] * scalev[i];
+                }
+            }
+            else if (tid < 32) {
+                double ri = 0;
+                if (tid < me) {
+                    double pacc = 0;
+                    for (int sg = 0; sg < SEG; ++sg)
+                        pacc += Pp[sg * NC + tid];
+                    ri = tv[tid] + scalev[tid] * pacc;
+                }
+                for (int k = me - 1; k >= 0; --k) {
+                    const double zk = __shfl_sync(0xffffffffu, ri, k) * tauv[k];
+                    if (tid == k) {
+                        zv[k] = zk;
+                        zs[k] = zk * scalev[k];
+                    }
+                    if (tid < k)
+                        ri -= Gm[tid * (me + 1) + k] * zk;
                 }
             }
             fsync<T>();
             // w = -(t - V z)
-            {
-                const double* z = tv + (me + 2);
-                for (int j = tid; j < n; j += T) {
-                    double s = j < me ? tv[j] : Bat(j, me);
-                    const int kmax = j < me ? j : me - 1;
-                    for (int k = 0; k <= kmax; ++k) {
-                        if (j >= nv && k < F.cb0)
-                            continue;
-                        const double vjk = (j == k) ? 1.0 : scalev[k] * Bat(j, k);
-                        s -= vjk * z[k];
-                    }
-                    wv[j] = -s;
+            for (int j = tid; j < n; j += T) {
+                double sacc;
+                if (j < nv) {
+                    const double* row = Hs + nv + j * ld; // B(j, k) for k = 0 ..
+                    sacc = j < me ? tv[j] - zv[j] : row[me];
+                    const int kmax = j < me ? j : me;
+                    for (int k = 0; k < kmax; ++k)
+                        sacc -= row[k] * zs[k];
                 }
+                else {
+                    const double* row = Bf + (j - nv) * nfc;
+                    sacc = row[me - cb0];
+                    for (int k = cb0; k < me; ++k)
+                        sacc -= row[k - cb0] * zs[k];
+                }
+                wv[j] = -sacc;
             }
             fsync<T>();
         }
