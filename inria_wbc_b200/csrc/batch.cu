@@ -179,8 +179,8 @@ struct iwbc_batch {
     dev::FPlan fplan;
     dev::FPlan* d_fplan = nullptr;
     int *d_slow_list = nullptr, *d_slow_count = nullptr;
-    int fast_grid = 0;
-    size_t fast_smem = 0;
+    int fast_grid = 0, slow_grid = 0;
+    size_t fast_smem = 0, slow_smem = 0;
     bool plan_dirty = true;
     size_t smem_bytes = 0;
     int grid = 0;
@@ -236,7 +236,29 @@ int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
         b->launches++;
         iop.list = b->d_slow_list;
         iop.list_count = b->d_slow_count;
-        grid = std::min(b->grid, (io.B + IPC - 1) / IPC);
+        auto sk = dev::k_slow<FT_>;
+        if (b->slow_grid == 0) {
+            CUDA_TRY(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->slow_smem));
+            int per_sm = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk, FT_, b->slow_smem));
+            if (per_sm < 1) {
+                set_error("active-set continuation kernel does not fit on an SM");
+                return IWBC_ERR_CUDA;
+            }
+            b->slow_grid = b->sm_count * per_sm;
+        }
+        sk<<<std::min(b->slow_grid, io.B), FT_, b->slow_smem, st>>>(b->d_prob, b->d_fplan, iop);
+        if (b->timing) {
+            cudaEventRecord(b->ev1, st);
+            cudaEventSynchronize(b->ev1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+            b->ms_sum += ms;
+            b->ms_n++;
+        }
+        b->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return IWBC_OK;
     }
     if (b->profiling && !io.dbg_cycles)
         iop.prof = b->d_prof;
@@ -341,7 +363,9 @@ int prepare_shape(iwbc_batch* b, unsigned mask)
     b->shape_mask = mask;
     b->fast_ok = b->G > 32 && dev::build_fast_plan(P, S, 128, b->fshape, b->fplan);
     b->fast_smem = (size_t)b->fshape.total * sizeof(double);
+    b->slow_smem = (size_t)b->fshape.s_total * sizeof(double);
     b->fast_grid = 0;
+    b->slow_grid = 0;
     b->plan_dirty = true;
     return IWBC_OK;
 }

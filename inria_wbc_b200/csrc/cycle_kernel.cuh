@@ -1516,6 +1516,10 @@ namespace dev {
         return t[0];
     }
 
+    template <int G, class ROWS>
+    __device__ int gi_loop(const iwbc_problem_t* gP, const Sm& sm, const Sizes& z, const ROWS* dense, int me, int mi, int tid, int& flip,
+        int& iter_out, int& iq_out, double c1, double c2, double R_norm);
+
     // The Goldfarb-Idnani loop.  ROWS provides the constraint rows.
     // Returns the eiquadprog status mapped to iwbc_status; iq_out = final active-set size.
     template <int G, class ROWS>
@@ -1575,6 +1579,19 @@ namespace dev {
         }
         if (cyc && tid == 0)
             cyc[4] = clock64();
+        return gi_loop<G, ROWS>(gP, sm, z, dense, me, mi, tid, flip, iter_out, iq_out, c1, c2, R_norm);
+    }
+
+    // The inequality iterations of Goldfarb-Idnani, started from the minimiser on the equality constraints:
+    // J (n x n, J'HJ = I, first me columns span H^-1 N_eq), R (me x me), x, c1 = trace(H), c2 = trace(L^-T), R_norm given.
+    template <int G, class ROWS>
+    __device__ int gi_loop(const iwbc_problem_t* gP, const Sm& sm, const Sizes& z, const ROWS* dense, int me, int mi, int tid, int& flip,
+        int& iter_out, int& iq_out, double c1, double c2, double R_norm)
+    {
+        const int n = z.n, ld = z.ldJ;
+        const double eps = 2.220446049250313e-16;
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        int iq = me, iter = 0;
         // iai = K \ A ; all constraints eligible
         for (int k = tid; k < mi; k += G)
             sm.iai[k] = k;

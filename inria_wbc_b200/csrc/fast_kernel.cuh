@@ -80,6 +80,7 @@ namespace dev {
         int o_qs, o_vs, o_X, o_Y, o_Z, o_Jft, o_cb, o_nle, o_lb, o_ub, o_g, o_x, o_w, o_sc, o_rhs, o_sc4, o_P, o_Rm, o_tv, o_hd, o_il, o_tau, o_int, total;
         int d_liMi, d_oMi, d_Sw, d_vw, d_aw, d_Yw, d_fw, d_Fc, d_oMf, d_vf, d_af;
         int z_Bf, z_G;
+        int s_J, s_R, s_vec, s_int, s_total; // extra regions of the active-set continuation (k_slow)
     };
 
     __constant__ FShape c_F;
@@ -309,6 +310,11 @@ namespace dev {
         F.o_tau = take(nv);
         F.o_int = take((nv + 16) / 2 + 1);
         F.total = o;
+        F.s_J = take(n * S.ldJ);
+        F.s_R = take(n * (n + 1) / 2);
+        F.s_vec = take(11 * align2(n + 2) + align2(S.mi) + 32);
+        F.s_int = take((2 * (n + 2) + S.mi + 1) / 2 + 1);
+        F.s_total = o;
         F.ok = 1;
         return true;
     }
@@ -348,10 +354,10 @@ namespace dev {
         return s;
     }
 
-    // One instance.  Returns true when the instance is finished here (results written), false when it has to go through
-    // the active-set kernel.
+    // One instance.  Returns 1 when the instance is finished here (results written), 0 when it has to go through the
+    // active-set iteration (state left in shared memory for slow_continue()), -1 when H is not positive definite.
     template <int T>
-    __device__ bool fast_instance(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, double* smem, const IO& io, int inst, int tid,
+    __device__ int fast_instance(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, double* smem, const IO& io, int inst, int tid,
         long long* cyc)
     {
         const FShape& F = c_F;
@@ -1293,8 +1299,10 @@ namespace dev {
         }
         psi = fblock_sum<T>(psi, Pp, tid);
         const double c1 = tv[2 * (me + 2)], c2 = tv[2 * (me + 2) + 1];
-        if (!spd || !(fabs(psi) <= S.mi * 2.220446049250313e-16 * c1 * c2 * 100.0))
-            return false;
+        if (!spd)
+            return -1;
+        if (!(fabs(psi) <= S.mi * 2.220446049250313e-16 * c1 * c2 * 100.0))
+            return 0;
         if (cyc && tid == 0)
             cyc[5] = clock64();
         // ---------------------------------------------------------------- decode, integrate, store (status OPTIMAL after 1 iteration, empty active set)
@@ -1302,7 +1310,138 @@ namespace dev {
         sm.x_old = gvec;
         sm.act = nullptr;
         k_dec<T>(gP, sm, z, io, inst, tid, IWBC_STATUS_OPTIMAL, 1, S.me, taut);
-        return true;
+        return 1;
+    }
+
+    // Active-set continuation of fast_instance() (which returned <= 0 and left L, the reflectors, R, the Gram matrix, x_eq, M,
+    // the contact Jacobians and the bounds in shared memory): builds J = L^-T Q explicitly (eiquadprog's J after the
+    // equality phase, up to an orthogonal change of basis inside the two column groups, which leaves every quantity of
+    // the iteration -- z, r, step lengths, multipliers -- unchanged) and runs the Goldfarb-Idnani inequality loop.
+    template <int T>
+    __device__ void slow_continue(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, double* smem, const IO& io, int inst, int tid,
+        int code, int& flip, long long* cyc)
+    {
+        const FShape& F = c_F;
+        const Shape& S = c_S;
+        const int nv = c_P.nv, n = S.n, me = F.me, NC = F.NC, ld = F.ldh, ldJ = S.ldJ;
+        const int nfrc = 12 * F.nca, nfc = F.nf, cb0 = F.cb0;
+        double* const Hs = smem + F.o_Y;
+        double* const Z = smem + F.o_Z;
+        double* const Bf = Z + F.z_Bf;
+        double* const Gm = Z + F.z_G;
+        double* const Rm = smem + F.o_Rm;
+        double* const tauv = Rm + me * NC;
+        double* const scalev = tauv + me;
+        double* const tv = smem + F.o_tv;
+        double* const il = smem + F.o_il;
+        Sizes z;
+        z.nv = nv, z.nq = c_P.nq, z.nj = c_P.nj, z.nf = c_P.nframes, z.nc = c_P.ncontacts, z.n = n, z.mi = S.mi, z.rows_dense = S.rows_dense;
+        z.nref = c_P.nref, z.ldJ = ldJ, z.ldM = S.ldM;
+        Sm sm;
+        sm.qs = smem + F.o_qs, sm.vs = smem + F.o_vs, sm.ref = Z;
+        sm.M = smem + F.o_X, sm.Jft = smem + F.o_Jft, sm.cb = smem + F.o_cb, sm.nle = smem + F.o_nle, sm.lb = smem + F.o_lb, sm.ub = smem + F.o_ub;
+        sm.x = smem + F.o_x, sm.g = smem + F.o_g, sm.sc = smem + F.o_sc;
+        sm.dofj = reinterpret_cast<int*>(smem + F.o_int);
+        sm.J = smem + F.s_J;
+        sm.R = smem + F.s_R;
+        {
+            double* p = smem + F.s_vec;
+            const int L = align2(n + 2);
+            sm.d = p, p += L;
+            sm.z = p, p += L;
+            sm.np = p, p += L;
+            sm.r = p, p += L;
+            sm.u = p, p += L;
+            sm.x_old = p, p += L;
+            sm.u_old = p, p += L;
+            sm.gc = p, p += L;
+            sm.gs = p, p += L;
+            sm.gx = p, p += L;
+            sm.sub = p, p += L;
+            sm.s = p, p += align2(S.mi);
+            sm.red = p, p += 32;
+            int* ip = reinterpret_cast<int*>(smem + F.s_int);
+            sm.act = ip, ip += n + 2;
+            sm.act_old = ip, ip += n + 2;
+            sm.iai = ip;
+        }
+        if (code < 0) { // Cholesky failed: eiquadprog cannot start (gi_solve's convention)
+            for (int k = tid; k < n; k += T)
+                sm.x[k] = 0.0;
+            fsync<T>();
+            k_dec<T>(gP, sm, z, io, inst, tid, IWBC_STATUS_INFEASIBLE, 0, 0, nullptr);
+            return;
+        }
+        // ---- J: one column per thread.  Q[:, c] = e_c - V T V[c, :]', then J[:, c] = L^-T Q[:, c] in place
+        for (int c = tid; c < n; c += T) {
+            double* col = sm.J + c * ldJ;
+            double zq[IWBC_FMAXME], zs[IWBC_FMAXME];
+            for (int i = me - 1; i >= 0; --i) {
+                double y;
+                if (c < nv)
+                    y = (c == i) ? 1.0 : (c > i ? scalev[i] * Hs[(nv + i) + c * ld] : 0.0);
+                else
+                    y = i >= cb0 ? scalev[i] * Bf[(c - nv) * nfc + (i - cb0)] : 0.0;
+                for (int k = i + 1; k < me; ++k)
+                    y -= Gm[i * (me + 1) + k] * zq[k];
+                zq[i] = y * tauv[i];
+                zs[i] = zq[i] * scalev[i];
+            }
+            for (int j = 0; j < nv; ++j) {
+                const double* row = Hs + nv + j * ld;
+                double sacc = (j == c ? 1.0 : 0.0) - (j < me ? zq[j] : 0.0);
+                const int kmax = j < me ? j : me;
+                for (int k = 0; k < kmax; ++k)
+                    sacc -= row[k] * zs[k];
+                col[j] = sacc;
+            }
+            for (int jj = 0; jj < nfrc; ++jj) {
+                const double* row = Bf + jj * nfc;
+                double sacc = (nv + jj == c) ? 1.0 : 0.0;
+                for (int k = cb0; k < me; ++k)
+                    sacc -= row[k - cb0] * zs[k];
+                col[nv + jj] = sacc;
+            }
+            for (int k = nv - 1; k >= 0; --k) {
+                double sacc = col[k];
+                const double* Lk = Hs + k * ld;
+                for (int i = k + 1; i < nv; ++i)
+                    sacc -= Lk[i] * col[i];
+                col[k] = sacc * il[k];
+            }
+            for (int sidx = 0; sidx < F.nca; ++sidx) {
+                double* cf = col + nv + 12 * sidx;
+                for (int i = 0; i < 12; ++i) {
+                    const double* U = gF->Uff[sidx] + i * 12;
+                    double a = 0;
+                    for (int j = i; j < 12; ++j)
+                        a += U[j] * cf[j];
+                    cf[i] = a;
+                }
+            }
+        }
+        // ---- R (packed), R_norm, bookkeeping of the equality part of the active set
+        for (int e = tid; e < me * me; e += T) {
+            const int i = e / me, j = e - i * me;
+            if (i <= j)
+                sm.R[Ridx(i, j)] = Rm[i * NC + j];
+        }
+        for (int k = tid; k < me; k += T) {
+            sm.act[k] = -k - 1;
+            sm.u[k] = 0.0;
+        }
+        double R_norm = 1.0;
+        for (int k = 0; k < me; ++k)
+            R_norm = fmax(R_norm, fabs(Rm[k * NC + k]));
+        const double c1 = tv[2 * (me + 2)], c2 = tv[2 * (me + 2) + 1];
+        fsync<T>();
+        if (cyc && tid == 0)
+            cyc[2] = clock64();
+        int iters = 0, iq = me;
+        const int status = gi_loop<T, FusedRows>(gP, sm, z, (const FusedRows*)nullptr, me, S.mi, tid, flip, iters, iq, c1, c2, R_norm);
+        if (cyc && tid == 0)
+            cyc[3] = clock64();
+        k_dec<T>(gP, sm, z, io, inst, tid, status, iters, iq, nullptr);
     }
 
 #ifndef IWBC_CPU_SIM
@@ -1322,7 +1461,7 @@ namespace dev {
         for (int inst = blockIdx.x; inst < io.B; inst += gridDim.x) {
             long long stamps[8];
             long long* cyc = io.prof ? stamps : nullptr;
-            const bool done = fast_instance<T>(gP, gF, smem, io, inst, tid, cyc);
+            const bool done = fast_instance<T>(gP, gF, smem, io, inst, tid, cyc) > 0;
             if (tid == 0) {
                 if (!done)
                     io.slow_list[atomicAdd(io.slow_count, 1)] = inst;
@@ -1331,6 +1470,44 @@ namespace dev {
                     for (int k = 0; k < 6; ++k)
                         atomicAdd(io.prof + 8 + k, (unsigned long long)(cyc[k + 1] - cyc[k]));
                     atomicAdd(io.prof + 14, 1ull);
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // The instances the fast kernel could not finish (io.list): same front end, then J and the active-set iteration.
+    template <int T>
+    __global__ void __launch_bounds__(T, 1) k_slow(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, IO io)
+    {
+        extern __shared__ double smem[];
+        const int tid = threadIdx.x;
+        {
+            int* dofj = reinterpret_cast<int*>(smem + c_F.o_int);
+            for (int k = tid; k < c_P.nv; k += T)
+                dofj[k] = gF->dofj[k];
+        }
+        __syncthreads();
+        int flip = 0;
+        const int count = io.list ? *io.list_count : io.B;
+        for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+            const int inst = io.list ? io.list[idx] : idx;
+            long long stamps[8];
+            long long* cyc = io.prof ? stamps : nullptr;
+            if (cyc && tid == 0)
+                cyc[7] = clock64();
+            const int code = fast_instance<T>(gP, gF, smem, io, inst, tid, nullptr);
+            if (code <= 0) {
+                if (cyc && tid == 0)
+                    cyc[1] = clock64();
+                slow_continue<T>(gP, gF, smem, io, inst, tid, code, flip, cyc);
+                if (cyc && tid == 0 && code == 0) {
+                    const long long t4 = clock64();
+                    atomicAdd(io.prof + 0, (unsigned long long)(cyc[1] - cyc[7]));
+                    atomicAdd(io.prof + 1, (unsigned long long)(cyc[2] - cyc[1]));
+                    atomicAdd(io.prof + 2, (unsigned long long)(cyc[3] - cyc[2]));
+                    atomicAdd(io.prof + 3, (unsigned long long)(t4 - cyc[3]));
+                    atomicAdd(io.prof + 6, 1ull);
                 }
             }
             __syncthreads();

@@ -104,7 +104,7 @@ extern "C" int sim_fast_batch(const iwbc_problem_t* P, int B, const double* q, c
     static dev::FPlan plan;
     if (!dev::build_fast_plan(*P, dev::c_S, 1, dev::c_F, plan))
         return -1;
-    std::vector<double> smem(dev::c_S.total + 16, 0.0), fsmem(dev::c_F.total + 16, 0.0);
+    std::vector<double> smem(dev::c_S.total + 16, 0.0), fsmem(dev::c_F.s_total + 16, 0.0);
     dev::Sm sm = dev::make_sm(smem.data(), z);
     int* fdofj = reinterpret_cast<int*>(fsmem.data() + dev::c_F.o_int);
     for (int j = 0; j < z.nj; ++j) {
@@ -119,11 +119,11 @@ extern "C" int sim_fast_batch(const iwbc_problem_t* P, int B, const double* q, c
     io.q_cmd = q_cmd, io.momentum = momentum;
     int flip = 0;
     for (int i = 0; i < B; ++i) {
-        const bool done = dev::fast_instance<1>(P, &plan, fsmem.data(), io, i, 0, nullptr);
+        const int code = dev::fast_instance<1>(P, &plan, fsmem.data(), io, i, 0, nullptr);
         if (fast_used)
-            fast_used[i] = done ? 1 : 0;
-        if (!done)
-            dev::cycle_instance<1>(P, sm, z, io, i, 0, flip);
+            fast_used[i] = code > 0 ? 1 : 0;
+        if (code <= 0)
+            dev::slow_continue<1>(P, &plan, fsmem.data(), io, i, 0, code, flip, nullptr);
     }
     return 0;
 }
