@@ -195,6 +195,67 @@ struct ConstOwner {
     unsigned mask = ~0u;
 } g_const_owner[16];
 
+constexpr int FT_ = 128;
+
+template <int NV_, int ME_>
+int launch_fast_shape(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
+{
+    dev::IO iop = io;
+    auto fk = dev::k_fast<FT_, NV_, ME_>;
+    auto sk = dev::k_slow<FT_, NV_, ME_>;
+    if (b->fast_grid == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->fast_smem));
+        CUDA_TRY(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->slow_smem));
+        int per_sm = 0, per_sm_slow = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, FT_, b->fast_smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_slow, sk, FT_, b->slow_smem));
+        if (per_sm < 1 || per_sm_slow < 1) {
+            set_error("fast / active-set kernels do not fit on an SM");
+            return IWBC_ERR_CUDA;
+        }
+        b->fast_grid = b->sm_count * per_sm;
+        b->slow_grid = b->sm_count * per_sm_slow;
+    }
+    iop.slow_list = b->d_slow_list;
+    iop.slow_count = b->d_slow_count;
+    if (b->profiling)
+        iop.prof = b->d_prof;
+    CUDA_TRY(cudaMemsetAsync(b->d_slow_count, 0, sizeof(int), st));
+    if (b->timing)
+        cudaEventRecord(b->ev0, st);
+    fk<<<std::min(b->fast_grid, io.B), FT_, b->fast_smem, st>>>(b->d_prob, b->d_fplan, iop);
+    b->launches++;
+    iop.list = b->d_slow_list;
+    iop.list_count = b->d_slow_count;
+    sk<<<std::min(b->slow_grid, io.B), FT_, b->slow_smem, st>>>(b->d_prob, b->d_fplan, iop);
+    if (b->timing) {
+        cudaEventRecord(b->ev1, st);
+        cudaEventSynchronize(b->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+        b->ms_sum += ms;
+        b->ms_n++;
+    }
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IWBC_OK;
+}
+
+// fast pass + active-set continuation, specialised for the common (nv, me) shapes
+int launch_fast(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
+{
+    const int nv = b->prob->cs.prob.nv, me = b->fshape.me;
+    if (nv == 50 && me == 18)
+        return launch_fast_shape<50, 18>(b, io, st); // Talos (full URDF), double support
+    if (nv == 50 && me == 12)
+        return launch_fast_shape<50, 12>(b, io, st); // Talos, single support
+    if (nv == 38 && me == 18)
+        return launch_fast_shape<38, 18>(b, io, st); // iCub / Talos fast URDF, double support
+    if (nv == 38 && me == 12)
+        return launch_fast_shape<38, 12>(b, io, st);
+    return launch_fast_shape<0, 0>(b, io, st);
+}
+
 template <int G, int IPC>
 int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
 {
@@ -211,57 +272,9 @@ int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
     }
     int grid = std::min(b->grid, (io.B + IPC - 1) / IPC);
     dev::IO iop = io;
-    constexpr int FT_ = 128;
     const bool use_fast = b->fast_ok && b->fast_enabled && G > 32 && !io.dbg_M && !io.dbg_cycles;
-    if (use_fast) {
-        auto fk = dev::k_fast<FT_>;
-        if (b->fast_grid == 0) {
-            CUDA_TRY(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->fast_smem));
-            int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, FT_, b->fast_smem));
-            if (per_sm < 1) {
-                set_error("fast kernel does not fit on an SM");
-                return IWBC_ERR_CUDA;
-            }
-            b->fast_grid = b->sm_count * per_sm;
-        }
-        iop.slow_list = b->d_slow_list;
-        iop.slow_count = b->d_slow_count;
-        if (b->profiling)
-            iop.prof = b->d_prof;
-        CUDA_TRY(cudaMemsetAsync(b->d_slow_count, 0, sizeof(int), st));
-        if (b->timing)
-            cudaEventRecord(b->ev0, st);
-        fk<<<std::min(b->fast_grid, io.B), FT_, b->fast_smem, st>>>(b->d_prob, b->d_fplan, iop);
-        b->launches++;
-        iop.list = b->d_slow_list;
-        iop.list_count = b->d_slow_count;
-        auto sk = dev::k_slow<FT_>;
-        if (b->slow_grid == 0) {
-            CUDA_TRY(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->slow_smem));
-            int per_sm = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk, FT_, b->slow_smem));
-            if (per_sm < 1) {
-                set_error("active-set continuation kernel does not fit on an SM");
-                return IWBC_ERR_CUDA;
-            }
-            b->slow_grid = b->sm_count * per_sm;
-        }
-        sk<<<std::min(b->slow_grid, io.B), FT_, b->slow_smem, st>>>(b->d_prob, b->d_fplan, iop);
-        if (b->timing) {
-            cudaEventRecord(b->ev1, st);
-            cudaEventSynchronize(b->ev1);
-            float ms = 0;
-            cudaEventElapsedTime(&ms, b->ev0, b->ev1);
-            b->ms_sum += ms;
-            b->ms_n++;
-        }
-        b->launches++;
-        CUDA_TRY(cudaGetLastError());
-        return IWBC_OK;
-    }
-    if (b->profiling && !io.dbg_cycles)
-        iop.prof = b->d_prof;
+    if (use_fast)
+        return launch_fast(b, io, st);
     if (b->timing && !use_fast)
         cudaEventRecord(b->ev0, st);
     kern<<<grid, G * IPC, b->smem_bytes, st>>>(b->d_prob, iop);

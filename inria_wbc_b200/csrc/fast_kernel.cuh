@@ -356,14 +356,17 @@ namespace dev {
 
     // One instance.  Returns 1 when the instance is finished here (results written), 0 when it has to go through the
     // active-set iteration (state left in shared memory for slow_continue()), -1 when H is not positive definite.
-    template <int T>
+    // NV_, ME_: compile-time velocity dimension / number of equalities of the common shapes (0: read them at run time); with
+    // them every leading dimension and trip count below is a constant and the inner loops unroll.
+    template <int T, int NV_ = 0, int ME_ = 0>
     __device__ int fast_instance(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, double* smem, const IO& io, int inst, int tid,
         long long* cyc)
     {
         const FShape& F = c_F;
         const Shape& S = c_S;
-        const int nv = c_P.nv, nq = c_P.nq, nj = c_P.nj, na = c_P.na, nu = nv - na, nfr = c_P.nframes, n = S.n, me = F.me, NC = F.NC;
-        const int ld = F.ldh, nvp = F.nvp, ldM = S.ldM;
+        const int nv = NV_ ? NV_ : c_P.nv, me = ME_ ? ME_ : F.me, NC = me + 1;
+        const int nq = c_P.nq, nj = c_P.nj, nu = 6, na = nv - nu, nfr = c_P.nframes, n = ME_ ? nv + 2 * (me - 6) : S.n;
+        const int ld = (nv + me + 2) & ~1, nvp = (nv + 3) & ~3, ldM = nv | 1; // = F.ldh, F.nvp, S.ldM
         double* const qs = smem + F.o_qs;
         double* const vs = smem + F.o_vs;
         double* const X = smem + F.o_X;
@@ -1046,7 +1049,7 @@ namespace dev {
         // B(j, c): j < nv -> Hs[(nv + c) + j ld] ; j >= nv -> c >= cb0 ? Bf[(j - nv) nf + (c - cb0)] : 0.  Column k keeps its
         // sub-diagonal part unscaled (v_k = e_k + scale_k B(k+1:, k)).  Threads whose column is already factorised (c < k)
         // accumulate the Gram entries v_c'v_k needed to apply Q afterwards.
-        const int nfrc = 12 * F.nca, nfc = F.nf, cb0 = F.cb0;
+        const int nfrc = 2 * (me - 6), nfc = 7, cb0 = me - 6; // = 12 F.nca, F.nf, F.cb0
         constexpr int SEG = FT<T>::SEG;
         const int qc0 = (T > 1) ? tid % NC : 0, seg0 = (T > 1) ? tid / NC : 0;
         const int cstep = (T > 1) ? NC : 1;
@@ -1317,14 +1320,15 @@ namespace dev {
     // the contact Jacobians and the bounds in shared memory): builds J = L^-T Q explicitly (eiquadprog's J after the
     // equality phase, up to an orthogonal change of basis inside the two column groups, which leaves every quantity of
     // the iteration -- z, r, step lengths, multipliers -- unchanged) and runs the Goldfarb-Idnani inequality loop.
-    template <int T>
+    template <int T, int NV_ = 0, int ME_ = 0>
     __device__ void slow_continue(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, double* smem, const IO& io, int inst, int tid,
         int code, int& flip, long long* cyc)
     {
         const FShape& F = c_F;
         const Shape& S = c_S;
-        const int nv = c_P.nv, n = S.n, me = F.me, NC = F.NC, ld = F.ldh, ldJ = S.ldJ;
-        const int nfrc = 12 * F.nca, nfc = F.nf, cb0 = F.cb0;
+        const int nv = NV_ ? NV_ : c_P.nv, me = ME_ ? ME_ : F.me, NC = me + 1, n = ME_ ? nv + 2 * (me - 6) : S.n;
+        const int ld = (nv + me + 2) & ~1, ldJ = n | 1;
+        const int nfrc = 2 * (me - 6), nfc = 7, cb0 = me - 6;
         double* const Hs = smem + F.o_Y;
         double* const Z = smem + F.o_Z;
         double* const Bf = Z + F.z_Bf;
@@ -1336,7 +1340,7 @@ namespace dev {
         double* const il = smem + F.o_il;
         Sizes z;
         z.nv = nv, z.nq = c_P.nq, z.nj = c_P.nj, z.nf = c_P.nframes, z.nc = c_P.ncontacts, z.n = n, z.mi = S.mi, z.rows_dense = S.rows_dense;
-        z.nref = c_P.nref, z.ldJ = ldJ, z.ldM = S.ldM;
+        z.nref = c_P.nref, z.ldJ = ldJ, z.ldM = nv | 1;
         Sm sm;
         sm.qs = smem + F.o_qs, sm.vs = smem + F.o_vs, sm.ref = Z;
         sm.M = smem + F.o_X, sm.Jft = smem + F.o_Jft, sm.cb = smem + F.o_cb, sm.nle = smem + F.o_nle, sm.lb = smem + F.o_lb, sm.ub = smem + F.o_ub;
@@ -1447,7 +1451,7 @@ namespace dev {
 #ifndef IWBC_CPU_SIM
     // One CTA of T threads per instance, persistent over the batch.  Instances that need the active-set iteration are
     // appended to io.slow_list (order is arbitrary; every instance's results are independent of it).
-    template <int T>
+    template <int T, int NV_, int ME_>
     __global__ void __launch_bounds__(T, 3) k_fast(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, IO io)
     {
         extern __shared__ double smem[];
@@ -1461,7 +1465,7 @@ namespace dev {
         for (int inst = blockIdx.x; inst < io.B; inst += gridDim.x) {
             long long stamps[8];
             long long* cyc = io.prof ? stamps : nullptr;
-            const bool done = fast_instance<T>(gP, gF, smem, io, inst, tid, cyc) > 0;
+            const bool done = fast_instance<T, NV_, ME_>(gP, gF, smem, io, inst, tid, cyc) > 0;
             if (tid == 0) {
                 if (!done)
                     io.slow_list[atomicAdd(io.slow_count, 1)] = inst;
@@ -1477,7 +1481,7 @@ namespace dev {
     }
 
     // The instances the fast kernel could not finish (io.list): same front end, then J and the active-set iteration.
-    template <int T>
+    template <int T, int NV_, int ME_>
     __global__ void __launch_bounds__(T, 1) k_slow(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, IO io)
     {
         extern __shared__ double smem[];
@@ -1496,11 +1500,11 @@ namespace dev {
             long long* cyc = io.prof ? stamps : nullptr;
             if (cyc && tid == 0)
                 cyc[7] = clock64();
-            const int code = fast_instance<T>(gP, gF, smem, io, inst, tid, nullptr);
+            const int code = fast_instance<T, NV_, ME_>(gP, gF, smem, io, inst, tid, nullptr);
             if (code <= 0) {
                 if (cyc && tid == 0)
                     cyc[1] = clock64();
-                slow_continue<T>(gP, gF, smem, io, inst, tid, code, flip, cyc);
+                slow_continue<T, NV_, ME_>(gP, gF, smem, io, inst, tid, code, flip, cyc);
                 if (cyc && tid == 0 && code == 0) {
                     const long long t4 = clock64();
                     atomicAdd(io.prof + 0, (unsigned long long)(cyc[1] - cyc[7]));
