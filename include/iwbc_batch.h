@@ -133,6 +133,10 @@ int iwbc_batch_phase_profile(iwbc_batch* b, int enable, unsigned long long* out1
 /* launch shape of the cycle kernel for the last contact mask: threads per instance, instances per CTA, grid, dynamic smem */
 int iwbc_batch_launch_info(const iwbc_batch* b, int* G, int* ipc, int* grid, long* smem_bytes);
 
+/* launch shape of the fast pass / active-set continuation pair (floating-base robots with contacts):
+ * out6 = { enabled, fast grid, fast dynamic smem bytes, continuation grid, continuation smem bytes, threads per CTA } */
+int iwbc_batch_fast_info(const iwbc_batch* b, long* out6);
+
 /* measured FP64 FMA throughput of the device in TFLOP/s (dependent-FMA chains, 8-way ILP): the roofline
  * denominator of this FP64 CUDA-core-bound path; < 0 on error */
 double iwbc_measure_fp64_tflops(int device);

@@ -66,6 +66,7 @@ def lib():
         "iwbc_measure_fp64_tflops": (cd, [ci]),
         "iwbc_batch_debug_cycles": (ci, [vp, vp]),
         "iwbc_batch_phase_profile": (ci, [vp, ci, vp]),
+        "iwbc_batch_fast_info": (ci, [vp, vp]),
         "iwbc_batch_launch_info": (ci, [vp, pi, pi, pi, C.POINTER(C.c_long)]),
         "iwbc_qp_solve_batch": (ci, [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     }
@@ -272,6 +273,11 @@ class Batch:
         if t[14]:
             out["fast"] = dict(zip(("dyn", "rows", "H_chol", "qr_solve", "check", "decode"), (t[8:14] / float(t[14])).tolist()), instances=int(t[14]))
         return out or None
+
+    def fast_info(self):
+        t = np.zeros(6, dtype=np.int64)
+        lib().iwbc_batch_fast_info(self._h, t.ctypes.data)
+        return dict(zip(("enabled", "fast_grid", "fast_smem", "slow_grid", "slow_smem", "threads"), t.tolist()))
 
     def launch_info(self):
         g, i, gr, sm = C.c_int(), C.c_int(), C.c_int(), C.c_long()

@@ -720,6 +720,19 @@ int iwbc_batch_launch_info(const iwbc_batch* b, int* G, int* ipc, int* grid, lon
     return IWBC_OK;
 }
 
+int iwbc_batch_fast_info(const iwbc_batch* b, long* out6)
+{
+    if (!b || !out6)
+        return IWBC_ERR_ARG;
+    out6[0] = b->fast_ok && b->fast_enabled;
+    out6[1] = b->fast_grid;
+    out6[2] = (long)b->fast_smem;
+    out6[3] = b->slow_grid;
+    out6[4] = (long)b->slow_smem;
+    out6[5] = FT_;
+    return IWBC_OK;
+}
+
 double iwbc_measure_fp64_tflops(int device)
 {
     if (cudaSetDevice(device) != cudaSuccess) {

@@ -290,30 +290,39 @@ namespace dev {
         F.z_Bf = 0;
         F.z_G = align2(12 * F.nca * F.nf);
         const int zq = F.z_G + align2((F.me + 1) * (F.me + 1));
-        F.o_Z = take(P.nref > zq ? P.nref : zq);
+        // arrays that stay alive through the active-set continuation
         F.o_Jft = take(P.ncontacts * 6 * nv);
         F.o_cb = take(12 * P.ncontacts);
         F.o_nle = take(nv);
         F.o_lb = take(nv);
         F.o_ub = take(nv);
-        F.o_g = take(n + 2);
         F.o_x = take(n + 2);
-        F.o_w = take(n + 2);
         F.o_sc = take(48);
+        F.o_int = take((nv + 16) / 2 + 1);
+        // arrays that are dead once J has been formed: the iteration vectors of the continuation alias them
+        const int dead0 = o;
+        F.o_Z = take(P.nref > zq ? P.nref : zq);
+        F.o_g = take(n + 2);
+        F.o_w = take(n + 2);
         F.o_rhs = take(6 * (nslots > 0 ? nslots : 1));
         F.o_sc4 = take(4 * (npairslots > 0 ? npairslots : 1));
-        F.o_P = take(8 * F.NC);
+        F.o_P = take(6 * F.NC > 16 ? 6 * F.NC : 16); // QR partial sums (SEG x NC); the Cholesky keeps its 4 x 4 diagonal block copy here
         F.o_Rm = take(F.me * F.NC + 3 * F.me + 8); // R (me x NC), tau, scale, invbeta
         F.o_tv = take(3 * (F.me + 2) + 4);
         F.o_hd = take(nv);
         F.o_il = take(nv);
         F.o_tau = take(nv);
-        F.o_int = take((nv + 16) / 2 + 1);
         F.total = o;
-        F.s_J = take(n * S.ldJ);
-        F.s_R = take(n * (n + 1) / 2);
-        F.s_vec = take(11 * align2(n + 2) + align2(S.mi) + 32);
+        // continuation: R aliases the augmented matrix (dead after J), the vectors alias the dead block
+        const int rsz = n * (n + 1) / 2;
+        F.s_R = F.o_Y;
+        if (rsz > (d > hs ? d : hs))
+            return false;
+        const int vsz = 11 * align2(n + 2) + align2(S.mi) + 32;
+        F.s_vec = dead0;
+        o = dead0 + (vsz > F.total - dead0 ? vsz : F.total - dead0);
         F.s_int = take((2 * (n + 2) + S.mi + 1) / 2 + 1);
+        F.s_J = take(n * S.ldJ);
         F.s_total = o;
         F.ok = 1;
         return true;
@@ -1424,20 +1433,23 @@ namespace dev {
                 }
             }
         }
-        // ---- R (packed), R_norm, bookkeeping of the equality part of the active set
+        // ---- R (packed), R_norm, bookkeeping of the equality part of the active set.  R aliases the augmented matrix and the
+        // iteration vectors alias Rm / Gm / ...: every reader of those is done after the first barrier.
+        double R_norm = 1.0;
+        for (int k = 0; k < me; ++k)
+            R_norm = fmax(R_norm, fabs(Rm[k * NC + k]));
+        const double c1 = tv[2 * (me + 2)], c2 = tv[2 * (me + 2) + 1];
+        fsync<T>();
         for (int e = tid; e < me * me; e += T) {
             const int i = e / me, j = e - i * me;
             if (i <= j)
                 sm.R[Ridx(i, j)] = Rm[i * NC + j];
         }
+        fsync<T>();
         for (int k = tid; k < me; k += T) {
             sm.act[k] = -k - 1;
             sm.u[k] = 0.0;
         }
-        double R_norm = 1.0;
-        for (int k = 0; k < me; ++k)
-            R_norm = fmax(R_norm, fabs(Rm[k * NC + k]));
-        const double c1 = tv[2 * (me + 2)], c2 = tv[2 * (me + 2) + 1];
         fsync<T>();
         if (cyc && tid == 0)
             cyc[2] = clock64();
@@ -1482,7 +1494,7 @@ namespace dev {
 
     // The instances the fast kernel could not finish (io.list): same front end, then J and the active-set iteration.
     template <int T, int NV_, int ME_>
-    __global__ void __launch_bounds__(T, 1) k_slow(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, IO io)
+    __global__ void __launch_bounds__(T, 2) k_slow(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, IO io)
     {
         extern __shared__ double smem[];
         const int tid = threadIdx.x;
