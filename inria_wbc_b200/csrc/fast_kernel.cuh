@@ -1062,6 +1062,140 @@ namespace dev {
         constexpr int SEG = FT<T>::SEG;
         const int qc0 = (T > 1) ? tid % NC : 0, seg0 = (T > 1) ? tid / NC : 0;
         const int cstep = (T > 1) ? NC : 1;
+        if constexpr (T > 1 && NV_ > 0 && ME_ > 0) {
+            // Register-resident variant: thread (seg0, c) owns rows j = seg0 + SEG m of column c for the whole factorisation;
+            // only the pivot column and the pivot row are published through shared memory (wv / gvec are free here).
+            constexpr int MR = (NV_ + SEG - 1) / SEG, MF = (2 * (ME_ - 6) + SEG - 1) / SEG;
+            double* const colbuf = wv;   // B(:, k)
+            double* const rowbuf = gvec; // B(k, :), double-buffered: [2][NC]
+            const bool qact = seg0 < SEG;
+            const int c = qc0;
+            double cc[MR], cf[MF], ck[MR], ckf[MF];
+            if (qact) {
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    const int j = seg0 + SEG * m;
+                    cc[m] = j < nv ? Hs[(nv + c) + j * ld] : 0.0;
+                }
+#pragma unroll
+                for (int m = 0; m < MF; ++m) {
+                    const int jj = seg0 + SEG * m;
+                    cf[m] = (c >= cb0 && jj < nfrc) ? Bf[jj * nfc + (c - cb0)] : 0.0;
+                }
+                if (c == 0) {
+#pragma unroll
+                    for (int m = 0; m < MR; ++m)
+                        if (seg0 + SEG * m < nv)
+                            colbuf[seg0 + SEG * m] = cc[m];
+                }
+                if (seg0 == 0)
+                    rowbuf[c] = cc[0];
+            }
+            fsync<T>();
+            for (int k = 0; k < me; ++k) {
+                const bool frc = k >= cb0;
+                const double* rb = rowbuf + (k & 1) * NC;
+                double* rbn = rowbuf + ((k + 1) & 1) * NC;
+                if (qact) {
+                    double sacc = 0;
+#pragma unroll
+                    for (int m = 0; m < MR; ++m) {
+                        const int j = seg0 + SEG * m;
+                        ck[m] = (j > k && j < nv) ? colbuf[j] : 0.0;
+                        sacc += ck[m] * cc[m];
+                    }
+#pragma unroll
+                    for (int m = 0; m < MF; ++m) {
+                        const int jj = seg0 + SEG * m;
+                        ckf[m] = (frc && jj < nfrc) ? colbuf[nv + jj] : 0.0;
+                        sacc += ckf[m] * cf[m];
+                    }
+                    Pp[seg0 * NC + c] = sacc;
+                }
+                fsync<T>();
+                double sigma = 0;
+#pragma unroll
+                for (int sg = 0; sg < SEG; ++sg)
+                    sigma += Pp[sg * NC + k];
+                const double alpha = rb[k];
+                double beta = alpha, tau = 0, scale = 0, ibeta = 1.0 / alpha;
+                if (sigma != 0.0) {
+                    const double nn = alpha * alpha + sigma;
+                    const double inr = rsqrt(nn), nr = nn * inr;
+                    beta = alpha >= 0 ? -nr : nr;
+                    ibeta = alpha >= 0 ? -inr : inr;
+                    tau = 1.0 + fabs(alpha) * inr; // (beta - alpha) / beta
+                    scale = 1.0 / (alpha - beta);
+                }
+                if (qact) {
+                    if (c == k) {
+                        if (seg0 == 0) {
+                            Rm[k * NC + k] = beta;
+                            tauv[k] = tau;
+                            scalev[k] = scale;
+                            invb[k] = ibeta;
+                        }
+                    }
+                    else {
+                        double pc = 0;
+#pragma unroll
+                        for (int sg = 0; sg < SEG; ++sg)
+                            pc += Pp[sg * NC + c];
+                        const double bkc = rb[c];
+                        if (c < k) {
+                            if (seg0 == 0)
+                                Gm[c * (me + 1) + k] = scalev[c] * (bkc + scale * pc);
+                        }
+                        else {
+                            const double coef = tau * (bkc + scale * pc);
+                            if (seg0 == 0)
+                                Rm[k * NC + c] = bkc - coef;
+                            const double cs = coef * scale;
+#pragma unroll
+                            for (int m = 0; m < MR; ++m)
+                                cc[m] -= cs * ck[m];
+#pragma unroll
+                            for (int m = 0; m < MF; ++m)
+                                cf[m] -= cs * ckf[m];
+                        }
+                    }
+                    // publish the next pivot column and pivot row
+                    if (c == k + 1) {
+#pragma unroll
+                        for (int m = 0; m < MR; ++m)
+                            if (seg0 + SEG * m < nv)
+                                colbuf[seg0 + SEG * m] = cc[m];
+#pragma unroll
+                        for (int m = 0; m < MF; ++m)
+                            if (seg0 + SEG * m < nfrc)
+                                colbuf[nv + seg0 + SEG * m] = cf[m];
+                    }
+#pragma unroll
+                    for (int m = 0; m < MR; ++m)
+                        if (seg0 + SEG * m == k + 1)
+                            rbn[c] = cc[m];
+                }
+                fsync<T>();
+            }
+            if (qact) {
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    const int j = seg0 + SEG * m;
+                    if (j < nv)
+                        Hs[(nv + c) + j * ld] = cc[m];
+                }
+                if (c >= cb0) {
+#pragma unroll
+                    for (int m = 0; m < MF; ++m) {
+                        const int jj = seg0 + SEG * m;
+                        if (jj < nfrc)
+                            Bf[jj * nfc + (c - cb0)] = cf[m];
+                    }
+                }
+            }
+            fsync<T>();
+        }
+        else
         {
             for (int k = 0; k < me; ++k) {
                 const double* colk = Hs + (nv + k);
