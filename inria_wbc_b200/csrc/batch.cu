@@ -178,7 +178,10 @@ struct iwbc_batch {
     dev::FShape fshape;
     dev::FPlan fplan;
     dev::FPlan* d_fplan = nullptr;
-    int *d_slow_list = nullptr, *d_slow_count = nullptr;
+    int *d_slow_list = nullptr, *d_slow_count = nullptr; // per launch slot: list region [list_off, ...), counter d_slow_count[slot]
+    int slot = 0, list_off = 0;
+    cudaStream_t aux[2] = {nullptr, nullptr}; // copy / compute pipelining of iwbc_batch_update
+    cudaEvent_t ev_const = nullptr;
     int fast_grid = 0, slow_grid = 0;
     size_t fast_smem = 0, slow_smem = 0;
     bool plan_dirty = true;
@@ -216,17 +219,17 @@ int launch_fast_shape(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
         b->fast_grid = b->sm_count * per_sm;
         b->slow_grid = b->sm_count * per_sm_slow;
     }
-    iop.slow_list = b->d_slow_list;
-    iop.slow_count = b->d_slow_count;
+    iop.slow_list = b->d_slow_list + b->list_off;
+    iop.slow_count = b->d_slow_count + b->slot;
     if (b->profiling)
         iop.prof = b->d_prof;
-    CUDA_TRY(cudaMemsetAsync(b->d_slow_count, 0, sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(b->d_slow_count + b->slot, 0, sizeof(int), st));
     if (b->timing)
         cudaEventRecord(b->ev0, st);
     fk<<<std::min(b->fast_grid, io.B), FT_, b->fast_smem, st>>>(b->d_prob, b->d_fplan, iop);
     b->launches++;
-    iop.list = b->d_slow_list;
-    iop.list_count = b->d_slow_count;
+    iop.list = b->d_slow_list + b->list_off;
+    iop.list_count = b->d_slow_count + b->slot;
     sk<<<std::min(b->slow_grid, io.B), FT_, b->slow_smem, st>>>(b->d_prob, b->d_fplan, iop);
     if (b->timing) {
         cudaEventRecord(b->ev1, st);
@@ -467,7 +470,9 @@ iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch)
     const size_t B = (size_t)max_batch;
     bool ok = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&b->ev0) == cudaSuccess && cudaEventCreate(&b->ev1) == cudaSuccess;
-    ok = ok && dalloc(&b->d_fplan, 1) == 0 && dalloc(&b->d_slow_list, B) == 0 && dalloc(&b->d_slow_count, 1) == 0;
+    ok = ok && dalloc(&b->d_fplan, 1) == 0 && dalloc(&b->d_slow_list, B) == 0 && dalloc(&b->d_slow_count, 8) == 0;
+    ok = ok && cudaStreamCreateWithFlags(&b->aux[0], cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&b->aux[1], cudaStreamNonBlocking) == cudaSuccess
+        && cudaEventCreateWithFlags(&b->ev_const, cudaEventDisableTiming) == cudaSuccess;
     {
         const char* e = getenv("IWBC_NO_FAST");
         b->fast_enabled = !(e && e[0] == '1');
@@ -500,6 +505,13 @@ void iwbc_batch_free(iwbc_batch* b)
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
+    for (int k = 0; k < 2; ++k)
+        if (b->aux[k]) {
+            cudaStreamSynchronize(b->aux[k]);
+            cudaStreamDestroy(b->aux[k]);
+        }
+    if (b->ev_const)
+        cudaEventDestroy(b->ev_const);
     if (b->ev0)
         cudaEventDestroy(b->ev0);
     if (b->ev1)
@@ -587,7 +599,7 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
                 break;
             }
     const size_t nq = P.nq, nv = P.nv, na = P.na, nf = 12 * P.ncontacts, nref = P.nref;
-    auto copy_out = [&](int first, int count, const int* perm) -> int {
+    auto copy_out = [&](int first, int count, const int* perm, cudaStream_t st) -> int {
         // device slot s in [first, first+count) holds instance perm[s] (or s when perm == nullptr)
         auto back = [&](void* host, const void* devp, size_t elem_bytes, size_t per) -> int {
             if (!host)
@@ -630,6 +642,46 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
         r.active = out->active ? b->d_active + first * IWBC_ACTIVE_WORDS : nullptr;
         return r;
     };
+    if (uniform && B >= 8192 && !b->timing && !b->profiling) {
+        // pipeline: chunks alternate between two streams so that the H2D copy of one chunk, the kernels of the previous one
+        // and the D2H copy of the one before overlap (needs pinned host buffers to be effective)
+        const unsigned m = contact_mask ? contact_mask[0] : dflt;
+        int rc = prepare_shape(b, m);
+        if (rc)
+            return rc;
+        rc = upload_constants(b, st);
+        if (rc)
+            return rc;
+        CUDA_TRY(cudaEventRecord(b->ev_const, st));
+        CUDA_TRY(cudaStreamWaitEvent(b->aux[0], b->ev_const, 0));
+        CUDA_TRY(cudaStreamWaitEvent(b->aux[1], b->ev_const, 0));
+        const int nchunk = 4;
+        for (int c = 0; c < nchunk; ++c) {
+            const size_t first = (size_t)B * c / nchunk, last = (size_t)B * (c + 1) / nchunk, cnt = last - first;
+            cudaStream_t cs = b->aux[c & 1];
+            CUDA_TRY(cudaMemcpyAsync(b->d_q + first * nq, q + first * nq, cnt * nq * 8, cudaMemcpyHostToDevice, cs));
+            CUDA_TRY(cudaMemcpyAsync(b->d_v + first * nv, v + first * nv, cnt * nv * 8, cudaMemcpyHostToDevice, cs));
+            if (refs_stride)
+                CUDA_TRY(cudaMemcpyAsync(b->d_refs + first * nref, refs + first * nref, cnt * nref * 8, cudaMemcpyHostToDevice, cs));
+            else if (c < 2) // shared reference vector: each stream uploads it once (into the same place, same bytes)
+                CUDA_TRY(cudaMemcpyAsync(b->d_refs, refs, nref * 8, cudaMemcpyHostToDevice, cs));
+            iwbc_results_t r = dev_results(first);
+            b->slot = c;
+            b->list_off = (int)first;
+            rc = iwbc_batch_update_device(b, (int)cnt, b->d_q + first * nq, b->d_v + first * nv, b->d_refs + (refs_stride ? first * nref : 0), refs_stride,
+                m, &r, cs);
+            b->slot = 0;
+            b->list_off = 0;
+            if (rc)
+                return rc;
+            rc = copy_out((int)first, (int)cnt, nullptr, cs);
+            if (rc)
+                return rc;
+        }
+        CUDA_TRY(cudaStreamSynchronize(b->aux[0]));
+        CUDA_TRY(cudaStreamSynchronize(b->aux[1]));
+        return IWBC_OK;
+    }
     if (uniform) {
         CUDA_TRY(cudaMemcpyAsync(b->d_q, q, B * nq * 8, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(b->d_v, v, B * nv * 8, cudaMemcpyHostToDevice, st));
@@ -638,7 +690,7 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
         int rc = iwbc_batch_update_device(b, B, b->d_q, b->d_v, b->d_refs, refs_stride, contact_mask ? contact_mask[0] : dflt, &r, st);
         if (rc)
             return rc;
-        rc = copy_out(0, B, nullptr);
+        rc = copy_out(0, B, nullptr, st);
         if (rc)
             return rc;
         CUDA_TRY(cudaStreamSynchronize(st));
@@ -676,7 +728,7 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
             return rc;
         first = last;
     }
-    int rc = copy_out(0, B, b->perm.data());
+    int rc = copy_out(0, B, b->perm.data(), st);
     if (rc)
         return rc;
     CUDA_TRY(cudaStreamSynchronize(st));
