@@ -1,0 +1,343 @@
+// batch_pos_tracker.hpp -- C++ host-side mirror of the reference's controller surface for the batched path.
+//
+// Header-only, STL-only wrapper over the C ABI (include/iwbc_batch.h).  It keeps the reference's names, argument
+// meaning and error behaviour for the ONE path this library replaces, with a batch index added where the reference
+// has one robot:
+//   inria_wbc::controllers::Controller      include/inria_wbc/controllers/controller.hpp:46-237   -> BatchController
+//   inria_wbc::controllers::PosTracker      include/inria_wbc/controllers/pos_tracker.hpp:17-98   -> BatchPosTracker
+//   inria_wbc::utils::Factory               include/inria_wbc/utils/factory.hpp:14-76             -> Factory (same names:
+//                                           "pos-tracker", "humanoid-pos-tracker", "talos-pos-tracker")
+//   tsid::solvers::SolverHQPBase            (used at src/controllers/pos_tracker.cpp:86-102,
+//                                           src/controllers/controller.cpp:247)                     -> BatchSolverHQuadProgFast
+//   inria_wbc::Exception                    include/inria_wbc/exceptions.hpp:52-65                 -> inria_wbc::Exception
+// Arrays are instance-major std::vector<double> (row i = robot i), the layout of the C ABI.
+#ifndef INRIA_WBC_B200_BATCH_POS_TRACKER_HPP
+#define INRIA_WBC_B200_BATCH_POS_TRACKER_HPP
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+extern "C" {
+#include "../iwbc_batch.h"
+}
+
+namespace inria_wbc {
+
+    // include/inria_wbc/exceptions.hpp:52-65: runtime_error carrying message + file:line
+    class Exception : public std::runtime_error {
+    public:
+        Exception(const std::string& msg, const char* file, int line) : std::runtime_error(make(msg, file, line)) {}
+
+    private:
+        static std::string make(const std::string& msg, const char* file, int line)
+        {
+            std::ostringstream o;
+            o << msg << " (" << file << ":" << line << ")";
+            return o.str();
+        }
+    };
+#define IWBC_B200_EXCEPTION(msg) ::inria_wbc::Exception((msg), __FILE__, __LINE__)
+#define IWBC_B200_ASSERT(cond, msg)       \
+    do {                                  \
+        if (!(cond))                      \
+            throw IWBC_B200_EXCEPTION(msg); \
+    } while (0)
+
+    namespace controllers {
+
+        // HQP status codes surfaced at src/controllers/controller.cpp:287-304
+        enum Status { UNKNOWN = -1, OPTIMAL = 0, INFEASIBLE = 1, UNBOUNDED = 2, MAX_ITER_REACHED = 3, ERROR = 4 };
+
+        struct Config {
+            std::string controller_yaml;      // what the reference loads with YAML::LoadFile before Factory::create
+            std::string robots_path;          // where CONTROLLER.urdf is resolved (utheque's role, controller.cpp:71-79)
+            std::string etc_path;             // replaces "@ETC@" in CONTROLLER.base_path ("" = next to the yaml)
+            std::string overrides_yaml;       // CONTROLLER keys mutated after loading, as tests/test_determinism.cpp:66-70 does
+            int batch = 1;
+            int device = 0;
+        };
+
+        class BatchController {
+        public:
+            explicit BatchController(const Config& c) : config_(c)
+            {
+                prob_ = iwbc_problem_load(c.controller_yaml.c_str(), c.robots_path.empty() ? nullptr : c.robots_path.c_str(),
+                    c.etc_path.empty() ? nullptr : c.etc_path.c_str(), c.overrides_yaml.empty() ? nullptr : c.overrides_yaml.c_str());
+                if (!prob_)
+                    throw IWBC_B200_EXCEPTION(std::string("cannot build the controller: ") + iwbc_last_error());
+                IWBC_B200_ASSERT(c.batch > 0, "batch must be positive");
+                iwbc_problem_dims(prob_, &nq_, &nv_, &na_, &nc_, &nref_);
+                B_ = c.batch;
+                dt_ = iwbc_problem_data(prob_)->dt;
+                std::vector<double> q0(nq_), r0(nref_);
+                iwbc_problem_q0(prob_, q0.data());
+                iwbc_problem_default_refs(prob_, r0.data());
+                q_tsid_.resize((size_t)B_ * nq_);
+                refs_.resize((size_t)B_ * nref_);
+                for (int i = 0; i < B_; ++i) {
+                    std::copy(q0.begin(), q0.end(), q_tsid_.begin() + (size_t)i * nq_);
+                    std::copy(r0.begin(), r0.end(), refs_.begin() + (size_t)i * nref_);
+                }
+                v_tsid_.assign((size_t)B_ * nv_, 0.0);
+                mask_.assign(B_, iwbc_problem_default_contact_mask(prob_));
+                tau_.assign((size_t)B_ * na_, 0.0), a_tsid_.assign((size_t)B_ * nv_, 0.0), q_.assign((size_t)B_ * nv_, 0.0);
+                forces_.assign((size_t)B_ * 12 * (nc_ > 0 ? nc_ : 1), 0.0), momentum_.assign((size_t)B_ * 3, 0.0);
+                status_.assign(B_, UNKNOWN), iters_.assign(B_, 0);
+                qn_.resize(q_tsid_.size()), vn_.resize(v_tsid_.size());
+            }
+            BatchController(const BatchController&) = delete; // controller.hpp:50-51
+            BatchController& operator=(const BatchController&) = delete;
+            virtual ~BatchController()
+            {
+                if (batch_)
+                    iwbc_batch_free(batch_);
+                if (prob_)
+                    iwbc_problem_free(prob_);
+            }
+
+            // Controller::update(sensor_data), closed-loop form (controller.cpp:172-205): q[B][nq] = [floating_base_position(7); positions],
+            // dq[B][nv] = [floating_base_velocity(6); joint_velocities].  Size mismatch throws like the reference's asserts.
+            virtual void update(const std::vector<double>& q, const std::vector<double>& dq)
+            {
+                IWBC_B200_ASSERT(q.size() == (size_t)B_ * nq_, "update: q must have batch * nq entries");
+                IWBC_B200_ASSERT(dq.size() == (size_t)B_ * nv_, "update: dq must have batch * nv entries");
+                solve(q.data(), dq.data());
+            }
+            // Controller::update() open loop (controller.cpp:163-170): the controller's own integrated state
+            virtual void update() { solve(q_tsid_.data(), v_tsid_.data()); }
+
+            // results, instance-major (controller.hpp:117-122, controller.cpp:250-282)
+            const std::vector<double>& tau() const { return tau_; }             // [B][na]
+            const std::vector<double>& ddq() const { return a_tsid_; }          // [B][nv]
+            const std::vector<double>& dq() const { return v_tsid_; }           // [B][nv]
+            const std::vector<double>& q() const { return q_; }                 // [B][nv] base as angle-axis (the "DART" layout)
+            const std::vector<double>& q_tsid() const { return q_tsid_; }       // [B][nq]
+            const std::vector<double>& activated_contacts_forces() const { return forces_; } // [B][12 * ncontacts]
+            const std::vector<double>& momentum() const { return momentum_; }   // [B][3]
+            const std::vector<int>& status() const { return status_; }          // per-instance HQP status (data, not an exception)
+            const std::vector<int>& solver_iterations() const { return iters_; }
+            bool all_optimal() const
+            {
+                for (int s : status_)
+                    if (s != OPTIMAL)
+                        return false;
+                return true;
+            }
+            double t() const { return t_; }
+            double dt() const { return dt_; }
+            int batch() const { return B_; }
+            int nq() const { return nq_; }
+            int nv() const { return nv_; }
+            int na() const { return na_; }
+            std::vector<std::string> controllable_dofs(bool filter_mimics = true) const
+            {
+                std::vector<std::string> all = names(0), mim = names(3), out;
+                for (const auto& n : all) {
+                    bool is_mimic = false;
+                    for (const auto& m : mim)
+                        is_mimic = is_mimic || m == n;
+                    if (!filter_mimics || !is_mimic)
+                        out.push_back(n);
+                }
+                return out;
+            }
+            const iwbc_problem* problem() const { return prob_; }
+
+        protected:
+            std::vector<std::string> names(int kind) const
+            {
+                std::vector<std::string> out;
+                const int n = iwbc_problem_name(prob_, kind, 0, nullptr, 0);
+                char buf[256];
+                for (int i = 0; i < n; ++i) {
+                    iwbc_problem_name(prob_, kind, i, buf, sizeof(buf));
+                    out.emplace_back(buf);
+                }
+                return out;
+            }
+            void solve(const double* q, const double* dq)
+            {
+                if (!batch_) {
+                    batch_ = iwbc_batch_create(prob_, config_.device, B_);
+                    if (!batch_)
+                        throw IWBC_B200_EXCEPTION(std::string("cannot create the GPU batch: ") + iwbc_last_error());
+                }
+                iwbc_results_t out = {tau_.data(), a_tsid_.data(), forces_.data(), qn_.data(), vn_.data(), q_.data(), momentum_.data(), status_.data(),
+                    iters_.data(), nullptr};
+                if (iwbc_batch_update(batch_, B_, q, dq, refs_.data(), nref_, mask_.data(), &out) != IWBC_OK)
+                    throw IWBC_B200_EXCEPTION(std::string("update failed: ") + iwbc_last_error());
+                q_tsid_.swap(qn_);
+                v_tsid_.swap(vn_);
+                t_ += dt_;
+            }
+
+            Config config_;
+            iwbc_problem* prob_ = nullptr;
+            iwbc_batch* batch_ = nullptr;
+            int B_ = 0, nq_ = 0, nv_ = 0, na_ = 0, nc_ = 0, nref_ = 0;
+            double t_ = 0.0, dt_ = 0.0;
+            std::vector<double> q_tsid_, v_tsid_, a_tsid_, tau_, q_, forces_, momentum_, refs_, qn_, vn_;
+            std::vector<int> status_, iters_;
+            std::vector<unsigned> mask_;
+        };
+
+        // PosTracker's reference setters, per instance (pos_tracker.hpp:52-67, pos_tracker.cpp:220-260)
+        class BatchPosTracker : public BatchController {
+        public:
+            explicit BatchPosTracker(const Config& c) : BatchController(c) {}
+
+            bool has_task(const std::string& n) const { return slot(n, false).second > 0; }
+            bool has_contact(const std::string& n) const { return iwbc_problem_contact_index(prob_, n.c_str()) >= 0; }
+            // TrajectorySample layout (include/inria_wbc/trajs/utils.hpp:28-36): pos = p(3) ++ R column-major(9), vel(6), acc(6)
+            void set_se3_ref(int i, const double* pos12, const std::string& task_name, const double* vel6 = nullptr, const double* acc6 = nullptr)
+            {
+                double* r = ref(i, task_name, 24);
+                std::copy(pos12, pos12 + 12, r);
+                for (int k = 0; k < 6; ++k) {
+                    r[12 + k] = vel6 ? vel6[k] : 0.0;
+                    r[18 + k] = acc6 ? acc6[k] : 0.0;
+                }
+            }
+            void set_contact_se3_ref(int i, const double* pos12, const std::string& contact_name) { set_se3_ref(i, pos12, contact_name); }
+            void get_se3_ref(int i, const std::string& task_name, double* pos12) const
+            {
+                const double* r = const_cast<BatchPosTracker*>(this)->ref(i, task_name, 24);
+                std::copy(r, r + 12, pos12);
+            }
+            void set_com_ref(int i, const double* com3, const double* vel3 = nullptr, const double* acc3 = nullptr)
+            {
+                double* r = ref(i, "com", 9);
+                for (int k = 0; k < 3; ++k) {
+                    r[k] = com3[k];
+                    r[3 + k] = vel3 ? vel3[k] : 0.0;
+                    r[6 + k] = acc3 ? acc3[k] : 0.0;
+                }
+            }
+            void get_com_ref(int i, double* com3) const
+            {
+                const double* r = const_cast<BatchPosTracker*>(this)->ref(i, "com", 9);
+                std::copy(r, r + 3, com3);
+            }
+            void set_momentum_ref(int i, const double* L6, const double* dL6)
+            {
+                double* r = ref(i, "momentum", 18);
+                for (int k = 0; k < 6; ++k) {
+                    r[6 + k] = L6[k];
+                    r[12 + k] = dL6 ? dL6[k] : 0.0;
+                }
+            }
+            void set_posture_ref(int i, const double* q_na, const std::string& task_name = "posture")
+            {
+                double* r = ref(i, task_name, 3 * na_);
+                std::copy(q_na, q_na + na_, r);
+            }
+            // add_contact / remove_contact (pos_tracker.cpp:246-287): the contact's bit in the instance's mask; instances with
+            // different masks are bucketed inside update()
+            void add_contact(int i, const std::string& contact_name) { mask_.at(i) |= 1u << contact_bit(contact_name); }
+            void remove_contact(int i, const std::string& contact_name) { mask_.at(i) &= ~(1u << contact_bit(contact_name)); }
+            // set_task_weight (pos_tracker.hpp:67): shared by the whole batch (it is part of the compiled problem)
+            void set_task_weight(const std::string& task_name, double w)
+            {
+                if (iwbc_problem_set_task_weight(prob_, task_name.c_str(), w) != IWBC_OK)
+                    throw IWBC_B200_EXCEPTION(std::string("set_task_weight: ") + iwbc_last_error());
+            }
+            std::vector<std::string> tasks() const { return names(1); }
+            std::vector<std::string> contacts() const { return names(2); }
+
+        private:
+            std::pair<int, int> slot(const std::string& n, bool must) const
+            {
+                int off = -1, len = 0;
+                if (iwbc_problem_ref_slot(prob_, n.c_str(), &off, &len) != IWBC_OK) {
+                    if (must)
+                        throw IWBC_B200_EXCEPTION("Task [" + n + "] not found"); // pos_tracker.hpp:34-39
+                    return {-1, 0};
+                }
+                return {off, len};
+            }
+            double* ref(int i, const std::string& n, int need)
+            {
+                IWBC_B200_ASSERT(i >= 0 && i < B_, "instance index out of range");
+                auto s = slot(n, true);
+                IWBC_B200_ASSERT(s.second >= need, "Task [" + n + "] has no reference of this type");
+                return refs_.data() + (size_t)i * nref_ + s.first;
+            }
+            int contact_bit(const std::string& n) const
+            {
+                const int c = iwbc_problem_contact_index(prob_, n.c_str());
+                if (c < 0)
+                    throw IWBC_B200_EXCEPTION("Contact [" + n + "] not found"); // pos_tracker.hpp:28-33
+                return c;
+            }
+        };
+
+        // utils::Factory (factory.hpp:14-76): name -> creator; unknown name throws listing what is registered
+        class Factory {
+        public:
+            using creator_t = std::function<std::shared_ptr<BatchController>(const Config&)>;
+            static Factory& instance()
+            {
+                static Factory f;
+                return f;
+            }
+            void register_creator(const std::string& name, creator_t c) { map_[name] = c; }
+            std::shared_ptr<BatchController> create(const std::string& name, const Config& c) const
+            {
+                auto it = map_.find(name);
+                if (it == map_.end()) {
+                    std::string msg = "Error :" + name + " is not in the factory. Available:";
+                    for (const auto& kv : map_)
+                        msg += " " + kv.first;
+                    throw IWBC_B200_EXCEPTION(msg);
+                }
+                return it->second(c);
+            }
+
+        private:
+            Factory()
+            {
+                for (const char* n : {"pos-tracker", "humanoid-pos-tracker", "talos-pos-tracker"})
+                    map_[n] = [](const Config& c) { return std::make_shared<BatchPosTracker>(c); };
+            }
+            std::map<std::string, creator_t> map_;
+        };
+    } // namespace controllers
+
+    namespace solvers {
+        // tsid::solvers::SolverHQPBase through the three virtuals the reference uses (resize / solve / status), for B stacked QPs:
+        //   min 1/2 x'Hx + g'x  s.t.  CE x + ce0 = 0,  CI x + ci0 >= 0   (row-major, instance-major)
+        struct BatchHQPOutput {
+            std::vector<double> x;
+            std::vector<int> status, iterations;
+            std::vector<unsigned> activeSet; // [B][IWBC_ACTIVE_WORDS] bitmask over CI rows
+        };
+        class BatchSolverHQuadProgFast {
+        public:
+            explicit BatchSolverHQuadProgFast(const std::string& name = "solver-eiquadprog", int device = 0) : name_(name), device_(device) {}
+            void resize(unsigned n, unsigned neq, unsigned nin) { n_ = n, neq_ = neq, nin_ = nin; }
+            const BatchHQPOutput& solve(int B, const double* H, const double* g, const double* CE, const double* ce0, const double* CI, const double* ci0)
+            {
+                out_.x.assign((size_t)B * n_, 0.0), out_.status.assign(B, -1), out_.iterations.assign(B, 0);
+                out_.activeSet.assign((size_t)B * IWBC_ACTIVE_WORDS, 0u);
+                if (iwbc_qp_solve_batch(device_, B, n_, neq_, nin_, H, g, CE, ce0, CI, ci0, out_.x.data(), out_.status.data(), out_.iterations.data(),
+                        out_.activeSet.data())
+                    != IWBC_OK)
+                    throw IWBC_B200_EXCEPTION(std::string("solve failed: ") + iwbc_last_error());
+                return out_;
+            }
+            const std::string& name() const { return name_; }
+
+        private:
+            std::string name_;
+            int device_;
+            unsigned n_ = 0, neq_ = 0, nin_ = 0;
+            BatchHQPOutput out_;
+        };
+    } // namespace solvers
+} // namespace inria_wbc
+#endif
