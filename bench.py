@@ -37,6 +37,9 @@ WORKLOADS = {
     # name: (controller yaml, overrides, per-GPU batch, recipe)
     "talos_ds_16384": ("talos/talos_pos_tracker.yaml", None, 16384, "talos"),
     "franka_65536": ("franka/pos_tracker.yaml", None, 65536, "franka"),
+    # config 5: Talos walking, a mix of double- and single-support shapes bucketed by contact mask
+    "talos_walk_131072": ("talos/talos_pos_tracker.yaml", None, 131072, "walk"),
+    "icub_ds_16384": ("icub/humanoid_pos_tracker.yaml", {"stabilizer": {"activated": False}}, 16384, "talos"),
     "tiago_65536": ("tiago/pos_tracker.yaml", {"urdf": "tiago/tiago_steel_no_wheel.urdf"}, 65536, "arm"),
 }
 DEFAULT_WORKLOAD = "talos_ds_16384"
@@ -50,14 +53,14 @@ def make_inputs(P, B, recipe, seed):
     v = np.zeros((B, P.nv))
     refs = np.tile(P.default_refs(), (B, 1))
     na = P.na
-    if recipe == "talos":
+    if recipe in ("talos", "walk"):
         dofs = P.names("dofs")
         mimics = set(P.names("mimics"))
         free = np.array([d not in mimics for d in dofs])
         q[:, P.nq - na:][:, free] += rng.normal(0, 0.02, (B, int(free.sum())))
         v[:, P.nv - na:] = rng.normal(0, 0.05, (B, na))
         off, _ = P.ref_slot("com")
-        refs[:, off + 2] += rng.uniform(-0.2, 0.0, B)
+        refs[:, off + 2] += rng.uniform(-0.2, 0.0, B) if recipe == "talos" else 0.0
     else:
         from inria_wbc_b200 import trajs
         S = P.struct()
@@ -77,6 +80,27 @@ def make_inputs(P, B, recipe, seed):
             R = R0 @ trajs._rot(ax[i], ang[i])
             refs[i, off:off + 24] = trajs.se3_sample(p0 + dp[i], R)
     return q, v, refs
+
+
+def make_walk_masks(P, B, refs, seed):
+    """Config 5 stand-in for a uniformly random tick of humanoid::walk (etc/talos/walk.yaml; src/behaviors/humanoid/walk.cpp:42-60):
+    half of the instances in double support, a quarter on each foot; the swing foot's SE3 reference is lifted (step_height
+    0.05) and the CoM reference moved over the support foot.  Instances are ordered by mask so that every launch is
+    shape-uniform."""
+    rng = np.random.default_rng(seed)
+    mask = rng.choice(np.array([3, 3, 1, 2], dtype=np.uint32), B)
+    mask.sort()
+    mask = mask[::-1].copy()  # 3 (double support) first
+    lf, _ = P.ref_slot("lf")
+    rf, _ = P.ref_slot("rf")
+    com, _ = P.ref_slot("com")
+    cl, cr = P.contact_index("contact_lfoot"), P.contact_index("contact_rfoot")
+    lift = rng.uniform(0.0, 0.05, B)
+    for m, swing, support in ((1 << cl, rf, lf), (1 << cr, lf, rf)):
+        sel = mask == m
+        refs[sel, swing + 2] += lift[sel]
+        refs[sel, com:com + 2] = refs[sel, support:support + 2]
+    return mask
 
 
 # ----------------------------------------------------------------------------- flop model
@@ -245,6 +269,17 @@ def main():
     bt = iw.Batch(P, local, B)
     n, me, mi, rows = P.qp_shape()
     mask = P.default_contact_mask
+    masks = None
+    buckets = [(0, B, mask)]
+    if recipe == "walk":
+        P.set_task_weight("momentum", 0.0)  # etc/talos/walk.yaml:8-9
+        masks = make_walk_masks(P, B, refs, 0xB200 + 5 + 1000 * rank)
+        buckets, first = [], 0
+        for m in (3, 2, 1):
+            cnt = int((masks == m).sum())
+            if cnt:
+                buckets.append((first, cnt, m))
+            first += cnt
 
     # ---- device-resident arm
     dq, dv_, dr = (torch.from_numpy(x).to(dev) for x in (q, v, refs))
@@ -257,8 +292,13 @@ def main():
     stream = torch.cuda.Stream(device=dev)  # an explicit stream: the events below must see the kernel
     torch.cuda.synchronize()
 
+    esz = {"tau": 8 * P.na, "dv": 8 * P.nv, "f": 8 * max(12 * P.ncontacts, 1), "q_next": 8 * P.nq, "v_next": 8 * P.nv, "status": 4, "iters": 4}
+
     def step():
-        bt.update_device(B, dq.data_ptr(), dv_.data_ptr(), dr.data_ptr(), P.nref, mask, ptrs, stream.cuda_stream)
+        # one shape-uniform launch set per contact-mask bucket (instances are ordered by mask)
+        for first, cnt, m in buckets:
+            bt.update_device(cnt, dq.data_ptr() + 8 * P.nq * first, dv_.data_ptr() + 8 * P.nv * first, dr.data_ptr() + 8 * P.nref * first, P.nref, m,
+                             {k: p + esz[k] * first for k, p in ptrs.items()}, stream.cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -300,11 +340,11 @@ def main():
         setattr(res, fld, t.numpy())
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        bt.update(hq.numpy(), hv.numpy(), hr.numpy(), out=res)
+        bt.update(hq.numpy(), hv.numpy(), hr.numpy(), contact_mask=masks, out=res)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        bt.update(hq.numpy(), hv.numpy(), hr.numpy(), out=res)
+        bt.update(hq.numpy(), hv.numpy(), hr.numpy(), contact_mask=masks, out=res)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d = q.nbytes + v.nbytes + refs.nbytes

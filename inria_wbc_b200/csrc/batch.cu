@@ -161,6 +161,7 @@ struct iwbc_batch {
     // bucketing scratch (host)
     std::vector<int> perm;
     std::vector<double> hq, hv, hr;
+    std::vector<char> stage;
     // launch bookkeeping
     long launches = 0;
     bool timing = false;
@@ -696,25 +697,43 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
         CUDA_TRY(cudaStreamSynchronize(st));
         return IWBC_OK;
     }
-    // mixed masks: stable sort of instance indices by mask, gather on the host, one launch per mask
+    // mixed masks.  If equal masks already form contiguous runs (the caller bucketed the batch) the runs are launched in
+    // place; otherwise: stable sort of instance indices by mask, gather on the host, one launch per mask, results copied
+    // back in bulk and scattered on the host.
+    bool grouped = true;
+    {
+        std::vector<unsigned> seen;
+        for (int i = 0; i < B && grouped; ++i)
+            if (i == 0 || contact_mask[i] != contact_mask[i - 1]) {
+                if (std::find(seen.begin(), seen.end(), contact_mask[i]) != seen.end())
+                    grouped = false;
+                seen.push_back(contact_mask[i]);
+            }
+    }
+    const double *sq = q, *sv = v, *sr = refs;
     b->perm.resize(B);
     for (int i = 0; i < B; ++i)
         b->perm[i] = i;
-    std::stable_sort(b->perm.begin(), b->perm.end(), [&](int a, int c) { return contact_mask[a] < contact_mask[c]; });
-    b->hq.resize(B * nq);
-    b->hv.resize(B * nv);
-    if (refs_stride)
-        b->hr.resize(B * nref);
-    for (int s = 0; s < B; ++s) {
-        const int i = b->perm[s];
-        std::memcpy(&b->hq[s * nq], q + i * nq, nq * 8);
-        std::memcpy(&b->hv[s * nv], v + i * nv, nv * 8);
+    if (!grouped) {
+        std::stable_sort(b->perm.begin(), b->perm.end(), [&](int a, int c) { return contact_mask[a] < contact_mask[c]; });
+        b->hq.resize(B * nq);
+        b->hv.resize(B * nv);
         if (refs_stride)
-            std::memcpy(&b->hr[s * nref], refs + (size_t)i * nref, nref * 8);
+            b->hr.resize(B * nref);
+        for (int s = 0; s < B; ++s) {
+            const int i = b->perm[s];
+            std::memcpy(&b->hq[s * nq], q + i * nq, nq * 8);
+            std::memcpy(&b->hv[s * nv], v + i * nv, nv * 8);
+            if (refs_stride)
+                std::memcpy(&b->hr[s * nref], refs + (size_t)i * nref, nref * 8);
+        }
+        sq = b->hq.data(), sv = b->hv.data();
+        if (refs_stride)
+            sr = b->hr.data();
     }
-    CUDA_TRY(cudaMemcpyAsync(b->d_q, b->hq.data(), B * nq * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(b->d_v, b->hv.data(), B * nv * 8, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(b->d_refs, refs_stride ? b->hr.data() : refs, (refs_stride ? (size_t)B : 1) * nref * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->d_q, sq, B * nq * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->d_v, sv, B * nv * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->d_refs, sr, (refs_stride ? (size_t)B : 1) * nref * 8, cudaMemcpyHostToDevice, st));
     int first = 0;
     while (first < B) {
         const unsigned m = contact_mask[b->perm[first]];
@@ -728,10 +747,41 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
             return rc;
         first = last;
     }
-    int rc = copy_out(0, B, b->perm.data(), st);
-    if (rc)
-        return rc;
+    if (grouped) {
+        int rc = copy_out(0, B, nullptr, st);
+        if (rc)
+            return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return IWBC_OK;
+    }
+    // bulk D2H into staging, then scatter slot s -> instance perm[s]
+    struct Field {
+        void* host;
+        const void* dev;
+        size_t bytes;
+    };
+    const Field fields[] = {{out->tau, b->d_tau, na * 8}, {out->dv, b->d_dv, nv * 8}, {out->f, b->d_f, nf * 8}, {out->q_next, b->d_qn, nq * 8},
+        {out->v_next, b->d_vn, nv * 8}, {out->q_cmd, b->d_qc, nv * 8}, {out->momentum, b->d_mom, 3 * 8}, {out->status, b->d_status, 4},
+        {out->iters, b->d_iters, 4}, {out->active, b->d_active, IWBC_ACTIVE_WORDS * 4}};
+    size_t total = 0;
+    for (const Field& f : fields)
+        if (f.host)
+            total += f.bytes * B;
+    b->stage.resize(total);
+    size_t off = 0;
+    for (const Field& f : fields)
+        if (f.host && f.bytes) {
+            CUDA_TRY(cudaMemcpyAsync(b->stage.data() + off, f.dev, f.bytes * B, cudaMemcpyDeviceToHost, st));
+            off += f.bytes * B;
+        }
     CUDA_TRY(cudaStreamSynchronize(st));
+    off = 0;
+    for (const Field& f : fields)
+        if (f.host && f.bytes) {
+            for (int s2 = 0; s2 < B; ++s2)
+                std::memcpy((char*)f.host + (size_t)b->perm[s2] * f.bytes, b->stage.data() + off + (size_t)s2 * f.bytes, f.bytes);
+            off += f.bytes * B;
+        }
     return IWBC_OK;
 }
 

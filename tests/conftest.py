@@ -40,6 +40,12 @@ def tiago():
     return iw.Problem("tiago/pos_tracker.yaml", overrides={"urdf": "tiago/tiago_steel_no_wheel.urdf"})
 
 
+@pytest.fixture(scope="session")
+def icub():
+    import inria_wbc_b200 as iw
+    return iw.Problem("icub/humanoid_pos_tracker.yaml", overrides={"stabilizer": {"activated": False}})
+
+
 def random_states(P, B, seed, qn=0.02, vn=0.05, base=False):
     import numpy as np
     rng = np.random.default_rng(seed)

@@ -115,6 +115,18 @@ def test_fast_path_moving_base_and_single_support(talos):
     _compare_fast(talos, q, v, mask=0b10, min_fast=0.0)
 
 
+def test_icub_double_support(icub):
+    """iCub (config 4): n = 62, me = 18, mi = 132, 83 cost rows, contact frames with z pointing to the ground."""
+    assert icub.qp_shape() == (62, 18, 132, 83)
+    q, v = random_states(icub, 32, 6)
+    _compare(icub, q, v)
+    _compare_fast(icub, q, v, min_fast=0.5)
+    q, v = random_states(icub, 24, 7, qn=0.1, vn=0.6)  # joint bounds become active
+    ref = _compare(icub, q, v)
+    assert ref["iters"].max() > 1
+    _compare_fast(icub, q, v, min_fast=0.0)
+
+
 @pytest.mark.parametrize("n,me,mi", [(9, 0, 4), (20, 5, 30), (74, 18, 244)])
 def test_dense_qp(n, me, mi):
     rng = np.random.default_rng(n)

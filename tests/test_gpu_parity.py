@@ -59,6 +59,25 @@ def test_tiago_active_bounds(tiago):
     assert np.array_equal(r.iters, o["iters"]) and r.iters.max() > 3
 
 
+def test_mixed_icub_tiago_config4(icub, tiago):
+    """BASELINE config 4: a 50/50 iCub + Tiago batch, bucketed by robot (one handle and one launch set per robot on the
+    same device), each half against the oracle."""
+    B = 1024
+    qi, vi = random_states(icub, B, 0xB200 + 4)
+    qt, vt = random_states(tiago, B, 0xB200 + 5, qn=0.2, vn=0.3)
+    bi, btg = iw.Batch(icub, 0, B), iw.Batch(tiago, 0, B)
+    ri, oi = _check(icub, bi, qi, vi)
+    rt, ot = _check(tiago, btg, qt, vt)
+    assert np.array_equal(ri.iters, oi["iters"]) and np.array_equal(rt.iters, ot["iters"])
+    # interleaved calls on the two handles keep their own constants (the __constant__ copies are re-uploaded on a switch)
+    ri2 = bi.update(qi, vi)
+    assert np.array_equal(ri.tau, ri2.tau) and np.array_equal(ri.active, ri2.active)
+    # harder iCub states: joint bounds active, the active-set continuation runs
+    qh, vh = random_states(icub, 512, 9, qn=0.1, vn=0.6)
+    rh, oh = _check(icub, bi, qh, vh, tol=1e-6)
+    assert oh["iters"].max() > 1
+
+
 def test_talos_double_support_config3(talos):
     import bench
     B = 2048
