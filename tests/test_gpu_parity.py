@@ -218,3 +218,37 @@ def test_argument_errors(franka):
         bt.update(q, v)
     with pytest.raises(iw.IwbcError):
         iw.Batch(franka, 99, 16)
+
+
+def test_franka_known_answer_through_the_gpu_path(franka):
+    """tests/ref_test_franka.yaml through the CUDA path: 10 s @ 1 kHz open loop with the cartesian_line behavior, every tick a
+    C-ABI update on the GPU (B = 3: the three open-loop actuator modes of the golden file are the same controller run)."""
+    import json
+    from inria_wbc_b200 import behaviors, ETC_PATH
+    gold_all = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_test_franka.json")))
+    gold = gold_all["cases"]["servo"]
+    ticks = int(gold_all["duration_s"] / gold_all["dt"])
+    off, _ = franka.ref_slot("ee")
+    B = 3
+    bt = iw.Batch(franka, 0, B)
+
+    def mean_error(refs):
+        q = np.tile(franka.q0(), (B, 1))
+        v = np.zeros((B, franka.nv))
+        qs = [q[0].copy()]
+        res = iw.Results(franka, B, fields=("q_next", "v_next", "q_cmd", "status"))
+        for t in range(ticks):
+            bt.update(q, v, np.tile(refs[t], (B, 1)), out=res)
+            assert (res.status == 0).all()
+            assert np.array_equal(res.q_next[0], res.q_next[1]) and np.array_equal(res.q_next[0], res.q_next[2])
+            q, v = res.q_next.copy(), res.v_next.copy()
+            qs.append(res.q_cmd[0].copy())
+        ee = np.array([ol.frame(franka, qs[t], np.zeros(franka.nv), 0)["oMf"][9:12] for t in range(ticks + 1)])
+        return (np.linalg.norm(ee[:-1] - refs[:, off:off + 3], axis=1).mean(), np.linalg.norm(ee[1:] - refs[:, off:off + 3], axis=1).mean())
+
+    cfg = os.path.join(ETC_PATH, "franka", "cartesian_line.yaml")
+    before, _ = mean_error(behaviors.Cartesian(franka, cfg).table(ticks))
+    assert before <= gold["ee_error_tsid"] + gold_all["tolerance"]  # the reference's own acceptance test (tests/test_franka.cpp:266)
+    before, after = mean_error(behaviors.Cartesian(franka, cfg, feed_forward=False).table(ticks))
+    assert abs(before - gold["ee_error_tsid"]) < 3e-4 * gold["ee_error_tsid"], before  # the recorded value itself (see test_franka_kat.py)
+    assert abs(after - gold["ee_error_dart"]) < 3e-4 * gold["ee_error_dart"], after
