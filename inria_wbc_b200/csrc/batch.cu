@@ -181,6 +181,9 @@ struct iwbc_batch {
     dev::FPlan* d_fplan = nullptr;
     int *d_slow_list = nullptr, *d_slow_count = nullptr; // per launch slot: list region [list_off, ...), counter d_slow_count[slot]
     int slot = 0, list_off = 0;
+    double* d_scratch = nullptr; // front-end images handed from k_fast to k_slow
+    int* d_slow_code = nullptr;
+    int scratch_cap = 0, scratch_off = 0, scratch_len = 0, scratch_img = 0; // capacity (instances); sub-range used by the current launch
     cudaStream_t aux[2] = {nullptr, nullptr}; // copy / compute pipelining of iwbc_batch_update
     cudaEvent_t ev_const = nullptr;
     int fast_grid = 0, slow_grid = 0;
@@ -222,6 +225,23 @@ int launch_fast_shape(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
     }
     iop.slow_list = b->d_slow_list + b->list_off;
     iop.slow_count = b->d_slow_count + b->slot;
+    if (b->d_scratch == nullptr || b->scratch_img < b->fshape.total) {
+        // (re)allocate the hand-over scratch (grow only): at most 65536 images (70 kB each for Talos double support)
+        if (b->d_scratch) {
+            CUDA_TRY(cudaDeviceSynchronize());
+            cudaFree(b->d_scratch);
+            b->d_scratch = nullptr;
+        }
+        b->scratch_cap = std::min(b->max_batch, 65536);
+        b->scratch_img = b->fshape.total + 64;
+        CUDA_TRY(cudaMalloc((void**)&b->d_scratch, (size_t)b->scratch_cap * b->scratch_img * sizeof(double)));
+    }
+    {
+        const int off = b->scratch_len ? b->scratch_off : 0, len = b->scratch_len ? b->scratch_len : b->scratch_cap;
+        iop.scratch = b->d_scratch + (size_t)off * b->scratch_img; // (images are packed with the current plan's size inside this range)
+        iop.slow_code = b->d_slow_code + off;
+        iop.scratch_cap = len;
+    }
     if (b->profiling)
         iop.prof = b->d_prof;
     CUDA_TRY(cudaMemsetAsync(b->d_slow_count + b->slot, 0, sizeof(int), st));
@@ -471,7 +491,7 @@ iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch)
     const size_t B = (size_t)max_batch;
     bool ok = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&b->ev0) == cudaSuccess && cudaEventCreate(&b->ev1) == cudaSuccess;
-    ok = ok && dalloc(&b->d_fplan, 1) == 0 && dalloc(&b->d_slow_list, B) == 0 && dalloc(&b->d_slow_count, 8) == 0;
+    ok = ok && dalloc(&b->d_fplan, 1) == 0 && dalloc(&b->d_slow_list, B) == 0 && dalloc(&b->d_slow_count, 8) == 0 && dalloc(&b->d_slow_code, 65536) == 0;
     ok = ok && cudaStreamCreateWithFlags(&b->aux[0], cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&b->aux[1], cudaStreamNonBlocking) == cudaSuccess
         && cudaEventCreateWithFlags(&b->ev_const, cudaEventDisableTiming) == cudaSuccess;
     {
@@ -502,7 +522,7 @@ void iwbc_batch_free(iwbc_batch* b)
         o.batch = nullptr;
     if (b->stream)
         cudaStreamSynchronize(b->stream);
-    void* ptrs[] = {b->d_fplan, b->d_slow_list, b->d_slow_count, b->d_prof, b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
+    void* ptrs[] = {b->d_scratch, b->d_slow_code, b->d_fplan, b->d_slow_list, b->d_slow_count, b->d_prof, b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);
@@ -669,10 +689,13 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
             iwbc_results_t r = dev_results(first);
             b->slot = c;
             b->list_off = (int)first;
+            b->scratch_len = std::min(b->max_batch, 65536) / nchunk;
+            b->scratch_off = c * b->scratch_len;
             rc = iwbc_batch_update_device(b, (int)cnt, b->d_q + first * nq, b->d_v + first * nv, b->d_refs + (refs_stride ? first * nref : 0), refs_stride,
                 m, &r, cs);
             b->slot = 0;
             b->list_off = 0;
+            b->scratch_len = 0;
             if (rc)
                 return rc;
             rc = copy_out((int)first, (int)cnt, nullptr, cs);

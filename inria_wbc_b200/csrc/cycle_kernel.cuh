@@ -117,6 +117,9 @@ namespace dev {
         const int* list_count; // device-side length of `list`
         int* slow_list;        // fast path: instances that need the active-set iteration are appended here
         int* slow_count;
+        double* scratch;       // fast path -> continuation: shared-memory image of the front end of the first scratch_cap listed instances
+        int* slow_code;        // ... and their fast_instance() return code
+        int scratch_cap;
         unsigned long long* prof; // steady-state phase profile: [0..5] summed SM cycles of dyn, asm, factor, eq, ineq, decode; [6] instances
     };
 

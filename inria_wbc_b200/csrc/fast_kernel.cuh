@@ -96,7 +96,7 @@ namespace dev {
         for (int c = 0; c < P.ncontacts; ++c)
             if (S.cidx[c] >= 0)
                 F.cact[F.nca++] = c;
-        if (F.nca == 0 || S.me != 6 * F.nca + nu)
+        if (F.nca == 0 || S.me != 6 * F.nca + nu || 2 * S.me > nv)
             return false;
         for (int j = 0; j < nj; ++j) {
             if (P.depth[j] + 1 > IWBC_FMAXD)
@@ -1519,51 +1519,124 @@ namespace dev {
             k_dec<T>(gP, sm, z, io, inst, tid, IWBC_STATUS_INFEASIBLE, 0, 0, nullptr);
             return;
         }
-        // ---- J: one column per thread.  Q[:, c] = e_c - V T V[c, :]', then J[:, c] = L^-T Q[:, c] in place
+        // ---- J = L^-T Q = U - (U V)(T V'),  U = L^-T (block diagonal: dv block from L, constant force blocks)
+        // (1) U into J: thread j builds row j of U (= column j of L^-1) by forward substitution; everything else is zero
+        for (int e = tid; e < n * ldJ; e += T)
+            sm.J[e] = 0.0;
+        fsync<T>();
+        for (int j = tid; j < n; j += T) {
+            if (j < nv) {
+                double* Uj = sm.J + j; // U[j][i] = Uj[i * ldJ]
+                Uj[j * ldJ] = il[j];
+                for (int i = j + 1; i < nv; ++i) {
+                    const double* Li = Hs + i; // L[i][k] = Li[k * ld]
+                    double s0 = 0, s1 = 0;
+                    int k = j;
+                    for (; k + 1 < i; k += 2) {
+                        s0 += Li[k * ld] * Uj[k * ldJ];
+                        s1 += Li[(k + 1) * ld] * Uj[(k + 1) * ldJ];
+                    }
+                    if (k < i)
+                        s0 += Li[k * ld] * Uj[k * ldJ];
+                    Uj[i * ldJ] = -(s0 + s1) * il[i];
+                }
+            }
+            else {
+                const int ii = j - nv, sidx = ii / 12, i2 = ii - 12 * sidx;
+                const double* U = gF->Uff[sidx] + i2 * 12;
+                for (int j2 = i2; j2 < 12; ++j2)
+                    sm.J[j + (nv + 12 * sidx + j2) * ldJ] = U[j2];
+            }
+        }
+        fsync<T>();
+        // (2) W = U_vv V_v (nv x me) into the top block of the augmented matrix (L is dead): W[i][k] -> Hs[i + k ld]
+        for (int e = tid; e < nv * me; e += T) {
+            const int k = e / nv, i = e - k * nv;
+            double val;
+            {
+                const double* Ui = sm.J + i;
+                const double* colk = Hs + (nv + k);
+                double d0 = 0, d1 = 0;
+                int j = i > k + 1 ? i : k + 1;
+                for (; j + 1 < nv; j += 2) {
+                    d0 += Ui[j * ldJ] * colk[j * ld];
+                    d1 += Ui[(j + 1) * ldJ] * colk[(j + 1) * ld];
+                }
+                if (j < nv)
+                    d0 += Ui[j * ldJ] * colk[j * ld];
+                val = (i <= k ? Ui[k * ldJ] : 0.0) + scalev[k] * (d0 + d1);
+                Hs[i + k * ld] = val;
+            }
+        }
+        fsync<T>();
+        // (3) one column per thread: x_c = T V[c, :]' (back-substitution on T^-1 = striu(V'V) + diag(1/tau)), J[:, c] -= W x_c
         for (int c = tid; c < n; c += T) {
             double* col = sm.J + c * ldJ;
-            double zq[IWBC_FMAXME], zs[IWBC_FMAXME];
-            for (int i = me - 1; i >= 0; --i) {
+            constexpr int MEC = ME_ > 0 ? ME_ : IWBC_FMAXME; // compile-time bound: zq stays in registers
+            double zq[MEC];
+#pragma unroll
+            for (int i = MEC - 1; i >= 0; --i) {
+                if (i >= me) {
+                    zq[i] = 0.0;
+                    continue;
+                }
                 double y;
                 if (c < nv)
                     y = (c == i) ? 1.0 : (c > i ? scalev[i] * Hs[(nv + i) + c * ld] : 0.0);
                 else
                     y = i >= cb0 ? scalev[i] * Bf[(c - nv) * nfc + (i - cb0)] : 0.0;
-                for (int k = i + 1; k < me; ++k)
-                    y -= Gm[i * (me + 1) + k] * zq[k];
+#pragma unroll
+                for (int k = i + 1; k < MEC; ++k)
+                    if (k < me)
+                        y -= Gm[i * (me + 1) + k] * zq[k];
                 zq[i] = y * tauv[i];
-                zs[i] = zq[i] * scalev[i];
             }
-            for (int j = 0; j < nv; ++j) {
-                const double* row = Hs + nv + j * ld;
-                double sacc = (j == c ? 1.0 : 0.0) - (j < me ? zq[j] : 0.0);
-                const int kmax = j < me ? j : me;
-                for (int k = 0; k < kmax; ++k)
-                    sacc -= row[k] * zs[k];
-                col[j] = sacc;
+            for (int i = 0; i < nv; i += 2) {
+                const double* w0 = Hs + i;
+                double a0 = 0, a1 = 0;
+                if (i + 1 < nv) {
+#pragma unroll
+                    for (int k = 0; k < MEC; ++k)
+                        if (k < me) {
+                            a0 += w0[k * ld] * zq[k];
+                            a1 += w0[k * ld + 1] * zq[k];
+                        }
+                    col[i] -= a0;
+                    col[i + 1] -= a1;
+                }
+                else {
+#pragma unroll
+                    for (int k = 0; k < MEC; ++k)
+                        if (k < me)
+                            a0 += w0[k * ld] * zq[k];
+                    col[i] -= a0;
+                }
             }
-            for (int jj = 0; jj < nfrc; ++jj) {
-                const double* row = Bf + jj * nfc;
-                double sacc = (nv + jj == c) ? 1.0 : 0.0;
-                for (int k = cb0; k < me; ++k)
-                    sacc -= row[k - cb0] * zs[k];
-                col[nv + jj] = sacc;
-            }
-            for (int k = nv - 1; k >= 0; --k) {
-                double sacc = col[k];
-                const double* Lk = Hs + k * ld;
-                for (int i = k + 1; i < nv; ++i)
-                    sacc -= Lk[i] * col[i];
-                col[k] = sacc * il[k];
-            }
+            // force rows: Q_f[:, c] first (O(1) entries, no cancellation against the 1e4-sized constant factor), then U_ff Q_f.
+            // (U_ff e_c - (U_ff V_f) x_c loses the null-space-of-T force components, whose Hessian eigenvalue is the 1e-8
+            // regularisation.)
             for (int sidx = 0; sidx < F.nca; ++sidx) {
-                double* cf = col + nv + 12 * sidx;
-                for (int i = 0; i < 12; ++i) {
-                    const double* U = gF->Uff[sidx] + i * 12;
-                    double a = 0;
-                    for (int j = i; j < 12; ++j)
-                        a += U[j] * cf[j];
-                    cf[i] = a;
+                double qf[12];
+#pragma unroll
+                for (int j2 = 0; j2 < 12; ++j2) {
+                    const int jj = 12 * sidx + j2;
+                    const double* row = Bf + jj * nfc;
+                    double a0 = (nv + jj == c) ? 1.0 : 0.0;
+#pragma unroll
+                    for (int k = 0; k < MEC; ++k)
+                        if (k >= cb0 && k < me)
+                            a0 -= row[k - cb0] * (zq[k] * scalev[k]);
+                    qf[j2] = a0;
+                }
+#pragma unroll
+                for (int i2 = 0; i2 < 12; ++i2) {
+                    const double* U = gF->Uff[sidx] + i2 * 12;
+                    double a0 = 0;
+#pragma unroll
+                    for (int j2 = 0; j2 < 12; ++j2)
+                        if (j2 >= i2)
+                            a0 += U[j2] * qf[j2];
+                    col[nv + 12 * sidx + i2] = a0;
                 }
             }
         }
@@ -1611,16 +1684,34 @@ namespace dev {
         for (int inst = blockIdx.x; inst < io.B; inst += gridDim.x) {
             long long stamps[8];
             long long* cyc = io.prof ? stamps : nullptr;
-            const bool done = fast_instance<T, NV_, ME_>(gP, gF, smem, io, inst, tid, cyc) > 0;
-            if (tid == 0) {
-                if (!done)
-                    io.slow_list[atomicAdd(io.slow_count, 1)] = inst;
-                else if (cyc) {
-                    cyc[6] = clock64();
-                    for (int k = 0; k < 6; ++k)
-                        atomicAdd(io.prof + 8 + k, (unsigned long long)(cyc[k + 1] - cyc[k]));
-                    atomicAdd(io.prof + 14, 1ull);
+            const int code = fast_instance<T, NV_, ME_>(gP, gF, smem, io, inst, tid, cyc);
+            const bool done = code > 0;
+            if (!done) {
+                // hand the instance to the active-set kernel, together with the shared-memory image of the front end
+                // (L, reflectors, R, Gram matrix, x_eq, M, Jacobians, bounds: c_F.total doubles) so that it is not recomputed
+                __shared__ int s_pos;
+                __syncthreads();
+                if (tid == 0) {
+                    s_pos = atomicAdd(io.slow_count, 1);
+                    io.slow_list[s_pos] = inst;
                 }
+                __syncthreads();
+                const int pos = s_pos;
+                if (pos < io.scratch_cap) {
+                    const int n2 = c_F.total >> 1; // offsets are even: whole double2's
+                    double2* dst = reinterpret_cast<double2*>(io.scratch) + (size_t)pos * n2;
+                    const double2* src = reinterpret_cast<const double2*>(smem);
+                    for (int e = tid; e < n2; e += T)
+                        dst[e] = src[e];
+                    if (tid == 0)
+                        io.slow_code[pos] = code;
+                }
+            }
+            else if (tid == 0 && cyc) {
+                cyc[6] = clock64();
+                for (int k = 0; k < 6; ++k)
+                    atomicAdd(io.prof + 8 + k, (unsigned long long)(cyc[k + 1] - cyc[k]));
+                atomicAdd(io.prof + 14, 1ull);
             }
             __syncthreads();
         }
@@ -1646,7 +1737,18 @@ namespace dev {
             long long* cyc = io.prof ? stamps : nullptr;
             if (cyc && tid == 0)
                 cyc[7] = clock64();
-            const int code = fast_instance<T, NV_, ME_>(gP, gF, smem, io, inst, tid, nullptr);
+            int code;
+            if (io.list && idx < io.scratch_cap) {
+                const int n2 = c_F.total >> 1;
+                const double2* src = reinterpret_cast<const double2*>(io.scratch) + (size_t)idx * n2;
+                double2* dst = reinterpret_cast<double2*>(smem);
+                for (int e = tid; e < n2; e += T)
+                    dst[e] = src[e];
+                code = io.slow_code[idx];
+                __syncthreads();
+            }
+            else
+                code = fast_instance<T, NV_, ME_>(gP, gF, smem, io, inst, tid, nullptr);
             if (code <= 0) {
                 if (cyc && tid == 0)
                     cyc[1] = clock64();
