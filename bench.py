@@ -66,7 +66,8 @@ def make_inputs(P, B, recipe, seed):
         S = P.struct()
         lo, hi = np.array(S.q_lo[:na]), np.array(S.q_hi[:na])
         narm = 7 if recipe == "franka" else na
-        qa = rng.uniform(lo[:narm] + 0.1, hi[:narm] - 0.1, (B, narm))
+        mg = np.minimum(0.1, 0.25 * (hi[:narm] - lo[:narm]))  # short-range joints (grippers, torso lift) keep a proportional margin
+        qa = rng.uniform(lo[:narm] + mg, hi[:narm] - mg, (B, narm))
         q[:, P.nq - na:P.nq - na + narm] = qa
         v[:, P.nv - na:P.nv - na + narm] = rng.normal(0, 0.1, (B, narm))
         # ee reference = construction-time pose composed with a random offset (cheap stand-in for FK(q) o delta)
@@ -139,28 +140,67 @@ def problem_counts(P):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (NVML from a thread every 5 ms; nvidia-smi -lms as the
+    fallback when the NVML binding is missing)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         self.index = index
         self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.proc = None
+        self.nvml = None
+        self.run = False
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = [float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))]
+            self.nvml = pynvml
+            self.run = True
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for nm, bit in self.BITS.items():
+                    if bits & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.run = False
+            self.th.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 5 ms period, during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -184,7 +224,7 @@ class ClockSampler:
                 if p[3 + k].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -237,7 +277,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
@@ -338,13 +378,16 @@ def main():
         t = torch.from_numpy(getattr(res, fld)).pin_memory()
         pinned[fld] = t
         setattr(res, fld, t.numpy())
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
+    e2e_steps = max(3, args.steps)
+    for _ in range(3):
         bt.update(hq.numpy(), hv.numpy(), hr.numpy(), contact_mask=masks, out=res)
     barrier()
+    e2e_lat = []
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        bt.update(hq.numpy(), hv.numpy(), hr.numpy(), contact_mask=masks, out=res)
+        t1 = time.perf_counter()
+        bt.update(hq.numpy(), hv.numpy(), hr.numpy(), contact_mask=masks, out=res)  # synchronous: results are in host memory on return
+        e2e_lat.append(time.perf_counter() - t1)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d = q.nbytes + v.nbytes + refs.nbytes
@@ -378,7 +421,7 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("bytes_per_launch")
         except Exception:
             pass
         line = {
@@ -387,12 +430,13 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "controller": yaml, "per_gpu_batch": B, "qp": {"n": n, "me": me, "mi": mi, "cost_rows": rows},
                        "l2": "flushed (256 MB write) between timed steps", "optimal_fraction": n_opt_all / (B * world),
-                       "mean_active_set_iterations": iters_all / (B * world), "p50_cycle_latency_ms_per_batch": float(np.median(step_ms)),
+                       "mean_active_set_iterations": iters_all / (B * world), "p50_device_ms_per_batch": float(np.median(step_ms)), "p95_device_ms_per_batch": float(np.percentile(step_ms, 95)),
                        "parallelism": "dp%d (independent shards, no collective)" % world},
             "e2e": {"value": e2e_val, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps},
+                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                    "p50_cycle_latency_ms": 1e3 * float(np.percentile(e2e_lat, 50)), "p95_cycle_latency_ms": 1e3 * float(np.percentile(e2e_lat, 95))},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64-fma (CUDA cores); not hbm / tensor bound", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp64", "bound_note": "FP64 FMA on CUDA cores + shared-memory bandwidth; neither hbm nor tensor bound (SURVEY.md 8(d))", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak > 0 else None, "peak_source": "measured live (dependent-FMA probe, iwbc_measure_fp64_tflops)",
                          "flops_per_update": fl, "kernel_ms": kern_ms, "traffic": traffic,
                          "hbm": {"achieved": io_bytes * B / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
