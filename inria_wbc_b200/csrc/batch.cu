@@ -136,62 +136,7 @@ namespace dev {
 
 using namespace iwbc;
 
-#define CUDA_TRY(expr)                                                                                        \
-    do {                                                                                                      \
-        cudaError_t e_ = (expr);                                                                              \
-        if (e_ != cudaSuccess) {                                                                              \
-            set_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
-            return IWBC_ERR_CUDA;                                                                             \
-        }                                                                                                     \
-    } while (0)
-
-struct iwbc_batch {
-    const iwbc_problem* prob = nullptr;
-    unsigned long revision = ~0ul;
-    int device = 0;
-    int max_batch = 0;
-    int sm_count = 0;
-    iwbc_problem_t* d_prob = nullptr;
-    cudaStream_t stream = nullptr;
-    // staging buffers (device)
-    double *d_q = nullptr, *d_v = nullptr, *d_refs = nullptr;
-    double *d_tau = nullptr, *d_dv = nullptr, *d_f = nullptr, *d_qn = nullptr, *d_vn = nullptr, *d_qc = nullptr, *d_mom = nullptr;
-    int *d_status = nullptr, *d_iters = nullptr;
-    unsigned* d_active = nullptr;
-    // bucketing scratch (host)
-    std::vector<int> perm;
-    std::vector<double> hq, hv, hr;
-    std::vector<char> stage;
-    // launch bookkeeping
-    long launches = 0;
-    bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double ms_sum = 0;
-    long ms_n = 0;
-    unsigned shape_mask = ~0u;
-    dev::Shape shape;
-    int G = 0, IPC = 0;
-    long long last_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    unsigned long long* d_prof = nullptr; // steady-state phase profile accumulators (enabled on demand): [0..6] active-set kernel, [8..14] fast kernel
-    bool profiling = false;
-    // fast path (fast_kernel.cuh): equality-constrained first pass, 3 CTAs / SM; the active-set kernel continues the rest
-    bool fast_ok = false, fast_enabled = true;
-    dev::FShape fshape;
-    dev::FPlan fplan;
-    dev::FPlan* d_fplan = nullptr;
-    int *d_slow_list = nullptr, *d_slow_count = nullptr; // per launch slot: list region [list_off, ...), counter d_slow_count[slot]
-    int slot = 0, list_off = 0;
-    double* d_scratch = nullptr; // front-end images handed from k_fast to k_slow
-    int* d_slow_code = nullptr;
-    int scratch_cap = 0, scratch_off = 0, scratch_len = 0, scratch_img = 0; // capacity (instances); sub-range used by the current launch
-    cudaStream_t aux[2] = {nullptr, nullptr}; // copy / compute pipelining of iwbc_batch_update
-    cudaEvent_t ev_const = nullptr;
-    int fast_grid = 0, slow_grid = 0;
-    size_t fast_smem = 0, slow_smem = 0;
-    bool plan_dirty = true;
-    size_t smem_bytes = 0;
-    int grid = 0;
-};
+#include "batch_state.hpp"
 
 namespace {
 
@@ -202,82 +147,19 @@ struct ConstOwner {
     unsigned mask = ~0u;
 } g_const_owner[16];
 
-constexpr int FT_ = 128;
-
-template <int NV_, int ME_>
-int launch_fast_shape(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
-{
-    dev::IO iop = io;
-    auto fk = dev::k_fast<FT_, NV_, ME_>;
-    auto sk = dev::k_slow<FT_, NV_, ME_>;
-    if (b->fast_grid == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->fast_smem));
-        CUDA_TRY(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->slow_smem));
-        int per_sm = 0, per_sm_slow = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, FT_, b->fast_smem));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_slow, sk, FT_, b->slow_smem));
-        if (per_sm < 1 || per_sm_slow < 1) {
-            set_error("fast / active-set kernels do not fit on an SM");
-            return IWBC_ERR_CUDA;
-        }
-        b->fast_grid = b->sm_count * per_sm;
-        b->slow_grid = b->sm_count * per_sm_slow;
-    }
-    iop.slow_list = b->d_slow_list + b->list_off;
-    iop.slow_count = b->d_slow_count + b->slot;
-    if (b->d_scratch == nullptr || b->scratch_img < b->fshape.total) {
-        // (re)allocate the hand-over scratch (grow only): at most 65536 images (70 kB each for Talos double support)
-        if (b->d_scratch) {
-            CUDA_TRY(cudaDeviceSynchronize());
-            cudaFree(b->d_scratch);
-            b->d_scratch = nullptr;
-        }
-        b->scratch_cap = std::min(b->max_batch, 65536);
-        b->scratch_img = b->fshape.total + 64;
-        CUDA_TRY(cudaMalloc((void**)&b->d_scratch, (size_t)b->scratch_cap * b->scratch_img * sizeof(double)));
-    }
-    {
-        const int off = b->scratch_len ? b->scratch_off : 0, len = b->scratch_len ? b->scratch_len : b->scratch_cap;
-        iop.scratch = b->d_scratch + (size_t)off * b->scratch_img; // (images are packed with the current plan's size inside this range)
-        iop.slow_code = b->d_slow_code + off;
-        iop.scratch_cap = len;
-    }
-    if (b->profiling)
-        iop.prof = b->d_prof;
-    CUDA_TRY(cudaMemsetAsync(b->d_slow_count + b->slot, 0, sizeof(int), st));
-    if (b->timing)
-        cudaEventRecord(b->ev0, st);
-    fk<<<std::min(b->fast_grid, io.B), FT_, b->fast_smem, st>>>(b->d_prob, b->d_fplan, iop);
-    b->launches++;
-    iop.list = b->d_slow_list + b->list_off;
-    iop.list_count = b->d_slow_count + b->slot;
-    sk<<<std::min(b->slow_grid, io.B), FT_, b->slow_smem, st>>>(b->d_prob, b->d_fplan, iop);
-    if (b->timing) {
-        cudaEventRecord(b->ev1, st);
-        cudaEventSynchronize(b->ev1);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, b->ev0, b->ev1);
-        b->ms_sum += ms;
-        b->ms_n++;
-    }
-    b->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return IWBC_OK;
-}
-
-// fast pass + active-set continuation, specialised for the common (nv, me) shapes
+// fast pass + active-set continuation: one translation unit per compile-time (nv, me) shape (fast_tu.cuh)
 int launch_fast(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
 {
     const int nv = b->prob->cs.prob.nv, me = b->fshape.me;
     if (nv == 50 && me == 18)
-        return launch_fast_shape<50, 18>(b, io, st); // Talos (full URDF), double support
+        return iwbc_launch_fast_50_18(b, io, st); // Talos (full URDF), double support
     if (nv == 50 && me == 12)
-        return launch_fast_shape<50, 12>(b, io, st); // Talos, single support
+        return iwbc_launch_fast_50_12(b, io, st); // Talos, single support
     if (nv == 38 && me == 18)
-        return launch_fast_shape<38, 18>(b, io, st); // iCub / Talos fast URDF, double support
+        return iwbc_launch_fast_38_18(b, io, st); // iCub / Talos fast URDF, double support
     if (nv == 38 && me == 12)
-        return launch_fast_shape<38, 12>(b, io, st);
-    return launch_fast_shape<0, 0>(b, io, st);
+        return iwbc_launch_fast_38_12(b, io, st);
+    return iwbc_launch_fast_0_0(b, io, st);
 }
 
 template <int G, int IPC>
@@ -854,7 +736,7 @@ int iwbc_batch_fast_info(const iwbc_batch* b, long* out6)
     out6[2] = (long)b->fast_smem;
     out6[3] = b->slow_grid;
     out6[4] = (long)b->slow_smem;
-    out6[5] = FT_;
+    out6[5] = IWBC_FAST_THREADS;
     return IWBC_OK;
 }
 

@@ -1,0 +1,86 @@
+// batch_state.hpp -- the opaque handle behind `iwbc_batch` and the launch entry points of the per-shape
+// translation units (fast_tu.cuh); shared by batch.cu and fast_*.cu.
+#pragma once
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/iwbc_batch.h"
+#include "cycle_kernel.cuh"
+#include "fast_kernel.cuh"
+#include "host_state.hpp"
+
+#define CUDA_TRY(expr)                                                                                        \
+    do {                                                                                                      \
+        cudaError_t e_ = (expr);                                                                              \
+        if (e_ != cudaSuccess) {                                                                              \
+            iwbc::set_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+            return IWBC_ERR_CUDA;                                                                             \
+        }                                                                                                     \
+    } while (0)
+
+struct iwbc_batch {
+    const iwbc_problem* prob = nullptr;
+    unsigned long revision = ~0ul;
+    int device = 0;
+    int max_batch = 0;
+    int sm_count = 0;
+    iwbc_problem_t* d_prob = nullptr;
+    cudaStream_t stream = nullptr;
+    // staging buffers (device)
+    double *d_q = nullptr, *d_v = nullptr, *d_refs = nullptr;
+    double *d_tau = nullptr, *d_dv = nullptr, *d_f = nullptr, *d_qn = nullptr, *d_vn = nullptr, *d_qc = nullptr, *d_mom = nullptr;
+    int *d_status = nullptr, *d_iters = nullptr;
+    unsigned* d_active = nullptr;
+    // bucketing scratch (host)
+    std::vector<int> perm;
+    std::vector<double> hq, hv, hr;
+    std::vector<char> stage;
+    // launch bookkeeping
+    long launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double ms_sum = 0;
+    long ms_n = 0;
+    unsigned shape_mask = ~0u;
+    iwbc::dev::Shape shape;
+    int G = 0, IPC = 0;
+    long long last_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long* d_prof = nullptr; // steady-state phase profile accumulators (enabled on demand): [0..6] active-set kernel, [8..14] fast kernel
+    bool profiling = false;
+    // fast path (fast_kernel.cuh): equality-constrained first pass, 3 CTAs / SM; the active-set kernel continues the rest
+    bool fast_ok = false, fast_enabled = true;
+    iwbc::dev::FShape fshape;
+    iwbc::dev::FPlan fplan;
+    iwbc::dev::FPlan* d_fplan = nullptr;
+    int *d_slow_list = nullptr, *d_slow_count = nullptr; // per launch slot: list region [list_off, ...), counter d_slow_count[slot]
+    int slot = 0, list_off = 0;
+    double* d_scratch = nullptr; // front-end images handed from k_fast to k_slow
+    int* d_slow_code = nullptr;
+    int scratch_cap = 0, scratch_off = 0, scratch_len = 0, scratch_img = 0; // capacity (instances); sub-range used by the current launch
+    cudaStream_t aux[2] = {nullptr, nullptr}; // copy / compute pipelining of iwbc_batch_update
+    cudaEvent_t ev_const = nullptr;
+    int fast_grid = 0, slow_grid = 0;
+    size_t fast_smem = 0, slow_smem = 0;
+    bool plan_dirty = true;
+    size_t smem_bytes = 0;
+    int grid = 0;
+};
+
+
+constexpr int IWBC_FAST_THREADS = 128; // threads per CTA of k_fast / k_slow
+
+// which (problem revision, contact mask) a translation unit's __constant__ copies currently hold, per device
+struct iwbc_const_owner {
+    const void* batch = nullptr;
+    unsigned long revision = 0;
+    unsigned mask = ~0u;
+};
+
+// k_fast / k_slow launch pair of one compile-time (nv, me) shape; uploads that unit's own __constant__ copies when stale
+int iwbc_launch_fast_50_18(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
+int iwbc_launch_fast_50_12(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
+int iwbc_launch_fast_38_18(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
+int iwbc_launch_fast_38_12(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
+int iwbc_launch_fast_0_0(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);

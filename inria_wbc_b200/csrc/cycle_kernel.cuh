@@ -123,8 +123,8 @@ namespace dev {
         unsigned long long* prof; // steady-state phase profile: [0..5] summed SM cycles of dyn, asm, factor, eq, ineq, decode; [6] instances
     };
 
-    __constant__ iwbc_problem_t c_P; // uniform-access copy (task tables, sizes)
-    __constant__ Shape c_S;
+    static __constant__ iwbc_problem_t c_P; // uniform-access copy (task tables, sizes)
+    static __constant__ Shape c_S;
 
     // ------------------------------------------------------------------ small device math
     struct V3 {

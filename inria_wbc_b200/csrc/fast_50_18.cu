@@ -1,0 +1,5 @@
+// k_fast / k_slow specialised for nv = 50, me = 18 (see fast_tu.cuh)
+#define IWBC_TU_NV 50
+#define IWBC_TU_ME 18
+#define IWBC_TU_ENTRY iwbc_launch_fast_50_18
+#include "fast_tu.cuh"

@@ -26,6 +26,10 @@
 // composes the transforms along its own root path (the path table is static), velocities and drift
 // accelerations are prefix sums of per-joint terms along the same path.
 #pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
 #include "cycle_kernel.cuh"
 
 namespace iwbc {
@@ -83,7 +87,7 @@ namespace dev {
         int s_J, s_R, s_vec, s_int, s_total; // extra regions of the active-set continuation (k_slow)
     };
 
-    __constant__ FShape c_F;
+    static __constant__ FShape c_F;
 
     // ------------------------------------------------------------------------------------------ host: plan
     inline bool build_fast_plan(const iwbc_problem_t& P, const Shape& S, int T, FShape& F, FPlan& pl)

@@ -1,0 +1,95 @@
+// fast_tu.cuh -- one translation unit per compile-time (nv, me) shape of the k_fast / k_slow pair, so that the shapes
+// compile in parallel.  Each unit owns its copies of the __constant__ tables (c_P, c_S, c_F are TU-local) and refreshes
+// them when the (batch, problem revision, contact mask) it last served changes.
+// Usage: #define IWBC_TU_NV / IWBC_TU_ME / IWBC_TU_ENTRY, then #include "fast_tu.cuh".
+#include <algorithm>
+
+#include "batch_state.hpp"
+
+using namespace iwbc;
+
+namespace {
+
+iwbc_const_owner g_owner[16];
+
+constexpr int FT_ = IWBC_FAST_THREADS;
+
+template <int NV_, int ME_>
+int launch_fast_shape(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
+{
+    dev::IO iop = io;
+    auto fk = dev::k_fast<FT_, NV_, ME_>;
+    auto sk = dev::k_slow<FT_, NV_, ME_>;
+    if (b->fast_grid == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->fast_smem));
+        CUDA_TRY(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->slow_smem));
+        int per_sm = 0, per_sm_slow = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, FT_, b->fast_smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_slow, sk, FT_, b->slow_smem));
+        if (per_sm < 1 || per_sm_slow < 1) {
+            set_error("fast / active-set kernels do not fit on an SM");
+            return IWBC_ERR_CUDA;
+        }
+        b->fast_grid = b->sm_count * per_sm;
+        b->slow_grid = b->sm_count * per_sm_slow;
+    }
+    iop.slow_list = b->d_slow_list + b->list_off;
+    iop.slow_count = b->d_slow_count + b->slot;
+    if (b->d_scratch == nullptr || b->scratch_img < b->fshape.total) {
+        // (re)allocate the hand-over scratch (grow only): at most 65536 images (70 kB each for Talos double support)
+        if (b->d_scratch) {
+            CUDA_TRY(cudaDeviceSynchronize());
+            cudaFree(b->d_scratch);
+            b->d_scratch = nullptr;
+        }
+        b->scratch_cap = std::min(b->max_batch, 65536);
+        b->scratch_img = b->fshape.total + 64;
+        CUDA_TRY(cudaMalloc((void**)&b->d_scratch, (size_t)b->scratch_cap * b->scratch_img * sizeof(double)));
+    }
+    {
+        const int off = b->scratch_len ? b->scratch_off : 0, len = b->scratch_len ? b->scratch_len : b->scratch_cap;
+        iop.scratch = b->d_scratch + (size_t)off * b->scratch_img; // (images are packed with the current plan's size inside this range)
+        iop.slow_code = b->d_slow_code + off;
+        iop.scratch_cap = len;
+    }
+    if (b->profiling)
+        iop.prof = b->d_prof;
+    CUDA_TRY(cudaMemsetAsync(b->d_slow_count + b->slot, 0, sizeof(int), st));
+    if (b->timing)
+        cudaEventRecord(b->ev0, st);
+    fk<<<std::min(b->fast_grid, io.B), FT_, b->fast_smem, st>>>(b->d_prob, b->d_fplan, iop);
+    b->launches++;
+    iop.list = b->d_slow_list + b->list_off;
+    iop.list_count = b->d_slow_count + b->slot;
+    sk<<<std::min(b->slow_grid, io.B), FT_, b->slow_smem, st>>>(b->d_prob, b->d_fplan, iop);
+    if (b->timing) {
+        cudaEventRecord(b->ev1, st);
+        cudaEventSynchronize(b->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, b->ev0, b->ev1);
+        b->ms_sum += ms;
+        b->ms_n++;
+    }
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IWBC_OK;
+}
+
+} // namespace
+
+int IWBC_TU_ENTRY(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
+{
+    iwbc_const_owner& o = g_owner[b->device & 15];
+    if (o.batch != b || o.revision != b->revision || o.mask != b->shape_mask) {
+        // other streams may still be running a kernel of this unit that reads the old constants
+        if (o.batch != nullptr && o.batch != b)
+            CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_P, &b->prob->cs.prob, sizeof(iwbc_problem_t), 0, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_S, &b->shape, sizeof(dev::Shape), 0, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_F, &b->fshape, sizeof(dev::FShape), 0, cudaMemcpyHostToDevice, st));
+        o.batch = b;
+        o.revision = b->revision;
+        o.mask = b->shape_mask;
+    }
+    return launch_fast_shape<IWBC_TU_NV, IWBC_TU_ME>(b, io, st);
+}
