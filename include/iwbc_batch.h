@@ -146,6 +146,34 @@ double iwbc_measure_fp64_tflops(int device);
 int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, const double* ref, unsigned contact_mask,
     double* M, double* nle, double* H, double* g, double* x);
 
+/* ------------------------------------------------------------------ behaviours on the device
+ * Replaces `behaviors::Factory::instance().create(name, controller, YAML::LoadFile(path))`
+ * (include/inria_wbc/behaviors/behavior.hpp:28-30) and the per-tick `Behavior::update` setters
+ * (e.g. src/behaviors/humanoid/walk.cpp:198-246): the behaviour's waypoint tables
+ * (include/inria_wbc/trajs/trajectory_generator.hpp:29-160) are compiled into a segment table that
+ * the GPU evaluates in closed form for every (instance, tick).  BEHAVIOR.name selects the
+ * behaviour ("humanoid::walk"); overrides_yaml: optional YAML text of BEHAVIOR keys to override.
+ */
+typedef struct iwbc_behavior iwbc_behavior;
+iwbc_behavior* iwbc_behavior_load(const iwbc_problem* p, const char* behavior_yaml, const char* overrides_yaml);
+void iwbc_behavior_free(iwbc_behavior* h);
+/* length in control ticks, segment / channel counts, the distinct contact masks (<= 8, most frequent first) */
+int iwbc_behavior_info(const iwbc_behavior* h, int* total_ticks, int* nsegments, int* nchannels, int* nmasks, unsigned* masks8);
+/* one segment of the table (host): first tick, length, contact mask during / at the last tick of the segment, and per
+ * channel 8 doubles {p0(3), p1(3), duration, minjerk ? 1 : 0} (waypoints may be NULL) */
+int iwbc_behavior_segment(const iwbc_behavior* h, int seg, int* start, int* ticks, unsigned* mask, unsigned* mask_last, double* waypoints);
+/* DEVICE pointers.  refs[B][nref] and contact_mask[B] (may be NULL) as the behaviour leaves them before the controller
+ * update of global tick `tick + phase[i]` (phase: per-instance offset or NULL); init_refs != 0 first fills every row
+ * with the construction-time references.  Enqueued on `stream`, no synchronisation. */
+int iwbc_behavior_eval_device(iwbc_behavior* h, int device, int B, const int* phase, int tick, double* refs, unsigned* contact_mask,
+    int init_refs, void* stream);
+/* Closed device-side roll-out: `ticks` times { behaviour -> refs, masks; instances bucketed by contact mask on the device;
+ * one shape-uniform launch set of the control cycle per mask; (q, v) integrated in place }.  No host round trip and no
+ * reference upload per tick.  refs[B][nref] is caller-owned device scratch (kept between calls so that a roll-out can be
+ * continued with init_refs = 0); out_last (device pointers, any may be NULL): results of the last tick. */
+int iwbc_batch_behavior_rollout_device(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, double* refs, const int* phase,
+    int tick0, int ticks, int init_refs, const iwbc_results_t* out_last, unsigned* contact_mask, void* stream);
+
 /* ------------------------------------------------------------------ solver interface
  * Batched form of `tsid::solvers::SolverHQPBase::solve` for the EiquadprogFast backend
  * (src/controllers/pos_tracker.cpp:96,102; src/controllers/controller.cpp:247): B dense QPs of one

@@ -69,6 +69,12 @@ def lib():
         "iwbc_batch_fast_info": (ci, [vp, vp]),
         "iwbc_batch_launch_info": (ci, [vp, pi, pi, pi, C.POINTER(C.c_long)]),
         "iwbc_qp_solve_batch": (ci, [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "iwbc_behavior_load": (vp, [vp, cp, cp]),
+        "iwbc_behavior_free": (None, [vp]),
+        "iwbc_behavior_info": (ci, [vp, pi, pi, pi, pi, vp]),
+        "iwbc_behavior_segment": (ci, [vp, ci, pi, pi, vp, vp, vp]),
+        "iwbc_behavior_eval_device": (ci, [vp, ci, ci, vp, ci, vp, vp, ci, vp]),
+        "iwbc_batch_behavior_rollout_device": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, C.POINTER(_Results), vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
@@ -168,6 +174,48 @@ class Problem:
         return out
 
 
+class Behavior:
+    """A behaviour (reference generator) compiled into a device-evaluable segment table: `humanoid::walk`."""
+
+    def __init__(self, problem, behavior_yaml, overrides=None):
+        self.problem = problem
+        if not os.path.isabs(behavior_yaml):
+            behavior_yaml = os.path.join(ETC_PATH, behavior_yaml)
+        ov = None
+        if overrides:
+            ov = "\n".join("%s: %s" % (k, _yaml_scalar(v)) for k, v in overrides.items()).encode()
+        self._h = lib().iwbc_behavior_load(problem.handle, behavior_yaml.encode(), ov)
+        if not self._h:
+            raise IwbcError(_err(lib()))
+        tt, ns, nc, nm = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        masks = (C.c_uint * 8)()
+        lib().iwbc_behavior_info(self._h, C.byref(tt), C.byref(ns), C.byref(nc), C.byref(nm), masks)
+        self.total_ticks, self.nsegments, self.nchannels = tt.value, ns.value, nc.value
+        self.masks = [int(masks[k]) for k in range(nm.value)]
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.iwbc_behavior_free(self._h)
+            self._h = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def segment(self, k):
+        """(start, ticks, mask, mask_last, waypoints[nchannels][8] = p0(3) p1(3) duration minjerk)"""
+        st, tk, m, ml = C.c_int(), C.c_int(), C.c_uint(), C.c_uint()
+        wp = np.zeros((self.nchannels, 8))
+        if lib().iwbc_behavior_segment(self._h, k, C.byref(st), C.byref(tk), C.byref(m), C.byref(ml), wp.ctypes.data) != 0:
+            raise IwbcError(_err(lib()))
+        return st.value, tk.value, m.value, ml.value, wp
+
+    def eval_device(self, device, B, phase_ptr, tick, refs_ptr, mask_ptr=None, init_refs=True, stream=0):
+        rc = lib().iwbc_behavior_eval_device(self._h, device, B, phase_ptr, tick, refs_ptr, mask_ptr, 1 if init_refs else 0, stream)
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+
+
 def _yaml_scalar(v):
     if isinstance(v, bool):
         return "true" if v else "false"
@@ -237,6 +285,15 @@ class Batch:
     def rollout_device(self, B, q_ptr, v_ptr, refs_ptr, refs_stride, contact_mask, ticks, out_ptrs=None, stream=0):
         st = _Results(*[(out_ptrs or {}).get(f) for f in Results.FIELDS])
         rc = lib().iwbc_batch_rollout_device(self._h, B, q_ptr, v_ptr, refs_ptr, refs_stride, contact_mask, ticks, C.byref(st), stream)
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+
+    def behavior_rollout_device(self, behavior, B, q_ptr, v_ptr, refs_ptr, phase_ptr, tick0, ticks, init_refs=True, out_ptrs=None, mask_ptr=None,
+                                stream=0):
+        """Closed device-side roll-out of a compiled behaviour; all pointers are device addresses."""
+        st = _Results(*[(out_ptrs or {}).get(f) for f in Results.FIELDS])
+        rc = lib().iwbc_batch_behavior_rollout_device(self._h, behavior.handle, B, q_ptr, v_ptr, refs_ptr, phase_ptr, tick0, ticks,
+                                                      1 if init_refs else 0, C.byref(st), mask_ptr, stream)
         if rc != 0:
             raise IwbcError(_err(lib()))
 

@@ -181,6 +181,8 @@ int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
     const bool use_fast = b->fast_ok && b->fast_enabled && G > 32 && !io.dbg_M && !io.dbg_cycles;
     if (use_fast)
         return launch_fast(b, io, st);
+    if (io.in_list) // a behaviour's bucket: the generic kernel walks it as its instance list
+        iop.list = io.in_list, iop.list_count = io.in_count;
     if (b->timing && !use_fast)
         cudaEventRecord(b->ev0, st);
     kern<<<grid, G * IPC, b->smem_bytes, st>>>(b->d_prob, iop);
@@ -316,7 +318,10 @@ int upload_constants(iwbc_batch* b, cudaStream_t st)
     return IWBC_OK;
 }
 
-int run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t st)
+} // namespace
+
+// one pass of the cycle over io's instances (all of them, or io.list) with one contact mask; shared with behavior.cu
+int iwbc_run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t st)
 {
     int rc = prepare_shape(b, mask);
     if (rc)
@@ -332,6 +337,9 @@ int run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t st)
         return launch_cycle<96, 1>(b, io, st);
     return launch_cycle<128, 1>(b, io, st);
 }
+
+namespace {
+int run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t st) { return iwbc_run_cycle(b, io, mask, st); }
 
 template <class T>
 int dalloc(T** p, size_t count)

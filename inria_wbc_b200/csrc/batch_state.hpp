@@ -84,3 +84,7 @@ int iwbc_launch_fast_50_12(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t 
 int iwbc_launch_fast_38_18(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
 int iwbc_launch_fast_38_12(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
 int iwbc_launch_fast_0_0(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
+
+// one pass of the control cycle over io's instances (io.list / io.list_count: optional device-side instance list) with one
+// contact mask: prepares the shape, refreshes constants, launches (batch.cu)
+int iwbc_run_cycle(iwbc_batch* b, const iwbc::dev::IO& io, unsigned mask, cudaStream_t st);

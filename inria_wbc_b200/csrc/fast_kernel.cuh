@@ -1685,7 +1685,10 @@ namespace dev {
                 dofj[k] = gF->dofj[k];
         }
         __syncthreads();
-        for (int inst = blockIdx.x; inst < io.B; inst += gridDim.x) {
+        // all instances, or the device-side list a behaviour built for this contact mask (io.in_list)
+        const int count = io.in_list ? *io.in_count : io.B;
+        for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+            const int inst = io.in_list ? io.in_list[idx] : idx;
             long long stamps[8];
             long long* cyc = io.prof ? stamps : nullptr;
             const int code = fast_instance<T, NV_, ME_>(gP, gF, smem, io, inst, tid, cyc);

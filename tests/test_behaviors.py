@@ -1,0 +1,137 @@
+"""Device-side behaviours: the compiled segment table and its GPU evaluation against the numpy restatement
+of the reference's humanoid::walk (oracle/behaviors_oracle.py, which follows src/behaviors/humanoid/walk.cpp and
+include/inria_wbc/trajs/trajectory_generator.hpp), and the closed device-side roll-out against the CPU oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import inria_wbc_b200 as iw
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import behaviors_oracle as bo  # noqa: E402
+
+WALK = os.path.join(iw.ETC_PATH, "talos", "walk.yaml")
+
+
+@pytest.fixture(scope="module")
+def walk_problem():
+    P = iw.Problem("talos/talos_pos_tracker.yaml")
+    P.set_task_weight("momentum", 0.0)  # BEHAVIOR.customize_task_weights (etc/talos/walk.yaml:8-9; src/behaviors/behavior.cpp:7-22)
+    return P
+
+
+def test_walk_table_matches_the_reference_state_machine(walk_problem):
+    P = walk_problem
+    for ncyc in (1, 3):
+        beh = iw.Behavior(P, "talos/walk.yaml", overrides={"num_of_cycles": ncyc})
+        ora = bo.Walk(P, WALK, num_of_cycles=ncyc)
+        assert beh.total_ticks == ora.total_ticks == 1000 * (4 + 6 * ncyc)
+        assert beh.nsegments == len(ora.cycle) and beh.nchannels == 5
+        refs, masks = ora.table()
+        assert sorted(beh.masks) == sorted(set(int(m) for m in masks))
+        slots = [ora.slot[k] for k in ("com", "lf", "rf", "lh", "rh")]
+        for k in range(beh.nsegments):
+            start, ticks, mask, mask_last, wp = beh.segment(k)
+            assert start == sum(ora.seg_len[:k]) and ticks == ora.seg_len[k]
+            assert np.all(masks[start:start + ticks - 1] == mask) and masks[start + ticks - 1] == mask_last
+            for c, off in enumerate(slots):
+                # first sample of the segment is the start waypoint; a constant channel keeps it, a moving one follows the polynomial
+                assert np.array_equal(refs[start, off:off + 3], wp[c, 0:3]), (k, c)
+                if wp[c, 7] == 0:
+                    assert np.array_equal(refs[start + ticks - 1, off:off + 3], wp[c, 0:3])
+                else:
+                    i = ticks // 3
+                    want = bo.minimum_jerk_polynom(wp[c, 0:3], wp[c, 3:6], P.struct().dt * i, wp[c, 6])
+                    assert np.abs(refs[start + i, off:off + 3] - want).max() < 1e-15
+
+
+def test_walk_contact_schedule(walk_problem):
+    """walk.cpp:203-221: a foot's contact is removed at the first tick of its LIFT_UP state and comes back at the LAST tick of
+    its LIFT_DOWN state."""
+    P = walk_problem
+    beh = iw.Behavior(P, "talos/walk.yaml", overrides={"num_of_cycles": 1})
+    lf, rf = 1 << P.contact_index("contact_lfoot"), 1 << P.contact_index("contact_rfoot")
+    seq = [beh.segment(k)[2:4] for k in range(beh.nsegments)]
+    ds = lf | rf
+    assert seq == [(ds, ds), (rf, rf), (rf, ds), (ds, ds), (lf, lf), (lf, ds), (ds, ds), (rf, rf), (rf, ds), (ds, ds)]
+
+
+def test_behavior_config_errors(walk_problem, franka):
+    with pytest.raises(iw.IwbcError, match="num_of_cycles"):
+        iw.Behavior(walk_problem, "talos/walk.yaml", overrides={"num_of_cycles": 0})
+    with pytest.raises(iw.IwbcError, match="lf"):  # Walk needs lf / rf / lh / rh / com tasks and both foot contacts (walk.cpp:14-20)
+        iw.Behavior(franka, "talos/walk.yaml")
+    with pytest.raises(iw.IwbcError, match="device-side form"):
+        iw.Behavior(walk_problem, "talos/squat.yaml")
+
+
+@pytest.mark.gpu
+def test_walk_refs_on_device_match_the_restatement(walk_problem):
+    import torch
+    P = walk_problem
+    beh = iw.Behavior(P, "talos/walk.yaml", overrides={"num_of_cycles": 2})
+    ora = bo.Walk(P, WALK, num_of_cycles=2)
+    refs_t, masks_t = ora.table()
+    B = 4096
+    rng = np.random.default_rng(5)
+    phase = rng.integers(0, ora.total_ticks + 500, B).astype(np.int32)  # some instances are past the end: the last references stay
+    edges = np.cumsum(ora.seg_len)
+    phase[:len(edges)] = edges - 1  # the last tick of every segment (contact re-added there)
+    phase[len(edges):2 * len(edges)] = edges % ora.total_ticks
+    d_phase = torch.from_numpy(phase).cuda()
+    d_refs = torch.full((B, P.nref), float("nan"), dtype=torch.float64, device="cuda")
+    d_mask = torch.zeros(B, dtype=torch.int32, device="cuda")
+    for tick in (0, 7):
+        beh.eval_device(0, B, d_phase.data_ptr(), tick, d_refs.data_ptr(), d_mask.data_ptr(), init_refs=True)
+        torch.cuda.synchronize()
+        g = np.minimum(phase.astype(np.int64) + tick, ora.total_ticks - 1)
+        assert np.array_equal(d_mask.cpu().numpy().astype(np.uint32), masks_t[g])
+        got = d_refs.cpu().numpy()
+        assert np.isfinite(got).all()
+        assert np.abs(got - refs_t[g]).max() < 1e-14
+
+
+@pytest.mark.gpu
+def test_walk_rollout_on_device_matches_the_oracle(walk_problem):
+    """Closed device-side roll-out (behaviour -> refs, masks -> device-side bucketing -> one launch set per contact mask -> state
+    integrated in place) against tick-by-tick calls of the CPU oracle with the restated behaviour's references.  Instances sit
+    at different phases of the walk so that every tick mixes double- and single-support shapes and two of them cross a contact
+    removal / re-insertion."""
+    import torch
+    import oracle_lib as ol
+    P = walk_problem
+    beh = iw.Behavior(P, "talos/walk.yaml", overrides={"num_of_cycles": 1})
+    ora = bo.Walk(P, WALK, num_of_cycles=1)
+    T = 30
+    phase = np.array([0, 400, 985, 1500, 2985, 3300, 3990, 4500, 9990], dtype=np.int32)
+    B = len(phase)
+    q = np.tile(P.q0(), (B, 1))
+    v = np.zeros((B, P.nv))
+    dq, dv_ = torch.from_numpy(q.copy()).cuda(), torch.from_numpy(v.copy()).cuda()
+    d_phase = torch.from_numpy(phase).cuda()
+    d_refs = torch.empty(B, P.nref, dtype=torch.float64, device="cuda")
+    d_mask = torch.zeros(B, dtype=torch.int32, device="cuda")
+    st = torch.full((B,), -7, dtype=torch.int32, device="cuda")
+    tau = torch.zeros(B, P.na, dtype=torch.float64, device="cuda")
+    bt = iw.Batch(P, 0, B)
+    bt.behavior_rollout_device(beh, B, dq.data_ptr(), dv_.data_ptr(), d_refs.data_ptr(), d_phase.data_ptr(), 0, T,
+                               out_ptrs={"status": st.data_ptr(), "tau": tau.data_ptr()}, mask_ptr=d_mask.data_ptr())
+    torch.cuda.synchronize()
+    got_q, got_v, got_st, got_tau = dq.cpu().numpy(), dv_.cpu().numpy(), st.cpu().numpy(), tau.cpu().numpy()
+    masks_seen = set()
+    for i in range(B):
+        qi, vi = q[i].copy(), v[i].copy()
+        for t in range(T):
+            r, m = ora.tick(int(phase[i]) + t)
+            masks_seen.add(m)
+            o = ol.cycle_batch(P, qi[None], vi[None], r, contact_mask=m)
+            qi, vi = o["q_next"][0], o["v_next"][0]
+        assert got_st[i] == o["status"][0] == 0, i
+        assert np.abs(got_q[i] - qi).max() < 1e-8, i    # tests/test_determinism.cpp:51,63 tolerance on q
+        assert np.abs(got_v[i] - vi).max() < 1e-6, i
+        assert np.abs(got_tau[i] - o["tau"][0]).max() <= 1e-7 * np.abs(o["tau"][0]).max(), i
+        assert int(d_mask[i]) == ora.tick(int(phase[i]) + T - 1)[1]
+    assert len(masks_seen) == 3
