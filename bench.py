@@ -39,6 +39,8 @@ WORKLOADS = {
     "franka_65536": ("franka/pos_tracker.yaml", None, 65536, "franka"),
     # config 5: Talos walking, a mix of double- and single-support shapes bucketed by contact mask
     "talos_walk_131072": ("talos/talos_pos_tracker.yaml", None, 131072, "walk"),
+    # the same shapes from the CPU-only stand-in recipe (make_walk_masks): what the walking workload was before the device-side behaviour
+    "talos_walk_standin_131072": ("talos/talos_pos_tracker.yaml", None, 131072, "walk_standin"),
     "icub_ds_16384": ("icub/humanoid_pos_tracker.yaml", {"stabilizer": {"activated": False}}, 16384, "talos"),
     "tiago_65536": ("tiago/pos_tracker.yaml", {"urdf": "tiago/tiago_steel_no_wheel.urdf"}, 65536, "arm"),
 }
@@ -53,7 +55,7 @@ def make_inputs(P, B, recipe, seed):
     v = np.zeros((B, P.nv))
     refs = np.tile(P.default_refs(), (B, 1))
     na = P.na
-    if recipe in ("talos", "walk"):
+    if recipe in ("talos", "walk", "walk_standin"):
         dofs = P.names("dofs")
         mimics = set(P.names("mimics"))
         free = np.array([d not in mimics for d in dofs])
@@ -102,6 +104,56 @@ def make_walk_masks(P, B, refs, seed):
         refs[sel, swing + 2] += lift[sel]
         refs[sel, com:com + 2] = refs[sel, support:support + 2]
     return mask
+
+
+def make_walk_workload(P, bt, B, seed, device, ncycles=2, stride=20):
+    """Config 5 (SURVEY.md 8(d)): instance i sits at a uniformly random tick of the humanoid::walk cycle (etc/talos/walk.yaml).
+    To make (q, v) consistent with that tick's references, ONE instance is first walked through the whole behaviour on the
+    device (closed device-side roll-out, open loop as tests/test_determinism.cpp runs the controller) and its state is kept
+    every `stride` ticks; instance i = a random snapshot + small noise.  Returns host arrays ordered by contact mask (double
+    support first) so that the host-buffer call finds contiguous runs, the per-instance phase, and the behaviour."""
+    import torch
+    import inria_wbc_b200 as iw
+    beh = iw.Behavior(P, "talos/walk.yaml", overrides={"num_of_cycles": ncycles})
+    dev = torch.device("cuda", device)
+    q1 = torch.from_numpy(P.q0()[None].copy()).to(dev)
+    v1 = torch.zeros(1, P.nv, dtype=torch.float64, device=dev)
+    r1 = torch.empty(1, P.nref, dtype=torch.float64, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    nsnap = beh.total_ticks // stride
+    snap_q = torch.empty(nsnap, P.nq, dtype=torch.float64, device=dev)
+    snap_v = torch.empty(nsnap, P.nv, dtype=torch.float64, device=dev)
+    worst = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for k in range(nsnap):
+        snap_q[k].copy_(q1[0])
+        snap_v[k].copy_(v1[0])
+        bt.behavior_rollout_device(beh, 1, q1.data_ptr(), v1.data_ptr(), r1.data_ptr(), None, k * stride, stride, init_refs=(k == 0),
+                                   out_ptrs={"status": st.data_ptr()}, stream=stream)
+        worst = torch.maximum(worst, st.abs())
+    torch.cuda.synchronize()
+    if int(worst[0]) != 0:
+        raise SystemExit("bench.py: the seed walk left the OPTIMAL status (%d)" % int(worst[0]))
+    rng = np.random.default_rng(seed)
+    pick = rng.integers(0, nsnap, B)
+    phase = (pick * stride).astype(np.int32)
+    # contact mask of every instance at its tick -> order by mask, double support first
+    d_phase = torch.from_numpy(phase).to(dev)
+    d_refs = torch.empty(B, P.nref, dtype=torch.float64, device=dev)
+    d_mask = torch.zeros(B, dtype=torch.int32, device=dev)
+    beh.eval_device(device, B, d_phase.data_ptr(), 0, d_refs.data_ptr(), d_mask.data_ptr(), init_refs=True, stream=stream)
+    torch.cuda.synchronize()
+    masks = d_mask.cpu().numpy().astype(np.uint32)
+    order = np.argsort(-masks.astype(np.int64), kind="stable")
+    pick, phase, masks = pick[order], phase[order], masks[order]
+    refs = d_refs.cpu().numpy()[order]
+    q = snap_q.cpu().numpy()[pick]
+    v = snap_v.cpu().numpy()[pick]
+    mimics = set(P.names("mimics"))
+    free = np.array([d not in mimics for d in P.names("dofs")])
+    q[:, P.nq - P.na:][:, free] += rng.normal(0, 0.002, (B, int(free.sum())))
+    v[:, P.nv - P.na:] += rng.normal(0, 0.01, (B, P.na))
+    return np.ascontiguousarray(q), np.ascontiguousarray(v), np.ascontiguousarray(refs), masks, phase, beh
 
 
 # ----------------------------------------------------------------------------- flop model
@@ -255,13 +307,17 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     sample = min(B, 2048)
     q, v, refs = make_inputs(P, sample, recipe, 0xB200 + 3)
+    masks = None
+    if recipe in ("walk", "walk_standin"):  # CPU-only stand-in for the walk's mix of contact shapes (the GPU arm walks a seed instance)
+        P.set_task_weight("momentum", 0.0)
+        masks = make_walk_masks(P, sample, refs, 0xB200 + 5)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as ol
     for _ in range(max(args.warmup, 1)):
-        ol.cycle_batch(P, q, v, refs, nthreads=threads)
+        ol.cycle_batch(P, q, v, refs, contact_mask=masks, nthreads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ol.cycle_batch(P, q, v, refs, nthreads=threads)
+        ol.cycle_batch(P, q, v, refs, contact_mask=masks, nthreads=threads)
     el = time.perf_counter() - t0
     val = sample * args.steps / el
     line = {"impl": "reference", "metric": "batched TSID control updates (QP solves) per second", "value": val, "unit": "updates/s",
@@ -305,14 +361,19 @@ def main():
     if args.batch:
         B = args.batch
     P = iw.Problem(yaml, overrides=ov)
-    q, v, refs = make_inputs(P, B, recipe, 0xB200 + 3 + 1000 * rank)
     bt = iw.Batch(P, local, B)
     n, me, mi, rows = P.qp_shape()
     mask = P.default_contact_mask
     masks = None
+    beh = None
     buckets = [(0, B, mask)]
     if recipe == "walk":
-        P.set_task_weight("momentum", 0.0)  # etc/talos/walk.yaml:8-9
+        P.set_task_weight("momentum", 0.0)  # BEHAVIOR.customize_task_weights, etc/talos/walk.yaml:8-9
+        q, v, refs, masks, phase, beh = make_walk_workload(P, bt, B, 0xB200 + 5 + 1000 * rank, local)
+    else:
+        q, v, refs = make_inputs(P, B, recipe, 0xB200 + 3 + 1000 * rank)
+    if recipe == "walk_standin":
+        P.set_task_weight("momentum", 0.0)
         masks = make_walk_masks(P, B, refs, 0xB200 + 5 + 1000 * rank)
         buckets, first = [], 0
         for m in (3, 2, 1):
@@ -334,7 +395,19 @@ def main():
 
     esz = {"tau": 8 * P.na, "dv": 8 * P.nv, "f": 8 * max(12 * P.ncontacts, 1), "q_next": 8 * P.nq, "v_next": 8 * P.nv, "status": 4, "iters": 4}
 
+    if beh is not None:
+        d_phase = torch.from_numpy(phase).to(dev)
+        d_maskbuf = torch.zeros(B, dtype=torch.int32, device=dev)
+        walk_tick = [0]
+
     def step():
+        if beh is not None:
+            # closed device-side tick: behaviour -> refs + contact masks, device-side bucketing, one launch set per mask, state
+            # integrated in place (every timed step is the NEXT tick of every instance's walk)
+            bt.behavior_rollout_device(beh, B, dq.data_ptr(), dv_.data_ptr(), dr.data_ptr(), d_phase.data_ptr(), walk_tick[0], 1,
+                                       init_refs=False, out_ptrs=ptrs, mask_ptr=d_maskbuf.data_ptr(), stream=stream.cuda_stream)
+            walk_tick[0] += 1
+            return
         # one shape-uniform launch set per contact-mask bucket (instances are ordered by mask)
         for first, cnt, m in buckets:
             bt.update_device(cnt, dq.data_ptr() + 8 * P.nq * first, dv_.data_ptr() + 8 * P.nv * first, dr.data_ptr() + 8 * P.nref * first, P.nref, m,
@@ -431,7 +504,10 @@ def main():
             "config": {"workload": args.workload, "controller": yaml, "per_gpu_batch": B, "qp": {"n": n, "me": me, "mi": mi, "cost_rows": rows},
                        "l2": "flushed (256 MB write) between timed steps", "optimal_fraction": n_opt_all / (B * world),
                        "mean_active_set_iterations": iters_all / (B * world), "p50_device_ms_per_batch": float(np.median(step_ms)), "p95_device_ms_per_batch": float(np.percentile(step_ms, 95)),
-                       "parallelism": "dp%d (independent shards, no collective)" % world},
+                       "parallelism": "dp%d (independent shards, no collective)" % world,
+                       "states": ("random ticks of humanoid::walk (etc/talos/walk.yaml): a seed instance is walked on the device, instances are its "
+                                  "snapshots + noise; every timed step is the next tick, references and contact masks generated on the device")
+                       if beh is not None else "SURVEY.md 8(d) randomized-state recipe '%s'" % recipe},
             "e2e": {"value": e2e_val, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
                     "p50_cycle_latency_ms": 1e3 * float(np.percentile(e2e_lat, 50)), "p95_cycle_latency_ms": 1e3 * float(np.percentile(e2e_lat, 95))},

@@ -334,6 +334,7 @@ int iwbc_batch_behavior_rollout_device(iwbc_batch* b, iwbc_behavior* h, int B, d
         rc = eval_tick(h, B, phase, tick0 + t, refs, contact_mask, true, st);
         if (rc)
             return rc;
+        b->launches++;
         for (size_t k = 0; k < h->masks.size(); ++k) {
             dev::IO io;
             std::memset(&io, 0, sizeof(io));

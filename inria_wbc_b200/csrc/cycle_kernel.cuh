@@ -1789,6 +1789,429 @@ namespace dev {
         return status;
     }
 
+    // ---- CTA-wide, latency-trimmed form of gi_loop for the fused problem (G >= 64: the CTA is the group).
+    // Same iteration, same tie-breaking, same termination test as gi_loop (eiquadprog); what
+    // changes is the schedule -- the loop is a chain of short dependent phases, so its cost is barriers and serial
+    // sections, not flops:
+    //   * s = CI x + ci0, psi = sum min(0, s) and the most violated eligible row come out of ONE pass and ONE combined
+    //     reduction (one two-sided row pair per thread);
+    //   * r = R^-1 d (the multipliers' direction) and the ratio test run in the last warp by shuffles while the other
+    //     warps compute z = J2 d2; the barrier of the |z|^2 / z'n+ reduction publishes both;
+    //   * the contact wrenches of the next pass, the new column of R and the iai update ride along the row rotations of
+    //     add_constraint; the suffix norm of d is taken from the rotation coefficients instead of being re-summed by every
+    //     thread;  iai is kept incrementally (no per-pass rebuild).
+    // Six barriers per added constraint instead of ~15.  Thread-indexed table reads (T, B, tau_max) go through global
+    // memory / L1 (gP) instead of the constant bank, which would replay once per distinct address.
+    template <int G>
+    __device__ int gi_loop_cta(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, int me, int mi, int tid, int& flip, int& iter_out,
+        int& iq_out, double c1, double c2, double R_norm)
+    {
+        static_assert(G >= 64 && G % 32 == 0, "gi_loop_cta: the CTA is the group");
+        const Shape& S = c_S;
+        const int n = z.n, ld = z.ldJ, nv = z.nv, na = c_P.na, nu = nv - na, ncon = c_P.ncontacts;
+        const double eps = 2.220446049250313e-16;
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        const int lane = tid & 31, lastw = G / 32 - 1, warp = tid >> 5;
+        int iq = me, iter = 0;
+        int nitems = 0;
+        for (int b = 0; b < S.nci; ++b)
+            nitems += S.ci[b].rows;
+        // wrench of each active contact w_c = T f_c -> sm.cb[6 ncontacts + 6 c + a], by the threads [t0, t0 + 6 ncontacts)
+        auto wrenches_by = [&](int t0) {
+            const int e = tid - t0;
+            if (e >= 0 && e < 6 * ncon) {
+                const int c = e / 6, a = e - 6 * c;
+                double w = 0;
+                if (S.cidx[c] >= 0) {
+                    const double* T = gP->contacts[c].T + a * 12;
+                    const double* f = sm.x + nv + S.cidx[c];
+#pragma unroll
+                    for (int k = 0; k < 12; ++k)
+                        w += T[k] * f[k];
+                }
+                sm.cb[6 * ncon + e] = w;
+            }
+        };
+        for (int k = tid; k < mi; k += G)
+            sm.iai[k] = k;
+        wrenches_by(G - 6 * ncon > 0 ? G - 6 * ncon : 0);
+        __syncthreads();
+
+        int status = IWBC_STATUS_UNKNOWN;
+        int ip = 0;
+        double sip = 0.0;
+        bool at_l1 = true, need_pick = false;
+        while (true) {
+            if (at_l1 || need_pick) {
+                // ---- l1 (+ l2): s, psi, most violated eligible row.  need_pick alone (after a degenerate add): s is unchanged,
+                // only the pick is redone with the excluded rows (iai == -2) left out.
+                double psi = 0.0, best = 0.0;
+                int bi = 0x7fffffff;
+                if (at_l1) {
+                    iter++;
+                    if (iter >= 1000) {
+                        status = IWBC_STATUS_MAX_ITER;
+                        break;
+                    }
+                    for (int it = tid; it < nitems; it += G) {
+                        int b = 0, r = it;
+                        while (r >= S.ci[b].rows) {
+                            r -= S.ci[b].rows;
+                            ++b;
+                        }
+                        const CiBlock& B = S.ci[b];
+                        double val, lo, hi;
+                        if (B.kind == 0) {
+                            val = sm.x[nu + r], lo = sm.lb[r], hi = sm.ub[r];
+                        }
+                        else if (B.kind == 1) {
+                            val = FusedRows::act_row_value(sm, z, r);
+                            const double tm = gP->tau_max[r], h = sm.nle[nu + r];
+                            lo = -tm - h, hi = tm - h;
+                        }
+                        else {
+                            const iwbc_contact_t& C = gP->contacts[B.index];
+                            const double* f = sm.x + nv + S.cidx[B.index];
+                            val = 0;
+#pragma unroll
+                            for (int k = 0; k < 12; ++k)
+                                val += C.B[r * 12 + k] * f[k];
+                            lo = C.lb[r], hi = C.ub[r];
+                        }
+                        const int k1 = B.off + r, k2 = k1 + B.rows;
+                        const double s1 = val - lo, s2 = -val + hi;
+                        sm.s[k1] = s1;
+                        sm.s[k2] = s2;
+                        psi += fmin(0.0, s1) + fmin(0.0, s2);
+                        int e1 = sm.iai[k1], e2 = sm.iai[k2];
+                        if (e1 == -2) // iaexcl <- 1 at every l1
+                            sm.iai[k1] = e1 = k1;
+                        if (e2 == -2)
+                            sm.iai[k2] = e2 = k2;
+                        if (e1 >= 0 && (s1 < best || (s1 == best && s1 < 0.0 && k1 < bi)))
+                            best = s1, bi = k1;
+                        if (e2 >= 0 && (s2 < best || (s2 == best && s2 < 0.0 && k2 < bi)))
+                            best = s2, bi = k2;
+                    }
+                }
+                else {
+                    for (int k = tid; k < mi; k += G)
+                        if (sm.iai[k] >= 0 && sm.s[k] < best)
+                            best = sm.s[k], bi = k;
+                }
+                // combined reduction: psi (sum) and (best, bi) (arg-min, first index wins)
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    psi += __shfl_xor_sync(0xffffffffu, psi, off);
+                    const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ov < best || (ov == best && oi < bi))
+                        best = ov, bi = oi;
+                }
+                {
+                    double* r = sm.red + flip * 16;
+                    flip ^= 1;
+                    if (lane == 0) {
+                        r[3 * warp] = psi;
+                        r[3 * warp + 1] = best;
+                        r[3 * warp + 2] = (double)bi;
+                    }
+                    __syncthreads();
+                    psi = r[0], best = r[1], bi = (int)r[2];
+                    for (int w = 1; w < G / 32; ++w) {
+                        psi += r[3 * w];
+                        const double ov = r[3 * w + 1];
+                        const int oi = (int)r[3 * w + 2];
+                        if (ov < best || (ov == best && oi < bi))
+                            best = ov, bi = oi;
+                    }
+                }
+                if (at_l1 && fabs(psi) <= mi * eps * c1 * c2 * 100.0) {
+                    status = IWBC_STATUS_OPTIMAL;
+                    break;
+                }
+                if (best >= 0.0) {
+                    status = IWBC_STATUS_OPTIMAL;
+                    break;
+                }
+                if (at_l1) { // save old values (read only by the degenerate-add path, several barriers later)
+                    for (int k = tid; k < iq; k += G) {
+                        sm.u_old[k] = sm.u[k];
+                        sm.act_old[k] = sm.act[k];
+                    }
+                    for (int k = tid; k < n; k += G)
+                        sm.x_old[k] = sm.x[k];
+                }
+                at_l1 = false;
+                need_pick = false;
+                ip = bi;
+                sip = best;
+                // np <- CI.row(ip)
+                {
+                    int b = 0;
+                    while (b + 1 < S.nci && ip >= S.ci[b + 1].off)
+                        ++b;
+                    const CiBlock& B = S.ci[b];
+                    int r = ip - B.off;
+                    const double sgn = r < B.rows ? 1.0 : -1.0;
+                    if (r >= B.rows)
+                        r -= B.rows;
+                    for (int k = tid; k < n; k += G) {
+                        double val = 0;
+                        if (B.kind == 0)
+                            val = (k == nu + r) ? 1.0 : 0.0;
+                        else if (B.kind == 1) {
+                            if (k < nv)
+                                val = sm.M[(nu + r) * z.ldM + k];
+                            else {
+                                int c = 0;
+                                for (int cc = 0; cc < ncon; ++cc)
+                                    if (S.cidx[cc] >= 0 && k - nv >= S.cidx[cc] && k - nv < S.cidx[cc] + 12)
+                                        c = cc;
+                                const int kk = k - nv - S.cidx[c];
+                                const double* T = gP->contacts[c].T;
+                                double a0 = 0;
+#pragma unroll
+                                for (int a = 0; a < 6; ++a)
+                                    a0 += T[a * 12 + kk] * sm.Jft[(c * 6 + a) * nv + nu + r];
+                                val = -a0;
+                            }
+                        }
+                        else {
+                            const int o = nv + S.cidx[B.index];
+                            if (k >= o && k < o + 12)
+                                val = gP->contacts[B.index].B[r * 12 + (k - o)];
+                        }
+                        sm.np[k] = sgn * val;
+                    }
+                }
+                if (tid == 0) {
+                    sm.u[iq] = 0.0;
+                    sm.act[iq] = ip;
+                }
+                __syncthreads();
+            }
+            // ---- l2a: d = J' n+
+            for (int j = tid; j < n; j += G) {
+                const double* col = sm.J + j * ld;
+                double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                int i = 0;
+                for (; i + 3 < n; i += 4) {
+                    s0 += col[i] * sm.np[i];
+                    s1 += col[i + 1] * sm.np[i + 1];
+                    s2 += col[i + 2] * sm.np[i + 2];
+                    s3 += col[i + 3] * sm.np[i + 3];
+                }
+                for (; i < n; ++i)
+                    s0 += col[i] * sm.np[i];
+                sm.d[j] = (s0 + s1) + (s2 + s3);
+            }
+            __syncthreads();
+            // ---- last warp: r = R^-1 d on the inequality part, ratio test;  everybody: z = J2 d2
+            const int m = iq - me;
+            if (warp == lastw) {
+                double t1 = inf;
+                int l = 0;
+                if (m > 0 && m <= 32) {
+                    const int i = me + lane;
+                    double acc = lane < m ? sm.d[i] : 0.0;
+                    const double invd = lane < m ? 1.0 / sm.R[Ridx(i, i)] : 0.0;
+                    double ri = 0.0;
+                    for (int jj = m - 1; jj >= 0; --jj) {
+                        const double cand = acc * invd;
+                        const double rj = __shfl_sync(0xffffffffu, cand, jj);
+                        if (lane == jj)
+                            ri = rj;
+                        else if (lane < jj)
+                            acc -= sm.R[Ridx(i, me + jj)] * rj;
+                    }
+                    double ratio = inf;
+                    int li = 0x7fffffff;
+                    if (lane < m) {
+                        sm.r[i] = ri;
+                        if (ri > 0.0) {
+                            ratio = sm.u[i] / ri;
+                            li = lane;
+                        }
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        const double ov = __shfl_xor_sync(0xffffffffu, ratio, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, li, off);
+                        if (ov < ratio || (ov == ratio && oi < li))
+                            ratio = ov, li = oi;
+                    }
+                    if (ratio < inf) {
+                        t1 = ratio;
+                        l = sm.act[me + li];
+                    }
+                }
+                else if (m > 32) {
+                    if (lane == 0) {
+                        update_r_tail(sm, me, iq);
+                        for (int k = me; k < iq; ++k) {
+                            const double rk = sm.r[k];
+                            if (rk > 0.0) {
+                                const double tmp = sm.u[k] / rk;
+                                if (tmp < t1) {
+                                    t1 = tmp;
+                                    l = sm.act[k];
+                                }
+                            }
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    sm.gs[n] = t1;
+                    sm.gx[n] = (double)l;
+                }
+            }
+            double t[2] = {0, 0};
+            for (int i = tid; i < n; i += G) {
+                double s0 = 0, s1 = 0;
+                int j = iq;
+                for (; j + 1 < n; j += 2) {
+                    s0 += sm.J[i + j * ld] * sm.d[j];
+                    s1 += sm.J[i + (j + 1) * ld] * sm.d[j + 1];
+                }
+                if (j < n)
+                    s0 += sm.J[i + j * ld] * sm.d[j];
+                const double zi = s0 + s1;
+                sm.z[i] = zi;
+                t[0] += zi * zi;
+                t[1] += zi * sm.np[i];
+            }
+            gsum<G, 2>(t, sm.red, flip); // (its barrier also publishes r, t1, l)
+            const double t1 = sm.gs[n];
+            const int l = (int)sm.gx[n];
+            const double t2 = fabs(t[0]) > eps ? -sip / t[1] : inf;
+            const double tt = fmin(t1, t2);
+            if (tt >= inf) {
+                status = IWBC_STATUS_INFEASIBLE; // eiquadprog UNBOUNDED (dual) = primal infeasible
+                break;
+            }
+            if (t2 >= inf) {
+                // step in dual space only, drop l
+                for (int k = me + tid; k < iq; k += G)
+                    sm.u[k] -= tt * sm.r[k];
+                if (tid == 0) {
+                    sm.u[iq] += tt;
+                    sm.iai[l] = l;
+                }
+                __syncthreads();
+                delete_constraint<G>(sm, n, ld, me, iq, l, tid);
+                continue; // l2a
+            }
+            // step in primal and dual space
+            for (int k = tid; k < n; k += G)
+                sm.x[k] += tt * sm.z[k];
+            for (int k = me + tid; k < iq; k += G)
+                sm.u[k] -= tt * sm.r[k];
+            if (tid == 0)
+                sm.u[iq] += tt;
+            if (tt == t2) {
+                // ---- full step: add ip.  Rotation coefficients (no dependence on the x / u updates above) ...
+                for (int j = iq + 1 + tid; j < n; j += G) {
+                    double acc = 0;
+                    for (int k = n - 1; k >= j; --k)
+                        acc += sm.d[k] * sm.d[k];
+                    const double hj1 = sqrt(acc);
+                    const double ssv = (j == n - 1) ? sm.d[j] : (sm.d[j] < 0.0 ? -hj1 : hj1);
+                    const double ccv = sm.d[j - 1];
+                    const double h = sqrt(acc + ccv * ccv);
+                    double cc = 1.0, ss = 0.0, xny = -2.0; // -2: h == 0, identity
+                    if (h != 0.0) {
+                        cc = ccv / h;
+                        ss = ssv / h;
+                        if (cc < 0.0) {
+                            cc = -cc;
+                            ss = -ss;
+                        }
+                        xny = ss / (1.0 + cc);
+                    }
+                    sm.gc[j] = cc;
+                    sm.gs[j] = ss;
+                    sm.gx[j] = xny;
+                    if (j == iq + 1) // what the sequential sweep leaves in d[iq]: the signed norm of d[iq..n-1]
+                        sm.gc[n] = (acc + ccv * ccv) == 0.0 ? ccv : (ccv < 0.0 ? -h : h);
+                }
+                if (iq + 1 > n - 1 && tid == 0)
+                    sm.gc[n] = sm.d[iq];
+                __syncthreads();
+                // ... then the row rotations of J, with the new column of R, iai and the next pass's wrenches riding along
+                const double diq = sm.gc[n];
+                for (int i = tid; i < n; i += G) {
+                    double* row = sm.J + i;
+                    double t2r = row[(n - 1) * ld];
+                    for (int j = n - 1; j >= iq + 1; --j) {
+                        const double t1r = row[(j - 1) * ld];
+                        const double xny = sm.gx[j];
+                        if (xny == -2.0) {
+                            row[j * ld] = t2r;
+                            t2r = t1r;
+                            continue;
+                        }
+                        const double cc = sm.gc[j], ss = sm.gs[j];
+                        const double nj1 = t1r * cc + t2r * ss;
+                        row[j * ld] = xny * (t1r + nj1) - t2r;
+                        t2r = nj1;
+                    }
+                    row[iq * ld] = t2r;
+                }
+                for (int i = G - 1 - tid; i <= iq; i += G) // (from the top thread down: those are idle in the rotations)
+                    sm.R[Ridx(i, iq)] = (i == iq) ? diq : sm.d[i];
+                wrenches_by(n < G - 6 * ncon ? n : 0);
+                if (tid == G - 1)
+                    sm.iai[ip] = -1;
+                iq++;
+                __syncthreads();
+                if (fabs(diq) <= eps * R_norm) {
+                    // degenerate: exclude ip, restore and pick another constraint
+                    delete_constraint<G>(sm, n, ld, me, iq, ip, tid);
+                    for (int k = tid; k < mi; k += G)
+                        if (sm.iai[k] != -2)
+                            sm.iai[k] = k;
+                    __syncthreads();
+                    if (tid == 0)
+                        sm.iai[ip] = -2; // iaexcl(ip) = 0
+                    for (int k = tid; k < iq; k += G) {
+                        sm.act[k] = sm.act_old[k];
+                        sm.u[k] = sm.u_old[k];
+                    }
+                    __syncthreads();
+                    for (int k = me + tid; k < iq; k += G)
+                        sm.iai[sm.act[k]] = -1;
+                    for (int k = tid; k < n; k += G)
+                        sm.x[k] = sm.x_old[k];
+                    __syncthreads();
+                    need_pick = true;
+                    continue;
+                }
+                R_norm = fmax(R_norm, fabs(diq));
+                at_l1 = true;
+                continue;
+            }
+            // ---- partial step: drop constraint l, update s(ip), back to l2a
+            if (tid == 0)
+                sm.iai[l] = l;
+            __syncthreads();
+            delete_constraint<G>(sm, n, ld, me, iq, l, tid);
+            {
+                double tv[1] = {0};
+                for (int k = tid; k < n; k += G)
+                    tv[0] += sm.np[k] * sm.x[k];
+                gsum<G, 1>(tv, sm.red, flip);
+                sip = tv[0] + FusedRows::ci0_of(gP, sm, z, ip);
+                if (tid == 0)
+                    sm.s[ip] = sip;
+                __syncthreads();
+            }
+        }
+        iter_out = iter;
+        iq_out = iq;
+        return status;
+    }
+
     // =================================================================================== k_dec
     // decode (controller.cpp:250-260) + integrate (:254-256) + command repack (:263-282) + result stores.
     // Scratch: sm.d (v+), sm.x_old (q+).  taut: precomputed M_a dv - J_a' f (or nullptr: evaluated here).

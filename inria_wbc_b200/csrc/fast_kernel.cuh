@@ -1523,124 +1523,205 @@ namespace dev {
             k_dec<T>(gP, sm, z, io, inst, tid, IWBC_STATUS_INFEASIBLE, 0, 0, nullptr);
             return;
         }
-        // ---- J = L^-T Q = U - (U V)(T V'),  U = L^-T (block diagonal: dv block from L, constant force blocks)
-        // (1) U into J: thread j builds row j of U (= column j of L^-1) by forward substitution; everything else is zero
-        for (int e = tid; e < n * ldJ; e += T)
-            sm.J[e] = 0.0;
-        fsync<T>();
-        for (int j = tid; j < n; j += T) {
-            if (j < nv) {
-                double* Uj = sm.J + j; // U[j][i] = Uj[i * ldJ]
-                Uj[j * ldJ] = il[j];
-                for (int i = j + 1; i < nv; ++i) {
-                    const double* Li = Hs + i; // L[i][k] = Li[k * ld]
-                    double s0 = 0, s1 = 0;
-                    int k = j;
-                    for (; k + 1 < i; k += 2) {
-                        s0 += Li[k * ld] * Uj[k * ldJ];
-                        s1 += Li[(k + 1) * ld] * Uj[(k + 1) * ldJ];
-                    }
-                    if (k < i)
-                        s0 += Li[k * ld] * Uj[k * ldJ];
-                    Uj[i * ldJ] = -(s0 + s1) * il[i];
-                }
-            }
-            else {
-                const int ii = j - nv, sidx = ii / 12, i2 = ii - 12 * sidx;
-                const double* U = gF->Uff[sidx] + i2 * 12;
-                for (int j2 = i2; j2 < 12; ++j2)
-                    sm.J[j + (nv + 12 * sidx + j2) * ldJ] = U[j2];
-            }
-        }
-        fsync<T>();
-        // (2) W = U_vv V_v (nv x me) into the top block of the augmented matrix (L is dead): W[i][k] -> Hs[i + k ld]
-        for (int e = tid; e < nv * me; e += T) {
-            const int k = e / nv, i = e - k * nv;
-            double val;
-            {
-                const double* Ui = sm.J + i;
-                const double* colk = Hs + (nv + k);
-                double d0 = 0, d1 = 0;
-                int j = i > k + 1 ? i : k + 1;
-                for (; j + 1 < nv; j += 2) {
-                    d0 += Ui[j * ldJ] * colk[j * ld];
-                    d1 += Ui[(j + 1) * ldJ] * colk[(j + 1) * ld];
-                }
-                if (j < nv)
-                    d0 += Ui[j * ldJ] * colk[j * ld];
-                val = (i <= k ? Ui[k * ldJ] : 0.0) + scalev[k] * (d0 + d1);
-                Hs[i + k * ld] = val;
-            }
-        }
-        fsync<T>();
-        // (3) one column per thread: x_c = T V[c, :]' (back-substitution on T^-1 = striu(V'V) + diag(1/tau)), J[:, c] -= W x_c
-        for (int c = tid; c < n; c += T) {
-            double* col = sm.J + c * ldJ;
-            constexpr int MEC = ME_ > 0 ? ME_ : IWBC_FMAXME; // compile-time bound: zq stays in registers
-            double zq[MEC];
+        if constexpr (NV_ > 0 && ME_ > 0) {
+            // ---- J = L^-T Q, one column per thread, register-resident.  Column c of Q = I - V T V' is e_c - V x_c with
+            // x_c = T V[c, :]' (back-substitution on T^-1 = striu(V'V) + diag(1/tau)); its dv rows are then pushed through
+            // L^-T by a right-looking back-substitution whose running right-hand side (NV_ doubles) never leaves registers.
+            // Every L / reflector operand is warp-uniform (a broadcast shared-memory load), so the phase is FP64-issue bound
+            // instead of waiting on the longest of NV_ unequal forward substitutions.
+            for (int c = tid; c < n; c += T) {
+                double* col = sm.J + c * ldJ;
+                double zq[ME_];
 #pragma unroll
-            for (int i = MEC - 1; i >= 0; --i) {
-                if (i >= me) {
-                    zq[i] = 0.0;
-                    continue;
+                for (int i = ME_ - 1; i >= 0; --i) {
+                    double y;
+                    if (c < NV_)
+                        y = (c == i) ? 1.0 : (c > i ? scalev[i] * Hs[(NV_ + i) + c * ld] : 0.0);
+                    else
+                        y = i >= cb0 ? scalev[i] * Bf[(c - NV_) * nfc + (i - cb0)] : 0.0;
+#pragma unroll
+                    for (int k = i + 1; k < ME_; ++k)
+                        y -= Gm[i * (ME_ + 1) + k] * zq[k];
+                    zq[i] = y * tauv[i];
                 }
-                double y;
-                if (c < nv)
-                    y = (c == i) ? 1.0 : (c > i ? scalev[i] * Hs[(nv + i) + c * ld] : 0.0);
-                else
-                    y = i >= cb0 ? scalev[i] * Bf[(c - nv) * nfc + (i - cb0)] : 0.0;
+                double r[NV_];
 #pragma unroll
-                for (int k = i + 1; k < MEC; ++k)
-                    if (k < me)
-                        y -= Gm[i * (me + 1) + k] * zq[k];
-                zq[i] = y * tauv[i];
-            }
-            for (int i = 0; i < nv; i += 2) {
-                const double* w0 = Hs + i;
-                double a0 = 0, a1 = 0;
-                if (i + 1 < nv) {
+                for (int j = 0; j < NV_; ++j)
+                    r[j] = (j == c ? 1.0 : 0.0) - (j < ME_ ? zq[j] : 0.0); // unit diagonal of V
 #pragma unroll
-                    for (int k = 0; k < MEC; ++k)
-                        if (k < me) {
-                            a0 += w0[k * ld] * zq[k];
-                            a1 += w0[k * ld + 1] * zq[k];
+                for (int k = 0; k < ME_; ++k)
+                    zq[k] *= scalev[k];
+                // strictly-lower part of V_v: V[j][k] = scalev[k] * Hs[(NV_ + k) + j ld], k < min(j, ME_)
+#pragma unroll
+                for (int j = 1; j < NV_; ++j) {
+                    const double* vj = Hs + NV_ + j * ld;
+                    double a0 = 0, a1 = 0;
+#pragma unroll
+                    for (int k = 0; k < ME_; ++k)
+                        if (k < j) {
+                            if (k & 1)
+                                a1 += vj[k] * zq[k];
+                            else
+                                a0 += vj[k] * zq[k];
                         }
-                    col[i] -= a0;
-                    col[i + 1] -= a1;
+                    r[j] -= a0 + a1;
+                }
+                // force rows: Q_f[:, c] first (O(1) entries, no cancellation against the 1e4-sized constant factor), then U_ff Q_f
+                for (int sidx = 0; sidx < (ME_ - 6) / 6; ++sidx) {
+                    double qf[12];
+#pragma unroll
+                    for (int j2 = 0; j2 < 12; ++j2) {
+                        const int jj = 12 * sidx + j2;
+                        const double* row = Bf + jj * nfc;
+                        double a0 = (NV_ + jj == c) ? 1.0 : 0.0;
+#pragma unroll
+                        for (int k = ME_ - 6; k < ME_; ++k)
+                            a0 -= row[k - (ME_ - 6)] * zq[k];
+                        qf[j2] = a0;
+                    }
+#pragma unroll
+                    for (int i2 = 0; i2 < 12; ++i2) {
+                        const double* U = gF->Uff[sidx] + i2 * 12;
+                        double a0 = 0;
+#pragma unroll
+                        for (int j2 = 0; j2 < 12; ++j2)
+                            if (j2 >= i2)
+                                a0 += U[j2] * qf[j2];
+                        col[NV_ + 12 * sidx + i2] = a0;
+                    }
+                }
+                // y = L^-T r (right-looking): y_i = r_i / L_ii, then r_k -= L[i][k] y_i for k < i
+#pragma unroll
+                for (int i = NV_ - 1; i >= 0; --i) {
+                    const double yi = r[i] * il[i];
+                    col[i] = yi;
+                    const double* Li = Hs + i; // L[i][k] = Li[k ld]
+#pragma unroll
+                    for (int k = 0; k < i; ++k)
+                        r[k] -= Li[k * ld] * yi;
+                }
+            }
+        }
+        else {
+            // ---- J = L^-T Q = U - (U V)(T V'),  U = L^-T (block diagonal: dv block from L, constant force blocks)
+            // (1) U into J: thread j builds row j of U (= column j of L^-1) by forward substitution; everything else is zero
+            for (int e = tid; e < n * ldJ; e += T)
+                sm.J[e] = 0.0;
+            fsync<T>();
+            for (int j = tid; j < n; j += T) {
+                if (j < nv) {
+                    double* Uj = sm.J + j; // U[j][i] = Uj[i * ldJ]
+                    Uj[j * ldJ] = il[j];
+                    for (int i = j + 1; i < nv; ++i) {
+                        const double* Li = Hs + i; // L[i][k] = Li[k * ld]
+                        double s0 = 0, s1 = 0;
+                        int k = j;
+                        for (; k + 1 < i; k += 2) {
+                            s0 += Li[k * ld] * Uj[k * ldJ];
+                            s1 += Li[(k + 1) * ld] * Uj[(k + 1) * ldJ];
+                        }
+                        if (k < i)
+                            s0 += Li[k * ld] * Uj[k * ldJ];
+                        Uj[i * ldJ] = -(s0 + s1) * il[i];
+                    }
                 }
                 else {
-#pragma unroll
-                    for (int k = 0; k < MEC; ++k)
-                        if (k < me)
-                            a0 += w0[k * ld] * zq[k];
-                    col[i] -= a0;
+                    const int ii = j - nv, sidx = ii / 12, i2 = ii - 12 * sidx;
+                    const double* U = gF->Uff[sidx] + i2 * 12;
+                    for (int j2 = i2; j2 < 12; ++j2)
+                        sm.J[j + (nv + 12 * sidx + j2) * ldJ] = U[j2];
                 }
             }
-            // force rows: Q_f[:, c] first (O(1) entries, no cancellation against the 1e4-sized constant factor), then U_ff Q_f.
-            // (U_ff e_c - (U_ff V_f) x_c loses the null-space-of-T force components, whose Hessian eigenvalue is the 1e-8
-            // regularisation.)
-            for (int sidx = 0; sidx < F.nca; ++sidx) {
-                double qf[12];
-#pragma unroll
-                for (int j2 = 0; j2 < 12; ++j2) {
-                    const int jj = 12 * sidx + j2;
-                    const double* row = Bf + jj * nfc;
-                    double a0 = (nv + jj == c) ? 1.0 : 0.0;
-#pragma unroll
-                    for (int k = 0; k < MEC; ++k)
-                        if (k >= cb0 && k < me)
-                            a0 -= row[k - cb0] * (zq[k] * scalev[k]);
-                    qf[j2] = a0;
+            fsync<T>();
+            // (2) W = U_vv V_v (nv x me) into the top block of the augmented matrix (L is dead): W[i][k] -> Hs[i + k ld]
+            for (int e = tid; e < nv * me; e += T) {
+                const int k = e / nv, i = e - k * nv;
+                double val;
+                {
+                    const double* Ui = sm.J + i;
+                    const double* colk = Hs + (nv + k);
+                    double d0 = 0, d1 = 0;
+                    int j = i > k + 1 ? i : k + 1;
+                    for (; j + 1 < nv; j += 2) {
+                        d0 += Ui[j * ldJ] * colk[j * ld];
+                        d1 += Ui[(j + 1) * ldJ] * colk[(j + 1) * ld];
+                    }
+                    if (j < nv)
+                        d0 += Ui[j * ldJ] * colk[j * ld];
+                    val = (i <= k ? Ui[k * ldJ] : 0.0) + scalev[k] * (d0 + d1);
+                    Hs[i + k * ld] = val;
                 }
-#pragma unroll
-                for (int i2 = 0; i2 < 12; ++i2) {
-                    const double* U = gF->Uff[sidx] + i2 * 12;
-                    double a0 = 0;
-#pragma unroll
-                    for (int j2 = 0; j2 < 12; ++j2)
-                        if (j2 >= i2)
-                            a0 += U[j2] * qf[j2];
-                    col[nv + 12 * sidx + i2] = a0;
+            }
+            fsync<T>();
+            // (3) one column per thread: x_c = T V[c, :]' (back-substitution on T^-1 = striu(V'V) + diag(1/tau)), J[:, c] -= W x_c
+            for (int c = tid; c < n; c += T) {
+                double* col = sm.J + c * ldJ;
+                constexpr int MEC = ME_ > 0 ? ME_ : IWBC_FMAXME; // compile-time bound: zq stays in registers
+                double zq[MEC];
+    #pragma unroll
+                for (int i = MEC - 1; i >= 0; --i) {
+                    if (i >= me) {
+                        zq[i] = 0.0;
+                        continue;
+                    }
+                    double y;
+                    if (c < nv)
+                        y = (c == i) ? 1.0 : (c > i ? scalev[i] * Hs[(nv + i) + c * ld] : 0.0);
+                    else
+                        y = i >= cb0 ? scalev[i] * Bf[(c - nv) * nfc + (i - cb0)] : 0.0;
+    #pragma unroll
+                    for (int k = i + 1; k < MEC; ++k)
+                        if (k < me)
+                            y -= Gm[i * (me + 1) + k] * zq[k];
+                    zq[i] = y * tauv[i];
+                }
+                for (int i = 0; i < nv; i += 2) {
+                    const double* w0 = Hs + i;
+                    double a0 = 0, a1 = 0;
+                    if (i + 1 < nv) {
+    #pragma unroll
+                        for (int k = 0; k < MEC; ++k)
+                            if (k < me) {
+                                a0 += w0[k * ld] * zq[k];
+                                a1 += w0[k * ld + 1] * zq[k];
+                            }
+                        col[i] -= a0;
+                        col[i + 1] -= a1;
+                    }
+                    else {
+    #pragma unroll
+                        for (int k = 0; k < MEC; ++k)
+                            if (k < me)
+                                a0 += w0[k * ld] * zq[k];
+                        col[i] -= a0;
+                    }
+                }
+                // force rows: Q_f[:, c] first (O(1) entries, no cancellation against the 1e4-sized constant factor), then U_ff Q_f.
+                // (U_ff e_c - (U_ff V_f) x_c loses the null-space-of-T force components, whose Hessian eigenvalue is the 1e-8
+                // regularisation.)
+                for (int sidx = 0; sidx < F.nca; ++sidx) {
+                    double qf[12];
+    #pragma unroll
+                    for (int j2 = 0; j2 < 12; ++j2) {
+                        const int jj = 12 * sidx + j2;
+                        const double* row = Bf + jj * nfc;
+                        double a0 = (nv + jj == c) ? 1.0 : 0.0;
+    #pragma unroll
+                        for (int k = 0; k < MEC; ++k)
+                            if (k >= cb0 && k < me)
+                                a0 -= row[k - cb0] * (zq[k] * scalev[k]);
+                        qf[j2] = a0;
+                    }
+    #pragma unroll
+                    for (int i2 = 0; i2 < 12; ++i2) {
+                        const double* U = gF->Uff[sidx] + i2 * 12;
+                        double a0 = 0;
+    #pragma unroll
+                        for (int j2 = 0; j2 < 12; ++j2)
+                            if (j2 >= i2)
+                                a0 += U[j2] * qf[j2];
+                        col[nv + 12 * sidx + i2] = a0;
+                    }
                 }
             }
         }
@@ -1665,7 +1746,11 @@ namespace dev {
         if (cyc && tid == 0)
             cyc[2] = clock64();
         int iters = 0, iq = me;
-        const int status = gi_loop<T, FusedRows>(gP, sm, z, (const FusedRows*)nullptr, me, S.mi, tid, flip, iters, iq, c1, c2, R_norm);
+        int status;
+        if constexpr (T >= 64)
+            status = gi_loop_cta<T>(gP, sm, z, me, S.mi, tid, flip, iters, iq, c1, c2, R_norm);
+        else
+            status = gi_loop<T, FusedRows>(gP, sm, z, (const FusedRows*)nullptr, me, S.mi, tid, flip, iters, iq, c1, c2, R_norm);
         if (cyc && tid == 0)
             cyc[3] = clock64();
         k_dec<T>(gP, sm, z, io, inst, tid, status, iters, iq, nullptr);

@@ -23,6 +23,7 @@
 // Deliberately *different in structure* from the CUDA path (local-frame recursive dynamics, dense
 // HQPData, dense CI, full R) so that agreement between the two is evidence, not tautology.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -36,6 +37,9 @@
 namespace {
 
 typedef std::vector<double> Vec;
+
+// instrumentation of the active-set loop (oracle_qp_stats): solves, l1 passes, step directions (l2a), dropped constraints
+std::atomic<long> g_stat[4];
 
 // ---------------------------------------------------------------------------------- small math
 struct V3 {
@@ -489,6 +493,7 @@ int solve_quadprog(const Mat& Hin, const Vec& g0, const Mat& CE, const Vec& ce0,
     int ip = 0, l = 0;
     double ss, psi, t, t1, t2;
 l1:
+    g_stat[1]++;
     w.iter++;
     if (w.iter >= max_iter)
         return QP_MAX_ITER;
@@ -528,6 +533,7 @@ l2:
     w.u[iq] = 0.0;
     w.A[iq] = ip;
 l2a:
+    g_stat[2]++;
     compute_d();
     update_z();
     update_r();
@@ -552,6 +558,7 @@ l2a:
             w.u[k] -= t * w.r[k];
         w.u[iq] += t;
         w.iai[l] = l;
+        g_stat[3]++;
         gi_delete_constraint(w, me, l);
         goto l2a;
     }
@@ -580,6 +587,7 @@ l2a:
         goto l1;
     }
     w.iai[l] = l;
+    g_stat[3]++;
     gi_delete_constraint(w, me, l);
     {
         double sum = ci0[ip];
@@ -1389,6 +1397,18 @@ void cycle(const iwbc_problem_t& P, const double* q, const double* v, const doub
 
 // ======================================================================================= C API
 extern "C" {
+
+// counters of the Goldfarb-Idnani loop since the last reset: {l1 passes, step directions, drops} (development aid)
+void oracle_qp_stats(long* out3, int reset)
+{
+    for (int k = 0; k < 3; ++k) {
+        if (out3)
+            out3[k] = g_stat[k + 1].load();
+        if (reset)
+            g_stat[k + 1] = 0;
+    }
+}
+
 
 #define ORACLE_ACTIVE_WORDS 12
 
