@@ -130,6 +130,10 @@ int iwbc_batch_debug_cycles(const iwbc_batch* b, long long* out7);
  * active-set kernel and [6] its instance count; [8..13] dyn, rows, H + Cholesky, QR + solve, termination test, decode of
  * the fast kernel and [14] the instances it finished), clears them and switches profiling on/off.  Development aid; not part of the reference surface. */
 int iwbc_batch_phase_profile(iwbc_batch* b, int enable, unsigned long long* out16);
+/* phases of the active-set loop of the continuation kernel accumulated up to the last iwbc_batch_phase_profile call (SM cycles as
+ * seen by thread 0, barrier waits included): out8 = { pass (s, psi, pick), n+ load, d, z + r + ratio test + coefficients,
+ * step + rotations, drops, number of step directions, number of added constraints }.  Development aid. */
+int iwbc_batch_loop_profile(const iwbc_batch* b, unsigned long long* out8);
 /* launch shape of the cycle kernel for the last contact mask: threads per instance, instances per CTA, grid, dynamic smem */
 int iwbc_batch_launch_info(const iwbc_batch* b, int* G, int* ipc, int* grid, long* smem_bytes);
 

@@ -67,6 +67,7 @@ def lib():
         "iwbc_batch_debug_cycles": (ci, [vp, vp]),
         "iwbc_batch_phase_profile": (ci, [vp, ci, vp]),
         "iwbc_batch_fast_info": (ci, [vp, vp]),
+        "iwbc_batch_loop_profile": (ci, [vp, vp]),
         "iwbc_batch_launch_info": (ci, [vp, pi, pi, pi, C.POINTER(C.c_long)]),
         "iwbc_qp_solve_batch": (ci, [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "iwbc_behavior_load": (vp, [vp, cp, cp]),
@@ -329,6 +330,11 @@ class Batch:
             out["active_set"] = dict(zip(("dyn", "asm", "factor", "eq", "ineq", "decode"), (t[:6] / float(t[6])).tolist()), instances=int(t[6]))
         if t[14]:
             out["fast"] = dict(zip(("dyn", "rows", "H_chol", "qr_solve", "check", "decode"), (t[8:14] / float(t[14])).tolist()), instances=int(t[14]))
+        lp = np.zeros(8, dtype=np.uint64)
+        lib().iwbc_batch_loop_profile(self._h, lp.ctypes.data)
+        if lp[6]:
+            out["loop"] = dict(zip(("pass", "load_n", "d", "z_r_coef", "step_rotate", "drops"), (lp[:6] / float(lp[6])).tolist()),
+                               directions=int(lp[6]), adds=int(lp[7]), note="mean SM cycles per step direction")
         return out or None
 
     def fast_info(self):

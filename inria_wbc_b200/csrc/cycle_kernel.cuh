@@ -1804,8 +1804,18 @@ namespace dev {
     // memory / L1 (gP) instead of the constant bank, which would replay once per distinct address.
     template <int G>
     __device__ int gi_loop_cta(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, int me, int mi, int tid, int& flip, int& iter_out,
-        int& iq_out, double c1, double c2, double R_norm)
+        int& iq_out, double c1, double c2, double R_norm, unsigned long long* prof = nullptr)
     {
+        // development aid: SM cycles of the loop's phases as seen by thread 0 (barrier waits included), prof[0..7] =
+        // pass (s, psi, pick) | n+ load | d | z, r, ratio test, coefficients | step + rotations | drops | #directions | #adds
+        long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tc = prof ? clock64() : 0;
+#define IWBC_LOOP_TICK(slot)                 \
+    if (prof && tid == 0) {                  \
+        const long long now_ = clock64();    \
+        pc[slot] += now_ - tc;               \
+        tc = now_;                           \
+    }
         static_assert(G >= 64 && G % 32 == 0, "gi_loop_cta: the CTA is the group");
         const Shape& S = c_S;
         const int n = z.n, ld = z.ldJ, nv = z.nv, na = c_P.na, nu = nv - na, ncon = c_P.ncontacts;
@@ -1832,9 +1842,26 @@ namespace dev {
                 sm.cb[6 * ncon + e] = w;
             }
         };
+        // the wrenches follow a primal step x += t z linearly: w += t (T z_f); no barrier between the step and the next pass
+        auto wrenches_step = [&](int t0, double tstep) {
+            const int e = tid - t0;
+            if (e >= 0 && e < 6 * ncon) {
+                const int c = e / 6, a = e - 6 * c;
+                if (S.cidx[c] >= 0) {
+                    const double* T = gP->contacts[c].T + a * 12;
+                    const double* zf = sm.z + nv + S.cidx[c];
+                    double w = 0;
+#pragma unroll
+                    for (int k = 0; k < 12; ++k)
+                        w += T[k] * zf[k];
+                    sm.cb[6 * ncon + e] += tstep * w;
+                }
+            }
+        };
+        const int wt0 = n + 6 * ncon <= G ? n : 0; // wrench threads: past the rows of J when there is room
         for (int k = tid; k < mi; k += G)
             sm.iai[k] = k;
-        wrenches_by(G - 6 * ncon > 0 ? G - 6 * ncon : 0);
+        wrenches_by(wt0);
         __syncthreads();
 
         int status = IWBC_STATUS_UNKNOWN;
@@ -1926,6 +1953,7 @@ namespace dev {
                             best = ov, bi = oi;
                     }
                 }
+                IWBC_LOOP_TICK(0)
                 if (at_l1 && fabs(psi) <= mi * eps * c1 * c2 * 100.0) {
                     status = IWBC_STATUS_OPTIMAL;
                     break;
@@ -1990,6 +2018,7 @@ namespace dev {
                     sm.act[iq] = ip;
                 }
                 __syncthreads();
+                IWBC_LOOP_TICK(1)
             }
             // ---- l2a: d = J' n+
             for (int j = tid; j < n; j += G) {
@@ -2007,6 +2036,7 @@ namespace dev {
                 sm.d[j] = (s0 + s1) + (s2 + s3);
             }
             __syncthreads();
+            IWBC_LOOP_TICK(2)
             // ---- last warp: r = R^-1 d on the inequality part, ratio test;  everybody: z = J2 d2
             const int m = iq - me;
             if (warp == lastw) {
@@ -2017,6 +2047,7 @@ namespace dev {
                     double acc = lane < m ? sm.d[i] : 0.0;
                     const double invd = lane < m ? 1.0 / sm.R[Ridx(i, i)] : 0.0;
                     double ri = 0.0;
+#pragma unroll 4
                     for (int jj = m - 1; jj >= 0; --jj) {
                         const double cand = acc * invd;
                         const double rj = __shfl_sync(0xffffffffu, cand, jj);
@@ -2066,6 +2097,106 @@ namespace dev {
                     sm.gx[n] = (double)l;
                 }
             }
+            // Givens coefficients that would fold d[iq+1..n-1] into d[iq] if ip is added (speculative: a partial step discards
+            // them), by ONE warp -- the second-to-last, idle in the z rows for n <= 64: suffix sums of d_k^2 by a shuffle scan
+            // (<= 3 elements per lane), then per element  h_j^2 = S_j + d_{j-1}^2  and the "ss" operand of rotation j, which
+            // is what rotation j+1 left in d[j]: sign(d_j) sqrt(S_j).
+            if (warp == (lastw > 0 ? lastw - 1 : 0)) {
+                const int cnt = n - 1 - iq; // j = iq + 1 + e, e = 0 .. cnt-1
+                if (cnt > 0 && cnt <= 96) {
+                    const int per = (cnt + 31) >> 5, e0 = lane * per;
+                    double q[3] = {0, 0, 0};
+#pragma unroll
+                    for (int u = 0; u < 3; ++u)
+                        if (u < per && e0 + u < cnt) {
+                            const double dv = sm.d[iq + 1 + e0 + u];
+                            q[u] = dv * dv;
+                        }
+                    const double tl = (q[0] + q[1]) + q[2];
+                    double suf = tl;
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) {
+                        const double o = __shfl_down_sync(0xffffffffu, suf, off);
+                        if (lane + off < 32)
+                            suf += o;
+                    }
+                    // S_j for this lane's elements (descending), h_j = sqrt(S_j + d_{j-1}^2) by one rsqrt each; sqrt(S_j) is the
+                    // h of element j+1 (S_j = S_{j+1} + d_j^2), taken from the neighbouring element / lane instead of a second root
+                    double run = suf - tl; // sum over the lanes after this one
+                    double hv[3] = {0, 0, 0}, ihv[3] = {0, 0, 0}, hhv[3] = {0, 0, 0};
+#pragma unroll
+                    for (int u = 2; u >= 0; --u) {
+                        if (u < per && e0 + u < cnt) {
+                            run += q[u];
+                            const double ccv = sm.d[iq + e0 + u];
+                            const double hh = run + ccv * ccv;
+                            hhv[u] = hh;
+                            if (hh != 0.0) {
+                                ihv[u] = rsqrt(hh);
+                                hv[u] = hh * ihv[u];
+                            }
+                        }
+                    }
+                    const double hnext = __shfl_down_sync(0xffffffffu, hv[0], 1); // h of the first element of the next lane
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        if (!(u < per && e0 + u < cnt))
+                            continue;
+                        const int j = iq + 1 + e0 + u;
+                        const double ccv = sm.d[j - 1], dj = sm.d[j];
+                        const double sq = (u + 1 < per) ? hv[u < 2 ? u + 1 : 2] : hnext; // sqrt(S_j) = h_{j+1}  (unused for j = n-1)
+                        double cc = 1.0, ss = 0.0, xny = -2.0; // -2: h == 0, identity
+                        if (hhv[u] != 0.0) {
+                            const double ssv = (j == n - 1) ? dj : (dj < 0.0 ? -sq : sq);
+                            cc = ccv * ihv[u];
+                            ss = ssv * ihv[u];
+                            if (cc < 0.0) {
+                                cc = -cc;
+                                ss = -ss;
+                            }
+                            // 1 / (1 + cc), 1 <= 1 + cc <= 2: single-precision seed + two Newton steps (full double accuracy) instead of a division
+                            const double a = 1.0 + cc;
+                            double rcp = (double)(1.0f / (float)a);
+                            rcp = rcp * (2.0 - a * rcp);
+                            rcp = rcp * (2.0 - a * rcp);
+                            xny = ss * rcp;
+                        }
+                        sm.gc[j] = cc;
+                        sm.gs[j] = ss;
+                        sm.gx[j] = xny;
+                        if (e0 + u == 0) // what the sequential sweep leaves in d[iq]: the signed norm of d[iq..n-1]
+                            sm.gc[n] = hhv[u] == 0.0 ? ccv : (ccv < 0.0 ? -hv[u] : hv[u]);
+                    }
+                }
+                else if (cnt > 96) { // (not reached by the robots of etc/: n <= 74)
+                    for (int c = lane; c < cnt; c += 32) {
+                        const int j = iq + 1 + c;
+                        double acc = 0;
+                        for (int k = n - 1; k >= j; --k)
+                            acc += sm.d[k] * sm.d[k];
+                        const double ccv = sm.d[j - 1], dj = sm.d[j];
+                        const double hh = acc + ccv * ccv, h = sqrt(hh);
+                        double cc = 1.0, ss = 0.0, xny = -2.0;
+                        if (hh != 0.0) {
+                            const double sq = sqrt(acc);
+                            cc = ccv / h;
+                            ss = ((j == n - 1) ? dj : (dj < 0.0 ? -sq : sq)) / h;
+                            if (cc < 0.0) {
+                                cc = -cc;
+                                ss = -ss;
+                            }
+                            xny = ss / (1.0 + cc);
+                        }
+                        sm.gc[j] = cc;
+                        sm.gs[j] = ss;
+                        sm.gx[j] = xny;
+                        if (c == 0)
+                            sm.gc[n] = hh == 0.0 ? ccv : (ccv < 0.0 ? -h : h);
+                    }
+                }
+                else if (lane == 0)
+                    sm.gc[n] = sm.d[iq];
+            }
             double t[2] = {0, 0};
             for (int i = tid; i < n; i += G) {
                 double s0 = 0, s1 = 0;
@@ -2082,6 +2213,8 @@ namespace dev {
                 t[1] += zi * sm.np[i];
             }
             gsum<G, 2>(t, sm.red, flip); // (its barrier also publishes r, t1, l)
+            IWBC_LOOP_TICK(3)
+            pc[6] += 1;
             const double t1 = sm.gs[n];
             const int l = (int)sm.gx[n];
             const double t2 = fabs(t[0]) > eps ? -sip / t[1] : inf;
@@ -2100,71 +2233,57 @@ namespace dev {
                 }
                 __syncthreads();
                 delete_constraint<G>(sm, n, ld, me, iq, l, tid);
+                IWBC_LOOP_TICK(5)
                 continue; // l2a
             }
             // step in primal and dual space
             for (int k = tid; k < n; k += G)
                 sm.x[k] += tt * sm.z[k];
+            wrenches_step(wt0, tt);
             for (int k = me + tid; k < iq; k += G)
                 sm.u[k] -= tt * sm.r[k];
             if (tid == 0)
                 sm.u[iq] += tt;
             if (tt == t2) {
-                // ---- full step: add ip.  Rotation coefficients (no dependence on the x / u updates above) ...
-                for (int j = iq + 1 + tid; j < n; j += G) {
-                    double acc = 0;
-                    for (int k = n - 1; k >= j; --k)
-                        acc += sm.d[k] * sm.d[k];
-                    const double hj1 = sqrt(acc);
-                    const double ssv = (j == n - 1) ? sm.d[j] : (sm.d[j] < 0.0 ? -hj1 : hj1);
-                    const double ccv = sm.d[j - 1];
-                    const double h = sqrt(acc + ccv * ccv);
-                    double cc = 1.0, ss = 0.0, xny = -2.0; // -2: h == 0, identity
-                    if (h != 0.0) {
-                        cc = ccv / h;
-                        ss = ssv / h;
-                        if (cc < 0.0) {
-                            cc = -cc;
-                            ss = -ss;
-                        }
-                        xny = ss / (1.0 + cc);
-                    }
-                    sm.gc[j] = cc;
-                    sm.gs[j] = ss;
-                    sm.gx[j] = xny;
-                    if (j == iq + 1) // what the sequential sweep leaves in d[iq]: the signed norm of d[iq..n-1]
-                        sm.gc[n] = (acc + ccv * ccv) == 0.0 ? ccv : (ccv < 0.0 ? -h : h);
-                }
-                if (iq + 1 > n - 1 && tid == 0)
-                    sm.gc[n] = sm.d[iq];
-                __syncthreads();
-                // ... then the row rotations of J, with the new column of R, iai and the next pass's wrenches riding along
+                // ---- full step: add ip.  The rotation coefficients were computed next to z (published by the reduction's
+                // barrier): straight to the row rotations of J, with the new column of R, iai and the next pass's wrenches
+                // riding along
                 const double diq = sm.gc[n];
                 for (int i = tid; i < n; i += G) {
                     double* row = sm.J + i;
                     double t2r = row[(n - 1) * ld];
-                    for (int j = n - 1; j >= iq + 1; --j) {
-                        const double t1r = row[(j - 1) * ld];
-                        const double xny = sm.gx[j];
-                        if (xny == -2.0) {
-                            row[j * ld] = t2r;
-                            t2r = t1r;
-                            continue;
-                        }
-                        const double cc = sm.gc[j], ss = sm.gs[j];
-                        const double nj1 = t1r * cc + t2r * ss;
-                        row[j * ld] = xny * (t1r + nj1) - t2r;
+                    // Four columns per trip, every operand loaded before the first store: the compiler may not move a shared-memory
+                    // load above a store it cannot disambiguate, and behind the stores each load would wait for the FMA carry
+                    // chain of the previous column.  Branch-free; xny == -2 marks an identity rotation.
+                    auto rot = [&](int j, double t1r, double xny, double cc, double ss) {
+                        const bool idt = xny == -2.0;
+                        const double nj1 = idt ? t1r : t1r * cc + t2r * ss;
+                        row[j * ld] = idt ? t2r : xny * (t1r + nj1) - t2r;
                         t2r = nj1;
+                    };
+                    int j = n - 1;
+                    for (; j - 3 >= iq + 1; j -= 4) {
+                        const double ta = row[(j - 1) * ld], tb = row[(j - 2) * ld], tc2 = row[(j - 3) * ld], td = row[(j - 4) * ld];
+                        const double xa = sm.gx[j], xb = sm.gx[j - 1], xc = sm.gx[j - 2], xd = sm.gx[j - 3];
+                        const double ca = sm.gc[j], cb2 = sm.gc[j - 1], cc2 = sm.gc[j - 2], cd = sm.gc[j - 3];
+                        const double sa = sm.gs[j], sb = sm.gs[j - 1], sc2 = sm.gs[j - 2], sd = sm.gs[j - 3];
+                        rot(j, ta, xa, ca, sa);
+                        rot(j - 1, tb, xb, cb2, sb);
+                        rot(j - 2, tc2, xc, cc2, sc2);
+                        rot(j - 3, td, xd, cd, sd);
                     }
+                    for (; j >= iq + 1; --j)
+                        rot(j, row[(j - 1) * ld], sm.gx[j], sm.gc[j], sm.gs[j]);
                     row[iq * ld] = t2r;
                 }
                 for (int i = G - 1 - tid; i <= iq; i += G) // (from the top thread down: those are idle in the rotations)
                     sm.R[Ridx(i, iq)] = (i == iq) ? diq : sm.d[i];
-                wrenches_by(n < G - 6 * ncon ? n : 0);
                 if (tid == G - 1)
                     sm.iai[ip] = -1;
                 iq++;
                 __syncthreads();
+                IWBC_LOOP_TICK(4)
+                pc[7] += 1;
                 if (fabs(diq) <= eps * R_norm) {
                     // degenerate: exclude ip, restore and pick another constraint
                     delete_constraint<G>(sm, n, ld, me, iq, ip, tid);
@@ -2183,6 +2302,8 @@ namespace dev {
                         sm.iai[sm.act[k]] = -1;
                     for (int k = tid; k < n; k += G)
                         sm.x[k] = sm.x_old[k];
+                    __syncthreads();
+                    wrenches_by(wt0);
                     __syncthreads();
                     need_pick = true;
                     continue;
@@ -2206,7 +2327,12 @@ namespace dev {
                     sm.s[ip] = sip;
                 __syncthreads();
             }
+            IWBC_LOOP_TICK(5)
         }
+        if (prof && tid == 0)
+            for (int k = 0; k < 8; ++k)
+                atomicAdd(prof + k, (unsigned long long)pc[k]);
+#undef IWBC_LOOP_TICK
         iter_out = iter;
         iq_out = iq;
         return status;

@@ -1748,7 +1748,7 @@ namespace dev {
         int iters = 0, iq = me;
         int status;
         if constexpr (T >= 64)
-            status = gi_loop_cta<T>(gP, sm, z, me, S.mi, tid, flip, iters, iq, c1, c2, R_norm);
+            status = gi_loop_cta<T>(gP, sm, z, me, S.mi, tid, flip, iters, iq, c1, c2, R_norm, (cyc && io.prof) ? io.prof + 16 : nullptr);
         else
             status = gi_loop<T, FusedRows>(gP, sm, z, (const FusedRows*)nullptr, me, S.mi, tid, flip, iters, iq, c1, c2, R_norm);
         if (cyc && tid == 0)

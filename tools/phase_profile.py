@@ -25,6 +25,7 @@ for _ in range(3):
 prof = bt.phase_profile(False)
 ms = bt.kernel_ms(True)
 out = {"workload": wl, "batch": B, "launch": bt.launch_info(), "fast": bt.fast_info(), "kernel_ms": ms, "mean_cycles_per_instance": prof,
-       "total_cycles": {k: sum(x for kk, x in d.items() if kk != "instances") for k, d in (prof or {}).items()},
+       "total_cycles": {k: sum(x for kk, x in d.items() if kk not in ("instances", "directions", "adds") and isinstance(x, float))
+                        for k, d in (prof or {}).items()},
        "mean_iters": float(r.iters.mean())}
 print(json.dumps(out))
