@@ -482,6 +482,17 @@ def main():
         adds = max(iters_all / (B * world) - 1.0, 0.0)
         nj, nfr, nsc = problem_counts(P)
         fl = algorithmic_flops(P.nv, P.na, n, me, mi, rows, adds, nj, nfr, nsc)
+        fl["source"] = "F_qp: SURVEY.md 8(d) reference-algorithm formula with the measured mean additions; F_dyn, F_asm: textbook estimate"
+        try:  # F_dyn / F_asm counted by the instrumented oracle (tools/count_flops.py, oracle/count_scalar.hpp)
+            counted = json.load(open(os.path.join(ROOT, "profiles", "flops_per_update.json"))).get(args.workload)
+            if counted:
+                fl["f_dyn"], fl["f_asm"] = counted["f_dyn"], counted["f_asm"]
+                fl["total"] = fl["f_qp"] + fl["f_dyn"] + fl["f_asm"]
+                fl["f_qp_executed_by_oracle"] = counted["f_qp_executed_by_oracle"]
+                fl["source"] = ("F_qp: SURVEY.md 8(d) reference-algorithm formula with the measured mean additions; F_dyn, F_asm: counted by the "
+                                "instrumented oracle (profiles/flops_per_update.json)")
+        except Exception:
+            pass
         kern_ms = float(np.mean(step_ms))
         peak = iw.measure_fp64_tflops(local)
         achieved = fl["total"] * B / (kern_ms * 1e-3) / 1e12

@@ -34,6 +34,21 @@
 
 #include "../include/iwbc_problem.h"
 
+typedef double real_t; // the problem description (iwbc_problem_t) always holds plain doubles
+
+#ifdef ORACLE_COUNT_FLOPS
+// instrumented build (make -C oracle count): every `double` below counts its own arithmetic per cycle phase (count_scalar.hpp)
+#include "count_scalar.hpp"
+namespace flopcount {
+thread_local long counts[NPH][NOP];
+thread_local int phase = 0;
+}
+#define double cdouble
+#define ORACLE_PHASE(p) (flopcount::phase = flopcount::p)
+#else
+#define ORACLE_PHASE(p) ((void)0)
+#endif
+
 namespace {
 
 typedef std::vector<double> Vec;
@@ -144,7 +159,7 @@ inline Inertia operator+(const Inertia& a, const Inertia& b)
         double dd = dot(d, d), dv[3] = {d.x, d.y, d.z};
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j)
-                o.I.m[3 * i + j] += x->I.m[3 * i + j] + x->m * ((i == j ? dd : 0.0) - dv[i] * dv[j]);
+                o.I.m[3 * i + j] += x->I.m[3 * i + j] + x->m * ((i == j ? dd : double(0.0)) - dv[i] * dv[j]);
     }
     return o;
 }
@@ -172,7 +187,7 @@ inline M3 exp3(V3 w)
 inline V3 log3(const M3& R)
 {
     double tr = R.m[0] + R.m[4] + R.m[8];
-    double c = std::min(1.0, std::max(-1.0, 0.5 * (tr - 1)));
+    double c = std::min(double(1.0), std::max(double(-1.0), 0.5 * (tr - 1)));
     double theta = std::acos(c);
     V3 v = {R.m[7] - R.m[5], R.m[2] - R.m[6], R.m[3] - R.m[1]};
     if (theta < 1.220703125e-4) // TaylorSeriesExpansion<double>::precision<3>() = eps^(1/4)
@@ -183,9 +198,9 @@ inline V3 log3(const M3& R)
         double beta = theta * theta / (1 + cphi);
         V3 t = {(R.m[0] + cphi) * beta, (R.m[4] + cphi) * beta, (R.m[8] + cphi) * beta};
         V3 r;
-        r.x = (v.x > 0 ? 1 : -1) * (t.x > 0 ? std::sqrt(t.x) : 0);
-        r.y = (v.y > 0 ? 1 : -1) * (t.y > 0 ? std::sqrt(t.y) : 0);
-        r.z = (v.z > 0 ? 1 : -1) * (t.z > 0 ? std::sqrt(t.z) : 0);
+        r.x = (v.x > 0 ? 1 : -1) * (t.x > 0 ? std::sqrt(t.x) : double(0));
+        r.y = (v.y > 0 ? 1 : -1) * (t.y > 0 ? std::sqrt(t.y) : double(0));
+        r.z = (v.z > 0 ? 1 : -1) * (t.z > 0 ? std::sqrt(t.z) : double(0));
         return r;
     }
     return (theta / (2 * std::sin(theta))) * v;
@@ -510,7 +525,7 @@ l1:
             sum += CI(i, k) * x[k];
         w.s[i] = sum;
         w.iaexcl[i] = 1;
-        psi += std::min(0.0, sum);
+        psi += std::min(double(0.0), sum);
     }
     if (std::fabs(psi) <= mi * eps * c1 * c2 * 100.0)
         return QP_OPTIMAL;
@@ -612,7 +627,8 @@ struct Dyn {
     std::vector<Force> Fcol; // per dof: Ycrb * S in the joint frame (before propagation)
 };
 
-inline SE3 load_se3(const double* p12)
+template <class Real>
+inline SE3 load_se3(const Real* p12)
 {
     SE3 X;
     for (int i = 0; i < 9; ++i)
@@ -636,7 +652,7 @@ inline Inertia joint_inertia(const iwbc_problem_t& P, int j)
     Inertia Y;
     Y.m = P.mass[j];
     Y.c = {P.com[j][0], P.com[j][1], P.com[j][2]};
-    const double* I = P.inertia[j];
+    const real_t* I = P.inertia[j];
     Y.I = {{I[0], I[1], I[2], I[1], I[3], I[4], I[2], I[4], I[5]}};
     return Y;
 }
@@ -882,7 +898,7 @@ void frame_kinematics(const iwbc_problem_t& P, const Dyn& D, int frame, FrameKin
 }
 
 // TaskSE3Equality::compute, local frame (ex_task.cpp:175-247, m_local_frame = true)
-void se3_task_rows(const iwbc_problem_t& P, const Dyn& D, int frame, const double* kp, const double* kd, const double* ref,
+void se3_task_rows(const iwbc_problem_t& P, const Dyn& D, int frame, const real_t* kp, const real_t* kd, const double* ref,
     Mat& A6, double* b6)
 {
     FrameKin K;
@@ -983,7 +999,9 @@ void cycle(const iwbc_problem_t& P, const double* q, const double* v, const doub
 {
     const int nv = P.nv, na = P.na, nu = nv - na;
     Dyn& D = O.D;
+    ORACLE_PHASE(PH_DYN);
     compute_all_terms(P, q, v, D);
+    ORACLE_PHASE(PH_ASM);
 
     // active contacts and their force-column offsets
     int cidx[IWBC_MAXC], nk = 0;
@@ -1107,6 +1125,7 @@ void cycle(const iwbc_problem_t& P, const double* q, const double* v, const doub
     Mat H(n, n);
     Vec g(n, 0.0);
     auto add_cost = [&](double w, const Mat& A, const double* b, int rows) {
+        ORACLE_PHASE(PH_QP); // SolverHQuadProgFast builds H and g from the level-1 rows
         for (int r = 0; r < rows; ++r) {
             for (int i = 0; i < n; ++i) {
                 double ai = A(r, i);
@@ -1117,6 +1136,7 @@ void cycle(const iwbc_problem_t& P, const double* q, const double* v, const doub
                 g[i] -= w * ai * b[r];
             }
         }
+        ORACLE_PHASE(PH_ASM);
     };
     for (int bl = 0; bl < P.nl1; ++bl) {
         const iwbc_block_t& B = P.l1[bl];
@@ -1266,6 +1286,7 @@ void cycle(const iwbc_problem_t& P, const double* q, const double* v, const doub
         H(i, i) += P.hess_reg;
 
     // ---- solve
+    ORACLE_PHASE(PH_QP);
     QPWork w;
     Vec x;
     int st = solve_quadprog(H, g, CE, ce0, CI, ci0, x, w);
@@ -1286,6 +1307,7 @@ void cycle(const iwbc_problem_t& P, const double* q, const double* v, const doub
         O.active.push_back(w.A[i]);
 
     // ---- decode (controller.cpp:250-260) and integrate (:254-256)
+    ORACLE_PHASE(PH_DEC);
     O.dv.assign(x.begin(), x.begin() + nv);
     O.f.assign(12 * P.ncontacts, 0.0);
     for (int c = 0; c < P.ncontacts; ++c)
@@ -1397,6 +1419,27 @@ void cycle(const iwbc_problem_t& P, const double* q, const double* v, const doub
 
 // ======================================================================================= C API
 extern "C" {
+
+// ORACLE_COUNT_FLOPS build only: operation counts of the calling thread since the last reset, out[phase][op] with phases
+// {other, dynamics, assembly, qp, decode} and ops {add/sub, mul, div, sqrt/trig/exp}; returns 0, or -1 in the plain build
+int oracle_flop_counts(long* out20, int reset)
+{
+#ifdef ORACLE_COUNT_FLOPS
+    for (int p = 0; p < flopcount::NPH; ++p)
+        for (int o = 0; o < flopcount::NOP; ++o) {
+            if (out20)
+                out20[p * flopcount::NOP + o] = flopcount::counts[p][o];
+            if (reset)
+                flopcount::counts[p][o] = 0;
+        }
+    flopcount::phase = 0;
+    return 0;
+#else
+    (void)out20;
+    (void)reset;
+    return -1;
+#endif
+}
 
 // counters of the Goldfarb-Idnani loop since the last reset: {l1 passes, step directions, drops} (development aid)
 void oracle_qp_stats(long* out3, int reset)
