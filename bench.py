@@ -124,13 +124,16 @@ def make_walk_workload(P, bt, B, seed, device, ncycles=2, stride=20):
     snap_q = torch.empty(nsnap, P.nq, dtype=torch.float64, device=dev)
     snap_v = torch.empty(nsnap, P.nv, dtype=torch.float64, device=dev)
     worst = torch.zeros(1, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    for k in range(nsnap):
-        snap_q[k].copy_(q1[0])
-        snap_v[k].copy_(v1[0])
-        bt.behavior_rollout_device(beh, 1, q1.data_ptr(), v1.data_ptr(), r1.data_ptr(), None, k * stride, stride, init_refs=(k == 0),
-                                   out_ptrs={"status": st.data_ptr()}, stream=stream)
-        worst = torch.maximum(worst, st.abs())
+    ts = torch.cuda.Stream(device=dev)  # an explicit stream (handle 0 means "the batch's own stream" to the C ABI): copies and ticks stay ordered
+    stream = ts.cuda_stream
+    torch.cuda.synchronize()
+    with torch.cuda.stream(ts):
+        for k in range(nsnap):
+            snap_q[k].copy_(q1[0])
+            snap_v[k].copy_(v1[0])
+            bt.behavior_rollout_device(beh, 1, q1.data_ptr(), v1.data_ptr(), r1.data_ptr(), None, k * stride, stride, init_refs=(k == 0),
+                                       out_ptrs={"status": st.data_ptr()}, stream=stream)
+            worst = torch.maximum(worst, st.abs())
     torch.cuda.synchronize()
     if int(worst[0]) != 0:
         raise SystemExit("bench.py: the seed walk left the OPTIMAL status (%d)" % int(worst[0]))

@@ -156,7 +156,8 @@ int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, c
  * (e.g. src/behaviors/humanoid/walk.cpp:198-246): the behaviour's waypoint tables
  * (include/inria_wbc/trajs/trajectory_generator.hpp:29-160) are compiled into a segment table that
  * the GPU evaluates in closed form for every (instance, tick).  BEHAVIOR.name selects the
- * behaviour ("humanoid::walk"); overrides_yaml: optional YAML text of BEHAVIOR keys to override.
+ * behaviour: "humanoid::walk" (src/behaviors/humanoid/walk.cpp), "generic::cartesian"
+ * (src/behaviors/generic/cartesian.cpp:8-94), "humanoid::move_com" (src/behaviors/humanoid/move_com.cpp:8-61); overrides_yaml: optional YAML text of BEHAVIOR keys to override.
  */
 typedef struct iwbc_behavior iwbc_behavior;
 iwbc_behavior* iwbc_behavior_load(const iwbc_problem* p, const char* behavior_yaml, const char* overrides_yaml);

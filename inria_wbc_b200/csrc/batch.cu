@@ -566,9 +566,27 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
         CUDA_TRY(cudaEventRecord(b->ev_const, st));
         CUDA_TRY(cudaStreamWaitEvent(b->aux[0], b->ev_const, 0));
         CUDA_TRY(cudaStreamWaitEvent(b->aux[1], b->ev_const, 0));
-        const int nchunk = 4;
+        // Chunk plan: sizes are multiples of the persistent grid's instance capacity (no partially filled last round), a short
+        // first chunk (its upload is the pipeline's fill: nothing overlaps it) and whatever is left at the end (its download
+        // is the drain).
+        const int unit = b->fast_ok && b->fast_grid > 0 ? b->fast_grid : (b->grid > 0 ? b->grid * b->IPC : 4 * b->sm_count);
+        std::vector<int> bounds;
+        bounds.push_back(0);
+        {
+            int u_first = 2, u_mid = 9; // (IWBC_PIPE="first,mid" in units of the grid capacity: tuning aid)
+            if (const char* e = std::getenv("IWBC_PIPE"))
+                std::sscanf(e, "%d,%d", &u_first, &u_mid);
+            int first = std::min(B, std::max(1, u_first) * unit);
+            bounds.push_back(first);
+            while (bounds.back() < B && bounds.size() < 15)
+                bounds.push_back(std::min(B, bounds.back() + std::max(1, u_mid) * unit));
+            if (bounds.back() < B)
+                bounds.push_back(B);
+        }
+        const int nchunk = (int)bounds.size() - 1;
+        const int cap = std::min(b->max_batch, 65536);
         for (int c = 0; c < nchunk; ++c) {
-            const size_t first = (size_t)B * c / nchunk, last = (size_t)B * (c + 1) / nchunk, cnt = last - first;
+            const size_t first = bounds[c], last = bounds[c + 1], cnt = last - first;
             cudaStream_t cs = b->aux[c & 1];
             CUDA_TRY(cudaMemcpyAsync(b->d_q + first * nq, q + first * nq, cnt * nq * 8, cudaMemcpyHostToDevice, cs));
             CUDA_TRY(cudaMemcpyAsync(b->d_v + first * nv, v + first * nv, cnt * nv * 8, cudaMemcpyHostToDevice, cs));
@@ -577,10 +595,16 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
             else if (c < 2) // shared reference vector: each stream uploads it once (into the same place, same bytes)
                 CUDA_TRY(cudaMemcpyAsync(b->d_refs, refs, nref * 8, cudaMemcpyHostToDevice, cs));
             iwbc_results_t r = dev_results(first);
-            b->slot = c;
+            b->slot = c & 7; // chunks c and c + 8 share a counter: same stream, ordered
             b->list_off = (int)first;
-            b->scratch_len = std::min(b->max_batch, 65536) / nchunk;
-            b->scratch_off = c * b->scratch_len;
+            if (B <= cap) { // hand-over images: the chunk's own range of the scratch
+                b->scratch_off = (int)first;
+                b->scratch_len = (int)cnt;
+            }
+            else {
+                b->scratch_len = cap / nchunk;
+                b->scratch_off = c * b->scratch_len;
+            }
             rc = iwbc_batch_update_device(b, (int)cnt, b->d_q + first * nq, b->d_v + first * nv, b->d_refs + (refs_stride ? first * nref : 0), refs_stride,
                 m, &r, cs);
             b->slot = 0;

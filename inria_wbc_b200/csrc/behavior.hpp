@@ -235,6 +235,186 @@ namespace host {
         bb.finish();
     }
 
+    namespace detail {
+        struct Rot3 {
+            double m[9]; // row-major
+        };
+        inline Rot3 rmul(const Rot3& a, const Rot3& b)
+        {
+            Rot3 c;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j)
+                    c.m[3 * i + j] = a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j] + a.m[3 * i + 2] * b.m[6 + j];
+            return c;
+        }
+        inline Rot3 rtrans(const Rot3& a)
+        {
+            Rot3 t;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j)
+                    t.m[3 * i + j] = a.m[3 * j + i];
+            return t;
+        }
+        inline Rot3 raxis(int axis, double th)
+        {
+            const double c = std::cos(th), s2 = std::sin(th);
+            Rot3 r = {{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+            const int a = (axis + 1) % 3, b = (axis + 2) % 3;
+            r.m[3 * a + a] = c, r.m[3 * a + b] = -s2, r.m[3 * b + a] = s2, r.m[3 * b + b] = c;
+            return r;
+        }
+        // Eigen::AngleAxisd(R): through the quaternion (Eigen's Quaternion(Matrix3) then AngleAxis(Quaternion)), angle in [0, pi]
+        inline void angle_axis(const Rot3& R, double& angle, double axis[3])
+        {
+            double w, q[3];
+            const double tr = R.m[0] + R.m[4] + R.m[8];
+            if (tr > 0) {
+                double t = std::sqrt(tr + 1.0);
+                w = 0.5 * t;
+                t = 0.5 / t;
+                q[0] = (R.m[7] - R.m[5]) * t, q[1] = (R.m[2] - R.m[6]) * t, q[2] = (R.m[3] - R.m[1]) * t;
+            }
+            else {
+                int i = 0;
+                if (R.m[4] > R.m[0])
+                    i = 1;
+                if (R.m[8] > R.m[4 * i])
+                    i = 2;
+                const int j = (i + 1) % 3, k = (i + 2) % 3;
+                double t = std::sqrt(R.m[4 * i] - R.m[4 * j] - R.m[4 * k] + 1.0);
+                q[i] = 0.5 * t;
+                t = 0.5 / t;
+                w = (R.m[3 * k + j] - R.m[3 * j + k]) * t;
+                q[j] = (R.m[3 * j + i] + R.m[3 * i + j]) * t;
+                q[k] = (R.m[3 * k + i] + R.m[3 * i + k]) * t;
+            }
+            double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+            if (n == 0.0) {
+                angle = 0.0;
+                axis[0] = 1.0, axis[1] = 0.0, axis[2] = 0.0;
+                return;
+            }
+            angle = 2.0 * std::atan2(n, std::fabs(w));
+            if (w < 0)
+                n = -n;
+            for (int c = 0; c < 3; ++c)
+                axis[c] = q[c] / n;
+        }
+        inline Rot3 slot_rotation(const double* ref24)
+        { // TrajectorySample(12,6): R column-major after the translation
+            Rot3 R;
+            for (int c = 0; c < 3; ++c)
+                for (int r = 0; r < 3; ++r)
+                    R.m[3 * r + c] = ref24[3 + 3 * c + r];
+            return R;
+        }
+    } // namespace detail
+
+    // generic::cartesian (src/behaviors/generic/cartesian.cpp:8-94): every listed SE3 task goes from its construction-time
+    // reference to a relative target along a minimum-jerk path (position and rotation angle about the fixed relative axis),
+    // with the polynomial's derivatives as feed-forward velocity / acceleration; `loop` appends the way back.
+    inline void compile_cartesian(iwbc_behavior& out, const iwbc_problem& prob, const yaml::Node& c)
+    {
+        BehaviorBuilder bb(out, prob);
+        const double duration = IWBC_HCHECK(c["trajectory_duration"].as<float>(), "trajectory_duration");
+        out.loop = IWBC_HCHECK(c["loop"].as<bool>(), "loop");
+        const std::vector<std::string> names = IWBC_HCHECK(c["task_names"].as<std::vector<std::string>>(), "task_names");
+        const yaml::Node& ts = c["relative_targets_pos"];
+        const yaml::Node& to = c["relative_targets_rpy"];
+        if (!ts.is_seq() || !to.is_seq())
+            throw ConfigError("config error reading relative_targets_pos / relative_targets_rpy");
+        if (names.size() != ts.size())
+            throw ConfigError("cartesian behavior needs the same number of tasks and targets"); // cartesian.cpp:22-23
+        if (to.size() < names.size())
+            throw ConfigError("cartesian behavior needs one relative_targets_rpy entry per task");
+        struct Way {
+            double p0[3], p1[3];
+            detail::Rot3 R0, R1;
+        };
+        std::vector<Way> ways;
+        for (size_t i = 0; i < names.size(); ++i) {
+            const int slot = bb.slot_of(names[i]);
+            bb.add_channel(1, 1, slot, -1);
+            Way w;
+            const double* ref = prob.cs.ref0.data() + slot;
+            for (int k = 0; k < 3; ++k)
+                w.p0[k] = w.p1[k] = ref[k];
+            w.R0 = w.R1 = detail::slot_rotation(ref);
+            const std::vector<double> dp = ts[i].as<std::vector<double>>(), rpy = to[i].as<std::vector<double>>();
+            if (dp.size() == 3)
+                for (int k = 0; k < 3; ++k)
+                    w.p1[k] = dp[k] + w.p0[k];
+            if (rpy.size() == 3) // AngleAxis(rz, Z) * AngleAxis(ry, Y) * AngleAxis(rx, X) * R_init (cartesian.cpp:35-40)
+                w.R1 = detail::rmul(detail::rmul(detail::rmul(detail::raxis(2, rpy[2]), detail::raxis(1, rpy[1])), detail::raxis(0, rpy[0])), w.R0);
+            ways.push_back(w);
+        }
+        const unsigned mask = iwbc_problem_default_contact_mask(&prob);
+        const int ticks = beh_n_steps(out.dt, duration);
+        for (int leg = 0; leg < (out.loop ? 2 : 1); ++leg) {
+            bb.begin_segment(ticks, mask, mask);
+            for (size_t i = 0; i < ways.size(); ++i) {
+                const Way& w = ways[i];
+                iwbc_beh_chanseg_t& cs = bb.at((int)i);
+                std::memset(&cs, 0, sizeof(cs));
+                const detail::Rot3 &Ra = leg == 0 ? w.R0 : w.R1, &Rb = leg == 0 ? w.R1 : w.R0;
+                for (int k = 0; k < 3; ++k) {
+                    cs.p0[k] = leg == 0 ? w.p0[k] : w.p1[k];
+                    cs.p1[k] = leg == 0 ? w.p1[k] : w.p0[k];
+                }
+                for (int col = 0; col < 3; ++col)
+                    for (int r = 0; r < 3; ++r)
+                        cs.R0[3 * col + r] = Ra.m[3 * r + col];
+                detail::angle_axis(detail::rmul(detail::rtrans(Ra), Rb), cs.angle, cs.axis); // trajectory_generator.hpp:124-126
+                cs.duration = duration;
+                cs.minjerk = 1;
+                cs.rot = cs.angle != 0.0 ? 1 : 0;
+            }
+        }
+        bb.finish();
+    }
+
+    // humanoid::move_com (src/behaviors/humanoid/move_com.cpp:8-61): the CoM reference visits the listed targets (masked,
+    // relative or absolute) along minimum-jerk segments with feed-forward derivatives; `loop` appends the way back to the start.
+    inline void compile_move_com(iwbc_behavior& out, const iwbc_problem& prob, const yaml::Node& c)
+    {
+        BehaviorBuilder bb(out, prob);
+        const double duration = IWBC_HCHECK(c["trajectory_duration"].as<float>(), "trajectory_duration");
+        out.loop = IWBC_HCHECK(c["loop"].as<bool>(), "loop");
+        const yaml::Node& tg = c["targets"];
+        const std::string mask = IWBC_HCHECK(c["mask"].as<std::string>(), "mask");
+        const bool absolute = IWBC_HCHECK(c["absolute"].as<bool>(), "absolute");
+        if (!tg.is_seq())
+            throw ConfigError("config error reading targets");
+        if (mask.size() != 3)
+            throw ConfigError("The mask for the CoM should be 3-dimensional"); // move_com.cpp:20
+        const int slot = bb.slot_of("com");
+        bb.add_channel(0, 1, slot, -1);
+        double init[3];
+        for (int k = 0; k < 3; ++k)
+            init[k] = prob.cs.ref0[slot + k];
+        std::vector<std::vector<double>> targets;
+        for (size_t i = 0; i < tg.size(); ++i)
+            targets.push_back(tg[i].as<std::vector<double>>());
+        if (out.loop)
+            targets.push_back(absolute ? std::vector<double>{init[0], init[1], init[2]} : std::vector<double>{0.0, 0.0, 0.0});
+        const unsigned cm = iwbc_problem_default_contact_mask(&prob);
+        const int ticks = beh_n_steps(out.dt, duration);
+        double start[3] = {init[0], init[1], init[2]};
+        for (const std::vector<double>& t : targets) {
+            if (t.size() != 3)
+                throw ConfigError("references need to be 3-dimensional"); // move_com.cpp:32
+            double end[3] = {init[0], init[1], init[2]};
+            for (int j = 0; j < 3; ++j)
+                if (mask[j] == '1')
+                    end[j] = absolute ? t[j] : t[j] + init[j];
+            bb.begin_segment(ticks, cm, cm);
+            bb.set(0, start, end, duration, true);
+            for (int k = 0; k < 3; ++k)
+                start[k] = end[k];
+        }
+        bb.finish();
+    }
+
     inline void compile_behavior(iwbc_behavior& out, const iwbc_problem& prob, const std::string& yaml_path, const std::string& overrides)
     {
         yaml::Node root = yaml::LoadFile(yaml_path);
@@ -249,8 +429,12 @@ namespace host {
         out.name = IWBC_HCHECK(c["name"].as<std::string>(), "BEHAVIOR.name");
         if (out.name == "humanoid::walk")
             compile_walk(out, prob, c);
+        else if (out.name == "generic::cartesian")
+            compile_cartesian(out, prob, c);
+        else if (out.name == "humanoid::move_com")
+            compile_move_com(out, prob, c);
         else
-            throw ConfigError("behavior '" + out.name + "' has no device-side form yet (available: humanoid::walk)");
+            throw ConfigError("behavior '" + out.name + "' has no device-side form yet (available: humanoid::walk, generic::cartesian, humanoid::move_com)");
     }
 
 } // namespace host

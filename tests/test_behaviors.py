@@ -65,7 +65,31 @@ def test_behavior_config_errors(walk_problem, franka):
     with pytest.raises(iw.IwbcError, match="lf"):  # Walk needs lf / rf / lh / rh / com tasks and both foot contacts (walk.cpp:14-20)
         iw.Behavior(franka, "talos/walk.yaml")
     with pytest.raises(iw.IwbcError, match="device-side form"):
-        iw.Behavior(walk_problem, "talos/squat.yaml")
+        iw.Behavior(walk_problem, "talos/clapping.yaml")
+
+
+def test_cartesian_and_move_com_tables(franka, talos):
+    """generic::cartesian (src/behaviors/generic/cartesian.cpp) and humanoid::move_com (src/behaviors/humanoid/move_com.cpp) compiled
+    into segment tables, against the host tables of inria_wbc_b200.behaviors (numpy restatements of the same files)."""
+    from inria_wbc_b200 import behaviors
+    beh = iw.Behavior(franka, "franka/cartesian_line.yaml")
+    host = behaviors.Cartesian(franka, os.path.join(iw.ETC_PATH, "franka", "cartesian_line.yaml"))
+    tab = host.table(4000)
+    off, _ = franka.ref_slot("ee")
+    assert beh.total_ticks == 4000 and beh.nsegments == 2 and beh.nchannels == 1 and beh.masks == [franka.default_contact_mask]
+    for k in range(2):
+        start, ticks, _, _, wp = beh.segment(k)
+        assert (start, ticks) == (2000 * k, 2000) and wp[0, 7] == 1 and wp[0, 6] == 2.0
+        assert np.abs(wp[0, 0:3] - tab[start, off:off + 3]).max() < 1e-15
+    assert np.abs(beh.segment(0)[4][0, 3:6] - beh.segment(1)[4][0, 0:3]).max() == 0  # the loop goes back from the target
+    mc = iw.Behavior(talos, "talos/move_com.yaml")
+    hmc = behaviors.MoveCom(talos, os.path.join(iw.ETC_PATH, "talos", "move_com.yaml"))
+    tab = hmc.table(mc.total_ticks)
+    off, _ = talos.ref_slot("com")
+    assert mc.nsegments == len(hmc.segs) and mc.nchannels == 1
+    for k in range(mc.nsegments):
+        start, ticks, _, _, wp = mc.segment(k)
+        assert np.abs(wp[0, 0:3] - tab[start, off:off + 3]).max() < 1e-15
 
 
 @pytest.mark.gpu
@@ -135,3 +159,67 @@ def test_walk_rollout_on_device_matches_the_oracle(walk_problem):
         assert np.abs(got_tau[i] - o["tau"][0]).max() <= 1e-7 * np.abs(o["tau"][0]).max(), i
         assert int(d_mask[i]) == ora.tick(int(phase[i]) + T - 1)[1]
     assert len(masks_seen) == 3
+
+
+@pytest.mark.gpu
+def test_cartesian_and_move_com_on_device(franka, talos):
+    """Every tick of the looping Franka cartesian line and of Talos move_com evaluated on the device in one call (instance i sits
+    at tick i) against the host tables: positions, rotations and the feed-forward velocity / acceleration."""
+    import torch
+    from inria_wbc_b200 import behaviors
+    for P, name, Host in ((franka, "franka/cartesian_line.yaml", behaviors.Cartesian), (talos, "talos/move_com.yaml", behaviors.MoveCom)):
+        beh = iw.Behavior(P, name)
+        B = beh.total_ticks + 300  # past the end: the loop wraps
+        tab = Host(P, os.path.join(iw.ETC_PATH, name)).table(B)
+        d_phase = torch.arange(B, dtype=torch.int32, device="cuda")
+        d_refs = torch.full((B, P.nref), float("nan"), dtype=torch.float64, device="cuda")
+        beh.eval_device(0, B, d_phase.data_ptr(), 0, d_refs.data_ptr(), None, init_refs=True)
+        torch.cuda.synchronize()
+        got = d_refs.cpu().numpy()
+        assert np.abs(got - tab).max() < 1e-13, (name, np.abs(got - tab).max())
+
+
+@pytest.mark.gpu
+def test_franka_known_answer_with_the_behaviour_on_the_device(franka):
+    """tests/ref_test_franka.yaml (SURVEY.md 8(c)) with BOTH halves on the GPU: generic::cartesian evaluated on the device every tick
+    and the control cycle, 10 s @ 1 kHz open loop; the reference's own acceptance criterion (tests/test_franka.cpp:266)."""
+    import json
+    import torch
+    import oracle_lib as ol
+    gold_all = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_test_franka.json")))
+    gold = gold_all["cases"]["servo"]
+    ticks = int(gold_all["duration_s"] / gold_all["dt"])
+    beh = iw.Behavior(franka, "franka/cartesian_line.yaml")
+    bt = iw.Batch(franka, 0, 8)
+    dq = torch.from_numpy(franka.q0()[None].copy()).cuda()
+    dv_ = torch.zeros(1, franka.nv, dtype=torch.float64, device="cuda")
+    d_refs = torch.empty(1, franka.nref, dtype=torch.float64, device="cuda")
+    st = torch.zeros(1, dtype=torch.int32, device="cuda")
+    hist = torch.empty(ticks + 1, franka.nq, dtype=torch.float64, device="cuda")
+    refs_hist = torch.empty(ticks, franka.nref, dtype=torch.float64, device="cuda")
+    bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ts = torch.cuda.Stream()  # an explicit stream: handle 0 would mean "the batch's own stream" to the C ABI
+    torch.cuda.synchronize()
+    with torch.cuda.stream(ts):
+        for t in range(ticks):
+            hist[t].copy_(dq[0])
+            bt.behavior_rollout_device(beh, 1, dq.data_ptr(), dv_.data_ptr(), d_refs.data_ptr(), None, t, 1, init_refs=(t == 0),
+                                       out_ptrs={"status": st.data_ptr()}, stream=ts.cuda_stream)
+            refs_hist[t].copy_(d_refs[0])
+            bad |= st
+        hist[ticks].copy_(dq[0])
+    torch.cuda.synchronize()
+    assert int(bad[0]) == 0
+    qs, refs = hist.cpu().numpy(), refs_hist.cpu().numpy()
+    off, _ = franka.ref_slot("ee")
+    # the reference reads the model pose at the state the tick started from (tests/test_franka.cpp:214-218)
+    ee = np.array([ol.frame(franka, qs[t], np.zeros(franka.nv), 0)["oMf"][9:12] for t in range(ticks)])
+    err = np.linalg.norm(ee - refs[:, off:off + 3], axis=1).mean()
+    assert err <= gold["ee_error_tsid"] + gold_all["tolerance"], err
+    # ... and the same number as the CPU oracle driven by the host table of the same behaviour (feed-forward terms included, as the
+    # tree has them today; the 2021 recording predates them: tests/test_franka_kat.py)
+    from inria_wbc_b200 import behaviors
+    tab = behaviors.Cartesian(franka, os.path.join(iw.ETC_PATH, "franka", "cartesian_line.yaml")).table(ticks)
+    r = ol.rollout(franka, franka.q0(), np.zeros(franka.nv), tab, ticks)
+    dq_max = np.abs(qs[-1] - r["q"]).max()
+    assert r["rc"] == 0 and dq_max < 1e-8, dq_max  # tests/test_determinism.cpp:51,63 tolerance after 10 000 ticks
