@@ -1789,6 +1789,105 @@ namespace dev {
         return status;
     }
 
+    // delete_constraint for the CTA-wide loop: the same update (drop column qq of R, restore the triangle by Givens rotations of
+    // rows (j, j+1), rotate the matching columns of J) with the serial part spread out -- rows of R shift in parallel (one thread
+    // per row), the rotations of R run in warp 0 with one lane per column (coefficients broadcast by shuffles; one rsqrt and
+    // a Newton reciprocal per rotation), act / u shift through registers.  The caller has synchronised.
+    template <int G>
+    __device__ void delete_constraint_cta(const Sm& sm, int n, int ld, int me, int& iq, int l, int tid)
+    {
+        int qq = me;
+        for (int i = me; i < iq; ++i)
+            if (sm.act[i] == l) {
+                qq = i;
+                break;
+            }
+        const int niq = iq - 1;
+        if (niq - qq > 32) { // (more columns than lanes: the generic form)
+            __syncthreads();
+            delete_constraint<G>(sm, n, ld, me, iq, l, tid);
+            return;
+        }
+        // ---- A: shift.  Row k of R: R(k, i) <- R(k, i+1); the old diagonal of column k becomes the sub-diagonal of column k-1
+        int a_next = 0;
+        double u_next = 0.0;
+        if (tid >= qq && tid < iq) {
+            a_next = sm.act[tid + 1];
+            u_next = sm.u[tid + 1];
+        }
+        for (int k = tid; k < iq; k += G) {
+            if (k >= qq + 1)
+                sm.sub[k - 1] = sm.R[Ridx(k, k)];
+            for (int i = (qq > k ? qq : k); i < niq; ++i)
+                sm.R[Ridx(k, i)] = sm.R[Ridx(k, i + 1)];
+        }
+        __syncthreads();
+        if (tid >= qq && tid < iq) {
+            sm.act[tid] = a_next;
+            sm.u[tid] = u_next;
+        }
+        if (tid == iq) {
+            sm.act[iq] = 0;
+            sm.u[iq] = 0.0;
+        }
+        // ---- B: warp 0, lane c <-> column qq + c
+        if (tid < 32) {
+            const int k = qq + tid;
+            for (int j = qq; j < niq; ++j) {
+                double cc = 1.0, ss = 0.0, xny = -2.0;
+                if (k == j) {
+                    const double a = sm.R[Ridx(j, j)], b2 = sm.sub[j];
+                    const double hh = a * a + b2 * b2;
+                    if (hh != 0.0) {
+                        const double ih = rsqrt(hh), h = hh * ih;
+                        cc = a * ih;
+                        ss = b2 * ih;
+                        if (cc < 0.0) {
+                            sm.R[Ridx(j, j)] = -h;
+                            cc = -cc;
+                            ss = -ss;
+                        }
+                        else
+                            sm.R[Ridx(j, j)] = h;
+                        const double a1 = 1.0 + cc;
+                        double rcp = (double)(1.0f / (float)a1);
+                        rcp = rcp * (2.0 - a1 * rcp);
+                        rcp = rcp * (2.0 - a1 * rcp);
+                        xny = ss * rcp;
+                    }
+                    sm.gc[j] = cc;
+                    sm.gs[j] = ss;
+                    sm.gx[j] = xny;
+                }
+                cc = __shfl_sync(0xffffffffu, cc, j - qq);
+                ss = __shfl_sync(0xffffffffu, ss, j - qq);
+                xny = __shfl_sync(0xffffffffu, xny, j - qq);
+                if (k > j && k < niq && xny != -2.0) {
+                    const double t1 = sm.R[Ridx(j, k)], t2 = sm.R[Ridx(j + 1, k)];
+                    const double r1 = t1 * cc + t2 * ss;
+                    sm.R[Ridx(j, k)] = r1;
+                    sm.R[Ridx(j + 1, k)] = xny * (t1 + r1) - t2;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- C: the same rotations on the columns of J, one row per thread
+        for (int i = tid; i < n; i += G) {
+            double* row = sm.J + i;
+            for (int j = qq; j < niq; ++j) {
+                const double xny = sm.gx[j];
+                if (xny == -2.0)
+                    continue;
+                const double t1 = row[j * ld], t2 = row[(j + 1) * ld];
+                const double r1 = t1 * sm.gc[j] + t2 * sm.gs[j];
+                row[j * ld] = r1;
+                row[(j + 1) * ld] = xny * (r1 + t1) - t2;
+            }
+        }
+        iq = niq;
+        __syncthreads();
+    }
+
     // ---- CTA-wide, latency-trimmed form of gi_loop for the fused problem (G >= 64: the CTA is the group).
     // Same iteration, same tie-breaking, same termination test as gi_loop (eiquadprog); what
     // changes is the schedule -- the loop is a chain of short dependent phases, so its cost is barriers and serial
@@ -2232,7 +2331,7 @@ namespace dev {
                     sm.iai[l] = l;
                 }
                 __syncthreads();
-                delete_constraint<G>(sm, n, ld, me, iq, l, tid);
+                delete_constraint_cta<G>(sm, n, ld, me, iq, l, tid);
                 IWBC_LOOP_TICK(5)
                 continue; // l2a
             }
@@ -2286,7 +2385,7 @@ namespace dev {
                 pc[7] += 1;
                 if (fabs(diq) <= eps * R_norm) {
                     // degenerate: exclude ip, restore and pick another constraint
-                    delete_constraint<G>(sm, n, ld, me, iq, ip, tid);
+                    delete_constraint_cta<G>(sm, n, ld, me, iq, ip, tid);
                     for (int k = tid; k < mi; k += G)
                         if (sm.iai[k] != -2)
                             sm.iai[k] = k;
@@ -2316,7 +2415,7 @@ namespace dev {
             if (tid == 0)
                 sm.iai[l] = l;
             __syncthreads();
-            delete_constraint<G>(sm, n, ld, me, iq, l, tid);
+            delete_constraint_cta<G>(sm, n, ld, me, iq, l, tid);
             {
                 double tv[1] = {0};
                 for (int k = tid; k < n; k += G)
