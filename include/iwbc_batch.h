@@ -132,8 +132,9 @@ int iwbc_batch_debug_cycles(const iwbc_batch* b, long long* out7);
 int iwbc_batch_phase_profile(iwbc_batch* b, int enable, unsigned long long* out16);
 /* phases of the active-set loop of the continuation kernel accumulated up to the last iwbc_batch_phase_profile call (SM cycles as
  * seen by thread 0, barrier waits included): out8 = { pass (s, psi, pick), n+ load, d, z + r + ratio test + coefficients,
- * step + rotations, drops, number of step directions, number of added constraints }.  Development aid. */
-int iwbc_batch_loop_profile(const iwbc_batch* b, unsigned long long* out8);
+ * step + rotations, drops, number of step directions, number of added constraints, and inside the z phase the time to finish
+ * of: the last warp (r = R^-1 d, ratio test), the coefficient warp, warp 0's z rows; 5 spare }.  out16 has 16 entries.  Development aid. */
+int iwbc_batch_loop_profile(const iwbc_batch* b, unsigned long long* out16);
 /* launch shape of the cycle kernel for the last contact mask: threads per instance, instances per CTA, grid, dynamic smem */
 int iwbc_batch_launch_info(const iwbc_batch* b, int* G, int* ipc, int* grid, long* smem_bytes);
 
@@ -156,11 +157,13 @@ int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, c
  * (e.g. src/behaviors/humanoid/walk.cpp:198-246): the behaviour's waypoint tables
  * (include/inria_wbc/trajs/trajectory_generator.hpp:29-160) are compiled into a segment table that
  * the GPU evaluates in closed form for every (instance, tick).  BEHAVIOR.name selects the
+ * As in the reference, constructing a behaviour applies BEHAVIOR.customize_task_weights to the controller
+ * (Behavior::_customize_tasks, src/behaviors/behavior.cpp:7-22), which is why `p` is not const.  Available
  * behaviour: "humanoid::walk" (src/behaviors/humanoid/walk.cpp), "generic::cartesian"
  * (src/behaviors/generic/cartesian.cpp:8-94), "humanoid::move_com" (src/behaviors/humanoid/move_com.cpp:8-61); overrides_yaml: optional YAML text of BEHAVIOR keys to override.
  */
 typedef struct iwbc_behavior iwbc_behavior;
-iwbc_behavior* iwbc_behavior_load(const iwbc_problem* p, const char* behavior_yaml, const char* overrides_yaml);
+iwbc_behavior* iwbc_behavior_load(iwbc_problem* p, const char* behavior_yaml, const char* overrides_yaml);
 void iwbc_behavior_free(iwbc_behavior* h);
 /* length in control ticks, segment / channel counts, the distinct contact masks (<= 8, most frequent first) */
 int iwbc_behavior_info(const iwbc_behavior* h, int* total_ticks, int* nsegments, int* nchannels, int* nmasks, unsigned* masks8);

@@ -330,11 +330,12 @@ class Batch:
             out["active_set"] = dict(zip(("dyn", "asm", "factor", "eq", "ineq", "decode"), (t[:6] / float(t[6])).tolist()), instances=int(t[6]))
         if t[14]:
             out["fast"] = dict(zip(("dyn", "rows", "H_chol", "qr_solve", "check", "decode"), (t[8:14] / float(t[14])).tolist()), instances=int(t[14]))
-        lp = np.zeros(8, dtype=np.uint64)
+        lp = np.zeros(16, dtype=np.uint64)
         lib().iwbc_batch_loop_profile(self._h, lp.ctypes.data)
         if lp[6]:
             out["loop"] = dict(zip(("pass", "load_n", "d", "z_r_coef", "step_rotate", "drops"), (lp[:6] / float(lp[6])).tolist()),
-                               directions=int(lp[6]), adds=int(lp[7]), note="mean SM cycles per step direction")
+                               directions=int(lp[6]), adds=int(lp[7]), note="mean SM cycles per step direction",
+                               z_phase=dict(zip(("r_ratio_last_warp", "coefficients_warp", "z_rows_warp0"), (lp[8:11] / float(lp[6])).tolist())))
         return out or None
 
     def fast_info(self):

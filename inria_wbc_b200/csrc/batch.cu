@@ -388,7 +388,7 @@ iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch)
         const char* e = getenv("IWBC_NO_FAST");
         b->fast_enabled = !(e && e[0] == '1');
     }
-    ok = ok && dalloc(&b->d_prof, 32) == 0 && dalloc(&b->d_prob, 1) == 0 && dalloc(&b->d_q, B * P.nq) == 0 && dalloc(&b->d_v, B * P.nv) == 0
+    ok = ok && dalloc(&b->d_prof, 48) == 0 && dalloc(&b->d_prob, 1) == 0 && dalloc(&b->d_q, B * P.nq) == 0 && dalloc(&b->d_v, B * P.nv) == 0
         && dalloc(&b->d_refs, B * P.nref) == 0 && dalloc(&b->d_tau, B * P.na) == 0 && dalloc(&b->d_dv, B * P.nv) == 0
         && dalloc(&b->d_f, B * 12 * P.ncontacts) == 0 && dalloc(&b->d_qn, B * P.nq) == 0 && dalloc(&b->d_vn, B * P.nv) == 0
         && dalloc(&b->d_qc, B * P.nv) == 0 && dalloc(&b->d_mom, B * 3) == 0 && dalloc(&b->d_status, B) == 0 && dalloc(&b->d_iters, B) == 0
@@ -739,8 +739,8 @@ int iwbc_batch_phase_profile(iwbc_batch* b, int enable, unsigned long long* out7
     CUDA_TRY(cudaDeviceSynchronize());
     if (out7)
         CUDA_TRY(cudaMemcpy(out7, b->d_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(b->loop_prof, b->d_prof + 16, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemset(b->d_prof, 0, 32 * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemcpy(b->loop_prof, b->d_prof + 16, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemset(b->d_prof, 0, 48 * sizeof(unsigned long long)));
     b->profiling = enable != 0;
     return IWBC_OK;
 }
@@ -749,7 +749,7 @@ int iwbc_batch_loop_profile(const iwbc_batch* b, unsigned long long* out8)
 {
     if (!b || !out8)
         return IWBC_ERR_ARG;
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < 16; ++k)
         out8[k] = b->loop_prof[k];
     return IWBC_OK;
 }

@@ -49,7 +49,7 @@ struct iwbc_batch {
     long long last_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned long long* d_prof = nullptr; // steady-state phase profile accumulators (enabled on demand): [0..6] active-set kernel, [8..14] fast kernel
     bool profiling = false;
-    unsigned long long loop_prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // active-set loop phases read by the last iwbc_batch_phase_profile
+    unsigned long long loop_prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; // active-set loop phases read by the last iwbc_batch_phase_profile
     // fast path (fast_kernel.cuh): equality-constrained first pass, 3 CTAs / SM; the active-set kernel continues the rest
     bool fast_ok = false, fast_enabled = true;
     iwbc::dev::FShape fshape;

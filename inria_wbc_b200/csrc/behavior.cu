@@ -207,7 +207,7 @@ int eval_tick(iwbc_behavior* h, int B, const int* phase, int tick, double* refs,
 
 extern "C" {
 
-iwbc_behavior* iwbc_behavior_load(const iwbc_problem* p, const char* behavior_yaml, const char* overrides_yaml)
+iwbc_behavior* iwbc_behavior_load(iwbc_problem* p, const char* behavior_yaml, const char* overrides_yaml)
 {
     if (!p || !behavior_yaml) {
         set_error("iwbc_behavior_load: NULL argument");

@@ -427,6 +427,13 @@ namespace host {
                 c.at(kv.first) = kv.second;
         }
         out.name = IWBC_HCHECK(c["name"].as<std::string>(), "BEHAVIOR.name");
+        // Behavior::_customize_tasks (src/behaviors/behavior.cpp:7-22): constructing a behaviour re-weights the controller's tasks
+        if (c["customize_task_weights"].is_map())
+            for (auto& kv : c["customize_task_weights"].map) {
+                const double w = IWBC_HCHECK(kv.second.as<double>(), "customize_task_weights." + kv.first);
+                if (iwbc_problem_set_task_weight(const_cast<iwbc_problem*>(&prob), kv.first.c_str(), w) != IWBC_OK)
+                    throw ConfigError("customize_task_weights: unknown task '" + kv.first + "'");
+            }
         if (out.name == "humanoid::walk")
             compile_walk(out, prob, c);
         else if (out.name == "generic::cartesian")

@@ -46,6 +46,9 @@ inline void __syncwarp(unsigned) {}
 inline void __syncthreads() {}
 template <class T> inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
 template <class T> inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
+template <class T> inline T __shfl_down_sync(unsigned, T v, int, int = 32) { return v; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }
+inline int atomicAdd(int* p, int v) { const int o = *p; *p += v; return o; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 struct double2 { double x, y; };
 inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
@@ -1088,22 +1091,24 @@ namespace dev {
             const Shape& S = c_S;
             const int nv = z.nv, nu = nv - c_P.na;
             const double* Mr = sm.M + (nu + i) * z.ldM;
-            double s0 = 0, s1 = 0;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
             int k = 0;
-            for (; k + 1 < nv; k += 2) {
+            for (; k + 3 < nv; k += 4) {
                 s0 += Mr[k] * sm.x[k];
                 s1 += Mr[k + 1] * sm.x[k + 1];
+                s2 += Mr[k + 2] * sm.x[k + 2];
+                s3 += Mr[k + 3] * sm.x[k + 3];
             }
-            if (k < nv)
+            for (; k < nv; ++k)
                 s0 += Mr[k] * sm.x[k];
-            double s = s0 + s1;
+            double s = (s0 + s1) + (s2 + s3);
             for (int c = 0; c < c_P.ncontacts; ++c) {
                 if (S.cidx[c] < 0)
                     continue;
                 const double* w = sm.cb + 6 * c_P.ncontacts + 6 * c;
-#pragma unroll
-                for (int a = 0; a < 6; ++a)
-                    s -= sm.Jft[(c * 6 + a) * nv + nu + i] * w[a];
+                const double* Jc = sm.Jft + (c * 6) * nv + nu + i;
+                const double c0 = Jc[0] * w[0] + Jc[nv] * w[1], c1 = Jc[2 * nv] * w[2] + Jc[3 * nv] * w[3], c2 = Jc[4 * nv] * w[4] + Jc[5 * nv] * w[5];
+                s -= (c0 + c1) + c2;
             }
             return s;
         }
@@ -2138,22 +2143,22 @@ namespace dev {
             IWBC_LOOP_TICK(2)
             // ---- last warp: r = R^-1 d on the inequality part, ratio test;  everybody: z = J2 d2
             const int m = iq - me;
+            const long long ph3 = prof ? clock64() : 0;
             if (warp == lastw) {
                 double t1 = inf;
                 int l = 0;
                 if (m > 0 && m <= 32) {
                     const int i = me + lane;
-                    double acc = lane < m ? sm.d[i] : 0.0;
                     const double invd = lane < m ? 1.0 / sm.R[Ridx(i, i)] : 0.0;
+                    double acc = lane < m ? sm.d[i] * invd : 0.0; // row i pre-scaled by 1 / R_ii: the chain per column is shuffle + FMA
                     double ri = 0.0;
 #pragma unroll 4
                     for (int jj = m - 1; jj >= 0; --jj) {
-                        const double cand = acc * invd;
-                        const double rj = __shfl_sync(0xffffffffu, cand, jj);
+                        const double rj = __shfl_sync(0xffffffffu, acc, jj);
                         if (lane == jj)
                             ri = rj;
                         else if (lane < jj)
-                            acc -= sm.R[Ridx(i, me + jj)] * rj;
+                            acc = fma(-(sm.R[Ridx(i, me + jj)] * invd), rj, acc);
                     }
                     double ratio = inf;
                     int li = 0x7fffffff;
@@ -2194,6 +2199,8 @@ namespace dev {
                 if (lane == 0) {
                     sm.gs[n] = t1;
                     sm.gx[n] = (double)l;
+                    if (prof)
+                        atomicAdd(prof + 8, (unsigned long long)(clock64() - ph3)); // r = R^-1 d + ratio test (last warp)
                 }
             }
             // Givens coefficients that would fold d[iq+1..n-1] into d[iq] if ip is added (speculative: a partial step discards
@@ -2295,6 +2302,8 @@ namespace dev {
                 }
                 else if (lane == 0)
                     sm.gc[n] = sm.d[iq];
+                if (prof && lane == 0)
+                    atomicAdd(prof + 9, (unsigned long long)(clock64() - ph3)); // rotation coefficients (second-to-last warp)
             }
             double t[2] = {0, 0};
             for (int i = tid; i < n; i += G) {
@@ -2311,6 +2320,8 @@ namespace dev {
                 t[0] += zi * zi;
                 t[1] += zi * sm.np[i];
             }
+            if (prof && tid == 0)
+                atomicAdd(prof + 10, (unsigned long long)(clock64() - ph3)); // z rows (warp 0)
             gsum<G, 2>(t, sm.red, flip); // (its barrier also publishes r, t1, l)
             IWBC_LOOP_TICK(3)
             pc[6] += 1;
@@ -2354,10 +2365,10 @@ namespace dev {
                     // Four columns per trip, every operand loaded before the first store: the compiler may not move a shared-memory
                     // load above a store it cannot disambiguate, and behind the stores each load would wait for the FMA carry
                     // chain of the previous column.  Branch-free; xny == -2 marks an identity rotation.
+                    // (an identity rotation is stored as cc = 1, ss = 0: the carry needs no select, only the stored value does)
                     auto rot = [&](int j, double t1r, double xny, double cc, double ss) {
-                        const bool idt = xny == -2.0;
-                        const double nj1 = idt ? t1r : t1r * cc + t2r * ss;
-                        row[j * ld] = idt ? t2r : xny * (t1r + nj1) - t2r;
+                        const double nj1 = fma(t2r, ss, t1r * cc); // the carry chain: one FMA per column
+                        row[j * ld] = (xny == -2.0) ? t2r : xny * (t1r + nj1) - t2r;
                         t2r = nj1;
                     };
                     int j = n - 1;

@@ -59,10 +59,24 @@ def test_walk_contact_schedule(walk_problem):
     assert seq == [(ds, ds), (rf, rf), (rf, ds), (ds, ds), (lf, lf), (lf, ds), (ds, ds), (rf, rf), (rf, ds), (ds, ds)]
 
 
+def test_loading_a_behaviour_customizes_task_weights():
+    """Behavior::_customize_tasks (src/behaviors/behavior.cpp:7-22): etc/talos/walk.yaml sets the momentum task's weight to 0."""
+    P = iw.Problem("talos/talos_pos_tracker.yaml")
+    k = P.names("tasks").index("momentum")
+    assert P.struct().tasks[k].weight > 0
+    iw.Behavior(P, "talos/walk.yaml")
+    assert P.struct().tasks[k].weight == 0.0
+
+
 def test_behavior_config_errors(walk_problem, franka):
     with pytest.raises(iw.IwbcError, match="num_of_cycles"):
         iw.Behavior(walk_problem, "talos/walk.yaml", overrides={"num_of_cycles": 0})
-    with pytest.raises(iw.IwbcError, match="lf"):  # Walk needs lf / rf / lh / rh / com tasks and both foot contacts (walk.cpp:14-20)
+    # the base-class constructor customizes the task weights first (unknown task on a Franka), then Walk asserts its tasks (walk.cpp:14-20)
+    with pytest.raises(iw.IwbcError, match="momentum"):
+        iw.Behavior(franka, "talos/walk.yaml")
+    with pytest.raises(iw.IwbcError, match="lf"):
+        iw.Behavior(franka, "talos/walk.yaml", overrides={"customize_task_weights": "{}"})
+    with pytest.raises(iw.IwbcError, match="momentum"):
         iw.Behavior(franka, "talos/walk.yaml")
     with pytest.raises(iw.IwbcError, match="device-side form"):
         iw.Behavior(walk_problem, "talos/clapping.yaml")
