@@ -20,8 +20,10 @@ namespace dev {
 
     // ------------------------------------------------------------------------------ the kernel
     // One group of G threads per instance, IPC instances per CTA, persistent over the batch.
+    // (the warp-per-instance form is occupancy-bound by registers: three CTAs per SM need <= 168; without the bound ptxas drifts to
+    // 216 and Franka drops from 38 M to 27 M updates/s)
     template <int G, int IPC>
-    __global__ void __launch_bounds__(G* IPC) k_cycle(const iwbc_problem_t* __restrict__ gP, IO io)
+    __global__ void __launch_bounds__(G* IPC, (G <= 32 ? 3 : 1)) k_cycle(const iwbc_problem_t* __restrict__ gP, IO io)
     {
         extern __shared__ double smem[];
         const int grp = threadIdx.x / G;
@@ -49,6 +51,31 @@ namespace dev {
         }
         const int ngroups = gridDim.x * IPC;
         const int count = io.list ? *io.list_count : io.B;
+        if (io.work) {
+            // dynamic hand-out: instances differ in active-set iterations (Tiago: 1 .. 30), a static stride leaves groups idle at the end
+            __shared__ int s_next[IPC];
+            for (;;) {
+                int idx;
+                if (G <= 32) {
+                    idx = 0;
+                    if (tid == 0)
+                        idx = atomicAdd(io.work, 1);
+                    idx = __shfl_sync(Grp<G>::mask(), idx, (threadIdx.x & 31) / G * G);
+                }
+                else {
+                    if (tid == 0)
+                        s_next[grp] = atomicAdd(io.work, 1);
+                    __syncthreads();
+                    idx = s_next[grp];
+                }
+                if (idx >= count)
+                    break;
+                const int inst = io.list ? io.list[idx] : idx;
+                cycle_instance<G>(gP, sm, z, io, inst, tid, flip);
+                Grp<G>::sync();
+            }
+            return;
+        }
         for (int idx = blockIdx.x * IPC + grp; idx < count; idx += ngroups) {
             const int inst = io.list ? io.list[idx] : idx;
             cycle_instance<G>(gP, sm, z, io, inst, tid, flip);
@@ -183,6 +210,10 @@ int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
         return launch_fast(b, io, st);
     if (io.in_list) // a behaviour's bucket: the generic kernel walks it as its instance list
         iop.list = io.in_list, iop.list_count = io.in_count;
+    if (!io.dbg_M && !io.dbg_cycles) {
+        iop.work = b->d_slow_count + 2 * b->slot + 1;
+        CUDA_TRY(cudaMemsetAsync(iop.work, 0, sizeof(int), st));
+    }
     if (b->timing && !use_fast)
         cudaEventRecord(b->ev0, st);
     kern<<<grid, G * IPC, b->smem_bytes, st>>>(b->d_prob, iop);
@@ -202,6 +233,8 @@ int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
 // choose the thread-group width for this problem shape
 void choose_group(const iwbc_problem_t& P, int n, int& G, int& IPC)
 {
+    // (a 16-wide group with 8 instances per CTA was measured for the small arms -- Franka n = 9, Tiago n = 12: the kernel then needs
+    // 218 registers, two CTAs per SM instead of three, and runs 30 % SLOWER: 26.8 M vs 38.4 M Franka updates/s.)
     if (n <= 32 && P.nj * 16 <= 8 * 32) {
         G = 32;
         IPC = 4;
@@ -381,7 +414,7 @@ iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch)
     const size_t B = (size_t)max_batch;
     bool ok = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&b->ev0) == cudaSuccess && cudaEventCreate(&b->ev1) == cudaSuccess;
-    ok = ok && dalloc(&b->d_fplan, 1) == 0 && dalloc(&b->d_slow_list, B) == 0 && dalloc(&b->d_slow_count, 8) == 0 && dalloc(&b->d_slow_code, 65536) == 0;
+    ok = ok && dalloc(&b->d_fplan, 1) == 0 && dalloc(&b->d_slow_list, B) == 0 && dalloc(&b->d_slow_count, 16) == 0 && dalloc(&b->d_slow_code, 65536) == 0;
     ok = ok && cudaStreamCreateWithFlags(&b->aux[0], cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&b->aux[1], cudaStreamNonBlocking) == cudaSuccess
         && cudaEventCreateWithFlags(&b->ev_const, cudaEventDisableTiming) == cudaSuccess;
     {

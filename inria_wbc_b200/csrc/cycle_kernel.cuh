@@ -118,6 +118,7 @@ namespace dev {
         long long* dbg_cycles; // phase timestamps (clock64) of instance 0: load, dyn, asm, factor, eq, ineq, decode
         const int* list;       // optional: instance indices to process (active-set continuation of the fast path)
         const int* list_count; // device-side length of `list`
+        int* work;             // optional: device counter (zeroed before the launch) for dynamic hand-out of list / batch positions to the groups
         const int* in_list;    // optional: the instances of this launch set (a behaviour's per-contact-mask bucket), device-side length
         const int* in_count;
         int* slow_list;        // fast path: instances that need the active-set iteration are appended here

@@ -1823,7 +1823,18 @@ namespace dev {
         __syncthreads();
         int flip = 0;
         const int count = io.list ? *io.list_count : io.B;
-        for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+        // dynamic hand-out of list positions: the listed instances differ in active-set iterations (1 .. 40), a static stride
+        // leaves most CTAs idle while the longest ones finish
+        __shared__ int s_next;
+        for (int idx = blockIdx.x;; idx += gridDim.x) {
+            if (io.work) {
+                if (tid == 0)
+                    s_next = atomicAdd(io.work, 1);
+                __syncthreads();
+                idx = s_next;
+            }
+            if (idx >= count)
+                break;
             const int inst = io.list ? io.list[idx] : idx;
             long long stamps[8];
             long long* cyc = io.prof ? stamps : nullptr;

@@ -34,7 +34,7 @@ int launch_fast_shape(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
         b->slow_grid = b->sm_count * per_sm_slow;
     }
     iop.slow_list = b->d_slow_list + b->list_off;
-    iop.slow_count = b->d_slow_count + b->slot;
+    iop.slow_count = b->d_slow_count + 2 * b->slot; // [2 slot]: length of the slow list, [2 slot + 1]: k_slow's work counter
     if (b->d_scratch == nullptr || b->scratch_img < b->fshape.total) {
         // (re)allocate the hand-over scratch (grow only): at most 65536 images (70 kB each for Talos double support)
         if (b->d_scratch) {
@@ -54,13 +54,14 @@ int launch_fast_shape(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
     }
     if (b->profiling)
         iop.prof = b->d_prof;
-    CUDA_TRY(cudaMemsetAsync(b->d_slow_count + b->slot, 0, sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(b->d_slow_count + 2 * b->slot, 0, 2 * sizeof(int), st));
     if (b->timing)
         cudaEventRecord(b->ev0, st);
     fk<<<std::min(b->fast_grid, io.B), FT_, b->fast_smem, st>>>(b->d_prob, b->d_fplan, iop);
     b->launches++;
     iop.list = b->d_slow_list + b->list_off;
-    iop.list_count = b->d_slow_count + b->slot;
+    iop.list_count = b->d_slow_count + 2 * b->slot;
+    iop.work = b->d_slow_count + 2 * b->slot + 1;
     sk<<<std::min(b->slow_grid, io.B), FT_, b->slow_smem, st>>>(b->d_prob, b->d_fplan, iop);
     if (b->timing) {
         cudaEventRecord(b->ev1, st);

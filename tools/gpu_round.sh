@@ -8,7 +8,7 @@ timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest_gpu.
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/${tag}_smoke.log
 timeout 600 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench_talos_ds.json 2> gpurun_out/${tag}_bench_talos_ds.err
 tail -c 600 gpurun_out/${tag}_bench_talos_ds.json
-for w in franka_65536 talos_walk_131072 icub_ds_16384 tiago_65536; do
+for w in franka_65536 talos_walk_131072 talos_walk_standin_131072 icub_ds_16384 tiago_65536; do
   timeout 600 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu > gpurun_out/${tag}_bench_$w.json 2> gpurun_out/${tag}_bench_$w.err
 done
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_reference.json 2> gpurun_out/${tag}_bench_reference.err
