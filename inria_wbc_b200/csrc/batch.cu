@@ -417,6 +417,9 @@ iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch)
     ok = ok && dalloc(&b->d_fplan, 1) == 0 && dalloc(&b->d_slow_list, B) == 0 && dalloc(&b->d_slow_count, 16) == 0 && dalloc(&b->d_slow_code, 65536) == 0;
     ok = ok && cudaStreamCreateWithFlags(&b->aux[0], cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&b->aux[1], cudaStreamNonBlocking) == cudaSuccess
         && cudaEventCreateWithFlags(&b->ev_const, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; k < 16 && ok; ++k)
+        ok = cudaEventCreateWithFlags(&b->ev_in[k], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&b->ev_done[k], cudaEventDisableTiming) == cudaSuccess;
     {
         const char* e = getenv("IWBC_NO_FAST");
         b->fast_enabled = !(e && e[0] == '1');
@@ -456,6 +459,17 @@ void iwbc_batch_free(iwbc_batch* b)
         }
     if (b->ev_const)
         cudaEventDestroy(b->ev_const);
+    for (cudaStream_t q : {b->s_in, b->s_out})
+        if (q) {
+            cudaStreamSynchronize(q);
+            cudaStreamDestroy(q);
+        }
+    for (int k = 0; k < 16; ++k) {
+        if (b->ev_in[k])
+            cudaEventDestroy(b->ev_in[k]);
+        if (b->ev_done[k])
+            cudaEventDestroy(b->ev_done[k]);
+    }
     if (b->ev0)
         cudaEventDestroy(b->ev0);
     if (b->ev1)
@@ -586,69 +600,115 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
         r.active = out->active ? b->d_active + first * IWBC_ACTIVE_WORDS : nullptr;
         return r;
     };
-    if (uniform && B >= 8192 && !b->timing && !b->profiling) {
-        // pipeline: chunks alternate between two streams so that the H2D copy of one chunk, the kernels of the previous one
-        // and the D2H copy of the one before overlap (needs pinned host buffers to be effective)
-        const unsigned m = contact_mask ? contact_mask[0] : dflt;
-        int rc = prepare_shape(b, m);
-        if (rc)
-            return rc;
-        rc = upload_constants(b, st);
-        if (rc)
-            return rc;
-        CUDA_TRY(cudaEventRecord(b->ev_const, st));
-        CUDA_TRY(cudaStreamWaitEvent(b->aux[0], b->ev_const, 0));
-        CUDA_TRY(cudaStreamWaitEvent(b->aux[1], b->ev_const, 0));
-        // Chunk plan: sizes are multiples of the persistent grid's instance capacity (no partially filled last round), a short
-        // first chunk (its upload is the pipeline's fill: nothing overlaps it) and whatever is left at the end (its download
-        // is the drain).
-        const int unit = b->fast_ok && b->fast_grid > 0 ? b->fast_grid : (b->grid > 0 ? b->grid * b->IPC : 4 * b->sm_count);
-        std::vector<int> bounds;
-        bounds.push_back(0);
-        {
-            int u_first = 2, u_mid = 9; // (IWBC_PIPE="first,mid" in units of the grid capacity: tuning aid)
+    // contiguous runs of equal contact mask (one run when the mask is uniform; the caller may have bucketed a mixed batch)
+    struct Run {
+        int first, count;
+        unsigned mask;
+    };
+    std::vector<Run> runs;
+    bool grouped = true;
+    if (uniform)
+        runs.push_back({0, B, contact_mask ? contact_mask[0] : dflt});
+    else {
+        for (int i = 0; i < B && grouped; ++i)
+            if (i == 0 || contact_mask[i] != contact_mask[i - 1]) {
+                for (const Run& r : runs)
+                    if (r.mask == contact_mask[i])
+                        grouped = false;
+                runs.push_back({i, 0, contact_mask[i]});
+            }
+        if (grouped) {
+            for (size_t k = 0; k < runs.size(); ++k)
+                runs[k].count = (k + 1 < runs.size() ? runs[k + 1].first : B) - runs[k].first;
+        }
+    }
+    if (grouped && B >= 8192 && runs.size() <= 4 && !b->timing && !b->profiling) {
+        // Pipeline (needs pinned host buffers to be effective).  Uploads queue back to back on their own stream (the copy engine
+        // never waits for a kernel or a download); the kernels of successive chunks alternate between two compute streams (their
+        // tails overlap); downloads follow on a third stream; events chain the three per chunk.  A change of contact mask
+        // drains the compute streams first: the __constant__ tables are per mask.
+        int c = 0; // global chunk index (<= 16: ev_in / ev_done)
+        const int cap = std::min(b->max_batch, 65536);
+        for (size_t ri = 0; ri < runs.size(); ++ri) {
+            const Run& run = runs[ri];
+            if (ri > 0) {
+                CUDA_TRY(cudaEventRecord(b->ev_done[15], b->aux[0]));
+                CUDA_TRY(cudaStreamWaitEvent(st, b->ev_done[15], 0));
+                CUDA_TRY(cudaEventRecord(b->ev_done[15], b->aux[1]));
+                CUDA_TRY(cudaStreamWaitEvent(st, b->ev_done[15], 0));
+            }
+            int rc = prepare_shape(b, run.mask);
+            if (rc)
+                return rc;
+            rc = upload_constants(b, st);
+            if (rc)
+                return rc;
+            CUDA_TRY(cudaEventRecord(b->ev_const, st));
+            CUDA_TRY(cudaStreamWaitEvent(b->aux[0], b->ev_const, 0));
+            CUDA_TRY(cudaStreamWaitEvent(b->aux[1], b->ev_const, 0));
+            if (ri == 0)
+                CUDA_TRY(cudaStreamWaitEvent(b->s_in, b->ev_const, 0)); // (the previous call's kernels are done: the call synchronises before returning)
+            // Chunk plan: sizes are multiples of the persistent grid's instance capacity (no partially filled last round), a short
+            // first chunk (its upload is the pipeline's fill: nothing overlaps it) and whatever is left at the end.
+            const int unit = b->fast_ok && b->fast_grid > 0 ? b->fast_grid : (b->grid > 0 ? b->grid * b->IPC : 4 * b->sm_count);
+            int u_first = 4, u_mid = 10; // (IWBC_PIPE="first,mid" in units of the grid capacity: tuning aid)
             if (const char* e = std::getenv("IWBC_PIPE"))
                 std::sscanf(e, "%d,%d", &u_first, &u_mid);
-            int first = std::min(B, std::max(1, u_first) * unit);
-            bounds.push_back(first);
-            while (bounds.back() < B && bounds.size() < 15)
-                bounds.push_back(std::min(B, bounds.back() + std::max(1, u_mid) * unit));
-            if (bounds.back() < B)
-                bounds.push_back(B);
-        }
-        const int nchunk = (int)bounds.size() - 1;
-        const int cap = std::min(b->max_batch, 65536);
-        for (int c = 0; c < nchunk; ++c) {
-            const size_t first = bounds[c], last = bounds[c + 1], cnt = last - first;
-            cudaStream_t cs = b->aux[c & 1];
-            CUDA_TRY(cudaMemcpyAsync(b->d_q + first * nq, q + first * nq, cnt * nq * 8, cudaMemcpyHostToDevice, cs));
-            CUDA_TRY(cudaMemcpyAsync(b->d_v + first * nv, v + first * nv, cnt * nv * 8, cudaMemcpyHostToDevice, cs));
-            if (refs_stride)
-                CUDA_TRY(cudaMemcpyAsync(b->d_refs + first * nref, refs + first * nref, cnt * nref * 8, cudaMemcpyHostToDevice, cs));
-            else if (c < 2) // shared reference vector: each stream uploads it once (into the same place, same bytes)
-                CUDA_TRY(cudaMemcpyAsync(b->d_refs, refs, nref * 8, cudaMemcpyHostToDevice, cs));
-            iwbc_results_t r = dev_results(first);
-            b->slot = c & 7; // chunks c and c + 8 share a counter: same stream, ordered
-            b->list_off = (int)first;
-            if (B <= cap) { // hand-over images: the chunk's own range of the scratch
-                b->scratch_off = (int)first;
-                b->scratch_len = (int)cnt;
+            const int budget = std::max(1, (15 - c) / (int)(runs.size() - ri)); // chunks this run may use
+            std::vector<int> bounds;
+            bounds.push_back(0);
+            bounds.push_back(std::min(run.count, std::max(1, ri == 0 ? u_first : u_mid) * unit));
+            int step = std::max(1, u_mid) * unit;
+            if ((run.count - bounds.back() + step - 1) / step > budget - 1) // long run: fewer, larger chunks (still multiples of the unit)
+                step = ((run.count - bounds.back() + (budget - 1) * unit - 1) / ((budget - 1 > 0 ? budget - 1 : 1) * unit)) * unit;
+            while (bounds.back() < run.count)
+                bounds.push_back(std::min(run.count, bounds.back() + std::max(step, unit)));
+            bool first_launch_of_run = true;
+            for (size_t k = 0; k + 1 < bounds.size(); ++k, ++c) {
+                if (c > 14) {
+                    set_error("iwbc_batch_update: internal error (pipeline chunk plan)");
+                    return IWBC_ERR_ARG;
+                }
+                const size_t first = (size_t)run.first + bounds[k], cnt = bounds[k + 1] - bounds[k];
+                cudaStream_t cs = b->aux[c & 1];
+                CUDA_TRY(cudaMemcpyAsync(b->d_q + first * nq, q + first * nq, cnt * nq * 8, cudaMemcpyHostToDevice, b->s_in));
+                CUDA_TRY(cudaMemcpyAsync(b->d_v + first * nv, v + first * nv, cnt * nv * 8, cudaMemcpyHostToDevice, b->s_in));
+                if (refs_stride)
+                    CUDA_TRY(cudaMemcpyAsync(b->d_refs + first * nref, refs + first * nref, cnt * nref * 8, cudaMemcpyHostToDevice, b->s_in));
+                else if (c == 0) // shared reference vector
+                    CUDA_TRY(cudaMemcpyAsync(b->d_refs, refs, nref * 8, cudaMemcpyHostToDevice, b->s_in));
+                CUDA_TRY(cudaEventRecord(b->ev_in[c], b->s_in));
+                CUDA_TRY(cudaStreamWaitEvent(cs, b->ev_in[c], 0));
+                iwbc_results_t r = dev_results(first);
+                b->slot = c & 7; // chunks c and c + 8 share their counters: same stream, ordered
+                b->list_off = (int)first;
+                if (B <= cap) { // hand-over images: the chunk's own range of the scratch
+                    b->scratch_off = (int)first;
+                    b->scratch_len = (int)cnt;
+                }
+                else { // one half per compute stream: chunks on the same stream are ordered
+                    b->scratch_len = cap / 2;
+                    b->scratch_off = (c & 1) * b->scratch_len;
+                }
+                b->tu_uploaded = false;
+                rc = iwbc_batch_update_device(b, (int)cnt, b->d_q + first * nq, b->d_v + first * nv, b->d_refs + (refs_stride ? first * nref : 0),
+                    refs_stride, run.mask, &r, cs);
+                b->slot = 0;
+                b->list_off = 0;
+                b->scratch_len = 0;
+                if (rc)
+                    return rc;
+                CUDA_TRY(cudaEventRecord(b->ev_done[c], cs));
+                if (first_launch_of_run && b->tu_uploaded) // this launch refreshed the kernel pair's own __constant__ tables on `cs`: the other compute stream must not run ahead of that
+                    CUDA_TRY(cudaStreamWaitEvent(b->aux[(c + 1) & 1], b->ev_done[c], 0));
+                first_launch_of_run = false;
+                CUDA_TRY(cudaStreamWaitEvent(b->s_out, b->ev_done[c], 0));
+                rc = copy_out((int)first, (int)cnt, nullptr, b->s_out);
+                if (rc)
+                    return rc;
             }
-            else {
-                b->scratch_len = cap / nchunk;
-                b->scratch_off = c * b->scratch_len;
-            }
-            rc = iwbc_batch_update_device(b, (int)cnt, b->d_q + first * nq, b->d_v + first * nv, b->d_refs + (refs_stride ? first * nref : 0), refs_stride,
-                m, &r, cs);
-            b->slot = 0;
-            b->list_off = 0;
-            b->scratch_len = 0;
-            if (rc)
-                return rc;
-            rc = copy_out((int)first, (int)cnt, nullptr, cs);
-            if (rc)
-                return rc;
         }
+        CUDA_TRY(cudaStreamSynchronize(b->s_out)); // (every upload and kernel precedes the last download)
         CUDA_TRY(cudaStreamSynchronize(b->aux[0]));
         CUDA_TRY(cudaStreamSynchronize(b->aux[1]));
         return IWBC_OK;
@@ -670,16 +730,6 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
     // mixed masks.  If equal masks already form contiguous runs (the caller bucketed the batch) the runs are launched in
     // place; otherwise: stable sort of instance indices by mask, gather on the host, one launch per mask, results copied
     // back in bulk and scattered on the host.
-    bool grouped = true;
-    {
-        std::vector<unsigned> seen;
-        for (int i = 0; i < B && grouped; ++i)
-            if (i == 0 || contact_mask[i] != contact_mask[i - 1]) {
-                if (std::find(seen.begin(), seen.end(), contact_mask[i]) != seen.end())
-                    grouped = false;
-                seen.push_back(contact_mask[i]);
-            }
-    }
     const double *sq = q, *sv = v, *sr = refs;
     b->perm.resize(B);
     for (int i = 0; i < B; ++i)

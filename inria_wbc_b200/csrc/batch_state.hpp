@@ -60,11 +60,14 @@ struct iwbc_batch {
     double* d_scratch = nullptr; // front-end images handed from k_fast to k_slow
     int* d_slow_code = nullptr;
     int scratch_cap = 0, scratch_off = 0, scratch_len = 0, scratch_img = 0; // capacity (instances); sub-range used by the current launch
-    cudaStream_t aux[2] = {nullptr, nullptr}; // copy / compute pipelining of iwbc_batch_update
+    cudaStream_t aux[2] = {nullptr, nullptr}; // copy / compute pipelining of iwbc_batch_update: two compute streams (kernel tails of successive chunks overlap),
+    cudaStream_t s_in = nullptr, s_out = nullptr; // ... one upload stream, one download stream,
+    cudaEvent_t ev_in[16] = {}, ev_done[16] = {}; // ... chained per chunk by events
     cudaEvent_t ev_const = nullptr;
     int fast_grid = 0, slow_grid = 0;
     size_t fast_smem = 0, slow_smem = 0;
     bool plan_dirty = true;
+    bool tu_uploaded = false; // set by a per-shape unit when its launch had to refresh its own __constant__ tables
     size_t smem_bytes = 0;
     int grid = 0;
 };

@@ -91,6 +91,7 @@ int IWBC_TU_ENTRY(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
         o.batch = b;
         o.revision = b->revision;
         o.mask = b->shape_mask;
+        b->tu_uploaded = true;
     }
     return launch_fast_shape<IWBC_TU_NV, IWBC_TU_ME>(b, io, st);
 }
