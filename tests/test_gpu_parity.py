@@ -125,6 +125,34 @@ def test_talos_mixed_contact_masks_are_bucketed(talos):
     assert np.all(f[mask == 1, 1] == 0) and np.all(f[mask == 2, 0] == 0)
 
 
+def test_pipelined_host_call_with_contact_mask_runs(talos):
+    """iwbc_batch_update's pipelined form (B >= 8192: upload / compute / download streams chained per chunk) on a batch bucketed into
+    three contact-mask runs, against the plain single-stream form of the same call (smaller pieces) bit for bit, and a sample
+    of instances against the oracle."""
+    B = 9216
+    q, v = random_states(talos, B, 33)
+    mask = np.repeat(np.array([3, 1, 2], dtype=np.uint32), B // 3)
+    bt = iw.Batch(talos, 0, B)
+    big = bt.update(q, v, contact_mask=mask)
+    for first in range(0, B, 3072):  # each piece is uniform and below the pipeline threshold
+        sl = slice(first, first + 3072)
+        small = bt.update(q[sl], v[sl], contact_mask=mask[sl])
+        for k in ("tau", "dv", "f", "q_next", "v_next", "q_cmd", "momentum", "status", "iters", "active"):
+            assert np.array_equal(getattr(big, k)[sl], getattr(small, k)), (k, first)
+    pick = np.random.default_rng(2).choice(B, 384, replace=False)
+    o = ol.cycle_batch(talos, q[pick], v[pick], contact_mask=mask[pick], nthreads=os.cpu_count())
+    assert np.array_equal(big.status[pick], o["status"])
+    same = np.all(big.active[pick] == o["active"], axis=1) & (o["status"] == 0)
+    assert same.mean() > 0.9
+    for k in ("tau", "dv", "f"):
+        assert _rel(getattr(big, k)[pick][same], o[k][same]) < TOL, k
+    # a second call on the same handle (constants already resident, different run lengths) stays consistent
+    mask2 = np.concatenate([np.full(5000, 3, np.uint32), np.full(B - 5000, 2, np.uint32)])
+    again = bt.update(q, v, contact_mask=mask2)
+    ref = bt.update(q[:5000], v[:5000], contact_mask=mask2[:5000])
+    assert np.array_equal(again.tau[:5000], ref.tau) and np.array_equal(again.status[:5000], ref.status)
+
+
 def test_full_size_properties(talos):
     """BASELINE config 3 at full size (16 384): size-independent properties instead of the oracle."""
     import bench
