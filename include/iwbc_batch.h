@@ -182,6 +182,24 @@ int iwbc_behavior_eval_device(iwbc_behavior* h, int device, int B, const int* ph
 int iwbc_batch_behavior_rollout_device(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, double* refs, const int* phase,
     int tick0, int ticks, int init_refs, const iwbc_results_t* out_last, unsigned* contact_mask, void* stream);
 
+/* ------------------------------------------------------------------ post-solve model collision check
+ * Replaces `utils::CollisionCheck::load_collision_file` + `is_colliding(model, data)` (src/safety/collision_check.cpp:5-87),
+ * which the controller runs after every solve when CONTROLLER.check_model_collisions is set (src/controllers/controller.cpp:89-98,
+ * 309-310): links covered by spheres {x, y, z, diameter} grouped in members; two spheres of DIFFERENT members closer than the sum of
+ * their radii = collision.  collision_yaml: the file CONTROLLER.collision_path names (e.g. etc/talos/collisions/talos_collisions_margin.yaml).
+ */
+typedef struct iwbc_collision iwbc_collision;
+iwbc_collision* iwbc_collision_load(const iwbc_problem* p, const char* collision_yaml);
+void iwbc_collision_free(iwbc_collision* h);
+/* sphere / member counts; links named by the file that the model does not have (the reference skips them silently) */
+int iwbc_collision_info(const iwbc_collision* h, int* nspheres, int* nmembers, int* skipped_links);
+/* the compiled table (host): per sphere {x, y, z, radius} and {supporting joint (-1 = universe), member index (members sorted by name)} */
+int iwbc_collision_spheres(const iwbc_collision* h, double* p_radius4, int* joint_member2);
+/* DEVICE pointers: q[B][nq] (the state the tick started from: the reference checks tsid's data), colliding[B] (0 / 1, the
+ * batched is_model_colliding_), pair4[B][4] or NULL = {member a, sphere i, member b, sphere j} of the first hit in the reference's
+ * iteration order (-1 when free).  Enqueued on `stream` (NULL: the batch's own stream), no synchronisation. */
+int iwbc_batch_check_collisions_device(iwbc_batch* b, iwbc_collision* h, int B, const double* q, int* colliding, int* pair4, void* stream);
+
 /* ------------------------------------------------------------------ solver interface
  * Batched form of `tsid::solvers::SolverHQPBase::solve` for the EiquadprogFast backend
  * (src/controllers/pos_tracker.cpp:96,102; src/controllers/controller.cpp:247): B dense QPs of one

@@ -5,5 +5,5 @@ include/iwbc_batch.h).  This package is the thin ctypes binding used by the test
 a Python mirror of the reference's controller surface (`controllers.py`).  There is no CPU fallback:
 the compute calls raise if the CUDA library or a GPU is missing.
 """
-from ._lib import (Problem, Batch, Results, Behavior, qp_solve_batch, lib, lib_path, IwbcError,  # noqa: F401
+from ._lib import (Problem, Batch, Results, Behavior, CollisionModel, qp_solve_batch, lib, lib_path, IwbcError,  # noqa: F401
                    ETC_PATH, ROBOTS_PATH, STATUS_OPTIMAL, ACTIVE_WORDS, measure_fp64_tflops)

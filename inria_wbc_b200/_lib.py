@@ -70,6 +70,11 @@ def lib():
         "iwbc_batch_loop_profile": (ci, [vp, vp]),
         "iwbc_batch_launch_info": (ci, [vp, pi, pi, pi, C.POINTER(C.c_long)]),
         "iwbc_qp_solve_batch": (ci, [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "iwbc_collision_load": (vp, [vp, cp]),
+        "iwbc_collision_free": (None, [vp]),
+        "iwbc_collision_info": (ci, [vp, pi, pi, pi]),
+        "iwbc_collision_spheres": (ci, [vp, vp, vp]),
+        "iwbc_batch_check_collisions_device": (ci, [vp, vp, ci, vp, vp, vp, vp]),
         "iwbc_behavior_load": (vp, [vp, cp, cp]),
         "iwbc_behavior_free": (None, [vp]),
         "iwbc_behavior_info": (ci, [vp, pi, pi, pi, pi, vp]),
@@ -173,6 +178,37 @@ class Problem:
             lib().iwbc_problem_name(self._h, k, i, buf, 256)
             out.append(buf.value.decode())
         return out
+
+
+class CollisionModel:
+    """Sphere cover of the robot's links for the post-solve model collision check (utils::CollisionCheck)."""
+
+    def __init__(self, problem, collision_yaml):
+        self.problem = problem
+        if not os.path.isabs(collision_yaml):
+            collision_yaml = os.path.join(ETC_PATH, collision_yaml)
+        self._h = lib().iwbc_collision_load(problem.handle, collision_yaml.encode())
+        if not self._h:
+            raise IwbcError(_err(lib()))
+        ns, nm, sk = C.c_int(), C.c_int(), C.c_int()
+        lib().iwbc_collision_info(self._h, C.byref(ns), C.byref(nm), C.byref(sk))
+        self.nspheres, self.nmembers, self.skipped_links = ns.value, nm.value, sk.value
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.iwbc_collision_free(self._h)
+            self._h = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def spheres(self):
+        """(p_radius[nspheres][4], joint_member[nspheres][2])"""
+        pr = np.zeros((self.nspheres, 4))
+        jm = np.zeros((self.nspheres, 2), dtype=np.int32)
+        lib().iwbc_collision_spheres(self._h, pr.ctypes.data, jm.ctypes.data)
+        return pr, jm
 
 
 class Behavior:
@@ -295,6 +331,12 @@ class Batch:
         st = _Results(*[(out_ptrs or {}).get(f) for f in Results.FIELDS])
         rc = lib().iwbc_batch_behavior_rollout_device(self._h, behavior.handle, B, q_ptr, v_ptr, refs_ptr, phase_ptr, tick0, ticks,
                                                       1 if init_refs else 0, C.byref(st), mask_ptr, stream)
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+
+    def check_collisions_device(self, collision_model, B, q_ptr, colliding_ptr, pair_ptr=None, stream=0):
+        """Batched CollisionCheck::is_colliding on device-resident states (SURVEY.md 8(f-4))."""
+        rc = lib().iwbc_batch_check_collisions_device(self._h, collision_model.handle, B, q_ptr, colliding_ptr, pair_ptr, stream)
         if rc != 0:
             raise IwbcError(_err(lib()))
 

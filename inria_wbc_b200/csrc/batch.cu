@@ -330,6 +330,7 @@ int upload_constants(iwbc_batch* b, cudaStream_t st)
     if (b->revision != b->prob->revision) {
         CUDA_TRY(cudaMemcpyAsync(b->d_prob, &b->prob->cs.prob, sizeof(iwbc_problem_t), cudaMemcpyHostToDevice, st));
         b->revision = b->prob->revision;
+        b->dprob_revision = b->prob->revision;
         o.batch = nullptr;
     }
     if (b->plan_dirty) {

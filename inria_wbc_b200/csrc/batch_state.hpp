@@ -23,6 +23,7 @@
 struct iwbc_batch {
     const iwbc_problem* prob = nullptr;
     unsigned long revision = ~0ul;
+    unsigned long dprob_revision = ~0ul; // revision of the problem held by d_prob
     int device = 0;
     int max_batch = 0;
     int sm_count = 0;
@@ -92,3 +93,5 @@ int iwbc_launch_fast_0_0(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st
 // one pass of the control cycle over io's instances (io.list / io.list_count: optional device-side instance list) with one
 // contact mask: prepares the shape, refreshes constants, launches (batch.cu)
 int iwbc_run_cycle(iwbc_batch* b, const iwbc::dev::IO& io, unsigned mask, cudaStream_t st);
+
+struct iwbc_collision;

@@ -1441,6 +1441,36 @@ int oracle_flop_counts(long* out20, int reset)
 #endif
 }
 
+// Model collision check, restated from src/safety/collision_check.cpp:27-87: sphere centres = oMi[joint] * p; every ordered pair of
+// DIFFERENT members, members in index order (the caller sorts them by name as the reference's std::map does), first hit returns.
+// spheres: p_radius4[s] = {x, y, z, radius}, joint_member2[s] = {joint (-1 universe), member}.  out5 = {hit, member a, i, member b, j}.
+int oracle_collision(const iwbc_problem_t* P, const double* q, int nspheres, const double* p_radius4, const int* joint_member2, int nmembers, int* out5)
+{
+    Dyn D;
+    std::vector<double> v0(P->nv, 0.0);
+    compute_all_terms(*P, q, v0.data(), D);
+    std::vector<std::vector<std::pair<V3, double>>> members(nmembers);
+    for (int s = 0; s < nspheres; ++s) {
+        V3 rel = {p_radius4[4 * s], p_radius4[4 * s + 1], p_radius4[4 * s + 2]};
+        const int j = joint_member2[2 * s];
+        V3 c = j >= 0 ? D.oMi[j].R * rel + D.oMi[j].p : rel;
+        members[joint_member2[2 * s + 1]].push_back(std::make_pair(c, p_radius4[4 * s + 3]));
+    }
+    out5[0] = 0, out5[1] = out5[2] = out5[3] = out5[4] = -1;
+    for (int a = 0; a < nmembers; ++a)
+        for (int b = 0; b < nmembers; ++b) {
+            if (a == b)
+                continue;
+            for (size_t i = 0; i < members[a].size(); ++i)
+                for (size_t j = 0; j < members[b].size(); ++j)
+                    if (norm(members[b][j].first - members[a][i].first) < members[b][j].second + members[a][i].second) {
+                        out5[0] = 1, out5[1] = a, out5[2] = (int)i, out5[3] = b, out5[4] = (int)j;
+                        return 0;
+                    }
+        }
+    return 0;
+}
+
 // counters of the Goldfarb-Idnani loop since the last reset: {l1 passes, step directions, drops} (development aid)
 void oracle_qp_stats(long* out3, int reset)
 {

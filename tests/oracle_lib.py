@@ -192,3 +192,14 @@ def sim_qp_solve(H, g, CE, ce0, CI, ci0):
     sim_lib().sim_qp_solve(C.c_int(n), C.c_int(me), C.c_int(mi), _p(H), _p(g), _p(CE), _p(ce0), _p(CI), _p(ci0), _p(x), _p(status),
                            _p(iters), _p(active))
     return dict(status=int(status[0]), x=x, iters=int(iters[0]), active=active)
+
+
+def collision(problem, q, spheres_p_radius, spheres_joint_member, nmembers):
+    """oracle_collision: (hit, member a, i, member b, j) for one configuration."""
+    pr = np.ascontiguousarray(spheres_p_radius, dtype=np.float64)
+    jm = np.ascontiguousarray(spheres_joint_member, dtype=np.int32)
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    out = np.zeros(5, dtype=np.int32)
+    rc = lib().oracle_collision(C.c_void_p(problem.data_ptr), _p(q), C.c_int(pr.shape[0]), _p(pr), _p(jm), C.c_int(nmembers), _p(out))
+    assert rc == 0
+    return out

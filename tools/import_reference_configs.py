@@ -21,9 +21,10 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "inria_wbc_
 YAMLS = {
     "franka": ["pos_tracker.yaml", "tasks.yaml", "cartesian_line.yaml"],
     "talos": ["talos_pos_tracker.yaml", "tasks.yaml", "frames.yaml", "squat.yaml", "arm.yaml",
-              "walk.yaml", "walk_on_spot.yaml", "move_com.yaml", "clapping.yaml"],
+              "walk.yaml", "walk_on_spot.yaml", "move_com.yaml", "clapping.yaml",
+              "collisions/talos_collisions_margin.yaml", "collisions/talos_collisions.yaml"],
     "icub": ["humanoid_pos_tracker.yaml", "tasks.yaml", "frames.yaml", "squat.yaml", "arm.yaml"],
-    "tiago": ["pos_tracker.yaml", "tasks.yaml", "frames.yaml", "cartesian_line.yaml"],
+    "tiago": ["pos_tracker.yaml", "tasks.yaml", "frames.yaml", "cartesian_line.yaml", "collisions.yaml"],
 }
 SRDFS = {
     "franka": ["configurations.srdf"],
@@ -57,6 +58,7 @@ def main():
             node = _mask_safe_load(open(src).read())
             if isinstance(node, dict) and "CONTROLLER" in node:
                 node["CONTROLLER"]["base_path"] = "@ETC@/" + robot   # resolved by the loader
+            os.makedirs(os.path.dirname(os.path.join(OUT, robot, f)), exist_ok=True)
             with open(os.path.join(OUT, robot, f), "w") as fo:
                 fo.write("# normalised from the reference's etc/%s/%s by tools/import_reference_configs.py\n" % (robot, f))
                 yaml.safe_dump(node, fo, sort_keys=False, default_flow_style=None, width=100)
