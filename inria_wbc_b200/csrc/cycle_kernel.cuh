@@ -2153,14 +2153,27 @@ namespace dev {
                     const double invd = lane < m ? 1.0 / sm.R[Ridx(i, i)] : 0.0;
                     double acc = lane < m ? sm.d[i] * invd : 0.0; // row i pre-scaled by 1 / R_ii: the chain per column is shuffle + FMA
                     double ri = 0.0;
-#pragma unroll 4
-                    for (int jj = m - 1; jj >= 0; --jj) {
+                    // four columns per trip, their (scaled) entries loaded before the chain: per column the chain is shuffle + FMA
+                    auto col = [&](int jj, double rv) {
                         const double rj = __shfl_sync(0xffffffffu, acc, jj);
                         if (lane == jj)
                             ri = rj;
                         else if (lane < jj)
-                            acc = fma(-(sm.R[Ridx(i, me + jj)] * invd), rj, acc);
+                            acc = fma(-rv, rj, acc);
+                    };
+                    int jj = m - 1;
+                    for (; jj >= 3; jj -= 4) {
+                        const double r0 = lane < jj ? sm.R[Ridx(i, me + jj)] * invd : 0.0;
+                        const double r1 = lane < jj - 1 ? sm.R[Ridx(i, me + jj - 1)] * invd : 0.0;
+                        const double r2 = lane < jj - 2 ? sm.R[Ridx(i, me + jj - 2)] * invd : 0.0;
+                        const double r3 = lane < jj - 3 ? sm.R[Ridx(i, me + jj - 3)] * invd : 0.0;
+                        col(jj, r0);
+                        col(jj - 1, r1);
+                        col(jj - 2, r2);
+                        col(jj - 3, r3);
                     }
+                    for (; jj >= 0; --jj)
+                        col(jj, lane < jj ? sm.R[Ridx(i, me + jj)] * invd : 0.0);
                     double ratio = inf;
                     int li = 0x7fffffff;
                     if (lane < m) {
