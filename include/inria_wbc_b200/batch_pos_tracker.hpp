@@ -160,6 +160,30 @@ namespace inria_wbc {
                 }
                 return out;
             }
+        public:
+            // `ticks` closed device-side ticks of a compiled behaviour on the controller's own (open-loop) state: what a loop of
+            // Behavior::update() calls does in the reference, without crossing PCIe in between.  Results = those of the last tick.
+            void run_behavior(iwbc_behavior* h, const int* phase, int tick0, int ticks)
+            {
+                ensure_batch();
+                iwbc_results_t out = {tau_.data(), a_tsid_.data(), forces_.data(), nullptr, nullptr, q_.data(), momentum_.data(), status_.data(),
+                    iters_.data(), nullptr};
+                if (iwbc_batch_behavior_run(batch_, h, B_, q_tsid_.data(), v_tsid_.data(), phase, tick0, ticks, &out, mask_.data()) != IWBC_OK)
+                    throw IWBC_B200_EXCEPTION(std::string("behaviour roll-out failed: ") + iwbc_last_error());
+                t_ += dt_ * ticks;
+            }
+            iwbc_problem* problem() { return prob_; }
+            const std::vector<unsigned>& contact_masks() const { return mask_; } // activated contacts per instance (bit = contact index)
+
+        protected:
+            void ensure_batch()
+            {
+                if (!batch_) {
+                    batch_ = iwbc_batch_create(prob_, config_.device, B_);
+                    if (!batch_)
+                        throw IWBC_B200_EXCEPTION(std::string("cannot create the GPU batch: ") + iwbc_last_error());
+                }
+            }
             void solve(const double* q, const double* dq)
             {
                 if (!batch_) {
@@ -307,6 +331,48 @@ namespace inria_wbc {
             std::map<std::string, creator_t> map_;
         };
     } // namespace controllers
+
+    namespace behaviors {
+        // behaviors::Behavior (include/inria_wbc/behaviors/behavior.hpp:17-30): constructed from a controller and the behaviour's YAML,
+        // `update()` = set this tick's references / contacts, then controller->update().  Here the behaviour is compiled into a table the
+        // GPU evaluates; every instance may sit at its own phase of the behaviour.
+        class BatchBehavior {
+        public:
+            using controller_ptr_t = std::shared_ptr<controllers::BatchController>;
+            BatchBehavior(const controller_ptr_t& controller, const std::string& behavior_yaml, const std::string& overrides_yaml = "")
+                : controller_(controller)
+            {
+                IWBC_B200_ASSERT(controller_ != nullptr, "Invalid controller pointer"); // behavior.cpp:25
+                h_ = iwbc_behavior_load(controller_->problem(), behavior_yaml.c_str(), overrides_yaml.empty() ? nullptr : overrides_yaml.c_str());
+                if (!h_)
+                    throw IWBC_B200_EXCEPTION(std::string("cannot build the behavior: ") + iwbc_last_error());
+                iwbc_behavior_info(h_, &total_ticks_, nullptr, nullptr, nullptr, nullptr);
+            }
+            BatchBehavior(const BatchBehavior&) = delete;
+            BatchBehavior& operator=(const BatchBehavior&) = delete;
+            virtual ~BatchBehavior() { iwbc_behavior_free(h_); }
+            // per-instance offset into the behaviour (instance i runs tick `t + phase[i]`); default: all in step
+            void set_phase(const std::vector<int>& phase)
+            {
+                IWBC_B200_ASSERT((int)phase.size() == controller_->batch(), "set_phase: one offset per instance");
+                phase_ = phase;
+            }
+            virtual void update(int ticks = 1)
+            {
+                controller_->run_behavior(h_, phase_.empty() ? nullptr : phase_.data(), tick_, ticks);
+                tick_ += ticks;
+            }
+            int tick() const { return tick_; }
+            int total_ticks() const { return total_ticks_; }
+            controller_ptr_t controller() { return controller_; }
+
+        private:
+            controller_ptr_t controller_;
+            iwbc_behavior* h_ = nullptr;
+            std::vector<int> phase_;
+            int tick_ = 0, total_ticks_ = 0;
+        };
+    } // namespace behaviors
 
     namespace solvers {
         // tsid::solvers::SolverHQPBase through the three virtuals the reference uses (resize / solve / status), for B stacked QPs:

@@ -182,6 +182,12 @@ int iwbc_behavior_eval_device(iwbc_behavior* h, int device, int B, const int* ph
 int iwbc_batch_behavior_rollout_device(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, double* refs, const int* phase,
     int tick0, int ticks, int init_refs, const iwbc_results_t* out_last, unsigned* contact_mask, void* stream);
 
+/* The same roll-out with HOST buffers: q[B][nq], v[B][nv] are uploaded, advanced `ticks` ticks on the device and written back; phase[B]
+ * (host) or NULL; out_last / contact_mask are host arrays (any may be NULL).  tick0 == 0 starts from the construction-time references; a
+ * later call (tick0 > 0, same B) continues where the previous one stopped.  Synchronous. */
+int iwbc_batch_behavior_run(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, const int* phase, int tick0, int ticks,
+    const iwbc_results_t* out_last, unsigned* contact_mask);
+
 /* ------------------------------------------------------------------ post-solve model collision check
  * Replaces `utils::CollisionCheck::load_collision_file` + `is_colliding(model, data)` (src/safety/collision_check.cpp:5-87),
  * which the controller runs after every solve when CONTROLLER.check_model_collisions is set (src/controllers/controller.cpp:89-98,

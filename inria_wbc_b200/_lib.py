@@ -70,6 +70,7 @@ def lib():
         "iwbc_batch_loop_profile": (ci, [vp, vp]),
         "iwbc_batch_launch_info": (ci, [vp, pi, pi, pi, C.POINTER(C.c_long)]),
         "iwbc_qp_solve_batch": (ci, [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+        "iwbc_batch_behavior_run": (ci, [vp, vp, ci, vp, vp, vp, ci, ci, C.POINTER(_Results), vp]),
         "iwbc_collision_load": (vp, [vp, cp]),
         "iwbc_collision_free": (None, [vp]),
         "iwbc_collision_info": (ci, [vp, pi, pi, pi]),
@@ -333,6 +334,21 @@ class Batch:
                                                       1 if init_refs else 0, C.byref(st), mask_ptr, stream)
         if rc != 0:
             raise IwbcError(_err(lib()))
+
+    def behavior_run(self, behavior, q, v, ticks, tick0=0, phase=None, out=None, fields=("tau", "status"), want_mask=False):
+        """`for tick: behavior.update()` with host arrays: q, v are advanced IN PLACE by `ticks` closed device-side ticks."""
+        P = self.problem
+        assert q.dtype == np.float64 and v.dtype == np.float64 and q.flags.c_contiguous and v.flags.c_contiguous
+        B = q.reshape(-1, P.nq).shape[0]
+        ph = None if phase is None else np.ascontiguousarray(phase, dtype=np.int32)
+        if out is None:
+            out = Results(P, B, fields)
+        st = out.as_struct()
+        mask = np.zeros(B, dtype=np.uint32) if want_mask else None
+        rc = lib().iwbc_batch_behavior_run(self._h, behavior.handle, B, q.ctypes.data, v.ctypes.data, _ptr(ph), tick0, ticks, C.byref(st), _ptr(mask))
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+        return (out, mask) if want_mask else out
 
     def check_collisions_device(self, collision_model, B, q_ptr, colliding_ptr, pair_ptr=None, stream=0):
         """Batched CollisionCheck::is_colliding on device-resident states (SURVEY.md 8(f-4))."""

@@ -449,7 +449,7 @@ void iwbc_batch_free(iwbc_batch* b)
         o.batch = nullptr;
     if (b->stream)
         cudaStreamSynchronize(b->stream);
-    void* ptrs[] = {b->d_scratch, b->d_slow_code, b->d_fplan, b->d_slow_list, b->d_slow_count, b->d_prof, b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
+    void* ptrs[] = {b->d_phase, b->d_cmask, b->d_scratch, b->d_slow_code, b->d_fplan, b->d_slow_list, b->d_slow_count, b->d_prof, b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);

@@ -34,6 +34,8 @@ struct iwbc_batch {
     double *d_tau = nullptr, *d_dv = nullptr, *d_f = nullptr, *d_qn = nullptr, *d_vn = nullptr, *d_qc = nullptr, *d_mom = nullptr;
     int *d_status = nullptr, *d_iters = nullptr;
     unsigned* d_active = nullptr;
+    int* d_phase = nullptr;       // iwbc_batch_behavior_run: per-instance phase offsets, contact masks (allocated on first use)
+    unsigned* d_cmask = nullptr;
     // bucketing scratch (host)
     std::vector<int> perm;
     std::vector<double> hq, hv, hr;

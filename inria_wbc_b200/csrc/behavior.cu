@@ -358,4 +358,69 @@ int iwbc_batch_behavior_rollout_device(iwbc_batch* b, iwbc_behavior* h, int B, d
     return IWBC_OK;
 }
 
+// Host-buffer form of the roll-out (what a `for (tick) behavior->update();` loop of the reference does, src/robot_dart/talos.cpp:380-390):
+// uploads the state once, runs `ticks` closed device-side ticks, downloads the advanced state and the last tick's results.
+int iwbc_batch_behavior_run(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, const int* phase, int tick0, int ticks,
+    const iwbc_results_t* out_last, unsigned* contact_mask)
+{
+    if (!b || !h || !q || !v || B < 0 || ticks < 0) {
+        set_error("iwbc_batch_behavior_run: bad argument");
+        return IWBC_ERR_ARG;
+    }
+    if (B > b->max_batch) {
+        set_error("iwbc_batch_behavior_run: B exceeds max_batch");
+        return IWBC_ERR_ARG;
+    }
+    if (B == 0 || ticks == 0)
+        return IWBC_OK;
+    CUDA_TRY(cudaSetDevice(b->device));
+    const iwbc_problem_t& P = b->prob->cs.prob;
+    cudaStream_t st = b->stream;
+    const size_t nq = P.nq, nv = P.nv, na = P.na, nf = 12 * P.ncontacts;
+    if (!b->d_phase) {
+        CUDA_TRY(cudaMalloc((void**)&b->d_phase, (size_t)b->max_batch * sizeof(int)));
+        CUDA_TRY(cudaMalloc((void**)&b->d_cmask, (size_t)b->max_batch * sizeof(unsigned)));
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->d_q, q, B * nq * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->d_v, v, B * nv * 8, cudaMemcpyHostToDevice, st));
+    if (phase)
+        CUDA_TRY(cudaMemcpyAsync(b->d_phase, phase, B * sizeof(int), cudaMemcpyHostToDevice, st));
+    iwbc_results_t r;
+    std::memset(&r, 0, sizeof(r));
+    if (out_last) {
+        r.tau = out_last->tau ? b->d_tau : nullptr, r.dv = out_last->dv ? b->d_dv : nullptr, r.f = out_last->f ? b->d_f : nullptr;
+        r.q_cmd = out_last->q_cmd ? b->d_qc : nullptr, r.momentum = out_last->momentum ? b->d_mom : nullptr;
+        r.status = out_last->status ? b->d_status : nullptr, r.iters = out_last->iters ? b->d_iters : nullptr;
+        r.active = out_last->active ? b->d_active : nullptr;
+    }
+    // a fresh behaviour (tick0 == 0) starts from the construction-time references; later calls continue from the rows the previous call left
+    int rc = iwbc_batch_behavior_rollout_device(b, h, B, b->d_q, b->d_v, b->d_refs, phase ? b->d_phase : nullptr, tick0, ticks, tick0 == 0 ? 1 : 0, &r,
+        contact_mask ? b->d_cmask : nullptr, st);
+    if (rc)
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(q, b->d_q, B * nq * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(v, b->d_v, B * nv * 8, cudaMemcpyDeviceToHost, st));
+    if (out_last) {
+        auto back = [&](void* host, const void* devp, size_t bytes) -> int {
+            if (host)
+                CUDA_TRY(cudaMemcpyAsync(host, devp, bytes, cudaMemcpyDeviceToHost, st));
+            return IWBC_OK;
+        };
+        rc = back(out_last->tau, b->d_tau, B * na * 8) | back(out_last->dv, b->d_dv, B * nv * 8) | back(out_last->f, b->d_f, B * nf * 8)
+            | back(out_last->q_cmd, b->d_qc, B * nv * 8) | back(out_last->momentum, b->d_mom, B * 3 * 8) | back(out_last->status, b->d_status, B * 4)
+            | back(out_last->iters, b->d_iters, B * 4) | back(out_last->active, b->d_active, (size_t)B * IWBC_ACTIVE_WORDS * 4);
+        if (rc)
+            return IWBC_ERR_CUDA;
+        // q_next / v_next of the last tick ARE the advanced state
+        if (out_last->q_next)
+            CUDA_TRY(cudaMemcpyAsync(out_last->q_next, b->d_q, B * nq * 8, cudaMemcpyDeviceToHost, st));
+        if (out_last->v_next)
+            CUDA_TRY(cudaMemcpyAsync(out_last->v_next, b->d_v, B * nv * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (contact_mask)
+        CUDA_TRY(cudaMemcpyAsync(contact_mask, b->d_cmask, B * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return IWBC_OK;
+}
+
 } // extern "C"

@@ -34,3 +34,10 @@ def test_batch_determinism_rehost():
     r = _run(_build("test_batch_determinism"), "300")
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("OK")
+
+
+@pytest.mark.gpu
+def test_batch_behavior_rehost():
+    r = _run(_build("test_batch_behavior"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("OK")
