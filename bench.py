@@ -36,6 +36,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (controller yaml, overrides, per-GPU batch, recipe)
     "talos_ds_16384": ("talos/talos_pos_tracker.yaml", None, 16384, "talos"),
+    # config 3, fast-URDF variant (the reference's `-f` runs: nq = 39, QP n = 62, me = 18, mi = 196, 85 cost rows)
+    "talos_fast_ds_16384": ("talos/talos_pos_tracker.yaml", {"urdf": "talos/talos_fast.urdf"}, 16384, "talos"),
     "franka_65536": ("franka/pos_tracker.yaml", None, 65536, "franka"),
     # config 5: Talos walking, a mix of double- and single-support shapes bucketed by contact mask
     "talos_walk_131072": ("talos/talos_pos_tracker.yaml", None, 131072, "walk"),

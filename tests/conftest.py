@@ -35,6 +35,13 @@ def talos():
 
 
 @pytest.fixture(scope="session")
+def talos_fast():
+    """Talos with the `talos_fast.urdf` model of the reference's `-f` runs (grippers reduced to their driven joint)."""
+    import inria_wbc_b200 as iw
+    return iw.Problem("talos/talos_pos_tracker.yaml", overrides={"urdf": "talos/talos_fast.urdf"})
+
+
+@pytest.fixture(scope="session")
 def tiago():
     import inria_wbc_b200 as iw
     return iw.Problem("tiago/pos_tracker.yaml", overrides={"urdf": "tiago/tiago_steel_no_wheel.urdf"})

@@ -105,6 +105,19 @@ def test_talos_double_support_config3(talos):
     assert np.array_equal(r.iters[same], o["iters"][same])
 
 
+def test_talos_fast_urdf_config3(talos_fast):
+    """BASELINE config 3 on the fast URDF (n = 62, me = 18, mi = 196, 85 cost rows), double and single support."""
+    import bench
+    P = talos_fast
+    assert (P.nq, P.nv, P.na) == (39, 38, 32) and P.qp_shape() == (62, 18, 196, 85)
+    B = 1536
+    q, v, refs = bench.make_inputs(P, B, "talos", 0xB200 + 3)
+    bt = iw.Batch(P, 0, B)
+    r, o = _check(P, bt, q, v, refs)
+    mask = np.repeat(np.array([3, 1, 2], dtype=np.uint32), B // 3)
+    _check(P, bt, q, v, refs, mask=mask)
+
+
 def test_talos_stage_dump(talos):
     q, v = random_states(talos, 1, 9, base=True)
     bt = iw.Batch(talos, 0, 8)
