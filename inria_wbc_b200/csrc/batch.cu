@@ -1,6 +1,7 @@
 // batch.cu -- GPU half of the C ABI (include/iwbc_batch.h): kernel entry points, launch logic,
 // device workspaces, host<->device staging.  sm_100a only; no CPU fallback.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -169,7 +170,7 @@ namespace {
 
 // which (device, problem revision, mask) the __constant__ copies currently hold
 struct ConstOwner {
-    const void* batch = nullptr;
+    unsigned long uid = 0; // iwbc_batch::uid (addresses get reused after a free; uids do not)
     unsigned long revision = 0;
     unsigned mask = ~0u;
 } g_const_owner[16];
@@ -331,21 +332,21 @@ int upload_constants(iwbc_batch* b, cudaStream_t st)
         CUDA_TRY(cudaMemcpyAsync(b->d_prob, &b->prob->cs.prob, sizeof(iwbc_problem_t), cudaMemcpyHostToDevice, st));
         b->revision = b->prob->revision;
         b->dprob_revision = b->prob->revision;
-        o.batch = nullptr;
+        o.uid = 0;
     }
     if (b->plan_dirty) {
         // (the stream may still run a kernel reading the previous plan: the copy is stream-ordered behind it)
         CUDA_TRY(cudaMemcpyAsync(b->d_fplan, &b->fplan, sizeof(dev::FPlan), cudaMemcpyHostToDevice, st));
         b->plan_dirty = false;
     }
-    if (o.batch != b || o.revision != b->revision || o.mask != b->shape_mask) {
+    if (o.uid != b->uid || o.revision != b->revision || o.mask != b->shape_mask) {
         // other streams may still be running a kernel that reads the old constants
-        if (o.batch != nullptr && o.batch != b)
+        if (o.uid != 0 && o.uid != b->uid)
             CUDA_TRY(cudaDeviceSynchronize());
         CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_P, &b->prob->cs.prob, sizeof(iwbc_problem_t), 0, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_S, &b->shape, sizeof(dev::Shape), 0, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_F, &b->fshape, sizeof(dev::FShape), 0, cudaMemcpyHostToDevice, st));
-        o.batch = b;
+        o.uid = b->uid;
         o.revision = b->revision;
         o.mask = b->shape_mask;
     }
@@ -407,6 +408,8 @@ iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch)
     }
     cudaSetDevice(device);
     auto* b = new iwbc_batch;
+    static std::atomic<unsigned long> next_uid{1};
+    b->uid = next_uid++;
     b->prob = p;
     b->device = device;
     b->max_batch = max_batch;
@@ -445,8 +448,8 @@ void iwbc_batch_free(iwbc_batch* b)
         return;
     cudaSetDevice(b->device);
     ConstOwner& o = g_const_owner[b->device & 15];
-    if (o.batch == b)
-        o.batch = nullptr;
+    if (o.uid == b->uid)
+        o.uid = 0;
     if (b->stream)
         cudaStreamSynchronize(b->stream);
     void* ptrs[] = {b->d_phase, b->d_cmask, b->d_scratch, b->d_slow_code, b->d_fplan, b->d_slow_list, b->d_slow_count, b->d_prof, b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
@@ -1025,7 +1028,7 @@ int iwbc_qp_solve_batch(int device, int B, int n, int me, int mi, const double* 
     }
     ConstOwner& o = g_const_owner[device & 15];
     CUDA_TRY(cudaDeviceSynchronize());
-    o.batch = nullptr;
+    o.uid = 0;
     CUDA_TRY(cudaMemcpyToSymbol(dev::c_S, &S, sizeof(S)));
     dev::QpIO io = {B, n, me, mi, dH, dg, dCE, dce, dCI, dci, dx, dst, dit, dact};
     int rc = IWBC_OK;

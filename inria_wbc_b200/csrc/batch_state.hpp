@@ -22,6 +22,7 @@
 
 struct iwbc_batch {
     const iwbc_problem* prob = nullptr;
+    unsigned long uid = 0; // unique per created batch (never reused, unlike the address): identity of the owner of the __constant__ tables
     unsigned long revision = ~0ul;
     unsigned long dprob_revision = ~0ul; // revision of the problem held by d_prob
     int device = 0;
@@ -80,7 +81,7 @@ constexpr int IWBC_FAST_THREADS = 128; // threads per CTA of k_fast / k_slow
 
 // which (problem revision, contact mask) a translation unit's __constant__ copies currently hold, per device
 struct iwbc_const_owner {
-    const void* batch = nullptr;
+    unsigned long uid = 0; // iwbc_batch::uid of the batch whose tables are resident (0: none)
     unsigned long revision = 0;
     unsigned mask = ~0u;
 };

@@ -81,14 +81,14 @@ int launch_fast_shape(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
 int IWBC_TU_ENTRY(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
 {
     iwbc_const_owner& o = g_owner[b->device & 15];
-    if (o.batch != b || o.revision != b->revision || o.mask != b->shape_mask) {
+    if (o.uid != b->uid || o.revision != b->revision || o.mask != b->shape_mask) {
         // other streams may still be running a kernel of this unit that reads the old constants
-        if (o.batch != nullptr && o.batch != b)
+        if (o.uid != 0 && o.uid != b->uid)
             CUDA_TRY(cudaDeviceSynchronize());
         CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_P, &b->prob->cs.prob, sizeof(iwbc_problem_t), 0, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_S, &b->shape, sizeof(dev::Shape), 0, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_F, &b->fshape, sizeof(dev::FShape), 0, cudaMemcpyHostToDevice, st));
-        o.batch = b;
+        o.uid = b->uid;
         o.revision = b->revision;
         o.mask = b->shape_mask;
         b->tu_uploaded = true;
