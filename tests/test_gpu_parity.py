@@ -118,6 +118,33 @@ def test_talos_fast_urdf_config3(talos_fast):
     _check(P, bt, q, v, refs, mask=mask)
 
 
+def test_talos_hard_states_exercise_adds_drops_and_the_large_active_sets(talos):
+    """Large joint offsets and velocities: tens of active-set iterations per instance (up to > 100), constraints dropped again
+    (delete_constraint_cta), single-support shapes too.  About a fifth of these states end on a degenerate vertex (joints on their
+    bounds with zero multiplier, unloaded contact corners): the two implementations may then name it by different weakly active
+    rows -- checked to be the same point (active_sets_equivalent) with the same torques and accelerations."""
+    B = 768
+    q, v = random_states(talos, B, 5, qn=0.08, vn=0.4)
+    bt = iw.Batch(talos, 0, B)
+    mask = np.repeat(np.array([3, 1, 2], dtype=np.uint32), B // 3)
+    r = bt.update(q, v, contact_mask=mask)
+    o = ol.cycle_batch(talos, q, v, contact_mask=mask, nthreads=os.cpu_count())
+    assert np.array_equal(r.status, o["status"])
+    ok = o["status"] == 0
+    assert ok.mean() > 0.9 and o["iters"][ok].max() > 40 and o["iters"][ok].mean() > 6
+    same = ok & np.all(r.active == o["active"], axis=1)
+    assert same.sum() > 0.7 * ok.sum()
+    assert (r.iters[same] == o["iters"][same]).mean() > 0.9  # (a tie on the way may cost or save an add / drop pair and still end on the same set)
+    for k in ("tau", "dv"):
+        assert _rel(getattr(r, k)[same], o[k][same]) < 1e-7, k
+    assert np.abs(r.f[same] - o["f"][same]).max() < 1e-3  # absolute, against forces of ~1e3 N
+    diff = np.where(ok & ~same)[0]
+    equivalent = [active_sets_equivalent(talos, q[i], v[i], None, o["active"][i], r.active[i], int(mask[i])) for i in diff[:80]]
+    assert np.mean(equivalent) > 0.95
+    for k in ("tau", "dv"):
+        assert _rel(getattr(r, k)[diff], o[k][diff]) < 1e-7, k
+
+
 def test_talos_stage_dump(talos):
     q, v = random_states(talos, 1, 9, base=True)
     bt = iw.Batch(talos, 0, 8)
