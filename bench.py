@@ -344,6 +344,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary BASELINE configs (Franka batch, Talos walking) appended at N = 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -545,6 +546,20 @@ def main():
                                     "sample": "%d updates of the same workload in %.2f s on %d threads (oracle port)" % (done, el, threads),
                                     "single_thread": rate1,
                                     "reference_recorded": "0.0126 ms/cycle Franka, different unknown hardware (tests/ref_test_franka.yaml:11)"}
+        if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_secondary and not args.batch:
+            # BASELINE.json's other single-GPU configs, measured by the same program right after (same GPU, sequentially): configs[1]
+            # (Franka batch 65 536) and one GPU's share of configs[4] (Talos walking, 131 072 states)
+            line["secondary"] = {}
+            for wl in ("franka_65536", "talos_walk_131072"):
+                try:
+                    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wl, "--steps", "10", "--warmup", "3", "--no-cpu",
+                                          "--no-secondary"], capture_output=True, text=True, timeout=240)
+                    d = json.loads(out.stdout.strip().splitlines()[-1])
+                    line["secondary"][wl] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "e2e": d["e2e"]["value"],
+                                             "p50_cycle_latency_ms": d["e2e"].get("p50_cycle_latency_ms"), "roofline_frac": d["roofline"]["frac"],
+                                             "gpu_launches": d["gpu_launches"], "per_gpu_batch": d["config"]["per_gpu_batch"]}
+                except Exception as e:  # the headline line must not depend on it
+                    line["secondary"][wl] = {"error": str(e)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
