@@ -159,7 +159,8 @@ int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, c
  * the GPU evaluates in closed form for every (instance, tick).  BEHAVIOR.name selects the
  * As in the reference, constructing a behaviour applies BEHAVIOR.customize_task_weights to the controller
  * (Behavior::_customize_tasks, src/behaviors/behavior.cpp:7-22), which is why `p` is not const.  Available
- * behaviour: "humanoid::walk" (src/behaviors/humanoid/walk.cpp), "generic::cartesian"
+ * behaviour: "humanoid::walk" (src/behaviors/humanoid/walk.cpp), "humanoid::walk-on-spot"
+ * (src/behaviors/humanoid/walk_on_spot.cpp), "humanoid::clapping" (src/behaviors/humanoid/clapping.cpp), "generic::cartesian"
  * (src/behaviors/generic/cartesian.cpp:8-94), "humanoid::move_com" (src/behaviors/humanoid/move_com.cpp:8-61); overrides_yaml: optional YAML text of BEHAVIOR keys to override.
  */
 typedef struct iwbc_behavior iwbc_behavior;

@@ -15,7 +15,7 @@ using namespace iwbc;
 namespace {
 
 struct BehDev {
-    int nseg, nch, total_ticks, loop, nref, nmasks;
+    int nseg, nch, total_ticks, loop, loop_start, nref, nmasks;
     double dt;
     const iwbc_beh_channel_t* channels;
     const iwbc_beh_seg_t* segs;
@@ -57,8 +57,10 @@ __global__ void k_behavior_refs(BehDev d, int B, const int* __restrict__ phase, 
     if (i >= B)
         return;
     long g = (long)tick + (phase ? phase[i] : 0);
-    if (d.loop)
-        g %= d.total_ticks;
+    if (d.loop) {
+        if (g >= d.total_ticks)
+            g = d.loop_start + (g - d.loop_start) % (d.total_ticks - d.loop_start);
+    }
     else if (g >= d.total_ticks)
         g = d.total_ticks - 1; // run_ = false: the last written references stay (walk.cpp:236-243)
     int s = 0;
@@ -183,7 +185,7 @@ BehDev dev_view(const iwbc_behavior* h)
 {
     BehDev d;
     std::memset(&d, 0, sizeof(d));
-    d.nseg = (int)h->segs.size(), d.nch = (int)h->channels.size(), d.total_ticks = h->total_ticks, d.loop = h->loop ? 1 : 0;
+    d.nseg = (int)h->segs.size(), d.nch = (int)h->channels.size(), d.total_ticks = h->total_ticks, d.loop = h->loop ? 1 : 0, d.loop_start = h->loop_start;
     d.nref = (int)h->prob->cs.ref0.size(), d.nmasks = (int)h->masks.size(), d.dt = h->dt;
     d.channels = h->d_channels, d.segs = h->d_segs, d.cs = h->d_cs, d.ref0 = h->d_ref0;
     for (size_t k = 0; k < h->masks.size(); ++k)

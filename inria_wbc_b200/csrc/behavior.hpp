@@ -47,6 +47,7 @@ struct iwbc_behavior {
     double dt = 0;
     int total_ticks = 0;
     bool loop = false;
+    int loop_start = 0; // a looping behaviour repeats the ticks [loop_start, total_ticks) (walk-on-spot plays its INIT segment once)
     std::vector<iwbc_beh_channel_t> channels;
     std::vector<iwbc_beh_seg_t> segs;
     std::vector<iwbc_beh_chanseg_t> cs; // [seg][channel]
@@ -232,6 +233,79 @@ namespace host {
             lf_high.v[0] = rf_low.v[0];
             emit(true, DS & ~LF, DS & ~LF, hold(com_rf), go(lf_low, lf_high), hold(rf_low), hold(lh), hold(rh));
         }
+        bb.finish();
+    }
+
+    // humanoid::walk-on-spot (src/behaviors/humanoid/walk_on_spot.cpp:36-208): CoM over the right foot once (INIT), then for ever
+    // { left foot up, down, CoM over the left foot, right foot up, down, CoM over the right foot }; a foot's contact is removed at
+    // the first tick of its LIFT_UP state and re-added at the last tick of its LIFT_DOWN state (walk_on_spot.cpp:163-182).
+    inline void compile_walk_on_spot(iwbc_behavior& out, const iwbc_problem& prob, const yaml::Node& c)
+    {
+        BehaviorBuilder bb(out, prob);
+        const double com_dur = IWBC_HCHECK(c["traj_com_duration"].as<float>(), "traj_com_duration");
+        const double foot_dur = IWBC_HCHECK(c["traj_foot_duration"].as<float>(), "traj_foot_duration");
+        const float step_height = IWBC_HCHECK(c["step_height"].as<float>(), "step_height");
+        const int lfb = iwbc_problem_contact_index(&prob, "contact_lfoot"), rfb = iwbc_problem_contact_index(&prob, "contact_rfoot");
+        if (lfb < 0 || rfb < 0)
+            throw ConfigError("Walk on spot requires a humanoid controller!"); // walk_on_spot.cpp:46
+        const unsigned LF = 1u << lfb, RF = 1u << rfb, DS = iwbc_problem_default_contact_mask(&prob) | LF | RF;
+        enum { COM, LFT, RFT };
+        bb.add_channel(0, 0, bb.slot_of("com"), -1);
+        bb.add_channel(1, 0, bb.slot_of("lf"), bb.slot_of("contact_lfoot"));
+        bb.add_channel(1, 0, bb.slot_of("rf"), bb.slot_of("contact_rfoot"));
+        double lf_low[3], rf_low[3], lf_high[3], rf_high[3], com_init[3], com_lf[3], com_rf[3];
+        for (int k = 0; k < 3; ++k) {
+            lf_low[k] = lf_high[k] = com_lf[k] = prob.cs.ref0[out.channels[LFT].slot[0] + k];
+            rf_low[k] = rf_high[k] = com_rf[k] = prob.cs.ref0[out.channels[RFT].slot[0] + k];
+            com_init[k] = prob.cs.ref0[out.channels[COM].slot[0] + k];
+        }
+        lf_high[2] += step_height, rf_high[2] += step_height;
+        com_lf[2] = com_rf[2] = com_init[2];
+        const int com_ticks = beh_n_steps(out.dt, com_dur), foot_ticks = beh_n_steps(out.dt, foot_dur);
+        auto seg = [&](bool foot_state, unsigned mask, unsigned mask_last, const double* c0, const double* c1, const double* l0, const double* l1,
+                       const double* r0, const double* r1) {
+            const double d = foot_state ? foot_dur : com_dur;
+            bb.begin_segment(foot_state ? foot_ticks : com_ticks, mask, mask_last);
+            bb.set(COM, c0, c1 ? c1 : c0, d, c1 != nullptr);
+            bb.set(LFT, l0, l1 ? l1 : l0, d, l1 != nullptr);
+            bb.set(RFT, r0, r1 ? r1 : r0, d, r1 != nullptr);
+        };
+        seg(false, DS, DS, com_init, com_rf, lf_low, nullptr, rf_low, nullptr);          // INIT (once)
+        seg(true, DS & ~LF, DS & ~LF, com_rf, nullptr, lf_low, lf_high, rf_low, nullptr); // LIFT_UP_LF
+        seg(true, DS & ~LF, DS, com_rf, nullptr, lf_high, lf_low, rf_low, nullptr);       // LIFT_DOWN_LF
+        seg(false, DS, DS, com_rf, com_lf, lf_low, nullptr, rf_low, nullptr);             // MOVE_COM_LEFT
+        seg(true, DS & ~RF, DS & ~RF, com_lf, nullptr, lf_low, nullptr, rf_low, rf_high); // LIFT_UP_RF
+        seg(true, DS & ~RF, DS, com_lf, nullptr, lf_low, nullptr, rf_high, rf_low);       // LIFT_DOWN_RF
+        seg(false, DS, DS, com_lf, com_rf, lf_low, nullptr, rf_low, nullptr);             // MOVE_COM_RIGHT
+        out.loop = true;
+        out.loop_start = com_ticks; // "we skip the init_traj" (walk_on_spot.cpp:202-204)
+        bb.finish();
+    }
+
+    // humanoid::clapping (src/behaviors/humanoid/clapping.cpp:8-52): both hands move `motion_size` towards each other along y and back, for ever
+    inline void compile_clapping(iwbc_behavior& out, const iwbc_problem& prob, const yaml::Node& c)
+    {
+        BehaviorBuilder bb(out, prob);
+        const double duration = IWBC_HCHECK(c["trajectory_duration"].as<float>(), "trajectory_duration");
+        const float motion_size = IWBC_HCHECK(c["motion_size"].as<float>(), "motion_size");
+        bb.add_channel(1, 0, bb.slot_of("lh"), -1);
+        bb.add_channel(1, 0, bb.slot_of("rh"), -1);
+        double lh0[3], rh0[3], lh1[3], rh1[3];
+        for (int k = 0; k < 3; ++k) {
+            lh0[k] = lh1[k] = prob.cs.ref0[out.channels[0].slot[0] + k];
+            rh0[k] = rh1[k] = prob.cs.ref0[out.channels[1].slot[0] + k];
+        }
+        lh1[1] -= motion_size;
+        rh1[1] += motion_size;
+        const unsigned mask = iwbc_problem_default_contact_mask(&prob);
+        const int ticks = beh_n_steps(out.dt, duration);
+        bb.begin_segment(ticks, mask, mask);
+        bb.set(0, lh0, lh1, duration, true);
+        bb.set(1, rh0, rh1, duration, true);
+        bb.begin_segment(ticks, mask, mask);
+        bb.set(0, lh1, lh0, duration, true);
+        bb.set(1, rh1, rh0, duration, true);
+        out.loop = true;
         bb.finish();
     }
 
@@ -436,12 +510,16 @@ namespace host {
             }
         if (out.name == "humanoid::walk")
             compile_walk(out, prob, c);
+        else if (out.name == "humanoid::walk-on-spot")
+            compile_walk_on_spot(out, prob, c);
+        else if (out.name == "humanoid::clapping")
+            compile_clapping(out, prob, c);
         else if (out.name == "generic::cartesian")
             compile_cartesian(out, prob, c);
         else if (out.name == "humanoid::move_com")
             compile_move_com(out, prob, c);
         else
-            throw ConfigError("behavior '" + out.name + "' has no device-side form yet (available: humanoid::walk, generic::cartesian, humanoid::move_com)");
+            throw ConfigError("behavior '" + out.name + "' has no device-side form yet (available: humanoid::walk, humanoid::walk-on-spot, humanoid::clapping, humanoid::move_com, generic::cartesian)");
     }
 
 } // namespace host

@@ -192,3 +192,76 @@ class Walk:
 
     def table(self):
         return self._refs, self._mask
+
+
+class WalkOnSpot:
+    """src/behaviors/humanoid/walk_on_spot.cpp:36-208.  INIT is played once, then the six remaining states repeat for ever
+    (`_current_traj = ++_current_traj % cycle_.size(); if (_current_traj == 0) _current_traj++`)."""
+
+    INIT, LIFT_UP_LF, LIFT_DOWN_LF, MOVE_COM_LEFT, LIFT_UP_RF, LIFT_DOWN_RF, MOVE_COM_RIGHT = range(7)
+
+    def __init__(self, problem, config):
+        c = (config if isinstance(config, dict) else yaml.safe_load(open(config)))["BEHAVIOR"]
+        self.P = problem
+        dt = problem.struct().dt
+        com_dur = float(np.float32(c["traj_com_duration"]))
+        foot_dur = float(np.float32(c["traj_foot_duration"]))
+        step_height = float(np.float32(c["step_height"]))
+        self.ref0 = problem.default_refs()
+        self.slot = {k: problem.ref_slot(k)[0] for k in ("com", "lf", "rf")}
+        self.cslot = {"lf": problem.ref_slot("contact_lfoot")[0], "rf": problem.ref_slot("contact_rfoot")[0]}
+        self.bit = {"lf": 1 << problem.contact_index("contact_lfoot"), "rf": 1 << problem.contact_index("contact_rfoot")}
+        pos = lambda n: self.ref0[self.slot[n]:self.slot[n] + 3].copy()  # noqa: E731
+        lf_low, rf_low, com_init = pos("lf"), pos("rf"), pos("com")
+        lf_high, rf_high = lf_low.copy(), rf_low.copy()
+        lf_high[2] += step_height
+        rf_high[2] += step_height
+        com_lf, com_rf = lf_low.copy(), rf_low.copy()
+        com_lf[2] = com_rf[2] = com_init[2]
+        mj, ct = min_jerk_vec, constant_traj
+        S = self
+        self.cycle = [S.INIT, S.LIFT_UP_LF, S.LIFT_DOWN_LF, S.MOVE_COM_LEFT, S.LIFT_UP_RF, S.LIFT_DOWN_RF, S.MOVE_COM_RIGHT]
+        self.T = {
+            "rf": [ct(rf_low, dt, com_dur), ct(rf_low, dt, foot_dur), ct(rf_low, dt, foot_dur), ct(rf_low, dt, com_dur),
+                   mj(rf_low, rf_high, dt, foot_dur), mj(rf_high, rf_low, dt, foot_dur), ct(rf_low, dt, com_dur)],
+            "lf": [ct(lf_low, dt, com_dur), mj(lf_low, lf_high, dt, foot_dur), mj(lf_high, lf_low, dt, foot_dur), ct(lf_low, dt, com_dur),
+                   ct(lf_low, dt, foot_dur), ct(lf_low, dt, foot_dur), ct(lf_low, dt, com_dur)],
+            "com": [mj(com_init, com_rf, dt, com_dur), ct(com_rf, dt, foot_dur), ct(com_rf, dt, foot_dur), mj(com_rf, com_lf, dt, com_dur),
+                    ct(com_lf, dt, foot_dur), ct(com_lf, dt, foot_dur), mj(com_lf, com_rf, dt, com_dur)],
+        }
+        self.seg_len = [len(x) for x in self.T["com"]]
+
+    def play(self, ticks):
+        """refs[ticks][nref], masks[ticks]: what the behaviour has written before the controller update of every tick."""
+        refs = np.tile(self.ref0, (ticks, 1))
+        masks = np.zeros(ticks, dtype=np.uint32)
+        mask = self.P.default_contact_mask
+        cur, time_ = 0, 0
+        state = self.cycle[0]
+        S = self
+        for g in range(ticks):
+            last = len(self.T["com"][cur]) - 1
+            if time_ == 0 and state == S.LIFT_UP_LF:
+                mask &= ~self.bit["lf"]
+            if time_ == 0 and state == S.LIFT_UP_RF:
+                mask &= ~self.bit["rf"]
+            if time_ == last and state == S.LIFT_DOWN_LF:
+                mask |= self.bit["lf"]
+            if time_ == last and state == S.LIFT_DOWN_RF:
+                mask |= self.bit["rf"]
+            r = refs[g]
+            r[self.slot["com"]:self.slot["com"] + 3] = self.T["com"][cur][time_]
+            r[self.slot["com"] + 3:self.slot["com"] + 9] = 0.0
+            for k in ("lf", "rf"):
+                for o in (self.slot[k], self.cslot[k]):
+                    r[o:o + 3] = self.T[k][cur][time_]
+                    r[o + 12:o + 24] = 0.0
+            masks[g] = mask
+            time_ += 1
+            if time_ == len(self.T["com"][cur]):
+                time_ = 0
+                cur = (cur + 1) % len(self.cycle)
+                if cur == 0:
+                    cur = 1
+                state = self.cycle[cur]
+        return refs, masks

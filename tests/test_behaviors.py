@@ -79,7 +79,7 @@ def test_behavior_config_errors(walk_problem, franka):
     with pytest.raises(iw.IwbcError, match="momentum"):
         iw.Behavior(franka, "talos/walk.yaml")
     with pytest.raises(iw.IwbcError, match="device-side form"):
-        iw.Behavior(walk_problem, "talos/clapping.yaml")
+        iw.Behavior(walk_problem, "talos/walk.yaml", overrides={"name": "humanoid::move-feet"})
 
 
 def test_cartesian_and_move_com_tables(franka, talos):
@@ -237,3 +237,55 @@ def test_franka_known_answer_with_the_behaviour_on_the_device(franka):
     r = ol.rollout(franka, franka.q0(), np.zeros(franka.nv), tab, ticks)
     dq_max = np.abs(qs[-1] - r["q"]).max()
     assert r["rc"] == 0 and dq_max < 1e-8, dq_max  # tests/test_determinism.cpp:51,63 tolerance after 10 000 ticks
+
+
+def test_walk_on_spot_table(talos):
+    """humanoid::walk-on-spot (src/behaviors/humanoid/walk_on_spot.cpp): INIT once, then six states for ever."""
+    P = iw.Problem("talos/talos_pos_tracker.yaml")
+    beh = iw.Behavior(P, "talos/walk_on_spot.yaml")
+    ora = bo.WalkOnSpot(P, os.path.join(iw.ETC_PATH, "talos", "walk_on_spot.yaml"))
+    assert beh.total_ticks == 7000 and beh.nsegments == 7 and beh.nchannels == 3
+    refs, masks = ora.play(7000)
+    lf, rf = 1 << P.contact_index("contact_lfoot"), 1 << P.contact_index("contact_rfoot")
+    ds = lf | rf
+    assert [beh.segment(k)[2:4] for k in range(7)] == [(ds, ds), (rf, rf), (rf, ds), (ds, ds), (lf, lf), (lf, ds), (ds, ds)]
+    slots = [ora.slot[k] for k in ("com", "lf", "rf")]
+    for k in range(7):
+        start, ticks, mask, mask_last, wp = beh.segment(k)
+        assert np.all(masks[start:start + ticks - 1] == mask) and masks[start + ticks - 1] == mask_last
+        for c, off in enumerate(slots):
+            assert np.array_equal(refs[start, off:off + 3], wp[c, 0:3])
+
+
+@pytest.mark.gpu
+def test_walk_on_spot_on_device_loops_past_its_init_segment(talos):
+    import torch
+    P = iw.Problem("talos/talos_pos_tracker.yaml")
+    beh = iw.Behavior(P, "talos/walk_on_spot.yaml")
+    ora = bo.WalkOnSpot(P, os.path.join(iw.ETC_PATH, "talos", "walk_on_spot.yaml"))
+    B = 7000 + 2 * 6000 + 17  # INIT + two and a bit loops
+    refs, masks = ora.play(B)
+    d_phase = torch.arange(B, dtype=torch.int32, device="cuda")
+    d_refs = torch.full((B, P.nref), float("nan"), dtype=torch.float64, device="cuda")
+    d_mask = torch.zeros(B, dtype=torch.int32, device="cuda")
+    beh.eval_device(0, B, d_phase.data_ptr(), 0, d_refs.data_ptr(), d_mask.data_ptr(), init_refs=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_mask.cpu().numpy().astype(np.uint32), masks)
+    assert np.abs(d_refs.cpu().numpy() - refs).max() < 1e-14
+
+
+def test_remaining_reference_behaviour_files_compile(talos, icub):
+    """squat = humanoid::move_com, arm / align = generic::cartesian, clapping: every behaviour file of etc/ except move_feet and the
+    teleoperation trajectory replays has a device-side form."""
+    from inria_wbc_b200 import trajs
+    for P, name, ticks, nseg, nch in ((talos, "talos/squat.yaml", 4000, 2, 1), (talos, "talos/arm.yaml", 2000, 2, 2), (icub, "icub/squat.yaml", 2000, 2, 1),
+                                      (icub, "icub/arm.yaml", 2000, 2, 2), (talos, "talos/clapping.yaml", None, 2, 2)):
+        b = iw.Behavior(P, name)
+        assert (b.nsegments, b.nchannels) == (nseg, nch) and (ticks is None or b.total_ticks == ticks), name
+    # clapping: hands towards each other along y and back (clapping.cpp:26-32)
+    b = iw.Behavior(talos, "talos/clapping.yaml")
+    (_, _, _, _, go), (_, _, _, _, back) = b.segment(0), b.segment(1)
+    ref0 = talos.default_refs()
+    lh, rh = talos.ref_slot("lh")[0], talos.ref_slot("rh")[0]
+    assert np.array_equal(go[0, 0:3], ref0[lh:lh + 3]) and np.array_equal(go[1, 0:3], ref0[rh:rh + 3])
+    assert go[0, 4] < go[0, 1] and go[1, 4] > go[1, 1] and np.array_equal(go[:, 3:6], back[:, 0:3]) and np.array_equal(back[:, 3:6], go[:, 0:3])
