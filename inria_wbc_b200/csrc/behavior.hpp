@@ -387,7 +387,9 @@ namespace host {
     // generic::cartesian (src/behaviors/generic/cartesian.cpp:8-94): every listed SE3 task goes from its construction-time
     // reference to a relative target along a minimum-jerk path (position and rotation angle about the fixed relative axis),
     // with the polynomial's derivatives as feed-forward velocity / acceleration; `loop` appends the way back.
-    inline void compile_cartesian(iwbc_behavior& out, const iwbc_problem& prob, const yaml::Node& c)
+    // humanoid::move-feet (src/behaviors/humanoid/move_feet.cpp:8-102) is the same generator with each sample also written into the
+    // contact that shares the task's frame (`contact_names`, move_feet.cpp:87): with_contacts = true.
+    inline void compile_cartesian(iwbc_behavior& out, const iwbc_problem& prob, const yaml::Node& c, bool with_contacts = false)
     {
         BehaviorBuilder bb(out, prob);
         const double duration = IWBC_HCHECK(c["trajectory_duration"].as<float>(), "trajectory_duration");
@@ -398,7 +400,7 @@ namespace host {
         if (!ts.is_seq() || !to.is_seq())
             throw ConfigError("config error reading relative_targets_pos / relative_targets_rpy");
         if (names.size() != ts.size())
-            throw ConfigError("cartesian behavior needs the same number of tasks and targets"); // cartesian.cpp:22-23
+            throw ConfigError(with_contacts ? "MoveFeet behavior needs the same number of tasks and targets" : "cartesian behavior needs the same number of tasks and targets"); // cartesian.cpp:22-23, move_feet.cpp:31-32
         if (to.size() < names.size())
             throw ConfigError("cartesian behavior needs one relative_targets_rpy entry per task");
         struct Way {
@@ -406,9 +408,15 @@ namespace host {
             detail::Rot3 R0, R1;
         };
         std::vector<Way> ways;
+        std::vector<std::string> contacts;
+        if (with_contacts) {
+            contacts = IWBC_HCHECK(c["contact_names"].as<std::vector<std::string>>(), "contact_names");
+            if (contacts.size() < names.size())
+                throw ConfigError("MoveFeet behavior needs one contact per task");
+        }
         for (size_t i = 0; i < names.size(); ++i) {
             const int slot = bb.slot_of(names[i]);
-            bb.add_channel(1, 1, slot, -1);
+            bb.add_channel(1, 1, slot, with_contacts ? bb.slot_of(contacts[i]) : -1);
             Way w;
             const double* ref = prob.cs.ref0.data() + slot;
             for (int k = 0; k < 3; ++k)
@@ -516,10 +524,12 @@ namespace host {
             compile_clapping(out, prob, c);
         else if (out.name == "generic::cartesian")
             compile_cartesian(out, prob, c);
+        else if (out.name == "humanoid::move-feet")
+            compile_cartesian(out, prob, c, true);
         else if (out.name == "humanoid::move_com")
             compile_move_com(out, prob, c);
         else
-            throw ConfigError("behavior '" + out.name + "' has no device-side form yet (available: humanoid::walk, humanoid::walk-on-spot, humanoid::clapping, humanoid::move_com, generic::cartesian)");
+            throw ConfigError("behavior '" + out.name + "' has no device-side form yet (available: humanoid::walk, humanoid::walk-on-spot, humanoid::clapping, humanoid::move_com, humanoid::move-feet, generic::cartesian)");
     }
 
 } // namespace host

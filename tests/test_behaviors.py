@@ -79,7 +79,7 @@ def test_behavior_config_errors(walk_problem, franka):
     with pytest.raises(iw.IwbcError, match="momentum"):
         iw.Behavior(franka, "talos/walk.yaml")
     with pytest.raises(iw.IwbcError, match="device-side form"):
-        iw.Behavior(walk_problem, "talos/walk.yaml", overrides={"name": "humanoid::move-feet"})
+        iw.Behavior(walk_problem, "talos/walk.yaml", overrides={"name": "generic::cartesian_traj"})
 
 
 def test_cartesian_and_move_com_tables(franka, talos):
@@ -279,9 +279,15 @@ def test_remaining_reference_behaviour_files_compile(talos, icub):
     teleoperation trajectory replays has a device-side form."""
     from inria_wbc_b200 import trajs
     for P, name, ticks, nseg, nch in ((talos, "talos/squat.yaml", 4000, 2, 1), (talos, "talos/arm.yaml", 2000, 2, 2), (icub, "icub/squat.yaml", 2000, 2, 1),
-                                      (icub, "icub/arm.yaml", 2000, 2, 2), (talos, "talos/clapping.yaml", None, 2, 2)):
+                                      (icub, "icub/arm.yaml", 2000, 2, 2), (talos, "talos/clapping.yaml", None, 2, 2), (talos, "talos/align.yaml", 10000, 1, 2),
+                                      (talos, "talos/move_feet.yaml", 4000, 1, 2)):
         b = iw.Behavior(P, name)
         assert (b.nsegments, b.nchannels) == (nseg, nch) and (ticks is None or b.total_ticks == ticks), name
+    # move-feet drives the foot task AND the contact sharing its frame (move_feet.cpp:86-87); the device writes both slots
+    mf = iw.Behavior(talos, "talos/move_feet.yaml")
+    wp = mf.segment(0)[4]
+    lf = talos.ref_slot("lf")[0]
+    assert np.allclose(wp[0, 3:6] - wp[0, 0:3], 0.05) and np.array_equal(wp[0, 0:3], talos.default_refs()[lf:lf + 3])
     # clapping: hands towards each other along y and back (clapping.cpp:26-32)
     b = iw.Behavior(talos, "talos/clapping.yaml")
     (_, _, _, _, go), (_, _, _, _, back) = b.segment(0), b.segment(1)

@@ -21,7 +21,7 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "inria_wbc_
 YAMLS = {
     "franka": ["pos_tracker.yaml", "tasks.yaml", "cartesian_line.yaml"],
     "talos": ["talos_pos_tracker.yaml", "tasks.yaml", "frames.yaml", "squat.yaml", "arm.yaml",
-              "walk.yaml", "walk_on_spot.yaml", "move_com.yaml", "clapping.yaml",
+              "walk.yaml", "walk_on_spot.yaml", "move_com.yaml", "move_feet.yaml", "clapping.yaml", "align.yaml",
               "collisions/talos_collisions_margin.yaml", "collisions/talos_collisions.yaml"],
     "icub": ["humanoid_pos_tracker.yaml", "tasks.yaml", "frames.yaml", "squat.yaml", "arm.yaml"],
     "tiago": ["pos_tracker.yaml", "tasks.yaml", "frames.yaml", "cartesian_line.yaml", "collisions.yaml"],
