@@ -6,9 +6,11 @@
          bench.py --gpus N --steps K --warmup W
   python bench.py --impl reference ...      # the CPU path (oracle, one instance per thread) on the same workload
 
-A "step" is one pass of the whole control cycle (k_dyn + k_asm + k_qp + k_dec, one fused kernel
-launch) over one batch of synthetic randomized robot states (SURVEY.md 8(d) recipes).  Weak scaling:
-every GPU steps its own batch of the same size, no collective on the data path.
+A "step" is one pass of the whole control cycle (kinematics / dynamics, task and contact stacking, the
+Goldfarb-Idnani QP, decode, integrate: the k_fast + k_slow launch pair per contact mask, or k_cycle for the
+arms) over one batch of synthetic randomized robot states (SURVEY.md 8(d) recipes).  The walking workload
+adds the device-side behaviour (references, contact switches, bucketing) to every step.  Weak scaling: every
+GPU steps its own batch of the same size, no collective on the data path.
 
 Printed JSON (one line, rank 0):
   value      whole-job updates/s with inputs resident in HBM, CUDA events on the launching stream,
@@ -540,8 +542,8 @@ def main():
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             ns = min(B, 4096)
-            rate, done, el = oracle_rate(P, q[:ns], v[:ns], refs[:ns], 2.5, threads)
-            rate1, done1, el1 = oracle_rate(P, q[:256], v[:256], refs[:256], 1.0, 1)
+            rate, done, el = oracle_rate(P, q[:ns], v[:ns], refs[:ns], 10.0, threads)
+            rate1, done1, el1 = oracle_rate(P, q[:256], v[:256], refs[:256], 2.0, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "updates/s", "cores": threads, "kind": "port",
                                     "sample": "%d updates of the same workload in %.2f s on %d threads (oracle port)" % (done, el, threads),
                                     "single_thread": rate1,
