@@ -185,7 +185,8 @@ int iwbc_batch_behavior_rollout_device(iwbc_batch* b, iwbc_behavior* h, int B, d
 
 /* The same roll-out with HOST buffers: q[B][nq], v[B][nv] are uploaded, advanced `ticks` ticks on the device and written back; phase[B]
  * (host) or NULL; out_last / contact_mask are host arrays (any may be NULL).  tick0 == 0 starts from the construction-time references; a
- * later call (tick0 > 0, same B) continues where the previous one stopped.  Synchronous. */
+ * later call (tick0 > 0, same B) continues where the previous one stopped (the reference rows live in the batch's own device
+ * workspace: an iwbc_batch_update call in between overwrites them -- restart with tick0 = 0 semantics or use the device form).  Synchronous. */
 int iwbc_batch_behavior_run(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, const int* phase, int tick0, int ticks,
     const iwbc_results_t* out_last, unsigned* contact_mask);
 
