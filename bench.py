@@ -360,6 +360,16 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the batched cycle has no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    try:  # N > 1: run this rank (and allocate its pinned buffers) on the CPUs next to its GPU: the host-buffer arm moves ~24 GB/s per GPU
+        if world <= 1:
+            raise RuntimeError("single rank: keep every core for the CPU-baseline leg")
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local]) if vis and vis.split(",")[local].isdigit() else local
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+    except Exception:
+        pass
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
