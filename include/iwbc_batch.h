@@ -160,7 +160,7 @@ int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, c
  * As in the reference, constructing a behaviour applies BEHAVIOR.customize_task_weights to the controller
  * (Behavior::_customize_tasks, src/behaviors/behavior.cpp:7-22), which is why `p` is not const.  Available
  * behaviour: "humanoid::walk" (src/behaviors/humanoid/walk.cpp), "humanoid::walk-on-spot"
- * (src/behaviors/humanoid/walk_on_spot.cpp), "humanoid::clapping" (src/behaviors/humanoid/clapping.cpp), "humanoid::move-feet" (src/behaviors/humanoid/move_feet.cpp), "generic::cartesian"
+ * (src/behaviors/humanoid/walk_on_spot.cpp), "humanoid::clapping" (src/behaviors/humanoid/clapping.cpp), "humanoid::move-feet" (src/behaviors/humanoid/move_feet.cpp), "generic::cartesian_traj" (src/behaviors/generic/cartesian_traj.cpp), "generic::cartesian"
  * (src/behaviors/generic/cartesian.cpp:8-94), "humanoid::move_com" (src/behaviors/humanoid/move_com.cpp:8-61); overrides_yaml: optional YAML text of BEHAVIOR keys to override.
  */
 typedef struct iwbc_behavior iwbc_behavior;

@@ -21,6 +21,7 @@ struct BehDev {
     const iwbc_beh_seg_t* segs;
     const iwbc_beh_chanseg_t* cs;
     const double* ref0;
+    const double* table;
     unsigned masks[8];
 };
 
@@ -70,6 +71,26 @@ __global__ void k_behavior_refs(BehDev d, int B, const int* __restrict__ phase, 
     const int local = (int)g - sg.start;
     const iwbc_beh_channel_t ch = d.channels[c];
     const iwbc_beh_chanseg_t& cs = d.cs[s * d.nch + c];
+    if (ch.table_rows > 0) {
+        // recorded trajectory, forwards then backwards (cartesian_traj.cpp:38-44); set_se3_ref(SE3) / set_com_ref(Vector3): zero derivatives
+        const int t = local < ch.table_rows ? local : 2 * ch.table_rows - 2 - local;
+        const int width = ch.kind == 0 ? 3 : 12;
+        const double* row = d.table + ch.table_off + (size_t)t * width;
+        double* o = refs + (size_t)i * d.nref + ch.slot[0];
+        for (int k = 0; k < 3; ++k)
+            o[k] = row[k] * ch.scale;
+        if (ch.kind == 0) {
+            for (int k = 3; k < 9; ++k)
+                o[k] = 0.0;
+        }
+        else {
+            for (int k = 3; k < 12; ++k)
+                o[k] = row[k];
+            for (int k = 12; k < 24; ++k)
+                o[k] = 0.0;
+        }
+    }
+    else {
     double p[3], vel[3] = {0, 0, 0}, acc[3] = {0, 0, 0};
     double f0 = 0, f1 = 0, f2 = 0;
     if (cs.minjerk) {
@@ -131,6 +152,7 @@ __global__ void k_behavior_refs(BehDev d, int B, const int* __restrict__ phase, 
             }
         }
     }
+    }
     if (c == 0) {
         const unsigned m = (local == sg.ticks - 1) ? sg.mask_last : sg.mask;
         if (mask_out)
@@ -154,20 +176,24 @@ int ensure_device(iwbc_behavior* h, int device, int B)
             return IWBC_ERR_ARG;
         }
         const size_t s_ch = h->channels.size() * sizeof(iwbc_beh_channel_t), s_sg = h->segs.size() * sizeof(iwbc_beh_seg_t),
-                     s_cs = h->cs.size() * sizeof(iwbc_beh_chanseg_t), s_r0 = h->prob->cs.ref0.size() * sizeof(double);
+                     s_cs = h->cs.size() * sizeof(iwbc_beh_chanseg_t), s_r0 = h->prob->cs.ref0.size() * sizeof(double),
+                     s_tb = h->table.size() * sizeof(double);
         auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
         char* blob = nullptr;
-        CUDA_TRY(cudaMalloc((void**)&blob, up(s_ch) + up(s_sg) + up(s_cs) + up(s_r0) + 256));
+        CUDA_TRY(cudaMalloc((void**)&blob, up(s_ch) + up(s_sg) + up(s_cs) + up(s_r0) + up(s_tb) + 256));
         h->d_blob = blob;
         h->d_channels = (iwbc_beh_channel_t*)blob, blob += up(s_ch);
         h->d_segs = (iwbc_beh_seg_t*)blob, blob += up(s_sg);
         h->d_cs = (iwbc_beh_chanseg_t*)blob, blob += up(s_cs);
         h->d_ref0 = (double*)blob, blob += up(s_r0);
+        h->d_table = (double*)blob, blob += up(s_tb);
         h->d_bcount = (int*)blob;
         CUDA_TRY(cudaMemcpy(h->d_channels, h->channels.data(), s_ch, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(h->d_segs, h->segs.data(), s_sg, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(h->d_cs, h->cs.data(), s_cs, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(h->d_ref0, h->prob->cs.ref0.data(), s_r0, cudaMemcpyHostToDevice));
+        if (s_tb)
+            CUDA_TRY(cudaMemcpy(h->d_table, h->table.data(), s_tb, cudaMemcpyHostToDevice));
         h->device = device;
     }
     if (B > h->blist_cap) {
@@ -187,7 +213,7 @@ BehDev dev_view(const iwbc_behavior* h)
     std::memset(&d, 0, sizeof(d));
     d.nseg = (int)h->segs.size(), d.nch = (int)h->channels.size(), d.total_ticks = h->total_ticks, d.loop = h->loop ? 1 : 0, d.loop_start = h->loop_start;
     d.nref = (int)h->prob->cs.ref0.size(), d.nmasks = (int)h->masks.size(), d.dt = h->dt;
-    d.channels = h->d_channels, d.segs = h->d_segs, d.cs = h->d_cs, d.ref0 = h->d_ref0;
+    d.channels = h->d_channels, d.segs = h->d_segs, d.cs = h->d_cs, d.ref0 = h->d_ref0, d.table = h->d_table;
     for (size_t k = 0; k < h->masks.size(); ++k)
         d.masks[k] = h->masks[k];
     return d;

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <fstream>
 #include <string>
 #include <vector>
 
@@ -34,6 +35,10 @@ struct iwbc_beh_channel_t {
     int kind;    // 0: 3-vector reference (CoM: pos(3) vel(3) acc(3));  1: SE3 reference (pos(12) vel(6) acc(6))
     int ff;      // write the polynomial's first / second derivative into vel / acc (cartesian, move_com); 0: zeros (walk)
     int slot[2]; // offsets into the reference vector (task, and the contact that shares the frame); -1: none
+    // recorded-trajectory channels (generic::cartesian_traj): rows of 3 (CoM) or 12 (translation + column-major rotation) doubles,
+    // replayed forwards then backwards; table_rows == 0: a waypoint channel (segments)
+    int table_off, table_rows;
+    double scale; // applied to the translation / CoM (cartesian_traj.cpp:24-35)
 };
 struct iwbc_beh_seg_t {
     int start, ticks;   // first global tick, length
@@ -52,6 +57,7 @@ struct iwbc_behavior {
     std::vector<iwbc_beh_seg_t> segs;
     std::vector<iwbc_beh_chanseg_t> cs; // [seg][channel]
     std::vector<unsigned> masks;        // distinct contact masks, most frequent first
+    std::vector<double> table;          // recorded trajectories of the table channels
     // device copies (one device; created on first use)
     int device = -1;
     void* d_blob = nullptr;
@@ -59,6 +65,7 @@ struct iwbc_behavior {
     iwbc_beh_seg_t* d_segs = nullptr;
     iwbc_beh_chanseg_t* d_cs = nullptr;
     double* d_ref0 = nullptr;
+    double* d_table = nullptr;
     int *d_bcount = nullptr, *d_blist = nullptr;
     int blist_cap = 0;
 };
@@ -85,7 +92,7 @@ namespace host {
         }
         int add_channel(int kind, int ff, int slot0, int slot1)
         {
-            b.channels.push_back({kind, ff, {slot0, slot1}});
+            b.channels.push_back({kind, ff, {slot0, slot1}, 0, 0, 1.0});
             return (int)b.channels.size() - 1;
         }
         void begin_segment(int ticks, unsigned mask, unsigned mask_last)
@@ -497,6 +504,57 @@ namespace host {
         bb.finish();
     }
 
+    // generic::cartesian_traj (src/behaviors/generic/cartesian_traj.cpp:8-46, src/trajs/loader.cpp:11-100): recorded SE3 / CoM
+    // trajectories (one CSV per task: 3 + 9 numbers per row, the rotation in Eigen's column-major order; 3 per row for "com") replayed
+    // row by row, forwards then backwards for ever (`step_` flips at both ends; the `loop` key is read but not used by the reference).
+    inline void compile_cartesian_traj(iwbc_behavior& out, const iwbc_problem& prob, const yaml::Node& c, const std::string& dir)
+    {
+        BehaviorBuilder bb(out, prob);
+        (void)IWBC_HCHECK(c["loop"].as<bool>(), "loop");
+        const std::string rel = IWBC_HCHECK(c["trajectories"].as<std::string>(), "trajectories");
+        const double scale = IWBC_HCHECK(c["scale"].as<float>(), "scale");
+        const std::string ypath = dir + "/" + rel;
+        const yaml::Node root = yaml::LoadFile(ypath);
+        const yaml::Node& refs = root["refs"];
+        if (!refs.is_map())
+            throw ConfigError("trajectory file without a 'refs' map: " + ypath);
+        const std::string tdir = ypath.substr(0, ypath.find_last_of('/'));
+        int rows = -1;
+        for (auto& kv : refs.map) {
+            if (kv.first == "posture")
+                throw ConfigError("cartesian_traj: posture trajectories have no device-side form yet");
+            const bool com = kv.first == "com";
+            const int width = com ? 3 : 12;
+            const std::string file = tdir + "/" + kv.second.as<std::string>();
+            std::ifstream ifs(file.c_str());
+            if (!ifs.good())
+                throw ConfigError("Error when loading trajectory:" + file); // loader.cpp:15
+            std::vector<double> data;
+            double x;
+            while (ifs >> x)
+                data.push_back(x);
+            if (data.empty() || data.size() % width != 0)
+                throw ConfigError("wrong number of values in " + file);
+            const int n = (int)(data.size() / width);
+            if (rows >= 0 && n != rows)
+                throw ConfigError("wrong number of rows in" + file); // loader.cpp:76,88
+            rows = n;
+            const int ch = bb.add_channel(com ? 0 : 1, 0, bb.slot_of(kv.first), -1);
+            out.channels[ch].table_off = (int)out.table.size();
+            out.channels[ch].table_rows = n;
+            out.channels[ch].scale = scale;
+            out.table.insert(out.table.end(), data.begin(), data.end());
+        }
+        if (rows < 2)
+            throw ConfigError("cartesian_traj needs at least two recorded rows");
+        const unsigned mask = iwbc_problem_default_contact_mask(&prob);
+        bb.begin_segment(2 * rows - 2, mask, mask); // 0, 1, ..., rows-1, rows-2, ..., 1 and again
+        for (size_t ch = 0; ch < out.channels.size(); ++ch)
+            std::memset(&bb.at((int)ch), 0, sizeof(iwbc_beh_chanseg_t));
+        out.loop = true;
+        bb.finish();
+    }
+
     inline void compile_behavior(iwbc_behavior& out, const iwbc_problem& prob, const std::string& yaml_path, const std::string& overrides)
     {
         yaml::Node root = yaml::LoadFile(yaml_path);
@@ -524,12 +582,14 @@ namespace host {
             compile_clapping(out, prob, c);
         else if (out.name == "generic::cartesian")
             compile_cartesian(out, prob, c);
+        else if (out.name == "generic::cartesian_traj")
+            compile_cartesian_traj(out, prob, c, yaml_path.find_last_of('/') == std::string::npos ? std::string(".") : yaml_path.substr(0, yaml_path.find_last_of('/')));
         else if (out.name == "humanoid::move-feet")
             compile_cartesian(out, prob, c, true);
         else if (out.name == "humanoid::move_com")
             compile_move_com(out, prob, c);
         else
-            throw ConfigError("behavior '" + out.name + "' has no device-side form yet (available: humanoid::walk, humanoid::walk-on-spot, humanoid::clapping, humanoid::move_com, humanoid::move-feet, generic::cartesian)");
+            throw ConfigError("behavior '" + out.name + "' has no device-side form yet (available: humanoid::walk, humanoid::walk-on-spot, humanoid::clapping, humanoid::move_com, humanoid::move-feet, generic::cartesian, generic::cartesian_traj)");
     }
 
 } // namespace host

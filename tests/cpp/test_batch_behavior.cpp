@@ -74,7 +74,7 @@ int main(int argc, char** argv)
             cc.etc_path = argv[1];
             cc.batch = 1;
             auto ctl = controllers::Factory::instance().create("talos-pos-tracker", cc);
-            behaviors::BatchBehavior bad(ctl, std::string(argv[1]) + "/talos/walk.yaml", "name: generic::cartesian_traj\n");
+            behaviors::BatchBehavior bad(ctl, std::string(argv[1]) + "/talos/walk.yaml", "name: humanoid::no-such-behavior\n");
         }
         catch (const inria_wbc::Exception& e) {
             thrown = std::string(e.what()).find("humanoid::walk") != std::string::npos;

@@ -79,7 +79,7 @@ def test_behavior_config_errors(walk_problem, franka):
     with pytest.raises(iw.IwbcError, match="momentum"):
         iw.Behavior(franka, "talos/walk.yaml")
     with pytest.raises(iw.IwbcError, match="device-side form"):
-        iw.Behavior(walk_problem, "talos/walk.yaml", overrides={"name": "generic::cartesian_traj"})
+        iw.Behavior(walk_problem, "talos/walk.yaml", overrides={"name": "humanoid::no-such-behavior"})
 
 
 def test_cartesian_and_move_com_tables(franka, talos):
@@ -295,3 +295,70 @@ def test_remaining_reference_behaviour_files_compile(talos, icub):
     lh, rh = talos.ref_slot("lh")[0], talos.ref_slot("rh")[0]
     assert np.array_equal(go[0, 0:3], ref0[lh:lh + 3]) and np.array_equal(go[1, 0:3], ref0[rh:rh + 3])
     assert go[0, 4] < go[0, 1] and go[1, 4] > go[1, 1] and np.array_equal(go[:, 3:6], back[:, 0:3]) and np.array_equal(back[:, 3:6], go[:, 0:3])
+
+
+def _write_recorded_trajectory(tmp_path, P, rows=37):
+    """A small recorded trajectory in the reference's format (src/trajs/loader.cpp:11-100): one CSV per task, 3 + 9 numbers per row."""
+    rng = np.random.default_rng(11)
+    ref0 = P.default_refs()
+    d = tmp_path / "traj_rec"
+    d.mkdir()
+    tabs = {}
+    for name, width in (("lh", 12), ("rh", 12), ("com", 3)):
+        off = P.ref_slot(name)[0]
+        base = ref0[off:off + width]
+        tab = base[None, :] + np.cumsum(rng.normal(0, 1e-3, (rows, width)), axis=0)
+        np.savetxt(d / (name + ".csv"), tab, fmt="%.17g")
+        tabs[name] = np.loadtxt(d / (name + ".csv"))
+    (d / "trajectory.yaml").write_text("refs:\n  lh: lh.csv\n  rh: rh.csv\n  com: com.csv\n")
+    (tmp_path / "replay.yaml").write_text("BEHAVIOR:\n  name : generic::cartesian_traj\n  trajectories: traj_rec/trajectory.yaml\n  loop: true\n  scale: 0.5\n")
+    return str(tmp_path / "replay.yaml"), tabs
+
+
+def _replay_reference(P, tabs, scale, ticks):
+    """cartesian_traj.cpp:19-45 restated: row `time_` of every table (translation / CoM scaled), then time_ += step_ with the step
+    flipping at both ends."""
+    refs = np.tile(P.default_refs(), (ticks, 1))
+    rows = len(tabs["com"])
+    time_, step = 0, 1
+    for g in range(ticks):
+        for name in ("lh", "rh"):
+            off = P.ref_slot(name)[0]
+            refs[g, off:off + 3] = tabs[name][time_, :3] * scale
+            refs[g, off + 3:off + 12] = tabs[name][time_, 3:]
+            refs[g, off + 12:off + 24] = 0.0
+        off = P.ref_slot("com")[0]
+        refs[g, off:off + 3] = tabs["com"][time_] * scale
+        refs[g, off + 3:off + 9] = 0.0
+        time_ += step
+        if time_ >= rows - 1:
+            step = -1
+        elif time_ <= 0:
+            step = 1
+    return refs
+
+
+def test_recorded_trajectory_replay_table(talos, tmp_path):
+    yaml_path, tabs = _write_recorded_trajectory(tmp_path, talos)
+    beh = iw.Behavior(talos, yaml_path)
+    assert beh.total_ticks == 2 * 37 - 2 and beh.nchannels == 3 and beh.masks == [talos.default_contact_mask]
+    ref = "/root/reference/etc/talos/traj_teleop1.yaml"
+    if os.path.exists(ref):  # the reference's own recording (2425 rows), read where it lies (build container only)
+        assert iw.Behavior(talos, ref).total_ticks == 2 * 2425 - 2
+    (tmp_path / "traj_rec" / "com.csv").write_text("0 0 0\n1 1\n")
+    with pytest.raises(iw.IwbcError, match="wrong number"):
+        iw.Behavior(talos, yaml_path)
+
+
+@pytest.mark.gpu
+def test_recorded_trajectory_replay_on_device(talos, tmp_path):
+    import torch
+    yaml_path, tabs = _write_recorded_trajectory(tmp_path, talos)
+    beh = iw.Behavior(talos, yaml_path)
+    B = 3 * beh.total_ticks + 5
+    want = _replay_reference(talos, tabs, 0.5, B)
+    d_phase = torch.arange(B, dtype=torch.int32, device="cuda")
+    d_refs = torch.full((B, talos.nref), float("nan"), dtype=torch.float64, device="cuda")
+    beh.eval_device(0, B, d_phase.data_ptr(), 0, d_refs.data_ptr(), None, init_refs=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_refs.cpu().numpy(), want)
