@@ -362,3 +362,45 @@ def test_recorded_trajectory_replay_on_device(talos, tmp_path):
     beh.eval_device(0, B, d_phase.data_ptr(), 0, d_refs.data_ptr(), None, init_refs=True)
     torch.cuda.synchronize()
     assert np.array_equal(d_refs.cpu().numpy(), want)
+
+
+@pytest.mark.gpu
+def test_icub_walk_rollout_on_device(icub):
+    """iCub walking (etc/icub/walk.yaml: 1 s CoM shifts, 0.25 s foot trajectories) as one closed device-side roll-out of 900 ticks against
+    900 oracle ticks driven by the restated behaviour.  Towards the end of the first CoM shift the stand-in iCub model takes the QP to
+    the edge of feasibility, where eiquadprog's outcome flips under a 1e-14 perturbation of the state (ticks 944 .. 994 depending on
+    rounding): status is data -- on the GPU's OWN state at its first non-optimal tick the oracle must report the same status after the
+    same number of iterations."""
+    import torch
+    import oracle_lib as ol
+    P = iw.Problem("icub/humanoid_pos_tracker.yaml", overrides={"stabilizer": {"activated": False}})
+    beh = iw.Behavior(P, "icub/walk.yaml", overrides={"num_of_cycles": 1})
+    ora = bo.Walk(P, os.path.join(iw.ETC_PATH, "icub", "walk.yaml"), num_of_cycles=1)
+    assert beh.total_ticks == ora.total_ticks == 5500
+    T = 900
+    q, v = P.q0().copy(), np.zeros(P.nv)
+    for t in range(T):
+        r, m = ora.tick(t)
+        o = ol.cycle_batch(P, q[None], v[None], r, contact_mask=m)
+        assert o["status"][0] == 0, t
+        q, v = o["q_next"][0], o["v_next"][0]
+    dq = torch.from_numpy(P.q0()[None].copy()).cuda()
+    dv_ = torch.zeros(1, P.nv, dtype=torch.float64, device="cuda")
+    d_refs = torch.empty(1, P.nref, dtype=torch.float64, device="cuda")
+    st = torch.full((1,), -7, dtype=torch.int32, device="cuda")
+    it = torch.zeros(1, dtype=torch.int32, device="cuda")
+    bt = iw.Batch(P, 0, 4)
+    bt.behavior_rollout_device(beh, 1, dq.data_ptr(), dv_.data_ptr(), d_refs.data_ptr(), None, 0, T, out_ptrs={"status": st.data_ptr()})
+    torch.cuda.synchronize()
+    assert int(st[0]) == 0
+    assert np.abs(dq.cpu().numpy()[0] - q).max() < 1e-8 and np.abs(dv_.cpu().numpy()[0] - v).max() < 1e-6
+    for t in range(T, 1100):
+        pq, pv = dq.cpu().numpy().copy(), dv_.cpu().numpy().copy()
+        bt.behavior_rollout_device(beh, 1, dq.data_ptr(), dv_.data_ptr(), d_refs.data_ptr(), None, t, 1, init_refs=False,
+                                   out_ptrs={"status": st.data_ptr(), "iters": it.data_ptr()})
+        torch.cuda.synchronize()
+        if int(st[0]) != 0:
+            break
+    assert int(st[0]) != 0 and 930 <= t <= 1000, t
+    o = ol.cycle_batch(P, pq, pv, d_refs.cpu().numpy(), contact_mask=ora.tick(t)[1])
+    assert o["status"][0] == int(st[0]) and o["iters"][0] == int(it[0])

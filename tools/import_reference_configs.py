@@ -23,7 +23,7 @@ YAMLS = {
     "talos": ["talos_pos_tracker.yaml", "tasks.yaml", "frames.yaml", "squat.yaml", "arm.yaml",
               "walk.yaml", "walk_on_spot.yaml", "move_com.yaml", "move_feet.yaml", "clapping.yaml", "align.yaml",
               "collisions/talos_collisions_margin.yaml", "collisions/talos_collisions.yaml"],
-    "icub": ["humanoid_pos_tracker.yaml", "tasks.yaml", "frames.yaml", "squat.yaml", "arm.yaml"],
+    "icub": ["humanoid_pos_tracker.yaml", "tasks.yaml", "frames.yaml", "squat.yaml", "arm.yaml", "walk.yaml", "walk_on_spot.yaml", "clapping.yaml"],
     "tiago": ["pos_tracker.yaml", "tasks.yaml", "frames.yaml", "cartesian_line.yaml", "collisions.yaml"],
 }
 SRDFS = {
