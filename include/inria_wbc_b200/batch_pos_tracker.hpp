@@ -163,14 +163,39 @@ namespace inria_wbc {
         public:
             // `ticks` closed device-side ticks of a compiled behaviour on the controller's own (open-loop) state: what a loop of
             // Behavior::update() calls does in the reference, without crossing PCIe in between.  Results = those of the last tick.
-            void run_behavior(iwbc_behavior* h, const int* phase, int tick0, int ticks)
+            // cmd_trace (optional): resized to [ticks][B][nv], every tick's q(false) -- what the reference's tests record after each update
+            void run_behavior(iwbc_behavior* h, const int* phase, int tick0, int ticks, std::vector<double>* cmd_trace = nullptr)
             {
                 ensure_batch();
                 iwbc_results_t out = {tau_.data(), a_tsid_.data(), forces_.data(), nullptr, nullptr, q_.data(), momentum_.data(), status_.data(),
                     iters_.data(), nullptr};
-                if (iwbc_batch_behavior_run(batch_, h, B_, q_tsid_.data(), v_tsid_.data(), phase, tick0, ticks, &out, mask_.data()) != IWBC_OK)
+                int rc;
+                if (cmd_trace) {
+                    cmd_trace->assign((size_t)ticks * B_ * nv_, 0.0);
+                    rc = iwbc_batch_behavior_run_trace(batch_, h, B_, q_tsid_.data(), v_tsid_.data(), phase, tick0, ticks, &out, mask_.data(), cmd_trace->data());
+                }
+                else
+                    rc = iwbc_batch_behavior_run(batch_, h, B_, q_tsid_.data(), v_tsid_.data(), phase, tick0, ticks, &out, mask_.data());
+                if (rc != IWBC_OK)
                     throw IWBC_B200_EXCEPTION(std::string("behaviour roll-out failed: ") + iwbc_last_error());
                 t_ += dt_ * ticks;
+            }
+            // Controller::filter_cmd / the filter_mimics = true getters (controller.cpp:372-400): positions of `row` ([nv] "DART" layout,
+            // 6 base entries first) that are not mimic dofs
+            std::vector<int> non_mimic_indexes() const
+            {
+                std::vector<std::string> all = names(0), mim = names(3);
+                std::vector<int> idx;
+                for (int k = 0; k < nv_ - na_; ++k)
+                    idx.push_back(k);
+                for (int k = 0; k < na_; ++k) {
+                    bool is_mimic = false;
+                    for (const auto& m : mim)
+                        is_mimic = is_mimic || m == all[k];
+                    if (!is_mimic)
+                        idx.push_back(nv_ - na_ + k);
+                }
+                return idx;
             }
             iwbc_problem* problem() { return prob_; }
             const std::vector<unsigned>& contact_masks() const { return mask_; } // activated contacts per instance (bit = contact index)
@@ -357,9 +382,10 @@ namespace inria_wbc {
                 IWBC_B200_ASSERT((int)phase.size() == controller_->batch(), "set_phase: one offset per instance");
                 phase_ = phase;
             }
-            virtual void update(int ticks = 1)
+            // `ticks` behaviour + controller updates on the device; cmd_trace (optional) receives q(false) after every one of them
+            virtual void update(int ticks = 1, std::vector<double>* cmd_trace = nullptr)
             {
-                controller_->run_behavior(h_, phase_.empty() ? nullptr : phase_.data(), tick_, ticks);
+                controller_->run_behavior(h_, phase_.empty() ? nullptr : phase_.data(), tick_, ticks, cmd_trace);
                 tick_ += ticks;
             }
             int tick() const { return tick_; }

@@ -110,7 +110,8 @@ int iwbc_batch_update_device(iwbc_batch* b, int B, const double* q, const double
     unsigned contact_mask, const iwbc_results_t* out, void* stream);
 
 /* Open-loop ticks (closed_loop: false, Controller::_solve() on the integrated state): advances
- * the device-resident state (q, v) `ticks` times in place with constant references. */
+ * the device-resident state (q, v) `ticks` times in place with constant references.  An instance whose QP is not solved to
+ * optimality at some tick is frozen at that state (controller.cpp:249-256 throws before integrating) and keeps that status. */
 int iwbc_batch_rollout_device(iwbc_batch* b, int B, double* q, double* v, const double* refs, long refs_stride,
     unsigned contact_mask, int ticks, const iwbc_results_t* out_last, void* stream);
 
@@ -189,6 +190,17 @@ int iwbc_batch_behavior_rollout_device(iwbc_batch* b, iwbc_behavior* h, int B, d
  * workspace: an iwbc_batch_update call in between overwrites them -- restart with tick0 = 0 semantics or use the device form).  Synchronous. */
 int iwbc_batch_behavior_run(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, const int* phase, int tick0, int ticks,
     const iwbc_results_t* out_last, unsigned* contact_mask);
+
+/* The two roll-outs with a per-tick command trace: q_cmd_trace[ticks][B][nv] receives the "DART"-layout command vector of EVERY
+ * tick, i.e. what the reference's tests record with `controller->q(false)` after each `behavior->update()`
+ * (tests/test_determinism.cpp:35-40, tests/test_franka.cpp:175-179).  Device form: a device buffer; host form: a host buffer
+ * (drained chunk by chunk from a device ring).  A tick whose QP is not solved to optimality does not advance that instance's state
+ * (the reference throws before q_tsid_ / v_tsid_ are touched, src/controllers/controller.cpp:249-256) and its status is kept for
+ * the rest of the call; the same holds for every roll-out entry point above. */
+int iwbc_batch_behavior_rollout_trace_device(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, double* refs, const int* phase,
+    int tick0, int ticks, int init_refs, const iwbc_results_t* out_last, unsigned* contact_mask, double* q_cmd_trace, void* stream);
+int iwbc_batch_behavior_run_trace(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, const int* phase, int tick0, int ticks,
+    const iwbc_results_t* out_last, unsigned* contact_mask, double* q_cmd_trace);
 
 /* ------------------------------------------------------------------ post-solve model collision check
  * Replaces `utils::CollisionCheck::load_collision_file` + `is_colliding(model, data)` (src/safety/collision_check.cpp:5-87),

@@ -71,6 +71,8 @@ def lib():
         "iwbc_batch_launch_info": (ci, [vp, pi, pi, pi, C.POINTER(C.c_long)]),
         "iwbc_qp_solve_batch": (ci, [ci, ci, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
         "iwbc_batch_behavior_run": (ci, [vp, vp, ci, vp, vp, vp, ci, ci, C.POINTER(_Results), vp]),
+        "iwbc_batch_behavior_run_trace": (ci, [vp, vp, ci, vp, vp, vp, ci, ci, C.POINTER(_Results), vp, vp]),
+        "iwbc_batch_behavior_rollout_trace_device": (ci, [vp, vp, ci, vp, vp, vp, vp, ci, ci, ci, C.POINTER(_Results), vp, vp, vp]),
         "iwbc_collision_load": (vp, [vp, cp]),
         "iwbc_collision_free": (None, [vp]),
         "iwbc_collision_info": (ci, [vp, pi, pi, pi]),
@@ -335,8 +337,9 @@ class Batch:
         if rc != 0:
             raise IwbcError(_err(lib()))
 
-    def behavior_run(self, behavior, q, v, ticks, tick0=0, phase=None, out=None, fields=("tau", "status"), want_mask=False):
-        """`for tick: behavior.update()` with host arrays: q, v are advanced IN PLACE by `ticks` closed device-side ticks."""
+    def behavior_run(self, behavior, q, v, ticks, tick0=0, phase=None, out=None, fields=("tau", "status"), want_mask=False, trace=None):
+        """`for tick: behavior.update()` with host arrays: q, v are advanced IN PLACE by `ticks` closed device-side ticks.
+        trace: optional float64 array [ticks][B][nv] receiving every tick's command vector (controller->q(false))."""
         P = self.problem
         assert q.dtype == np.float64 and v.dtype == np.float64 and q.flags.c_contiguous and v.flags.c_contiguous
         B = q.reshape(-1, P.nq).shape[0]
@@ -345,7 +348,12 @@ class Batch:
             out = Results(P, B, fields)
         st = out.as_struct()
         mask = np.zeros(B, dtype=np.uint32) if want_mask else None
-        rc = lib().iwbc_batch_behavior_run(self._h, behavior.handle, B, q.ctypes.data, v.ctypes.data, _ptr(ph), tick0, ticks, C.byref(st), _ptr(mask))
+        if trace is None:
+            rc = lib().iwbc_batch_behavior_run(self._h, behavior.handle, B, q.ctypes.data, v.ctypes.data, _ptr(ph), tick0, ticks, C.byref(st), _ptr(mask))
+        else:
+            assert trace.dtype == np.float64 and trace.flags.c_contiguous and trace.size == ticks * B * P.nv
+            rc = lib().iwbc_batch_behavior_run_trace(self._h, behavior.handle, B, q.ctypes.data, v.ctypes.data, _ptr(ph), tick0, ticks, C.byref(st),
+                                                     _ptr(mask), trace.ctypes.data)
         if rc != 0:
             raise IwbcError(_err(lib()))
         return (out, mask) if want_mask else out

@@ -490,6 +490,10 @@ int iwbc_batch_update_device(iwbc_batch* b, int B, const double* q, const double
         set_error("iwbc_batch_update_device: bad argument");
         return IWBC_ERR_ARG;
     }
+    if (B > b->max_batch) { // the continuation list, the hand-over scratch and the counters are sized for max_batch
+        set_error("iwbc_batch_update_device: B = " + std::to_string(B) + " exceeds max_batch = " + std::to_string(b->max_batch));
+        return IWBC_ERR_ARG;
+    }
     if (B == 0)
         return IWBC_OK;
     CUDA_TRY(cudaSetDevice(b->device));
@@ -509,6 +513,10 @@ int iwbc_batch_rollout_device(iwbc_batch* b, int B, double* q, double* v, const 
         set_error("iwbc_batch_rollout_device: bad argument");
         return IWBC_ERR_ARG;
     }
+    if (B > b->max_batch) {
+        set_error("iwbc_batch_rollout_device: B = " + std::to_string(B) + " exceeds max_batch = " + std::to_string(b->max_batch));
+        return IWBC_ERR_ARG;
+    }
     CUDA_TRY(cudaSetDevice(b->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : b->stream;
     for (int t = 0; t < ticks; ++t) {
@@ -517,7 +525,10 @@ int iwbc_batch_rollout_device(iwbc_batch* b, int B, double* q, double* v, const 
         io.B = B;
         io.q = q, io.v = v, io.refs = refs, io.refs_stride = refs_stride;
         io.q_rw = q, io.v_rw = v;
-        if (out_last) { // status is OR-ed over ticks by the caller reading it after the last tick
+        // A tick whose QP is not solved to optimality does not advance that instance's state (the reference throws before
+        // q_tsid_ / v_tsid_ are touched, controller.cpp:249-256) and its status is kept for the rest of the call (sticky).
+        io.sticky_status = t > 0;
+        if (out_last) {
             io.status = out_last->status, io.iters = out_last->iters;
             if (t == ticks - 1) {
                 io.tau = out_last->tau, io.dv = out_last->dv, io.f = out_last->f, io.q_cmd = out_last->q_cmd;

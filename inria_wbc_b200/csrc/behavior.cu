@@ -332,8 +332,8 @@ int iwbc_behavior_eval_device(iwbc_behavior* h, int device, int B, const int* ph
     return eval_tick(h, B, phase, tick, refs, contact_mask, false, st);
 }
 
-int iwbc_batch_behavior_rollout_device(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, double* refs, const int* phase, int tick0, int ticks,
-    int init_refs, const iwbc_results_t* out_last, unsigned* contact_mask, void* stream)
+static int behavior_rollout(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, double* refs, const int* phase, int tick0, int ticks,
+    int init_refs, const iwbc_results_t* out_last, unsigned* contact_mask, double* q_cmd_trace, void* stream)
 {
     if (!b || !h || !q || !v || !refs || B < 0 || ticks < 0) {
         set_error("iwbc_batch_behavior_rollout_device: bad argument");
@@ -369,6 +369,7 @@ int iwbc_batch_behavior_rollout_device(iwbc_batch* b, iwbc_behavior* h, int B, d
             io.B = B;
             io.q = q, io.v = v, io.refs = refs, io.refs_stride = nref;
             io.q_rw = q, io.v_rw = v;
+            io.sticky_status = t > 0; // a failed tick freezes the instance and its status survives the call (batch.cu, roll-out)
             io.in_list = h->d_blist + (size_t)k * B;
             io.in_count = h->d_bcount + k;
             if (out_last) {
@@ -378,18 +379,39 @@ int iwbc_batch_behavior_rollout_device(iwbc_batch* b, iwbc_behavior* h, int B, d
                     io.momentum = out_last->momentum, io.active = out_last->active, io.q_next = out_last->q_next, io.v_next = out_last->v_next;
                 }
             }
+            if (q_cmd_trace) // every tick's command vector (what the reference's tests record with controller->q(false) after each update)
+                io.q_cmd = q_cmd_trace + (size_t)t * B * h->prob->cs.prob.nv;
             rc = iwbc_run_cycle(b, io, h->masks[k], st);
             if (rc)
                 return rc;
         }
     }
+    if (q_cmd_trace && out_last && out_last->q_cmd)
+        CUDA_TRY(cudaMemcpyAsync(out_last->q_cmd, q_cmd_trace + (size_t)(ticks - 1) * B * h->prob->cs.prob.nv, (size_t)B * h->prob->cs.prob.nv * 8,
+            cudaMemcpyDeviceToDevice, st));
     return IWBC_OK;
+}
+
+int iwbc_batch_behavior_rollout_device(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, double* refs, const int* phase, int tick0, int ticks,
+    int init_refs, const iwbc_results_t* out_last, unsigned* contact_mask, void* stream)
+{
+    return behavior_rollout(b, h, B, q, v, refs, phase, tick0, ticks, init_refs, out_last, contact_mask, nullptr, stream);
+}
+
+int iwbc_batch_behavior_rollout_trace_device(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, double* refs, const int* phase, int tick0,
+    int ticks, int init_refs, const iwbc_results_t* out_last, unsigned* contact_mask, double* q_cmd_trace, void* stream)
+{
+    if (!q_cmd_trace) {
+        set_error("iwbc_batch_behavior_rollout_trace_device: NULL trace");
+        return IWBC_ERR_ARG;
+    }
+    return behavior_rollout(b, h, B, q, v, refs, phase, tick0, ticks, init_refs, out_last, contact_mask, q_cmd_trace, stream);
 }
 
 // Host-buffer form of the roll-out (what a `for (tick) behavior->update();` loop of the reference does, src/robot_dart/talos.cpp:380-390):
 // uploads the state once, runs `ticks` closed device-side ticks, downloads the advanced state and the last tick's results.
-int iwbc_batch_behavior_run(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, const int* phase, int tick0, int ticks,
-    const iwbc_results_t* out_last, unsigned* contact_mask)
+static int behavior_run(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, const int* phase, int tick0, int ticks,
+    const iwbc_results_t* out_last, unsigned* contact_mask, double* q_cmd_trace)
 {
     if (!b || !h || !q || !v || B < 0 || ticks < 0) {
         set_error("iwbc_batch_behavior_run: bad argument");
@@ -422,8 +444,29 @@ int iwbc_batch_behavior_run(iwbc_batch* b, iwbc_behavior* h, int B, double* q, d
         r.active = out_last->active ? b->d_active : nullptr;
     }
     // a fresh behaviour (tick0 == 0) starts from the construction-time references; later calls continue from the rows the previous call left
-    int rc = iwbc_batch_behavior_rollout_device(b, h, B, b->d_q, b->d_v, b->d_refs, phase ? b->d_phase : nullptr, tick0, ticks, tick0 == 0 ? 1 : 0, &r,
-        contact_mask ? b->d_cmask : nullptr, st);
+    int rc = IWBC_OK;
+    if (!q_cmd_trace)
+        rc = behavior_rollout(b, h, B, b->d_q, b->d_v, b->d_refs, phase ? b->d_phase : nullptr, tick0, ticks, tick0 == 0 ? 1 : 0, &r,
+            contact_mask ? b->d_cmask : nullptr, nullptr, st);
+    else {
+        // per-tick command trace: device ring of <= 16 MB, drained to the host chunk by chunk
+        const size_t row = (size_t)B * nv;
+        const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)ticks, (16u << 20) / (row * 8)));
+        double* d_trace = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&d_trace, (size_t)chunk * row * 8));
+        for (int t0 = 0; t0 < ticks && rc == IWBC_OK; t0 += chunk) {
+            const int n = std::min(chunk, ticks - t0);
+            rc = behavior_rollout(b, h, B, b->d_q, b->d_v, b->d_refs, phase ? b->d_phase : nullptr, tick0 + t0, n, (tick0 == 0 && t0 == 0) ? 1 : 0, &r,
+                contact_mask ? b->d_cmask : nullptr, d_trace, st);
+            if (rc == IWBC_OK && cudaMemcpyAsync(q_cmd_trace + (size_t)t0 * row, d_trace, (size_t)n * row * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+                rc = IWBC_ERR_CUDA;
+            if (rc == IWBC_OK && cudaStreamSynchronize(st) != cudaSuccess) // the ring is reused by the next chunk
+                rc = IWBC_ERR_CUDA;
+        }
+        cudaFree(d_trace);
+        if (rc == IWBC_ERR_CUDA && std::string(iwbc_last_error()).empty())
+            set_error("iwbc_batch_behavior_run_trace: CUDA error");
+    }
     if (rc)
         return rc;
     CUDA_TRY(cudaMemcpyAsync(q, b->d_q, B * nq * 8, cudaMemcpyDeviceToHost, st));
@@ -449,6 +492,22 @@ int iwbc_batch_behavior_run(iwbc_batch* b, iwbc_behavior* h, int B, double* q, d
         CUDA_TRY(cudaMemcpyAsync(contact_mask, b->d_cmask, B * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return IWBC_OK;
+}
+
+int iwbc_batch_behavior_run(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, const int* phase, int tick0, int ticks,
+    const iwbc_results_t* out_last, unsigned* contact_mask)
+{
+    return behavior_run(b, h, B, q, v, phase, tick0, ticks, out_last, contact_mask, nullptr);
+}
+
+int iwbc_batch_behavior_run_trace(iwbc_batch* b, iwbc_behavior* h, int B, double* q, double* v, const int* phase, int tick0, int ticks,
+    const iwbc_results_t* out_last, unsigned* contact_mask, double* q_cmd_trace)
+{
+    if (!q_cmd_trace) {
+        set_error("iwbc_batch_behavior_run_trace: NULL trace");
+        return IWBC_ERR_ARG;
+    }
+    return behavior_run(b, h, B, q, v, phase, tick0, ticks, out_last, contact_mask, q_cmd_trace);
 }
 
 } // extern "C"

@@ -109,6 +109,7 @@ namespace dev {
         // rollout: write q_next / v_next back into q / v (in place) when set
         double* q_rw;
         double* v_rw;
+        int sticky_status; // roll-outs, ticks after the first: a non-OPTIMAL status already stored for the instance is kept
         // debug dump of instance 0 (row-major): M nle H g x
         double* dbg_M;
         double* dbg_nle;
@@ -2577,8 +2578,15 @@ namespace dev {
             for (int k = tid; k < 3; k += G)
                 io.momentum[(size_t)inst * 3 + k] = sm.sc[34 + k]; // Ag.bottomRows(3) * v = angular part of hg
         if (tid == 0) {
-            if (io.status)
-                io.status[inst] = status;
+            if (io.status) {
+                int st = status;
+                if (io.sticky_status) {
+                    const int old = io.status[inst];
+                    if (old != IWBC_STATUS_OPTIMAL)
+                        st = old;
+                }
+                io.status[inst] = st;
+            }
             if (io.iters)
                 io.iters[inst] = iters;
             if (io.active) {
@@ -2595,7 +2603,7 @@ namespace dev {
                     a[k] = words[k];
             }
         }
-        if (io.q_rw) { // open-loop roll-out: the integrated state becomes the next tick's state
+        if (io.q_rw && status == IWBC_STATUS_OPTIMAL) { // open-loop roll-out: the integrated state becomes the next tick's state (a failed QP freezes the instance)
             double* qn2 = sm.x_old;
             for (int k = tid; k < nq; k += G)
                 io.q_rw[(size_t)inst * nq + k] = qn2[k];

@@ -145,6 +145,19 @@ def test_talos_hard_states_exercise_adds_drops_and_the_large_active_sets(talos):
         assert _rel(getattr(r, k)[diff], o[k][diff]) < 1e-7, k
 
 
+def test_moving_base_batches(talos, talos_fast, icub):
+    """Free-flyer away from the SRDF pose with a non-zero base twist (position +-5 cm, orientation ~0.2 rad, twist 0.05), double and
+    single support: the base columns of M / nle / the contact Jacobians and the SE(3) integration are exercised on the CUDA binary
+    itself (tests/test_cpu_sim.py does the same on the host-compiled device source)."""
+    for P, B in ((talos, 1536), (talos_fast, 1024), (icub, 1024)):
+        q, v = random_states(P, B, 77, base=True)
+        bt = iw.Batch(P, 0, B)
+        r, o = _check(P, bt, q, v)
+        assert np.abs(r.q_next[:, :7] - o["q_next"][:, :7]).max() < 1e-12  # SE(3) exponential of the base
+        mask = np.repeat(np.array([3, 1, 2], dtype=np.uint32), (B + 2) // 3)[:B]
+        _check(P, bt, q, v, mask=mask)
+
+
 def test_talos_stage_dump(talos):
     q, v = random_states(talos, 1, 9, base=True)
     bt = iw.Batch(talos, 0, 8)
