@@ -308,9 +308,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import inria_wbc_b200 as iw
+    # the oracle's own configuration reader (PyYAML + xml.etree): this arm never loads libiwbc_b200.so
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import problem_loader
     yaml, ov, B, recipe = WORKLOADS[args.workload]
-    P = iw.Problem(yaml, overrides=ov)
+    P = problem_loader.load(yaml, overrides=ov)
     threads = os.cpu_count() or 1
     sample = min(B, 2048)
     q, v, refs = make_inputs(P, sample, recipe, 0xB200 + 3)
@@ -330,7 +332,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "batched TSID control updates (QP solves) per second", "value": val, "unit": "updates/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "per_step_sample": sample, "note": "CPU oracle port of the reference path; one instance per thread"},
+            "config": {"workload": args.workload, "per_step_sample": sample,
+                       "note": "CPU oracle port of the reference path (oracle/wbc_oracle.cpp fed by oracle/problem_loader.py); one instance per thread; "
+                               "each step is a bounded sample of the workload's recipe"},
             "cpu_baseline": {"value": val, "unit": "updates/s", "cores": threads, "kind": "port", "sample": "%d instances x %d steps" % (sample, args.steps)},
             "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
