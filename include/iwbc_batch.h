@@ -220,6 +220,34 @@ int iwbc_collision_spheres(const iwbc_collision* h, double* p_radius4, int* join
  * iteration order (-1 when free).  Enqueued on `stream` (NULL: the batch's own stream), no synchronisation. */
 int iwbc_batch_check_collisions_device(iwbc_batch* b, iwbc_collision* h, int B, const double* q, int* colliding, int* pair4, void* stream);
 
+/* ------------------------------------------------------------------ send_cmd latch and qp_step_back (second half)
+ * Per-instance form of the controller's command gating (src/controllers/controller.cpp):
+ *   :238-242  while send_cmd_ the state a tick starts from is remembered (q_tsid_prev_, v_tsid_prev_);
+ *   :263-282  q_solver_ follows every OPTIMAL solve, the command vectors q_ / tau_ / dq_ / ddq_ only while send_cmd_;
+ *   :309-312  after the solve, a model collision (on the state the tick started from) latches send_cmd_ = false unless the
+ *             command is still all zero (`!q_.isZero(1e-3)`); the controller's own integrated state keeps advancing;
+ *   :445-450  qp_step_back() puts the remembered state back (include/inria_wbc/controllers/controller.hpp:170-171);
+ *   set_send_cmd(true) (controller.hpp:167) = write 1 into send_cmd[i].
+ * All pointers are DEVICE pointers; the caller owns the arrays and initialises send_cmd to 1 and q_cmd to 0 (q_ starts at zero).
+ */
+typedef struct {
+    int* send_cmd;     /* [B]      in/out: Controller::send_cmd_                                  */
+    int* colliding;    /* [B]      out: is_model_colliding_ of the last tick (needed iff a collision model is given) */
+    double* q_prev;    /* [B][nq]  q_tsid_prev_                                                   */
+    double* v_prev;    /* [B][nv]  v_tsid_prev_                                                   */
+    double* q_solver;  /* [B][nv]  q_solver_ ("DART" layout) -- may be NULL                        */
+    double* q_cmd;     /* [B][nv]  q_                                                             */
+    double* tau_cmd;   /* [B][na]  tau_ without its six leading zeros -- may be NULL               */
+    double* dq_cmd;    /* [B][nv]  dq_  -- may be NULL                                            */
+    double* ddq_cmd;   /* [B][nv]  ddq_ -- may be NULL                                            */
+} iwbc_safety_t;
+/* `ticks` open-loop ticks on the device-resident state (q, v) in place with the gating above; collision may be NULL
+ * (CONTROLLER.check_model_collisions: false); status[B] (may be NULL) as in iwbc_batch_rollout_device. */
+int iwbc_batch_safe_rollout_device(iwbc_batch* b, iwbc_collision* collision, int B, double* q, double* v, const double* refs, long refs_stride,
+    unsigned contact_mask, int ticks, const iwbc_safety_t* safety, int* status, void* stream);
+/* qp_step_back(): (q, v) <- (q_prev, v_prev) for the instances with select[i] != 0 (select == NULL: all) */
+int iwbc_batch_qp_step_back_device(iwbc_batch* b, int B, double* q, double* v, const iwbc_safety_t* safety, const int* select, void* stream);
+
 /* ------------------------------------------------------------------ solver interface
  * Batched form of `tsid::solvers::SolverHQPBase::solve` for the EiquadprogFast backend
  * (src/controllers/pos_tracker.cpp:96,102; src/controllers/controller.cpp:247): B dense QPs of one

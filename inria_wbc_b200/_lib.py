@@ -28,6 +28,11 @@ class _Results(C.Structure):
                 ("iters", C.c_void_p), ("active", C.c_void_p)]
 
 
+class _Safety(C.Structure):
+    _fields_ = [("send_cmd", C.c_void_p), ("colliding", C.c_void_p), ("q_prev", C.c_void_p), ("v_prev", C.c_void_p), ("q_solver", C.c_void_p),
+                ("q_cmd", C.c_void_p), ("tau_cmd", C.c_void_p), ("dq_cmd", C.c_void_p), ("ddq_cmd", C.c_void_p)]
+
+
 def lib():
     """Load the product library; fails loudly if it has not been built (python __graft_entry__.py)."""
     global _lib
@@ -78,6 +83,8 @@ def lib():
         "iwbc_collision_info": (ci, [vp, pi, pi, pi]),
         "iwbc_collision_spheres": (ci, [vp, vp, vp]),
         "iwbc_batch_check_collisions_device": (ci, [vp, vp, ci, vp, vp, vp, vp]),
+        "iwbc_batch_safe_rollout_device": (ci, [vp, vp, ci, vp, vp, vp, cl, cu, ci, C.POINTER(_Safety), vp, vp]),
+        "iwbc_batch_qp_step_back_device": (ci, [vp, ci, vp, vp, C.POINTER(_Safety), vp, vp]),
         "iwbc_behavior_load": (vp, [vp, cp, cp]),
         "iwbc_behavior_free": (None, [vp]),
         "iwbc_behavior_info": (ci, [vp, pi, pi, pi, pi, vp]),
@@ -361,6 +368,22 @@ class Batch:
     def check_collisions_device(self, collision_model, B, q_ptr, colliding_ptr, pair_ptr=None, stream=0):
         """Batched CollisionCheck::is_colliding on device-resident states (SURVEY.md 8(f-4))."""
         rc = lib().iwbc_batch_check_collisions_device(self._h, collision_model.handle, B, q_ptr, colliding_ptr, pair_ptr, stream)
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+
+    SAFETY_FIELDS = ("send_cmd", "colliding", "q_prev", "v_prev", "q_solver", "q_cmd", "tau_cmd", "dq_cmd", "ddq_cmd")
+
+    def safe_rollout_device(self, collision_model, B, q_ptr, v_ptr, refs_ptr, refs_stride, contact_mask, ticks, safety_ptrs, status_ptr=None, stream=0):
+        """Open-loop ticks with the controller's send_cmd latch / collision gating (controller.cpp:238-242, 263-282, 309-312); all device addresses."""
+        s = _Safety(*[safety_ptrs.get(f) for f in self.SAFETY_FIELDS])
+        rc = lib().iwbc_batch_safe_rollout_device(self._h, collision_model.handle if collision_model is not None else None, B, q_ptr, v_ptr, refs_ptr,
+                                                  refs_stride, contact_mask, ticks, C.byref(s), status_ptr, stream)
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+
+    def qp_step_back_device(self, B, q_ptr, v_ptr, safety_ptrs, select_ptr=None, stream=0):
+        s = _Safety(*[safety_ptrs.get(f) for f in self.SAFETY_FIELDS])
+        rc = lib().iwbc_batch_qp_step_back_device(self._h, B, q_ptr, v_ptr, C.byref(s), select_ptr, stream)
         if rc != 0:
             raise IwbcError(_err(lib()))
 

@@ -2,6 +2,7 @@
 // device workspaces, host<->device staging.  sm_100a only; no CPU fallback.
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -24,24 +25,26 @@ namespace dev {
     // (the warp-per-instance form is occupancy-bound by registers: three CTAs per SM need <= 168; without the bound ptxas drifts to
     // 216 and Franka drops from 38 M to 27 M updates/s)
     template <int G, int IPC>
-    __global__ void __launch_bounds__(G* IPC, (G <= 32 ? 3 : 1)) k_cycle(const iwbc_problem_t* __restrict__ gP, IO io)
+    __global__ void __launch_bounds__(G* IPC, (G <= 32 ? 3 : 1)) k_cycle(const iwbc_problem_t* __restrict__ gP, const __grid_constant__ Shape S, IO io)
     {
         extern __shared__ double smem[];
         const int grp = threadIdx.x / G;
         const int tid = threadIdx.x - grp * G;
         Sizes z;
-        z.nv = c_P.nv;
-        z.nq = c_P.nq;
-        z.nj = c_P.nj;
-        z.nf = c_P.nframes;
-        z.nc = c_P.ncontacts;
-        z.n = c_S.n;
-        z.mi = c_S.mi;
-        z.rows_dense = c_S.rows_dense;
-        z.nref = c_P.nref;
-        z.ldJ = c_S.ldJ;
-        z.ldM = c_S.ldM;
-        const Sm sm = make_sm(smem + (size_t)grp * c_S.total, z);
+        z.nv = gP->nv;
+        z.nq = gP->nq;
+        z.nj = gP->nj;
+        z.nf = gP->nframes;
+        z.nc = gP->ncontacts;
+        z.n = S.n;
+        z.mi = S.mi;
+        z.rows_dense = S.rows_dense;
+        z.nref = gP->nref;
+        z.ldJ = S.ldJ;
+        z.ldM = S.ldM;
+        z.S = &S;
+        z.P = gP;
+        const Sm sm = make_sm(smem + (size_t)grp * S.total, z);
         int flip = 0;
 
         // dof -> joint table
@@ -94,7 +97,7 @@ namespace dev {
         unsigned* active;
     };
     template <int G, int IPC>
-    __global__ void __launch_bounds__(G* IPC) k_qp_dense(QpIO io)
+    __global__ void __launch_bounds__(G* IPC) k_qp_dense(const __grid_constant__ Shape S, QpIO io)
     {
         extern __shared__ double smem[];
         const int grp = threadIdx.x / G;
@@ -103,9 +106,11 @@ namespace dev {
         z.nv = 0, z.nq = 0, z.nj = 0, z.nf = 0, z.nc = 0, z.nref = 0, z.rows_dense = 0;
         z.n = io.n;
         z.mi = io.mi;
-        z.ldJ = c_S.ldJ;
+        z.ldJ = S.ldJ;
         z.ldM = 1;
-        const Sm sm = make_sm(smem + (size_t)grp * c_S.total, z);
+        z.S = &S;
+        z.P = nullptr;
+        const Sm sm = make_sm(smem + (size_t)grp * S.total, z);
         const int n = io.n;
         int flip = 0;
         const int ngroups = gridDim.x * IPC;
@@ -168,12 +173,7 @@ using namespace iwbc;
 
 namespace {
 
-// which (device, problem revision, mask) the __constant__ copies currently hold
-struct ConstOwner {
-    unsigned long uid = 0; // iwbc_batch::uid (addresses get reused after a free; uids do not)
-    unsigned long revision = 0;
-    unsigned mask = ~0u;
-} g_const_owner[16];
+std::mutex g_attr_mutex;
 
 // fast pass + active-set continuation: one translation unit per compile-time (nv, me) shape (fast_tu.cuh)
 int launch_fast(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
@@ -194,7 +194,10 @@ template <int G, int IPC>
 int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
 {
     auto kern = dev::k_cycle<G, IPC>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem_bytes));
+    static size_t smem_set[16];
+    int rc0 = iwbc_raise_smem_limit((const void*)kern, b->device, b->smem_bytes, smem_set);
+    if (rc0)
+        return rc0;
     if (b->grid == 0) {
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G * IPC, b->smem_bytes));
@@ -217,7 +220,7 @@ int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
     }
     if (b->timing && !use_fast)
         cudaEventRecord(b->ev0, st);
-    kern<<<grid, G * IPC, b->smem_bytes, st>>>(b->d_prob, iop);
+    kern<<<grid, G * IPC, b->smem_bytes, st>>>(b->d_prob, b->shape, iop);
     if (b->timing) {
         cudaEventRecord(b->ev1, st);
         cudaEventSynchronize(b->ev1);
@@ -254,11 +257,46 @@ void choose_group(const iwbc_problem_t& P, int n, int& G, int& IPC)
     }
 }
 
+void stash_current(iwbc_batch* b)
+{
+    if (b->shape_mask == ~0u)
+        return;
+    iwbc_mask_state* slot = nullptr;
+    for (auto& m : b->mask_cache)
+        if (m.mask == b->shape_mask)
+            slot = &m;
+    if (!slot) {
+        b->mask_cache.emplace_back();
+        slot = &b->mask_cache.back();
+    }
+    slot->mask = b->shape_mask, slot->revision = b->shape_revision;
+    slot->shape = b->shape, slot->fshape = b->fshape, slot->d_fplan = b->d_fplan;
+    slot->G = b->G, slot->IPC = b->IPC, slot->grid = b->grid, slot->fast_grid = b->fast_grid, slot->slow_grid = b->slow_grid;
+    slot->smem_bytes = b->smem_bytes, slot->fast_smem = b->fast_smem, slot->slow_smem = b->slow_smem, slot->fast_ok = b->fast_ok;
+}
+
 int prepare_shape(iwbc_batch* b, unsigned mask)
 {
     const iwbc_problem_t& P = b->prob->cs.prob;
-    if (b->shape_mask == mask && b->revision == b->prob->revision)
+    if (b->shape_mask == mask && b->shape_revision == b->prob->revision)
         return IWBC_OK;
+    // ---- another contact mask: park the current state, take the mask's own from the cache when it is still valid
+    if (b->shape_mask != mask) {
+        stash_current(b);
+        b->d_fplan = nullptr;
+        for (auto& m : b->mask_cache)
+            if (m.mask == mask) {
+                b->d_fplan = m.d_fplan; // (reused as the upload target even when the revision is stale)
+                if (m.revision == b->prob->revision) {
+                    b->shape = m.shape, b->fshape = m.fshape;
+                    b->G = m.G, b->IPC = m.IPC, b->grid = m.grid, b->fast_grid = m.fast_grid, b->slow_grid = m.slow_grid;
+                    b->smem_bytes = m.smem_bytes, b->fast_smem = m.fast_smem, b->slow_smem = m.slow_smem, b->fast_ok = m.fast_ok;
+                    b->shape_mask = mask, b->shape_revision = m.revision;
+                    b->plan_dirty = false;
+                    return IWBC_OK;
+                }
+            }
+    }
     dev::Shape& S = b->shape;
     std::memset(&S, 0, sizeof(S));
     host::QPShape qs = host::qp_shape(P, mask);
@@ -311,11 +349,13 @@ int prepare_shape(iwbc_batch* b, unsigned mask)
     dev::Sizes z;
     z.nv = P.nv, z.nq = P.nq, z.nj = P.nj, z.nf = P.nframes, z.nc = P.ncontacts, z.n = S.n, z.mi = S.mi;
     z.rows_dense = S.rows_dense, z.nref = P.nref, z.ldJ = S.ldJ, z.ldM = S.ldM;
+    z.S = nullptr, z.P = nullptr;
     dev::make_layout(z, S);
     choose_group(P, S.n, b->G, b->IPC);
     b->smem_bytes = (size_t)S.total * sizeof(double) * b->IPC;
     b->grid = 0;
     b->shape_mask = mask;
+    b->shape_revision = b->prob->revision;
     b->fast_ok = b->G > 32 && dev::build_fast_plan(P, S, 128, b->fshape, b->fplan);
     b->fast_smem = (size_t)b->fshape.total * sizeof(double);
     b->slow_smem = (size_t)b->fshape.s_total * sizeof(double);
@@ -325,31 +365,27 @@ int prepare_shape(iwbc_batch* b, unsigned mask)
     return IWBC_OK;
 }
 
+// device copies of the problem (once per revision) and of the current mask's plan (once per (revision, mask)); stream-ordered
 int upload_constants(iwbc_batch* b, cudaStream_t st)
 {
-    ConstOwner& o = g_const_owner[b->device & 15];
+    bool fresh = false;
     if (b->revision != b->prob->revision) {
         CUDA_TRY(cudaMemcpyAsync(b->d_prob, &b->prob->cs.prob, sizeof(iwbc_problem_t), cudaMemcpyHostToDevice, st));
         b->revision = b->prob->revision;
         b->dprob_revision = b->prob->revision;
-        o.uid = 0;
+        fresh = true;
     }
     if (b->plan_dirty) {
-        // (the stream may still run a kernel reading the previous plan: the copy is stream-ordered behind it)
+        if (!b->d_fplan)
+            CUDA_TRY(cudaMalloc((void**)&b->d_fplan, sizeof(dev::FPlan)));
+        // (pageable source: the copy is staged before the call returns; kernels of this mask launched earlier on this stream
+        // still read the previous contents, later ones the new)
         CUDA_TRY(cudaMemcpyAsync(b->d_fplan, &b->fplan, sizeof(dev::FPlan), cudaMemcpyHostToDevice, st));
         b->plan_dirty = false;
+        fresh = true;
     }
-    if (o.uid != b->uid || o.revision != b->revision || o.mask != b->shape_mask) {
-        // other streams may still be running a kernel that reads the old constants
-        if (o.uid != 0 && o.uid != b->uid)
-            CUDA_TRY(cudaDeviceSynchronize());
-        CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_P, &b->prob->cs.prob, sizeof(iwbc_problem_t), 0, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_S, &b->shape, sizeof(dev::Shape), 0, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_F, &b->fshape, sizeof(dev::FShape), 0, cudaMemcpyHostToDevice, st));
-        o.uid = b->uid;
-        o.revision = b->revision;
-        o.mask = b->shape_mask;
-    }
+    if (fresh) // once per (revision, mask): later launches of this handle on OTHER streams must find the copies in place
+        CUDA_TRY(cudaStreamSynchronize(st));
     return IWBC_OK;
 }
 
@@ -385,6 +421,17 @@ int dalloc(T** p, size_t count)
 
 } // namespace
 
+int iwbc_raise_smem_limit(const void* func, int device, size_t bytes, size_t* max_set)
+{
+    std::lock_guard<std::mutex> lock(g_attr_mutex);
+    size_t& cur = max_set[device & 15];
+    if (bytes > cur) {
+        CUDA_TRY(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        cur = bytes;
+    }
+    return IWBC_OK;
+}
+
 extern "C" {
 
 iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch)
@@ -408,8 +455,6 @@ iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch)
     }
     cudaSetDevice(device);
     auto* b = new iwbc_batch;
-    static std::atomic<unsigned long> next_uid{1};
-    b->uid = next_uid++;
     b->prob = p;
     b->device = device;
     b->max_batch = max_batch;
@@ -418,7 +463,7 @@ iwbc_batch* iwbc_batch_create(const iwbc_problem* p, int device, int max_batch)
     const size_t B = (size_t)max_batch;
     bool ok = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreate(&b->ev0) == cudaSuccess && cudaEventCreate(&b->ev1) == cudaSuccess;
-    ok = ok && dalloc(&b->d_fplan, 1) == 0 && dalloc(&b->d_slow_list, B) == 0 && dalloc(&b->d_slow_count, 16) == 0 && dalloc(&b->d_slow_code, 65536) == 0;
+    ok = ok && dalloc(&b->d_slow_list, B) == 0 && dalloc(&b->d_slow_count, 16) == 0 && dalloc(&b->d_slow_code, 65536) == 0;
     ok = ok && cudaStreamCreateWithFlags(&b->aux[0], cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&b->aux[1], cudaStreamNonBlocking) == cudaSuccess
         && cudaEventCreateWithFlags(&b->ev_const, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&b->s_in, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&b->s_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -447,11 +492,11 @@ void iwbc_batch_free(iwbc_batch* b)
     if (!b)
         return;
     cudaSetDevice(b->device);
-    ConstOwner& o = g_const_owner[b->device & 15];
-    if (o.uid == b->uid)
-        o.uid = 0;
     if (b->stream)
         cudaStreamSynchronize(b->stream);
+    for (auto& m : b->mask_cache)
+        if (m.d_fplan && m.d_fplan != b->d_fplan)
+            cudaFree(m.d_fplan);
     void* ptrs[] = {b->d_phase, b->d_cmask, b->d_scratch, b->d_slow_code, b->d_fplan, b->d_slow_list, b->d_slow_count, b->d_prof, b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
     for (void* p : ptrs)
         if (p)
@@ -640,18 +685,12 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
     if (grouped && B >= 8192 && runs.size() <= 4 && !b->timing && !b->profiling) {
         // Pipeline (needs pinned host buffers to be effective).  Uploads queue back to back on their own stream (the copy engine
         // never waits for a kernel or a download); the kernels of successive chunks alternate between two compute streams (their
-        // tails overlap); downloads follow on a third stream; events chain the three per chunk.  A change of contact mask
-        // drains the compute streams first: the __constant__ tables are per mask.
+        // tails overlap); downloads follow on a third stream; events chain the three per chunk.  Every contact mask has its own
+        // shape parameters and device plan, so runs of different masks overlap like chunks of one run.
         int c = 0; // global chunk index (<= 16: ev_in / ev_done)
         const int cap = std::min(b->max_batch, 65536);
         for (size_t ri = 0; ri < runs.size(); ++ri) {
             const Run& run = runs[ri];
-            if (ri > 0) {
-                CUDA_TRY(cudaEventRecord(b->ev_done[15], b->aux[0]));
-                CUDA_TRY(cudaStreamWaitEvent(st, b->ev_done[15], 0));
-                CUDA_TRY(cudaEventRecord(b->ev_done[15], b->aux[1]));
-                CUDA_TRY(cudaStreamWaitEvent(st, b->ev_done[15], 0));
-            }
             int rc = prepare_shape(b, run.mask);
             if (rc)
                 return rc;
@@ -678,7 +717,6 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
                 step = ((run.count - bounds.back() + (budget - 1) * unit - 1) / ((budget - 1 > 0 ? budget - 1 : 1) * unit)) * unit;
             while (bounds.back() < run.count)
                 bounds.push_back(std::min(run.count, bounds.back() + std::max(step, unit)));
-            bool first_launch_of_run = true;
             for (size_t k = 0; k + 1 < bounds.size(); ++k, ++c) {
                 if (c > 14) {
                     set_error("iwbc_batch_update: internal error (pipeline chunk plan)");
@@ -705,7 +743,6 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
                     b->scratch_len = cap / 2;
                     b->scratch_off = (c & 1) * b->scratch_len;
                 }
-                b->tu_uploaded = false;
                 rc = iwbc_batch_update_device(b, (int)cnt, b->d_q + first * nq, b->d_v + first * nv, b->d_refs + (refs_stride ? first * nref : 0),
                     refs_stride, run.mask, &r, cs);
                 b->slot = 0;
@@ -714,9 +751,6 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
                 if (rc)
                     return rc;
                 CUDA_TRY(cudaEventRecord(b->ev_done[c], cs));
-                if (first_launch_of_run && b->tu_uploaded) // this launch refreshed the kernel pair's own __constant__ tables on `cs`: the other compute stream must not run ahead of that
-                    CUDA_TRY(cudaStreamWaitEvent(b->aux[(c + 1) & 1], b->ev_done[c], 0));
-                first_launch_of_run = false;
                 CUDA_TRY(cudaStreamWaitEvent(b->s_out, b->ev_done[c], 0));
                 rc = copy_out((int)first, (int)cnt, nullptr, b->s_out);
                 if (rc)
@@ -1037,15 +1071,14 @@ int iwbc_qp_solve_batch(int device, int B, int n, int me, int mi, const double* 
         CUDA_TRY(cudaMemcpy(dCI, CI, Bz * mi * n * 8, cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(dci, ci0, Bz * mi * 8, cudaMemcpyHostToDevice));
     }
-    ConstOwner& o = g_const_owner[device & 15];
-    CUDA_TRY(cudaDeviceSynchronize());
-    o.uid = 0;
-    CUDA_TRY(cudaMemcpyToSymbol(dev::c_S, &S, sizeof(S)));
     dev::QpIO io = {B, n, me, mi, dH, dg, dCE, dce, dCI, dci, dx, dst, dit, dact};
     int rc = IWBC_OK;
     auto launch = [&](auto kern, int G, int IPC) -> int {
         size_t smem = (size_t)S.total * 8 * IPC;
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            std::lock_guard<std::mutex> lock(g_attr_mutex); // (the attribute is per function and device; concurrent callers may differ in n)
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        }
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G * IPC, smem));
         if (per_sm < 1) {
@@ -1053,7 +1086,7 @@ int iwbc_qp_solve_batch(int device, int B, int n, int me, int mi, const double* 
             return IWBC_ERR_CUDA;
         }
         int grid = std::min(prop.multiProcessorCount * per_sm, (B + IPC - 1) / IPC);
-        kern<<<grid, G * IPC, smem>>>(io);
+        kern<<<grid, G * IPC, smem>>>(S, io);
         CUDA_TRY(cudaGetLastError());
         return IWBC_OK;
     };

@@ -20,10 +20,24 @@
         }                                                                                                     \
     } while (0)
 
+// Everything that depends on (problem revision, contact mask): the QP shape and shared-memory layout (passed to the kernels as
+// __grid_constant__ parameters), the fast path's plan (its own device buffer) and the launch shapes.  Cached per mask in the
+// batch, so a walking tick that alternates between three masks neither re-derives nor re-uploads anything.
+struct iwbc_mask_state {
+    unsigned mask = ~0u;
+    unsigned long revision = ~0ul;
+    iwbc::dev::Shape shape;
+    iwbc::dev::FShape fshape;
+    iwbc::dev::FPlan* d_fplan = nullptr;
+    int G = 0, IPC = 0, grid = 0, fast_grid = 0, slow_grid = 0;
+    size_t smem_bytes = 0, fast_smem = 0, slow_smem = 0;
+    bool fast_ok = false;
+};
+
 struct iwbc_batch {
     const iwbc_problem* prob = nullptr;
-    unsigned long uid = 0; // unique per created batch (never reused, unlike the address): identity of the owner of the __constant__ tables
     unsigned long revision = ~0ul;
+    std::vector<iwbc_mask_state> mask_cache; // the inactive masks' states (the active one lives in the fields below)
     unsigned long dprob_revision = ~0ul; // revision of the problem held by d_prob
     int device = 0;
     int max_batch = 0;
@@ -48,6 +62,7 @@ struct iwbc_batch {
     double ms_sum = 0;
     long ms_n = 0;
     unsigned shape_mask = ~0u;
+    unsigned long shape_revision = ~0ul; // problem revision the current shape / plan were derived from
     iwbc::dev::Shape shape;
     int G = 0, IPC = 0;
     long long last_cycles[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -71,7 +86,6 @@ struct iwbc_batch {
     int fast_grid = 0, slow_grid = 0;
     size_t fast_smem = 0, slow_smem = 0;
     bool plan_dirty = true;
-    bool tu_uploaded = false; // set by a per-shape unit when its launch had to refresh its own __constant__ tables
     size_t smem_bytes = 0;
     int grid = 0;
 };
@@ -79,14 +93,11 @@ struct iwbc_batch {
 
 constexpr int IWBC_FAST_THREADS = 128; // threads per CTA of k_fast / k_slow
 
-// which (problem revision, contact mask) a translation unit's __constant__ copies currently hold, per device
-struct iwbc_const_owner {
-    unsigned long uid = 0; // iwbc_batch::uid of the batch whose tables are resident (0: none)
-    unsigned long revision = 0;
-    unsigned mask = ~0u;
-};
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function and per device, not per batch: every launch site keeps the largest
+// value it has set (per device) and only ever raises it, under a lock (two host threads may drive two handles on one device)
+int iwbc_raise_smem_limit(const void* func, int device, size_t bytes, size_t* max_set /* [16] per launch site */);
 
-// k_fast / k_slow launch pair of one compile-time (nv, me) shape; uploads that unit's own __constant__ copies when stale
+// k_fast / k_slow launch pair of one compile-time (nv, me) shape
 int iwbc_launch_fast_50_18(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
 int iwbc_launch_fast_50_12(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
 int iwbc_launch_fast_38_18(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);

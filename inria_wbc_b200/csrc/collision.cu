@@ -52,6 +52,70 @@ __device__ __forceinline__ void se3_mul(const double* A, const double* B, double
     }
 }
 
+// ---- send_cmd latch / qp_step_back (controller.cpp:238-242, 263-282, 309-312, 445-450), one thread per (instance, entry)
+// before the solve: instances that still send commands remember the state the tick starts from
+__global__ void k_safety_pre(int B, int nq, int nv, const int* __restrict__ send_cmd, const double* __restrict__ q, const double* __restrict__ v,
+    double* __restrict__ q_prev, double* __restrict__ v_prev)
+{
+    const int w = nq + nv;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < (long)B * w; e += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / w), k = (int)(e - (long)i * w);
+        if (!send_cmd[i])
+            continue;
+        if (k < nq)
+            q_prev[(size_t)i * nq + k] = q[(size_t)i * nq + k];
+        else
+            v_prev[(size_t)i * nv + (k - nq)] = v[(size_t)i * nv + (k - nq)];
+    }
+}
+// after the solve (one warp per instance): q_solver_ always follows an OPTIMAL solve, the command vectors only while send_cmd_;
+// then a model collision latches send_cmd_ = false unless the command is still all zero (!q_.isZero(1e-3))
+__global__ void k_safety_post(int B, int nv, int na, const int* __restrict__ status, const int* __restrict__ colliding, const double* __restrict__ qc_new,
+    const double* __restrict__ tau_new, const double* __restrict__ v_new, const double* __restrict__ dv_new, int* __restrict__ send_cmd,
+    double* __restrict__ q_solver, double* __restrict__ q_cmd, double* __restrict__ tau_cmd, double* __restrict__ dq_cmd, double* __restrict__ ddq_cmd)
+{
+    const int lane = threadIdx.x & 31;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < B; i += (gridDim.x * blockDim.x) >> 5) {
+        if (status[i] != IWBC_STATUS_OPTIMAL)
+            continue; // the reference throws before any of this (controller.cpp:284-308)
+        const int send = send_cmd[i];
+        bool nonzero = false;
+        for (int k = lane; k < nv; k += 32) {
+            const double qn = qc_new[(size_t)i * nv + k];
+            if (q_solver)
+                q_solver[(size_t)i * nv + k] = qn;
+            if (send) {
+                q_cmd[(size_t)i * nv + k] = qn;
+                if (dq_cmd)
+                    dq_cmd[(size_t)i * nv + k] = v_new[(size_t)i * nv + k];
+                if (ddq_cmd)
+                    ddq_cmd[(size_t)i * nv + k] = dv_new[(size_t)i * nv + k];
+            }
+            nonzero = nonzero || fabs(q_cmd[(size_t)i * nv + k]) > 1e-3;
+        }
+        if (send && tau_cmd)
+            for (int k = lane; k < na; k += 32)
+                tau_cmd[(size_t)i * na + k] = tau_new[(size_t)i * na + k];
+        nonzero = __any_sync(0xffffffffu, nonzero);
+        if (lane == 0 && colliding && colliding[i] && nonzero)
+            send_cmd[i] = 0;
+    }
+}
+__global__ void k_step_back(int B, int nq, int nv, const int* __restrict__ select, const double* __restrict__ q_prev, const double* __restrict__ v_prev,
+    double* __restrict__ q, double* __restrict__ v)
+{
+    const int w = nq + nv;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < (long)B * w; e += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / w), k = (int)(e - (long)i * w);
+        if (select && !select[i])
+            continue;
+        if (k < nq)
+            q[(size_t)i * nq + k] = q_prev[(size_t)i * nq + k];
+        else
+            v[(size_t)i * nv + (k - nq)] = v_prev[(size_t)i * nv + (k - nq)];
+    }
+}
+
 // one thread per state
 __global__ void k_collision(const iwbc_problem_t* __restrict__ P, const iwbc_collision_sphere_t* __restrict__ S, const int* __restrict__ mstart,
     int nmembers, int nspheres, int B, const double* __restrict__ q, int* __restrict__ colliding, int* __restrict__ pair4)
@@ -264,6 +328,63 @@ int iwbc_batch_check_collisions_device(iwbc_batch* b, iwbc_collision* h, int B, 
     }
     k_collision<<<(B + 63) / 64, 64, 0, st>>>(b->d_prob, h->d_spheres, h->d_member_start, (int)h->members.size(), (int)h->spheres.size(), B, q, colliding,
         pair4);
+    b->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return IWBC_OK;
+}
+
+int iwbc_batch_safe_rollout_device(iwbc_batch* b, iwbc_collision* h, int B, double* q, double* v, const double* refs, long refs_stride,
+    unsigned contact_mask, int ticks, const iwbc_safety_t* s, int* status, void* stream)
+{
+    if (!b || !q || !v || !refs || !s || !s->send_cmd || !s->q_prev || !s->v_prev || !s->q_cmd || B < 0 || ticks < 0 || (h && !s->colliding)) {
+        set_error("iwbc_batch_safe_rollout_device: bad argument");
+        return IWBC_ERR_ARG;
+    }
+    if (B > b->max_batch) {
+        set_error("iwbc_batch_safe_rollout_device: B exceeds max_batch");
+        return IWBC_ERR_ARG;
+    }
+    if (B == 0 || ticks == 0)
+        return IWBC_OK;
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->stream;
+    const iwbc_problem_t& P = b->prob->cs.prob;
+    const int grid = std::min(1184, (B * (P.nq + P.nv) + 255) / 256);
+    for (int t = 0; t < ticks; ++t) {
+        k_safety_pre<<<grid, 256, 0, st>>>(B, P.nq, P.nv, s->send_cmd, q, v, s->q_prev, s->v_prev);
+        b->launches++;
+        if (h) { // check_model_collisions: on the model data of this tick, i.e. the state the tick starts from (controller.cpp:309-310)
+            int rc = iwbc_batch_check_collisions_device(b, h, B, q, s->colliding, nullptr, st);
+            if (rc)
+                return rc;
+        }
+        iwbc_results_t r;
+        std::memset(&r, 0, sizeof(r));
+        r.tau = b->d_tau, r.dv = b->d_dv, r.q_cmd = b->d_qc, r.status = status ? status : b->d_status;
+        // one open-loop tick on the state in place; a QP that is not solved to optimality freezes the instance (roll-out semantics)
+        int rc = iwbc_batch_rollout_device(b, B, q, v, refs, refs_stride, contact_mask, 1, &r, st);
+        if (rc)
+            return rc;
+        k_safety_post<<<std::min(1184, (B + 7) / 8), 256, 0, st>>>(B, P.nv, P.na, r.status, h ? s->colliding : nullptr, b->d_qc, b->d_tau, v, b->d_dv,
+            s->send_cmd, s->q_solver, s->q_cmd, s->tau_cmd, s->dq_cmd, s->ddq_cmd);
+        b->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return IWBC_OK;
+}
+
+int iwbc_batch_qp_step_back_device(iwbc_batch* b, int B, double* q, double* v, const iwbc_safety_t* s, const int* select, void* stream)
+{
+    if (!b || !q || !v || !s || !s->q_prev || !s->v_prev || B < 0) {
+        set_error("iwbc_batch_qp_step_back_device: bad argument");
+        return IWBC_ERR_ARG;
+    }
+    if (B == 0)
+        return IWBC_OK;
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : b->stream;
+    const iwbc_problem_t& P = b->prob->cs.prob;
+    k_step_back<<<std::min(1184, (B * (P.nq + P.nv) + 255) / 256), 256, 0, st>>>(B, P.nq, P.nv, select, s->q_prev, s->v_prev, q, v);
     b->launches++;
     CUDA_TRY(cudaGetLastError());
     return IWBC_OK;

@@ -38,6 +38,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __constant__
+#define __grid_constant__
 #define __restrict__
 namespace iwbc { namespace dev {
 struct SimIdx { int x; };
@@ -130,8 +131,6 @@ namespace dev {
         unsigned long long* prof; // steady-state phase profile: [0..5] summed SM cycles of dyn, asm, factor, eq, ineq, decode; [6] instances
     };
 
-    static __constant__ iwbc_problem_t c_P; // uniform-access copy (task tables, sizes)
-    static __constant__ Shape c_S;
 
     // ------------------------------------------------------------------ small device math
     struct V3 {
@@ -346,6 +345,11 @@ namespace dev {
     // The layout is computed on the host (fills Shape::o_* and total) and replayed on the device.
     struct Sizes {
         int nv, nq, nj, nf, nc, n, mi, rows_dense, nref, ldJ, ldM;
+        // per-launch tables: the QP shape of this launch's contact mask (a __grid_constant__ kernel parameter) and the problem
+        // (the handle's own global-memory copy, read through the read-only path).  No process-global __constant__ state: two
+        // handles, or two contact masks of one handle, never share anything on the device.
+        const Shape* S;
+        const iwbc_problem_t* P;
     };
     __host__ __device__ inline int vec_len(const Sizes& z) { return align2(z.n + 2); }
     // QP vectors: g x d z np r u x_old u_old gc gs gx (12) + Ldiag sub (2) -> 14 * vec_len ; s (mi) lb ub (na<=nv each)
@@ -387,7 +391,7 @@ namespace dev {
 
     __device__ __forceinline__ Sm make_sm(double* base, const Sizes& z)
     {
-        const Shape& S = c_S;
+        const Shape& S = *z.S;
         Sm s;
         s.J = base + S.o_J;
         s.R = base + S.o_R;
@@ -453,7 +457,7 @@ namespace dev {
         const int nj = z.nj, nv = z.nv;
         // ---- placements, world motion subspaces, velocities and drift accelerations, level by level
         // (a joint is handled by thread j % G when its depth comes up; parents are one level above)
-        for (int dpt = 0; dpt <= c_S.maxdepth; ++dpt) {
+        for (int dpt = 0; dpt <= z.S->maxdepth; ++dpt) {
             for (int j0 = tid; j0 < nj; j0 += G) {
                 if (gP->depth[j0] != dpt)
                     continue;
@@ -562,7 +566,7 @@ namespace dev {
             Y[4] = Ixx, Y[5] = Ixy, Y[6] = Ixz, Y[7] = Iyy, Y[8] = Iyz, Y[9] = Izz;
             // momentum Y v and force f = Y a_gf + v x* (Y v), a_gf = a_drift + (-g, 0)
             V3 vl = ld3(sm.vw + 6 * j), w = ld3(sm.vw + 6 * j + 3);
-            V3 al = ld3(sm.aw + 6 * j) - ld3(c_P.gravity), aa = ld3(sm.aw + 6 * j + 3);
+            V3 al = ld3(sm.aw + 6 * j) - ld3(z.P->gravity), aa = ld3(sm.aw + 6 * j + 3);
             auto Iapply = [&](V3 x) { return mk(Ixx * x.x + Ixy * x.y + Ixz * x.z, Ixy * x.x + Iyy * x.y + Iyz * x.z, Ixz * x.x + Iyz * x.y + Izz * x.z); };
             V3 hl = m * vl - cross(h, w), ha = Iapply(w) + cross(h, vl);
             V3 fl = m * al - cross(h, aa) + cross(w, hl);
@@ -646,7 +650,7 @@ namespace dev {
             V3 hl = ld3(sm.sc + 10), ha = ld3(sm.sc + 13);
             V3 fl = ld3(sm.sc + 16), fa = ld3(sm.sc + 19);
             // drift force = total force - Ytot * a_g, a_g = (-g, 0): lin = m(-g), ang = h x (-g)
-            V3 ag = -1.0 * ld3(c_P.gravity);
+            V3 ag = -1.0 * ld3(z.P->gravity);
             V3 dl = fl - mt * ag, da = fa - cross(ld3(sm.sc + 1), ag);
             st3(sm.sc + 22, com);
             st3(sm.sc + 25, (1.0 / mt) * hl);
@@ -734,8 +738,8 @@ namespace dev {
     // TaskJointPosVelAccBounds (upstream constructor stores 2*dt)
     __device__ inline void acc_bounds(const iwbc_problem_t* gP, int i, double qi, double dq, double& lb, double& ub)
     {
-        const double dt = 2.0 * c_P.dt;
-        const double qmin = gP->q_lo[i], qmax = gP->q_hi[i], dqmax = gP->v_max[i], ddqmax = gP->v_max[i] / c_P.dt;
+        const double dt = 2.0 * gP->dt;
+        const double qmin = gP->q_lo[i], qmax = gP->q_hi[i], dqmax = gP->v_max[i], ddqmax = gP->v_max[i] / gP->dt;
         const double m = -dq / dt;
         double lbP = -1e10, ubP = 1e10;
         const double q3max = 2 * (qmax - qi - dt * dq) / (dt * dt), q3min = 2 * (qmin - qi - dt * dq) / (dt * dt);
@@ -782,13 +786,13 @@ namespace dev {
     template <int G>
     __device__ void k_asm(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, int tid, int& flip)
     {
-        const int nv = z.nv, n = z.n, na = c_P.na, nu = nv - na;
-        const Shape& S = c_S;
+        const int nv = z.nv, n = z.n, na = z.P->na, nu = nv - na;
+        const Shape& S = *z.S;
         // ---- contact motion rows
-        for (int c = 0; c < c_P.ncontacts; ++c) {
+        for (int c = 0; c < z.P->ncontacts; ++c) {
             if (S.cidx[c] < 0)
                 continue;
-            const iwbc_contact_t& C = c_P.contacts[c];
+            const iwbc_contact_t& C = z.P->contacts[c];
             for (int k = tid; k < nv; k += G) {
                 V3 l, a;
                 frame_jac_col(gP, sm, C.frame, k, l, a);
@@ -806,10 +810,10 @@ namespace dev {
             sm.g[k] = 0.0;
         // ---- dense level-1 rows, in HQP order
         int row = 0;
-        for (int bl = 0; bl < c_P.nl1; ++bl) {
-            if (c_P.l1[bl].kind != IWBC_B_TASK)
+        for (int bl = 0; bl < z.P->nl1; ++bl) {
+            if (z.P->l1[bl].kind != IWBC_B_TASK)
                 continue;
-            const iwbc_task_t& T = c_P.tasks[c_P.l1[bl].index];
+            const iwbc_task_t& T = z.P->tasks[z.P->l1[bl].index];
             const double sw = sqrt(T.weight);
             if (T.type == IWBC_T_SE3) {
                 if (tid == (row + 7) % G) {
@@ -874,7 +878,7 @@ namespace dev {
             else if (T.type == IWBC_T_SELFCOL) {
                 // per avoided frame a: gradient (3) -> sc[44 + 4a .. +2], and the scalar B contribution -> sc[44 + 4a + 3]
                 const int f0 = T.frame;
-                const int lwa = !c_P.sc_jacobian_world;
+                const int lwa = !z.P->sc_jacobian_world;
                 for (int a = tid; a < T.nav; a += G) {
                     const int fa = T.av_frame[a];
                     const double* o0 = sm.oMf + 12 * f0;
@@ -978,13 +982,13 @@ namespace dev {
                 sm.J[i + rem * ld] = 0.0;
         }
         Grp<G>::sync();
-        for (int bl = 0; bl < c_P.nl1; ++bl) {
-            const iwbc_block_t& Bk = c_P.l1[bl];
+        for (int bl = 0; bl < z.P->nl1; ++bl) {
+            const iwbc_block_t& Bk = z.P->l1[bl];
             if (Bk.kind == IWBC_B_CONTACT_REG) {
                 const int c = Bk.index;
                 if (S.cidx[c] < 0)
                     continue;
-                const iwbc_contact_t& C = c_P.contacts[c];
+                const iwbc_contact_t& C = z.P->contacts[c];
                 const int o = nv + S.cidx[c];
                 for (int e = tid; e < 78; e += G) { // 12*13/2 lower entries
                     int i = 0, rem = e;
@@ -1008,7 +1012,7 @@ namespace dev {
                 }
             }
             else {
-                const iwbc_task_t& T = c_P.tasks[Bk.index];
+                const iwbc_task_t& T = z.P->tasks[Bk.index];
                 if (T.type != IWBC_T_POSTURE)
                     continue;
                 const double* r = sm.ref + T.ref_off;
@@ -1023,7 +1027,7 @@ namespace dev {
             Grp<G>::sync();
         }
         for (int k = tid; k < n; k += G)
-            sm.J[k + k * ld] += c_P.hess_reg;
+            sm.J[k + k * ld] += z.P->hess_reg;
         Grp<G>::sync();
         (void)flip;
     }
@@ -1035,7 +1039,7 @@ namespace dev {
         template <int G>
         static __device__ double load_ce(const Sm& sm, const Sizes& z, int i, int tid)
         {
-            const Shape& S = c_S;
+            const Shape& S = *z.S;
             const int nv = z.nv, n = z.n;
             int b = 0;
             while (b + 1 < S.nce && i >= S.ce[b + 1].off)
@@ -1049,11 +1053,11 @@ namespace dev {
                     else {
                         // -(T^T Jft_c)[kk][r]
                         int c = 0;
-                        for (int cc = 0; cc < c_P.ncontacts; ++cc)
+                        for (int cc = 0; cc < z.P->ncontacts; ++cc)
                             if (S.cidx[cc] >= 0 && k - nv >= S.cidx[cc] && k - nv < S.cidx[cc] + 12)
                                 c = cc;
                         const int kk = k - nv - S.cidx[c];
-                        const double* T = c_P.contacts[c].T;
+                        const double* T = z.P->contacts[c].T;
                         double s = 0;
 #pragma unroll
                         for (int a = 0; a < 6; ++a)
@@ -1073,25 +1077,25 @@ namespace dev {
         template <int G>
         static __device__ void wrenches(const Sm& sm, const Sizes& z, int tid)
         {
-            const Shape& S = c_S;
-            for (int e = tid; e < 6 * c_P.ncontacts; e += G) {
+            const Shape& S = *z.S;
+            for (int e = tid; e < 6 * z.P->ncontacts; e += G) {
                 const int c = e / 6, a = e - 6 * c;
                 double s = 0;
                 if (S.cidx[c] >= 0) {
-                    const double* T = c_P.contacts[c].T + a * 12;
+                    const double* T = z.P->contacts[c].T + a * 12;
                     const double* f = sm.x + z.nv + S.cidx[c];
 #pragma unroll
                     for (int k = 0; k < 12; ++k)
                         s += T[k] * f[k];
                 }
-                sm.cb[6 * c_P.ncontacts + e] = s;
+                sm.cb[6 * z.P->ncontacts + e] = s;
             }
         }
         // tau~_i = M_a[i] dv - J_a[:, i]^T f  (needs wrenches())
         static __device__ double act_row_value(const Sm& sm, const Sizes& z, int i)
         {
-            const Shape& S = c_S;
-            const int nv = z.nv, nu = nv - c_P.na;
+            const Shape& S = *z.S;
+            const int nv = z.nv, nu = nv - z.P->na;
             const double* Mr = sm.M + (nu + i) * z.ldM;
             double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
             int k = 0;
@@ -1104,10 +1108,10 @@ namespace dev {
             for (; k < nv; ++k)
                 s0 += Mr[k] * sm.x[k];
             double s = (s0 + s1) + (s2 + s3);
-            for (int c = 0; c < c_P.ncontacts; ++c) {
+            for (int c = 0; c < z.P->ncontacts; ++c) {
                 if (S.cidx[c] < 0)
                     continue;
-                const double* w = sm.cb + 6 * c_P.ncontacts + 6 * c;
+                const double* w = sm.cb + 6 * z.P->ncontacts + 6 * c;
                 const double* Jc = sm.Jft + (c * 6) * nv + nu + i;
                 const double c0 = Jc[0] * w[0] + Jc[nv] * w[1], c1 = Jc[2 * nv] * w[2] + Jc[3 * nv] * w[3], c2 = Jc[4 * nv] * w[4] + Jc[5 * nv] * w[5];
                 s -= (c0 + c1) + c2;
@@ -1118,8 +1122,8 @@ namespace dev {
         template <int G>
         static __device__ void eval_s(const iwbc_problem_t* gP, const Sm& sm, const Sizes& z, int tid)
         {
-            const Shape& S = c_S;
-            const int nv = z.nv, na = c_P.na, nu = nv - na;
+            const Shape& S = *z.S;
+            const int nv = z.nv, na = z.P->na, nu = nv - na;
             wrenches<G>(sm, z, tid);
             Grp<G>::sync();
             for (int b = 0; b < S.nci; ++b) {
@@ -1140,7 +1144,7 @@ namespace dev {
                     }
                 }
                 else {
-                    const iwbc_contact_t& C = c_P.contacts[B.index];
+                    const iwbc_contact_t& C = z.P->contacts[B.index];
                     const double* f = sm.x + nv + S.cidx[B.index];
                     for (int r = tid; r < 17; r += G) {
                         double y = 0;
@@ -1156,8 +1160,8 @@ namespace dev {
         // ci0(ip) of the implicit rows
         static __device__ double ci0_of(const iwbc_problem_t* gP, const Sm& sm, const Sizes& z, int ip)
         {
-            const Shape& S = c_S;
-            const int nu = z.nv - c_P.na;
+            const Shape& S = *z.S;
+            const int nu = z.nv - z.P->na;
             int b = 0;
             while (b + 1 < S.nci && ip >= S.ci[b + 1].off)
                 ++b;
@@ -1170,14 +1174,14 @@ namespace dev {
                 return neg ? sm.ub[r] : -sm.lb[r];
             if (B.kind == 1)
                 return neg ? (gP->tau_max[r] - sm.nle[nu + r]) : (gP->tau_max[r] + sm.nle[nu + r]);
-            return neg ? c_P.contacts[B.index].ub[r] : -c_P.contacts[B.index].lb[r];
+            return neg ? z.P->contacts[B.index].ub[r] : -z.P->contacts[B.index].lb[r];
         }
         // np <- CI.row(ip)
         template <int G>
         static __device__ void load_ci(const Sm& sm, const Sizes& z, int ip, int tid)
         {
-            const Shape& S = c_S;
-            const int nv = z.nv, n = z.n, na = c_P.na, nu = nv - na;
+            const Shape& S = *z.S;
+            const int nv = z.nv, n = z.n, na = z.P->na, nu = nv - na;
             int b = 0;
             while (b + 1 < S.nci && ip >= S.ci[b + 1].off)
                 ++b;
@@ -1195,11 +1199,11 @@ namespace dev {
                         val = sm.M[(nu + r) * z.ldM + k];
                     else {
                         int c = 0;
-                        for (int cc = 0; cc < c_P.ncontacts; ++cc)
+                        for (int cc = 0; cc < z.P->ncontacts; ++cc)
                             if (S.cidx[cc] >= 0 && k - nv >= S.cidx[cc] && k - nv < S.cidx[cc] + 12)
                                 c = cc;
                         const int kk = k - nv - S.cidx[c];
-                        const double* T = c_P.contacts[c].T;
+                        const double* T = z.P->contacts[c].T;
                         double s = 0;
 #pragma unroll
                         for (int a = 0; a < 6; ++a)
@@ -1210,7 +1214,7 @@ namespace dev {
                 else {
                     const int o = nv + S.cidx[B.index];
                     if (k >= o && k < o + 12)
-                        val = c_P.contacts[B.index].B[r * 12 + (k - o)];
+                        val = z.P->contacts[B.index].B[r * 12 + (k - o)];
                 }
                 sm.np[k] = sgn * val;
             }
@@ -1923,8 +1927,8 @@ namespace dev {
         tc = now_;                           \
     }
         static_assert(G >= 64 && G % 32 == 0, "gi_loop_cta: the CTA is the group");
-        const Shape& S = c_S;
-        const int n = z.n, ld = z.ldJ, nv = z.nv, na = c_P.na, nu = nv - na, ncon = c_P.ncontacts;
+        const Shape& S = *z.S;
+        const int n = z.n, ld = z.ldJ, nv = z.nv, na = z.P->na, nu = nv - na, ncon = z.P->ncontacts;
         const double eps = 2.220446049250313e-16;
         const double inf = __longlong_as_double(0x7ff0000000000000LL);
         const int lane = tid & 31, lastw = G / 32 - 1, warp = tid >> 5;
@@ -2470,7 +2474,7 @@ namespace dev {
     __device__ void k_dec(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, const IO& io, int inst, int tid, int status, int iters,
         int iq, const double* taut)
     {
-        const int nv = z.nv, nq = z.nq, n = z.n, na = c_P.na, nu = nv - na;
+        const int nv = z.nv, nq = z.nq, n = z.n, na = z.P->na, nu = nv - na;
         // ---- decode (controller.cpp:250-260) + integrate (:254-256) + command repack (:263-282)
         if (!taut) {
             FusedRows::wrenches<G>(sm, z, tid);
@@ -2479,7 +2483,7 @@ namespace dev {
         if (io.dbg_x && inst == 0)
             for (int k = tid; k < n; k += G)
                 io.dbg_x[k] = sm.x[k];
-        const double dt = c_P.dt;
+        const double dt = z.P->dt;
         if (io.tau)
             for (int i = tid; i < na; i += G)
                 io.tau[(size_t)inst * na + i] = sm.nle[nu + i] + (taut ? taut[i] : FusedRows::act_row_value(sm, z, i));
@@ -2489,7 +2493,7 @@ namespace dev {
         if (io.f)
             for (int k = tid; k < 12 * z.nc; k += G) {
                 const int c = k / 12;
-                io.f[(size_t)inst * 12 * z.nc + k] = c_S.cidx[c] >= 0 ? sm.x[nv + c_S.cidx[c] + (k - 12 * c)] : 0.0;
+                io.f[(size_t)inst * 12 * z.nc + k] = z.S->cidx[c] >= 0 ? sm.x[nv + z.S->cidx[c] + (k - 12 * c)] : 0.0;
             }
         // v+ -> sm.d (nv <= n), q+ -> sm.z region is too small for nq = nv + 1 when nk = 0: use sm.np / sm.gc
         for (int k = tid; k < nv; k += G)
@@ -2553,7 +2557,7 @@ namespace dev {
                 io.q_next[(size_t)inst * nq + k] = qn[k];
         if (io.q_cmd) {
             double* o = io.q_cmd + (size_t)inst * nv;
-            if (c_P.floating_base) {
+            if (z.P->floating_base) {
                 if (tid == 0) {
                     const double vx = qn[3], vy = qn[4], vz = qn[5], ww = qn[6];
                     double nrm = sqrt(vx * vx + vy * vy + vz * vz);
@@ -2594,7 +2598,7 @@ namespace dev {
                 unsigned words[IWBC_ACTIVE_WORDS];
                 for (int k = 0; k < IWBC_ACTIVE_WORDS; ++k)
                     words[k] = 0;
-                for (int k = c_S.me; k < iq; ++k) {
+                for (int k = z.S->me; k < iq; ++k) {
                     const int r = sm.act[k];
                     if (r >= 0 && r < 32 * IWBC_ACTIVE_WORDS)
                         words[r >> 5] |= 1u << (r & 31);
@@ -2617,7 +2621,7 @@ namespace dev {
     template <int G>
     __device__ void cycle_instance(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, const IO& io, int inst, int tid, int& flip)
     {
-        const int nv = z.nv, nq = z.nq, n = z.n, na = c_P.na, nu = nv - na;
+        const int nv = z.nv, nq = z.nq, n = z.n, na = z.P->na, nu = nv - na;
         // ---- load state and references (coalesced: the instance's q / v / refs are contiguous)
         const double* gq = io.q + (size_t)inst * nq;
         const double* gv = io.v + (size_t)inst * nv;
@@ -2656,7 +2660,7 @@ namespace dev {
         }
 
         int iters = 0, iq = 0;
-        const int status = gi_solve<G, FusedRows>(gP, sm, z, (const FusedRows*)nullptr, c_S.me, c_S.mi, tid, flip, iters, iq, cyc);
+        const int status = gi_solve<G, FusedRows>(gP, sm, z, (const FusedRows*)nullptr, z.S->me, z.S->mi, tid, flip, iters, iq, cyc);
         if (cyc && tid == 0)
             cyc[5] = clock64();
 

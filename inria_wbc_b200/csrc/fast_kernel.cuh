@@ -87,7 +87,6 @@ namespace dev {
         int s_J, s_R, s_vec, s_int, s_total; // extra regions of the active-set continuation (k_slow)
     };
 
-    static __constant__ FShape c_F;
 
     // ------------------------------------------------------------------------------------------ host: plan
     inline bool build_fast_plan(const iwbc_problem_t& P, const Shape& S, int T, FShape& F, FPlan& pl)
@@ -372,13 +371,11 @@ namespace dev {
     // NV_, ME_: compile-time velocity dimension / number of equalities of the common shapes (0: read them at run time); with
     // them every leading dimension and trip count below is a constant and the inner loops unroll.
     template <int T, int NV_ = 0, int ME_ = 0>
-    __device__ int fast_instance(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, double* smem, const IO& io, int inst, int tid,
-        long long* cyc)
+    __device__ int fast_instance(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, const Shape& S, const FShape& F, double* smem,
+        const IO& io, int inst, int tid, long long* cyc)
     {
-        const FShape& F = c_F;
-        const Shape& S = c_S;
-        const int nv = NV_ ? NV_ : c_P.nv, me = ME_ ? ME_ : F.me, NC = me + 1;
-        const int nq = c_P.nq, nj = c_P.nj, nu = 6, na = nv - nu, nfr = c_P.nframes, n = ME_ ? nv + 2 * (me - 6) : S.n;
+        const int nv = NV_ ? NV_ : gP->nv, me = ME_ ? ME_ : F.me, NC = me + 1;
+        const int nq = gP->nq, nj = gP->nj, nu = 6, na = nv - nu, nfr = gP->nframes, n = ME_ ? nv + 2 * (me - 6) : S.n;
         const int ld = (nv + me + 2) & ~1, nvp = (nv + 3) & ~3, ldM = nv | 1; // = F.ldh, F.nvp, S.ldM
         double* const qs = smem + F.o_qs;
         double* const vs = smem + F.o_vs;
@@ -425,7 +422,7 @@ namespace dev {
                 qs[k] = gq[k];
             for (int k = tid; k < nv; k += T)
                 vs[k] = gv[k];
-            for (int k = tid; k < c_P.nref; k += T)
+            for (int k = tid; k < gP->nref; k += T)
                 Z[k] = gr[k];
         }
         fsync<T>();
@@ -558,7 +555,7 @@ namespace dev {
             Yj[0] = m;
             st3(Yj + 1, h);
             Yj[4] = Ixx, Yj[5] = Ixy, Yj[6] = Ixz, Yj[7] = Iyy, Yj[8] = Iyz, Yj[9] = Izz;
-            V3 alg = al - ld3(c_P.gravity);
+            V3 alg = al - ld3(gP->gravity);
             auto Iapply = [&](V3 x) { return mk(Ixx * x.x + Ixy * x.y + Ixz * x.z, Ixy * x.x + Iyy * x.y + Iyz * x.z, Ixz * x.x + Iyz * x.y + Izz * x.z); };
             V3 hl = m * vl - cross(h, w), ha = Iapply(w) + cross(h, vl);
             V3 fl = m * alg - cross(h, aa) + cross(w, hl);
@@ -676,7 +673,7 @@ namespace dev {
                 V3 com = (1.0 / mt) * hh;
                 V3 hl = ld3(sc + 10), ha = ld3(sc + 13);
                 V3 fl = mk(tot[10], tot[11], tot[12]), fa = mk(tot[13], tot[14], tot[15]);
-                V3 ag = -1.0 * ld3(c_P.gravity);
+                V3 ag = -1.0 * ld3(gP->gravity);
                 V3 dl = fl - mt * ag, da = fa - cross(hh, ag);
                 st3(sc + 22, com);
                 st3(sc + 25, (1.0 / mt) * hl);
@@ -721,7 +718,7 @@ namespace dev {
             else {
                 const iwbc_task_t& Tk = gP->tasks[J.task];
                 const int f0 = Tk.frame, fa = Tk.av_frame[J.a];
-                const int lwa = !c_P.sc_jacobian_world;
+                const int lwa = !gP->sc_jacobian_world;
                 const double* o0 = sm.oMf + 12 * f0;
                 const double* oa = sm.oMf + 12 * fa;
                 V3 diff = ld3(o0 + 9) - ld3(oa + 9);
@@ -802,7 +799,7 @@ namespace dev {
                                 A[(Bk.row0 + idx++) * nvp + k] = sw * col[i];
                     }
                     else { // FB_SELFCOL
-                        const int lwa = !c_P.sc_jacobian_world;
+                        const int lwa = !gP->sc_jacobian_world;
                         auto col = [&](int f) {
                             int pj = gP->fparent[f];
                             if (pj < 0 || !supports(gP, jk, pj))
@@ -1420,8 +1417,9 @@ namespace dev {
 
         // ---------------------------------------------------------------- s = CI x + ci0: eiquadprog's termination test at x_eq
         Sizes z;
-        z.nv = nv, z.nq = nq, z.nj = nj, z.nf = nfr, z.nc = c_P.ncontacts, z.n = n, z.mi = S.mi, z.rows_dense = S.rows_dense, z.nref = c_P.nref;
+        z.nv = nv, z.nq = nq, z.nj = nj, z.nf = nfr, z.nc = gP->ncontacts, z.n = n, z.mi = S.mi, z.rows_dense = S.rows_dense, z.nref = gP->nref;
         z.ldJ = S.ldJ, z.ldM = ldM;
+        z.S = &S, z.P = gP;
         FusedRows::wrenches<T>(sm, z, tid);
         fsync<T>();
         double psi = 0;
@@ -1468,12 +1466,10 @@ namespace dev {
     // equality phase, up to an orthogonal change of basis inside the two column groups, which leaves every quantity of
     // the iteration -- z, r, step lengths, multipliers -- unchanged) and runs the Goldfarb-Idnani inequality loop.
     template <int T, int NV_ = 0, int ME_ = 0>
-    __device__ void slow_continue(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, double* smem, const IO& io, int inst, int tid,
-        int code, int& flip, long long* cyc)
+    __device__ void slow_continue(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, const Shape& S, const FShape& F, double* smem,
+        const IO& io, int inst, int tid, int code, int& flip, long long* cyc)
     {
-        const FShape& F = c_F;
-        const Shape& S = c_S;
-        const int nv = NV_ ? NV_ : c_P.nv, me = ME_ ? ME_ : F.me, NC = me + 1, n = ME_ ? nv + 2 * (me - 6) : S.n;
+        const int nv = NV_ ? NV_ : gP->nv, me = ME_ ? ME_ : F.me, NC = me + 1, n = ME_ ? nv + 2 * (me - 6) : S.n;
         const int ld = (nv + me + 2) & ~1, ldJ = n | 1;
         const int nfrc = 2 * (me - 6), nfc = 7, cb0 = me - 6;
         double* const Hs = smem + F.o_Y;
@@ -1486,8 +1482,9 @@ namespace dev {
         double* const tv = smem + F.o_tv;
         double* const il = smem + F.o_il;
         Sizes z;
-        z.nv = nv, z.nq = c_P.nq, z.nj = c_P.nj, z.nf = c_P.nframes, z.nc = c_P.ncontacts, z.n = n, z.mi = S.mi, z.rows_dense = S.rows_dense;
-        z.nref = c_P.nref, z.ldJ = ldJ, z.ldM = nv | 1;
+        z.nv = nv, z.nq = gP->nq, z.nj = gP->nj, z.nf = gP->nframes, z.nc = gP->ncontacts, z.n = n, z.mi = S.mi, z.rows_dense = S.rows_dense;
+        z.nref = gP->nref, z.ldJ = ldJ, z.ldM = nv | 1;
+        z.S = &S, z.P = gP;
         Sm sm;
         sm.qs = smem + F.o_qs, sm.vs = smem + F.o_vs, sm.ref = Z;
         sm.M = smem + F.o_X, sm.Jft = smem + F.o_Jft, sm.cb = smem + F.o_cb, sm.nle = smem + F.o_nle, sm.lb = smem + F.o_lb, sm.ub = smem + F.o_ub;
@@ -1760,13 +1757,14 @@ namespace dev {
     // One CTA of T threads per instance, persistent over the batch.  Instances that need the active-set iteration are
     // appended to io.slow_list (order is arbitrary; every instance's results are independent of it).
     template <int T, int NV_, int ME_>
-    __global__ void __launch_bounds__(T, 3) k_fast(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, IO io)
+    __global__ void __launch_bounds__(T, 3)
+        k_fast(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, const __grid_constant__ Shape S, const __grid_constant__ FShape F, IO io)
     {
         extern __shared__ double smem[];
         const int tid = threadIdx.x;
         {
-            int* dofj = reinterpret_cast<int*>(smem + c_F.o_int);
-            for (int k = tid; k < c_P.nv; k += T)
+            int* dofj = reinterpret_cast<int*>(smem + F.o_int);
+            for (int k = tid; k < gP->nv; k += T)
                 dofj[k] = gF->dofj[k];
         }
         __syncthreads();
@@ -1776,11 +1774,11 @@ namespace dev {
             const int inst = io.in_list ? io.in_list[idx] : idx;
             long long stamps[8];
             long long* cyc = io.prof ? stamps : nullptr;
-            const int code = fast_instance<T, NV_, ME_>(gP, gF, smem, io, inst, tid, cyc);
+            const int code = fast_instance<T, NV_, ME_>(gP, gF, S, F, smem, io, inst, tid, cyc);
             const bool done = code > 0;
             if (!done) {
                 // hand the instance to the active-set kernel, together with the shared-memory image of the front end
-                // (L, reflectors, R, Gram matrix, x_eq, M, Jacobians, bounds: c_F.total doubles) so that it is not recomputed
+                // (L, reflectors, R, Gram matrix, x_eq, M, Jacobians, bounds: F.total doubles) so that it is not recomputed
                 __shared__ int s_pos;
                 __syncthreads();
                 if (tid == 0) {
@@ -1790,7 +1788,7 @@ namespace dev {
                 __syncthreads();
                 const int pos = s_pos;
                 if (pos < io.scratch_cap) {
-                    const int n2 = c_F.total >> 1; // offsets are even: whole double2's
+                    const int n2 = F.total >> 1; // offsets are even: whole double2's
                     double2* dst = reinterpret_cast<double2*>(io.scratch) + (size_t)pos * n2;
                     const double2* src = reinterpret_cast<const double2*>(smem);
                     for (int e = tid; e < n2; e += T)
@@ -1811,13 +1809,14 @@ namespace dev {
 
     // The instances the fast kernel could not finish (io.list): same front end, then J and the active-set iteration.
     template <int T, int NV_, int ME_>
-    __global__ void __launch_bounds__(T, 2) k_slow(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, IO io)
+    __global__ void __launch_bounds__(T, 2)
+        k_slow(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, const __grid_constant__ Shape S, const __grid_constant__ FShape F, IO io)
     {
         extern __shared__ double smem[];
         const int tid = threadIdx.x;
         {
-            int* dofj = reinterpret_cast<int*>(smem + c_F.o_int);
-            for (int k = tid; k < c_P.nv; k += T)
+            int* dofj = reinterpret_cast<int*>(smem + F.o_int);
+            for (int k = tid; k < gP->nv; k += T)
                 dofj[k] = gF->dofj[k];
         }
         __syncthreads();
@@ -1842,7 +1841,7 @@ namespace dev {
                 cyc[7] = clock64();
             int code;
             if (io.list && idx < io.scratch_cap) {
-                const int n2 = c_F.total >> 1;
+                const int n2 = F.total >> 1;
                 const double2* src = reinterpret_cast<const double2*>(io.scratch) + (size_t)idx * n2;
                 double2* dst = reinterpret_cast<double2*>(smem);
                 for (int e = tid; e < n2; e += T)
@@ -1851,11 +1850,11 @@ namespace dev {
                 __syncthreads();
             }
             else
-                code = fast_instance<T, NV_, ME_>(gP, gF, smem, io, inst, tid, nullptr);
+                code = fast_instance<T, NV_, ME_>(gP, gF, S, F, smem, io, inst, tid, nullptr);
             if (code <= 0) {
                 if (cyc && tid == 0)
                     cyc[1] = clock64();
-                slow_continue<T, NV_, ME_>(gP, gF, smem, io, inst, tid, code, flip, cyc);
+                slow_continue<T, NV_, ME_>(gP, gF, S, F, smem, io, inst, tid, code, flip, cyc);
                 if (cyc && tid == 0 && code == 0) {
                     const long long t4 = clock64();
                     atomicAdd(io.prof + 0, (unsigned long long)(cyc[1] - cyc[7]));

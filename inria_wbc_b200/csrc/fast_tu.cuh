@@ -1,6 +1,6 @@
 // fast_tu.cuh -- one translation unit per compile-time (nv, me) shape of the k_fast / k_slow pair, so that the shapes
-// compile in parallel.  Each unit owns its copies of the __constant__ tables (c_P, c_S, c_F are TU-local) and refreshes
-// them when the (batch, problem revision, contact mask) it last served changes.
+// compile in parallel.  The kernels take the launch's shape tables as __grid_constant__ parameters and the problem / plan from the
+// handle's own global-memory copies: no per-unit __constant__ state, nothing to refresh when another handle or mask launches.
 // Usage: #define IWBC_TU_NV / IWBC_TU_ME / IWBC_TU_ENTRY, then #include "fast_tu.cuh".
 #include <algorithm>
 
@@ -10,7 +10,7 @@ using namespace iwbc;
 
 namespace {
 
-iwbc_const_owner g_owner[16];
+size_t g_fast_smem_set[16], g_slow_smem_set[16];
 
 constexpr int FT_ = IWBC_FAST_THREADS;
 
@@ -20,9 +20,12 @@ int launch_fast_shape(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
     dev::IO iop = io;
     auto fk = dev::k_fast<FT_, NV_, ME_>;
     auto sk = dev::k_slow<FT_, NV_, ME_>;
+    int rc = iwbc_raise_smem_limit((const void*)fk, b->device, b->fast_smem, g_fast_smem_set);
+    if (rc == IWBC_OK)
+        rc = iwbc_raise_smem_limit((const void*)sk, b->device, b->slow_smem, g_slow_smem_set);
+    if (rc)
+        return rc;
     if (b->fast_grid == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->fast_smem));
-        CUDA_TRY(cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->slow_smem));
         int per_sm = 0, per_sm_slow = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fk, FT_, b->fast_smem));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_slow, sk, FT_, b->slow_smem));
@@ -57,12 +60,12 @@ int launch_fast_shape(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
     CUDA_TRY(cudaMemsetAsync(b->d_slow_count + 2 * b->slot, 0, 2 * sizeof(int), st));
     if (b->timing)
         cudaEventRecord(b->ev0, st);
-    fk<<<std::min(b->fast_grid, io.B), FT_, b->fast_smem, st>>>(b->d_prob, b->d_fplan, iop);
+    fk<<<std::min(b->fast_grid, io.B), FT_, b->fast_smem, st>>>(b->d_prob, b->d_fplan, b->shape, b->fshape, iop);
     b->launches++;
     iop.list = b->d_slow_list + b->list_off;
     iop.list_count = b->d_slow_count + 2 * b->slot;
     iop.work = b->d_slow_count + 2 * b->slot + 1;
-    sk<<<std::min(b->slow_grid, io.B), FT_, b->slow_smem, st>>>(b->d_prob, b->d_fplan, iop);
+    sk<<<std::min(b->slow_grid, io.B), FT_, b->slow_smem, st>>>(b->d_prob, b->d_fplan, b->shape, b->fshape, iop);
     if (b->timing) {
         cudaEventRecord(b->ev1, st);
         cudaEventSynchronize(b->ev1);
@@ -78,20 +81,4 @@ int launch_fast_shape(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
 
 } // namespace
 
-int IWBC_TU_ENTRY(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
-{
-    iwbc_const_owner& o = g_owner[b->device & 15];
-    if (o.uid != b->uid || o.revision != b->revision || o.mask != b->shape_mask) {
-        // other streams may still be running a kernel of this unit that reads the old constants
-        if (o.uid != 0 && o.uid != b->uid)
-            CUDA_TRY(cudaDeviceSynchronize());
-        CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_P, &b->prob->cs.prob, sizeof(iwbc_problem_t), 0, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_S, &b->shape, sizeof(dev::Shape), 0, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyToSymbolAsync(dev::c_F, &b->fshape, sizeof(dev::FShape), 0, cudaMemcpyHostToDevice, st));
-        o.uid = b->uid;
-        o.revision = b->revision;
-        o.mask = b->shape_mask;
-        b->tu_uploaded = true;
-    }
-    return launch_fast_shape<IWBC_TU_NV, IWBC_TU_ME>(b, io, st);
-}
+int IWBC_TU_ENTRY(iwbc_batch* b, const dev::IO& io, cudaStream_t st) { return launch_fast_shape<IWBC_TU_NV, IWBC_TU_ME>(b, io, st); }

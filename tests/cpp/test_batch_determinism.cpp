@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "inria_wbc_b200/batch_pos_tracker.hpp"
@@ -59,15 +60,27 @@ int main(int argc, char** argv)
     int errors = 0;
     for (const char* bp : behaviors_paths)
         for (const char* urdf : urdfs) {
-            std::vector<Run> results;
-            try {
-                for (int e = 0; e < nexp; ++e)
-                    results.push_back(test_behavior(argv[1], argv[2], bp, urdf, duration));
-            }
-            catch (const std::exception& e) {
-                std::printf("exception in determinism_%s_%s: %s\n", bp, urdf, e.what());
-                return 1;
-            }
+            // one fresh controller per host thread, all on the same GPU at the same time (the reference's harness runs one controller
+            // per std::thread too, tests/utest.hpp:79-92): handles share nothing on the device
+            std::vector<Run> results(nexp);
+            std::vector<std::string> failures(nexp);
+            std::vector<std::thread> pool;
+            for (int e = 0; e < nexp; ++e)
+                pool.emplace_back([&, e]() {
+                    try {
+                        results[e] = test_behavior(argv[1], argv[2], bp, urdf, duration);
+                    }
+                    catch (const std::exception& ex) {
+                        failures[e] = ex.what();
+                    }
+                });
+            for (auto& t : pool)
+                t.join();
+            for (int e = 0; e < nexp; ++e)
+                if (!failures[e].empty()) {
+                    std::printf("exception in determinism_%s_%s: %s\n", bp, urdf, failures[e].c_str());
+                    return 1;
+                }
             const Run& a = results[0];
             const size_t row = (size_t)a.B * a.nv;
             double worst = 0, worst_f = 0, moved = 0;
@@ -114,10 +127,12 @@ int main(int argc, char** argv)
                         break;
                     frozen_from = t;
                 }
+            (void)frozen_from;
             std::printf("determinism_%s_%s: %d controllers x %d ticks, nv %d (%d controllable after the mimic filter): max pairwise |dq| %.3g (filtered %.3g), moved %.4f, "
                         "final status %d%s -> %s\n",
                 bp, urdf, nexp, duration, a.nv, a.ncontrollable, worst, worst_f, moved, a.final_status,
-                a.final_status ? (" (state frozen from tick " + std::to_string(frozen_from) + " in every run)").c_str() : "", bad ? "FAILED" : "ok");
+                a.final_status ? " (sticky: at some tick the QP was not solved to optimality; the robot kept its state over such ticks, identically in every run)" : "",
+                bad ? "FAILED" : "ok");
             errors += bad;
         }
     std::printf(errors ? "FAILED: %d differing ticks\n" : "OK\n", errors);

@@ -72,9 +72,10 @@ extern "C" int sim_cycle_batch(const iwbc_problem_t* P, int B, const double* q, 
     double* q_cmd, double* momentum)
 {
     dev::Sizes z;
-    prepare(*P, mask, dev::c_S, z);
-    dev::c_P = *P;
-    std::vector<double> smem(dev::c_S.total + 16, 0.0);
+    static dev::Shape S;
+    prepare(*P, mask, S, z);
+    z.S = &S, z.P = P;
+    std::vector<double> smem(S.total + 16, 0.0);
     dev::Sm sm = dev::make_sm(smem.data(), z);
     for (int j = 0; j < z.nj; ++j) {
         const int c0 = P->idx_v[j], cn = P->jtype[j] == IWBC_J_FREEFLYER ? 6 : 1;
@@ -99,14 +100,16 @@ extern "C" int sim_fast_batch(const iwbc_problem_t* P, int B, const double* q, c
     double* q_cmd, double* momentum, int* fast_used)
 {
     dev::Sizes z;
-    prepare(*P, mask, dev::c_S, z);
-    dev::c_P = *P;
+    static dev::Shape S;
+    static dev::FShape F;
+    prepare(*P, mask, S, z);
+    z.S = &S, z.P = P;
     static dev::FPlan plan;
-    if (!dev::build_fast_plan(*P, dev::c_S, 1, dev::c_F, plan))
+    if (!dev::build_fast_plan(*P, S, 1, F, plan))
         return -1;
-    std::vector<double> smem(dev::c_S.total + 16, 0.0), fsmem(dev::c_F.s_total + 16, 0.0);
+    std::vector<double> smem(S.total + 16, 0.0), fsmem(F.s_total + 16, 0.0);
     dev::Sm sm = dev::make_sm(smem.data(), z);
-    int* fdofj = reinterpret_cast<int*>(fsmem.data() + dev::c_F.o_int);
+    int* fdofj = reinterpret_cast<int*>(fsmem.data() + F.o_int);
     for (int j = 0; j < z.nj; ++j) {
         const int c0 = P->idx_v[j], cn = P->jtype[j] == IWBC_J_FREEFLYER ? 6 : 1;
         for (int k = 0; k < cn; ++k)
@@ -119,11 +122,11 @@ extern "C" int sim_fast_batch(const iwbc_problem_t* P, int B, const double* q, c
     io.q_cmd = q_cmd, io.momentum = momentum;
     int flip = 0;
     for (int i = 0; i < B; ++i) {
-        const int code = dev::fast_instance<1>(P, &plan, fsmem.data(), io, i, 0, nullptr);
+        const int code = dev::fast_instance<1>(P, &plan, S, F, fsmem.data(), io, i, 0, nullptr);
         if (fast_used)
             fast_used[i] = code > 0 ? 1 : 0;
         if (code <= 0)
-            dev::slow_continue<1>(P, &plan, fsmem.data(), io, i, 0, code, flip, nullptr);
+            dev::slow_continue<1>(P, &plan, S, F, fsmem.data(), io, i, 0, code, flip, nullptr);
     }
     return 0;
 }
@@ -131,12 +134,13 @@ extern "C" int sim_fast_batch(const iwbc_problem_t* P, int B, const double* q, c
 extern "C" int sim_qp_solve(int n, int me, int mi, const double* H, const double* g, const double* CE, const double* ce0, const double* CI,
     const double* ci0, double* x, int* status, int* iters, unsigned* active)
 {
-    dev::Shape& S = dev::c_S;
+    static dev::Shape S;
     std::memset(&S, 0, sizeof(S));
     S.n = n, S.me = me, S.mi = mi, S.ldJ = n | 1, S.ldM = 1;
     dev::Sizes z;
     std::memset(&z, 0, sizeof(z));
     z.n = n, z.mi = mi, z.ldJ = S.ldJ, z.ldM = 1;
+    z.S = &S;
     dev::make_layout(z, S);
     std::vector<double> smem(S.total + 16, 0.0);
     dev::Sm sm = dev::make_sm(smem.data(), z);

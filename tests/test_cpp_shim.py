@@ -15,7 +15,7 @@ def _build(name):
     deps = [src, os.path.join(ROOT, "include", "inria_wbc_b200", "batch_pos_tracker.hpp"), os.path.join(PKG, "libiwbc_b200.so")]
     if not os.path.exists(exe) or any(os.path.getmtime(exe) < os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", PKG, "-liwbc_b200",
-                               "-Wl,-rpath," + PKG, "-Wl,-rpath,/usr/local/cuda/lib64"])
+                               "-Wl,-rpath," + PKG, "-Wl,-rpath,/usr/local/cuda/lib64", "-pthread"])
     return exe
 
 

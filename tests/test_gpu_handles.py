@@ -24,3 +24,40 @@ def test_constant_tables_follow_the_batch_not_its_address(icub, talos_fast, talo
             err = np.abs(r.tau[same] - o["tau"][same]).max(axis=1) / np.abs(o["tau"][same]).max(axis=1)
             assert err.max() < 1e-8
             del bt
+
+
+def test_two_handles_driven_from_two_host_threads(icub, talos_fast, talos, tiago):
+    """Handles share no device state (shape tables are kernel parameters, the problem and the plans are the handle's own
+    global-memory copies): batches of different robots -- iCub and the fast-URDF Talos even share one compiled kernel pair --
+    driven concurrently from host threads on ONE device, with contact masks changing between calls, give bit-identical results
+    to serial use."""
+    import threading
+    jobs = []
+    for k, P in enumerate((icub, talos_fast, talos, tiago)):
+        q, v = random_states(P, 192, 40 + k, base=P.nv > P.na)
+        masks = [None] if P.ncontacts == 0 else [None, 1, 2, None]
+        jobs.append((P, q, v, masks))
+
+    def run(job, out, reps):
+        P, q, v, masks = job
+        bt = iw.Batch(P, 0, 192)
+        for _ in range(reps):
+            out.append([bt.update(q, v, contact_mask=m) for m in masks])
+
+    serial = []
+    for job in jobs:
+        res = []
+        run(job, res, 1)
+        serial.append(res[0])
+    outs = [[] for _ in jobs]
+    threads = [threading.Thread(target=run, args=(job, out, 6)) for job, out in zip(jobs, outs)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for want, got in zip(serial, outs):
+        assert len(got) == 6
+        for rep in got:
+            for a, b in zip(want, rep):
+                for k in ("tau", "dv", "f", "q_next", "v_next", "status", "iters", "active"):
+                    assert np.array_equal(getattr(a, k), getattr(b, k)), k
