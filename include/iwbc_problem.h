@@ -27,6 +27,7 @@ extern "C" {
 #define IWBC_MAXAV 12  /* avoided frames per self-collision task */
 #define IWBC_MAXL0 16  /* level-0 constraint blocks */
 #define IWBC_MAXL1 40  /* level-1 cost blocks */
+#define IWBC_MAXWV 4   /* distinct force-regularisation weight vectors (Contact6d::setRegularizationTaskWeightVector values in use) */
 
 enum iwbc_joint_type { IWBC_J_FREEFLYER = 0, IWBC_J_REVOLUTE = 1, IWBC_J_PRISMATIC = 2 };
 
@@ -84,6 +85,17 @@ typedef struct {
     int index;           /* task or contact index */
 } iwbc_block_t;
 
+/* one stabilizer parameter set = StabConfig (include/inria_wbc/stabilizers/stabilizer_conf.hpp:14-92), one per behaviour type */
+enum iwbc_behavior_type { IWBC_BT_FIXED_BASE = 0, IWBC_BT_SINGLE_SUPPORT = 1, IWBC_BT_DOUBLE_SUPPORT = 2 };
+typedef struct {
+    int filter_size;
+    int use_zmp;
+    int use_momentum;
+    int zmp_w_variant;   /* index of zmp_w in wreg_variants */
+    double com_gains[6], ankle_gains[6], ffda_gains[3], pad_;
+    double zmp_p[6], zmp_d[6], zmp_w[6], momentum_p[6], momentum_d[6];
+} iwbc_stab_conf_t;
+
 typedef struct {
     unsigned int magic;  /* 'IWBC' */
     unsigned int version;
@@ -122,19 +134,40 @@ typedef struct {
     iwbc_block_t l1[IWBC_MAXL1];     /* level 1 in insertion order = Hessian summation order */
     /* ---- construction-time state */
     double q0[IWBC_MAXNV + 1];       /* reference configuration (pinocchio layout, quaternion normalised) */
+    /* ---- force-regularisation weight vectors: [0] = Contact6d's default (1, 1, 1e-3, 2, 2, 2); the others are the stabilizer
+     * files' zmp_w (HumanoidPosTracker::update installs them with setRegularizationTaskWeightVector,
+     * src/controllers/humanoid_pos_tracker.cpp:220-221).  An instance selects one per contact through its reference row. */
+    int nwreg;
+    int pad2_;
+    double wreg_variants[IWBC_MAXWV][6];
+    /* ---- stabilizer (HumanoidPosTracker::parse_stabilizer, src/controllers/humanoid_pos_tracker.cpp:81-114) */
+    int stabilizer_activated;        /* CONTROLLER.stabilizer.activated */
+    int stab_present;                /* 1: the three parameter sets below were read (humanoid controllers) */
+    int stab_talos;                  /* 1: TalosPosTracker::update's IMU momentum admittance applies (talos_pos_tracker.cpp:135-150) */
+    int stab_task_com, stab_task_lf, stab_task_rf, stab_task_torso, stab_task_momentum; /* task indices, -1: absent */
+    int stab_contact_lf, stab_contact_rf; /* contact indices of contact_lfoot / contact_rfoot, -1: absent */
+    int stab_imu_frame;              /* frame table index of imu_link, -1: absent */
+    int pad3_;
+    iwbc_stab_conf_t stab[3];        /* indexed by iwbc_behavior_type */
 } iwbc_problem_t;
 
 #define IWBC_PROBLEM_MAGIC 0x43425749u
-#define IWBC_PROBLEM_VERSION 1u
+#define IWBC_PROBLEM_VERSION 2u
 
 /* layout of the per-instance reference vector (doubles):
- *   SE3 task / contact : pos[12] = p(3) ++ R column-major(9), vel[6], acc[6]   (24)
+ *   SE3 task           : pos[12] = p(3) ++ R column-major(9), vel[6], acc[6]   (24)
  *                        (TrajectorySample(12,6): include/inria_wbc/trajs/utils.hpp:28-36)
+ *   contact            : the same SE3 sample (24), then the contact's force reference f_ref[6] (Contact6d::setForceReference,
+ *                        0 by default), the index of its regularisation weight vector in wreg_variants (stored as a double,
+ *                        0 by default) and one pad                                (32)
  *   COM task           : pos[3], vel[3], acc[3]                                  (9)
  *   MOMENTUM task      : value[6] (unused), derivative[6] = L_ref, second[6] = dL_ref (18)
  *   POSTURE task       : pos[na], vel[na], acc[na]                               (3 na)
  */
 #define IWBC_REF_SE3 24
+#define IWBC_REF_CONTACT 32
+#define IWBC_REF_CONTACT_FREF 24   /* offset of f_ref inside a contact's block */
+#define IWBC_REF_CONTACT_WREG 30   /* offset of the weight-vector index */
 #define IWBC_REF_COM 9
 #define IWBC_REF_MOM 18
 

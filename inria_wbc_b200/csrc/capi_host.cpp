@@ -1,6 +1,7 @@
 // capi_host.cpp -- host-only half of the C ABI (include/iwbc_batch.h): config -> compiled problem.
 // No CUDA here; the batch half is batch.cu.
 #include <cstring>
+#include <functional>
 #include <string>
 
 #include "../../include/iwbc_batch.h"
@@ -31,9 +32,17 @@ iwbc_problem* iwbc_problem_load(const char* controller_yaml, const char* robots_
             yaml::Node ov = yaml::Load(overrides_yaml);
             if (!ov.is_map())
                 throw host::ConfigError("overrides must be a YAML map of CONTROLLER keys");
-            yaml::Node& c = config.at("CONTROLLER");
-            for (auto& kv : ov.map)
-                c.at(kv.first) = kv.second;
+            // nested keys are merged, not replaced: the reference's tests write `c["CONTROLLER"]["stabilizer"]["activated"] = false`
+            // and keep the map's other entries (tests/test_determinism.cpp:67-69)
+            std::function<void(yaml::Node&, const yaml::Node&)> merge = [&](yaml::Node& dst, const yaml::Node& src) {
+                for (auto& kv : src.map) {
+                    if (kv.second.is_map() && dst[kv.first].is_map())
+                        merge(dst.at(kv.first), kv.second);
+                    else
+                        dst.at(kv.first) = kv.second;
+                }
+            };
+            merge(config.at("CONTROLLER"), ov);
         }
         std::string etc;
         if (etc_path && *etc_path)
@@ -143,7 +152,7 @@ int iwbc_problem_ref_slot(const iwbc_problem* p, const char* name, int* offset, 
             if (offset)
                 *offset = P.contacts[i].ref_off;
             if (length)
-                *length = IWBC_REF_SE3;
+                *length = IWBC_REF_CONTACT; // SE3 sample (24) + f_ref (6) + weight-vector index + pad
             return IWBC_OK;
         }
     set_error(std::string("no task or contact with a reference named '") + name + "'");

@@ -990,6 +990,12 @@ namespace dev {
                     continue;
                 const iwbc_contact_t& C = z.P->contacts[c];
                 const int o = nv + S.cidx[c];
+                // f_ref and the installed weight vector come with the instance's reference row (iwbc_problem.h: contact block)
+                const double* fref = sm.ref + C.ref_off + IWBC_REF_CONTACT_FREF;
+                int wv = (int)sm.ref[C.ref_off + IWBC_REF_CONTACT_WREG];
+                if (wv < 0 || wv >= z.P->nwreg)
+                    wv = 0;
+                const double* wreg = z.P->wreg_variants[wv];
                 for (int e = tid; e < 78; e += G) { // 12*13/2 lower entries
                     int i = 0, rem = e;
                     while (rem >= i + 1) {
@@ -1000,14 +1006,14 @@ namespace dev {
                     double s = 0;
 #pragma unroll
                     for (int r = 0; r < 6; ++r)
-                        s += (C.wreg[r] * C.T[r * 12 + i]) * (C.wreg[r] * C.T[r * 12 + j]);
+                        s += (wreg[r] * C.T[r * 12 + i]) * (wreg[r] * C.T[r * 12 + j]);
                     sm.J[(o + i) + (o + j) * ld] += C.w_forcereg * s;
                 }
                 for (int k = tid; k < 12; k += G) {
                     double s = 0;
 #pragma unroll
                     for (int r = 0; r < 6; ++r)
-                        s += (C.wreg[r] * C.T[r * 12 + k]) * (C.wreg[r] * C.fref[r]);
+                        s += (wreg[r] * C.T[r * 12 + k]) * (wreg[r] * fref[r]);
                     sm.g[o + k] -= C.w_forcereg * s;
                 }
             }

@@ -65,8 +65,12 @@ namespace dev {
         FBlock blocks[IWBC_FMAXBLK];
         FRow rows[IWBC_FMAXROWS];
         double hdiag[IWBC_MAXNV];   // posture weights on the diagonal of H + the 1e-8 regularisation
-        double Uff[IWBC_MAXC][144]; // per active-contact slot: L_ff^-T (upper triangular, row-major) of the constant force block of H
-        double ygf[IWBC_MAXC][12];  // L_ff^-1 g_f
+        // Force blocks of H, one per (regularisation weight vector, active-contact slot): H_ff = w T' W^2 T + 1e-8 I depends on the
+        // problem and on WHICH weight vector W the instance has installed (iwbc_problem_t::wreg_variants: Contact6d's default or a
+        // stabilizer's zmp_w), so it is factorised on the host for every variant and the kernel picks by the instance's index.
+        double Uff[IWBC_MAXWV][IWBC_MAXC][144]; // L_ff^-T (upper triangular, row-major)
+        double Gf[IWBC_MAXWV][IWBC_MAXC][72];   // L_ff^-1 g_f = Gf f_ref (12 x 6, row-major): g_f = -w T' W^2 f_ref is per instance
+        double c1v[IWBC_MAXWV][IWBC_MAXC], c2v[IWBC_MAXWV][IWBC_MAXC]; // trace(H_ff), trace(L_ff^-T)
     };
 
     struct FShape {
@@ -79,9 +83,8 @@ namespace dev {
         int njobs, nblocks, nrows, ntiles, npairs, nposture, nslots;
         int ci_bounds, ci_act; // index of the bounds / actuation-bounds block in Shape::ci (-1: none)
         int posture[4];
-        double c1f, c2f;     // trace(H_ff), trace(L_ff^-T)
         // shared-memory offsets (doubles)
-        int o_qs, o_vs, o_X, o_Y, o_Z, o_Jft, o_cb, o_nle, o_lb, o_ub, o_g, o_x, o_w, o_sc, o_rhs, o_sc4, o_P, o_Rm, o_tv, o_hd, o_il, o_tau, o_int, total;
+        int o_qs, o_vs, o_X, o_Y, o_Z, o_Jft, o_cb, o_nle, o_lb, o_ub, o_g, o_x, o_w, o_sc, o_fr, o_rhs, o_sc4, o_P, o_Rm, o_tv, o_hd, o_il, o_tau, o_int, total;
         int d_liMi, d_oMi, d_Sw, d_vw, d_aw, d_Yw, d_fw, d_Fc, d_oMf, d_vf, d_af;
         int z_Bf, z_G;
         int s_J, s_R, s_vec, s_int, s_total; // extra regions of the active-set continuation (k_slow)
@@ -212,23 +215,21 @@ namespace dev {
                 pl.pair_i[F.npairs] = (unsigned char)i, pl.pair_k[F.npairs] = (unsigned char)k;
                 F.npairs++;
             }
-        // ---- constant force blocks: H_ff = w T' W^2 T + reg I, per active contact
-        F.c1f = 0, F.c2f = 0;
+        // ---- constant force blocks: H_ff = w T' W^2 T + reg I, per weight-vector variant and active contact
+        for (int wv = 0; wv < (P.nwreg > 0 ? P.nwreg : 1); ++wv)
         for (int s = 0; s < F.nca; ++s) {
             const iwbc_contact_t& C = P.contacts[F.cact[s]];
-            double H[144], L[144], gf[12];
+            const double* wreg = P.nwreg > 0 ? P.wreg_variants[wv] : C.wreg;
+            double H[144], L[144];
+            double c1 = 0, c2 = 0;
             for (int i = 0; i < 12; ++i) {
                 for (int j = 0; j < 12; ++j) {
                     double a = 0;
                     for (int r = 0; r < 6; ++r)
-                        a += (C.wreg[r] * C.T[r * 12 + i]) * (C.wreg[r] * C.T[r * 12 + j]);
+                        a += (wreg[r] * C.T[r * 12 + i]) * (wreg[r] * C.T[r * 12 + j]);
                     H[i * 12 + j] = C.w_forcereg * a + (i == j ? P.hess_reg : 0.0);
                 }
-                double a = 0;
-                for (int r = 0; r < 6; ++r)
-                    a += (C.wreg[r] * C.T[r * 12 + i]) * (C.wreg[r] * C.fref[r]);
-                gf[i] = -C.w_forcereg * a;
-                F.c1f += H[i * 12 + i];
+                c1 += H[i * 12 + i];
             }
             std::memset(L, 0, sizeof(L));
             for (int k = 0; k < 12; ++k) {
@@ -257,13 +258,17 @@ namespace dev {
                 }
             for (int i = 0; i < 12; ++i) {
                 for (int j = 0; j < 12; ++j)
-                    pl.Uff[s][i * 12 + j] = Li[j * 12 + i];
-                F.c2f += Li[i * 12 + i];
-                double a = 0;
-                for (int j = 0; j <= i; ++j)
-                    a += Li[i * 12 + j] * gf[j];
-                pl.ygf[s][i] = a;
+                    pl.Uff[wv][s][i * 12 + j] = Li[j * 12 + i];
+                c2 += Li[i * 12 + i];
+                // (L^-1 g_f)_i = sum_j Li[i][j] g_f[j],  g_f[j] = -w sum_r (W_r T[r][j]) (W_r f_ref[r])
+                for (int r = 0; r < 6; ++r) {
+                    double a = 0;
+                    for (int j = 0; j <= i; ++j)
+                        a += Li[i * 12 + j] * (wreg[r] * C.T[r * 12 + j]) * wreg[r];
+                    pl.Gf[wv][s][i * 6 + r] = -C.w_forcereg * a;
+                }
             }
+            pl.c1v[wv][s] = c1, pl.c2v[wv][s] = c2;
         }
         // ---- shared-memory layout
         const int nq = P.nq, nf = P.nframes, n = S.n;
@@ -301,6 +306,7 @@ namespace dev {
         F.o_ub = take(nv);
         F.o_x = take(n + 2);
         F.o_sc = take(48);
+        F.o_fr = take(8 * IWBC_MAXC); // per active-contact slot: the instance's f_ref (6), its weight-vector index, pad
         F.o_int = take((nv + 16) / 2 + 1);
         // arrays that are dead once J has been formed: the iteration vectors of the continuation alias them
         const int dead0 = o;
@@ -405,6 +411,7 @@ namespace dev {
         double* const taut = smem + F.o_tau;
         double* const Bf = Z + F.z_Bf;
         double* const Gm = Z + F.z_G;
+        double* const frv = smem + F.o_fr;
         Sm sm;
         sm.qs = qs, sm.vs = vs, sm.ref = Z;
         sm.oMi = Y + F.d_oMi, sm.Sw = Y + F.d_Sw, sm.vw = Y + F.d_vw, sm.aw = Y + F.d_aw, sm.Yw = Y + F.d_Yw, sm.fw = Y + F.d_fw, sm.Fc = Y + F.d_Fc;
@@ -424,6 +431,19 @@ namespace dev {
                 vs[k] = gv[k];
             for (int k = tid; k < gP->nref; k += T)
                 Z[k] = gr[k];
+            // the contacts' force references and weight-vector indices outlive the reference row (Z is reused below)
+            for (int e = tid; e < 8 * F.nca; e += T) {
+                const int s = e >> 3, a = e & 7;
+                const int off = gP->contacts[F.cact[s]].ref_off;
+                double val = 0.0;
+                if (a < 6)
+                    val = gr[off + IWBC_REF_CONTACT_FREF + a];
+                else if (a == 6) {
+                    const int wv = (int)gr[off + IWBC_REF_CONTACT_WREG];
+                    val = (wv >= 0 && wv < gP->nwreg) ? (double)wv : 0.0;
+                }
+                frv[e] = val;
+            }
         }
         fsync<T>();
         if (cyc && tid == 0)
@@ -934,12 +954,18 @@ namespace dev {
                 const int kk = e / F.nf, r = e - kk * F.nf;
                 const int s = kk / 12, k2 = kk - 12 * s;
                 double val;
-                if (r == nu)
-                    val = gF->ygf[s][k2];
+                const int wvs = (int)frv[8 * s + 6];
+                if (r == nu) { // (L_ff^-1 g_f)[k2] for this instance's force reference
+                    const double* G6 = gF->Gf[wvs][s] + k2 * 6;
+                    val = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+                        val += G6[a] * frv[8 * s + a];
+                }
                 else {
                     const int c = F.cact[s];
                     const double* Tm = gP->contacts[c].T;
-                    const double* U = gF->Uff[s];
+                    const double* U = gF->Uff[wvs][s];
                     val = 0;
                     for (int i = 0; i <= k2; ++i) {
                         double npf = 0;
@@ -1291,7 +1317,12 @@ namespace dev {
                 }
             }
             if (tid == (T > 32 ? 32 : 0)) { // fixed summation order
-                double c1 = F.c1f, c2 = F.c2f;
+                double c1 = 0, c2 = 0;
+                for (int s = 0; s < F.nca; ++s) {
+                    const int wvs = (int)frv[8 * s + 6];
+                    c1 += gF->c1v[wvs][s];
+                    c2 += gF->c2v[wvs][s];
+                }
                 for (int k = 0; k < nv; ++k) {
                     c1 += hd[k];
                     c2 += il[k];
@@ -1394,7 +1425,7 @@ namespace dev {
             else {
                 for (int kk = tid - 32; kk < 12 * F.nca; kk += (T > 32 ? T - 32 : 1)) {
                     const int s = kk / 12, i = kk - 12 * s;
-                    const double* U = gF->Uff[s] + i * 12;
+                    const double* U = gF->Uff[(int)frv[8 * s + 6]][s] + i * 12;
                     double a = 0;
                     for (int j = i; j < 12; ++j)
                         a += U[j] * wv[nv + 12 * s + j];
@@ -1404,7 +1435,7 @@ namespace dev {
             if (T == 1)
                 for (int kk = 0; kk < 12 * F.nca; ++kk) {
                     const int s = kk / 12, i = kk - 12 * s;
-                    const double* U = gF->Uff[s] + i * 12;
+                    const double* U = gF->Uff[(int)frv[8 * s + 6]][s] + i * 12;
                     double a = 0;
                     for (int j = i; j < 12; ++j)
                         a += U[j] * wv[nv + 12 * s + j];
@@ -1481,6 +1512,7 @@ namespace dev {
         double* const scalev = tauv + me;
         double* const tv = smem + F.o_tv;
         double* const il = smem + F.o_il;
+        double* const frv = smem + F.o_fr;
         Sizes z;
         z.nv = nv, z.nq = gP->nq, z.nj = gP->nj, z.nf = gP->nframes, z.nc = gP->ncontacts, z.n = n, z.mi = S.mi, z.rows_dense = S.rows_dense;
         z.nref = gP->nref, z.ldJ = ldJ, z.ldM = nv | 1;
@@ -1578,7 +1610,7 @@ namespace dev {
                     }
 #pragma unroll
                     for (int i2 = 0; i2 < 12; ++i2) {
-                        const double* U = gF->Uff[sidx] + i2 * 12;
+                        const double* U = gF->Uff[(int)frv[8 * sidx + 6]][sidx] + i2 * 12;
                         double a0 = 0;
 #pragma unroll
                         for (int j2 = 0; j2 < 12; ++j2)
@@ -1624,7 +1656,7 @@ namespace dev {
                 }
                 else {
                     const int ii = j - nv, sidx = ii / 12, i2 = ii - 12 * sidx;
-                    const double* U = gF->Uff[sidx] + i2 * 12;
+                    const double* U = gF->Uff[(int)frv[8 * sidx + 6]][sidx] + i2 * 12;
                     for (int j2 = i2; j2 < 12; ++j2)
                         sm.J[j + (nv + 12 * sidx + j2) * ldJ] = U[j2];
                 }
@@ -1711,7 +1743,7 @@ namespace dev {
                     }
     #pragma unroll
                     for (int i2 = 0; i2 < 12; ++i2) {
-                        const double* U = gF->Uff[sidx] + i2 * 12;
+                        const double* U = gF->Uff[(int)frv[8 * sidx + 6]][sidx] + i2 * 12;
                         double a0 = 0;
     #pragma unroll
                         for (int j2 = 0; j2 < 12; ++j2)

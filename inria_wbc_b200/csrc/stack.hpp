@@ -458,7 +458,7 @@ namespace host {
                 for (int i = 0; i < 6; ++i)
                     ct.wreg[i] = wreg[i];
                 ct.w_forcereg = 1e-3; // cst::w_force_feet, include/inria_wbc/controllers/tasks.hpp:23
-                ct.ref_off = alloc_ref(cs, IWBC_REF_SE3);
+                ct.ref_off = alloc_ref(cs, IWBC_REF_CONTACT); // SE3 sample, then f_ref (0) and the weight-vector index (0 = Contact6d's default)
                 put_sample_se3(kin.oMi[model.joint_id(jn)], &cs.ref0[ct.ref_off]);
                 // addRigidContact: motion (eq, level 0), force (ineq, level 0), regularisation (level 1)
                 if (P.nl0 + 2 > IWBC_MAXL0 || P.nl1 + 1 > IWBC_MAXL1)
@@ -473,6 +473,13 @@ namespace host {
                 throw ConfigError("unknown task type '" + type + "' for task " + name);
         }
         P.nref = (int)cs.ref0.size();
+        // force-regularisation weight vectors: [0] = Contact6d's default
+        P.nwreg = 1;
+        {
+            const double wreg0[6] = {1, 1, 1e-3, 2, 2, 2};
+            for (int i = 0; i < 6; ++i)
+                P.wreg_variants[0][i] = wreg0[i];
+        }
 
         // ---- joint_range_reduction (pos_tracker.cpp:115-148)
         if (c["joint_range_reduction"]) {
@@ -519,6 +526,76 @@ namespace host {
                 throw ConfigError("Wrong starting configuration: the CoM needs to be between the two feet with less than 1cm difference, but the distance is " + std::to_string(d));
             cref[0] = fx;
             cref[1] = fy;
+            // ---- stabilizer parameter sets (HumanoidPosTracker::parse_stabilizer, humanoid_pos_tracker.cpp:81-114; parse_stab_conf,
+            // include/inria_wbc/stabilizers/stabilizer_conf.hpp:46-92): one file per behaviour type
+            const yaml::Node& sn = c["stabilizer"];
+            if (!sn.is_map())
+                throw ConfigError("config error reading CONTROLLER.stabilizer");
+            P.stabilizer_activated = IWBC_HCHECK(sn["activated"].as<bool>(), "CONTROLLER.stabilizer.activated") ? 1 : 0;
+            const char* keys[3] = {"params_fixed_base", "params_ss", "params_ds"}; // indexed by iwbc_behavior_type
+            bool have_files = true;
+            for (const char* k : keys)
+                have_files = have_files && sn[k];
+            if (have_files) {
+                for (int bt = 0; bt < 3; ++bt) {
+                    const std::string file = base_path + "/" + IWBC_HCHECK(sn[keys[bt]].as<std::string>(), std::string("CONTROLLER.stabilizer.") + keys[bt]);
+                    yaml::Node st = yaml::LoadFile(file);
+                    iwbc_stab_conf_t& sc = P.stab[bt];
+                    auto vec = [&](const char* key, int n, double* out, const char* what) {
+                        auto v = IWBC_HCHECK(st[key].as<std::vector<double>>(), file + ":" + key);
+                        if ((int)v.size() != n)
+                            throw ConfigError(std::string("you need ") + std::to_string(n) + " coefficient in " + what);
+                        for (int i = 0; i < n; ++i)
+                            out[i] = v[i];
+                    };
+                    vec("com", 6, sc.com_gains, "p for the com stabilizer");
+                    vec("ankle", 6, sc.ankle_gains, "d for the ankle stabilizer");
+                    vec("ffda", 3, sc.ffda_gains, "p for the ffda stabilizer");
+                    vec("zmp_p", 6, sc.zmp_p, "p for the zmp stabilizer");
+                    vec("zmp_d", 6, sc.zmp_d, "d for the zmp stabilizer");
+                    vec("zmp_w", 6, sc.zmp_w, "w for the zmp stabilizer");
+                    vec("momentum_p", 6, sc.momentum_p, "p for the momentum stabilizer");
+                    vec("momentum_d", 6, sc.momentum_d, "d for the momentum stabilizer");
+                    sc.use_zmp = IWBC_HCHECK(st["use_zmp"].as<bool>(), file + ":use_zmp") ? 1 : 0;
+                    sc.use_momentum = IWBC_HCHECK(st["use_momentum"].as<bool>(), file + ":use_momentum") ? 1 : 0;
+                    sc.filter_size = IWBC_HCHECK(st["filter_size"].as<int>(), file + ":filter_size");
+                    if (sc.filter_size < 1 || sc.filter_size > 16)
+                        throw ConfigError(file + ": filter_size must be in 1 .. 16 on the batched path");
+                    sc.zmp_w_variant = 0;
+                    if (sc.use_zmp) { // zmp_w becomes the contacts' regularisation weight vector: one more (deduplicated) variant
+                        int v = -1;
+                        for (int k = 0; k < P.nwreg && v < 0; ++k) {
+                            bool same = true;
+                            for (int i = 0; i < 6; ++i)
+                                same = same && P.wreg_variants[k][i] == sc.zmp_w[i];
+                            if (same)
+                                v = k;
+                        }
+                        if (v < 0) {
+                            if (P.nwreg >= IWBC_MAXWV)
+                                throw ConfigError("too many distinct zmp_w vectors (IWBC_MAXWV)");
+                            v = P.nwreg++;
+                            for (int i = 0; i < 6; ++i)
+                                P.wreg_variants[v][i] = sc.zmp_w[i];
+                        }
+                        sc.zmp_w_variant = v;
+                    }
+                }
+                P.stab_present = 1;
+            }
+            else if (P.stabilizer_activated)
+                throw ConfigError("config error reading CONTROLLER.stabilizer.params_fixed_base / params_ss / params_ds");
+            P.stab_task_com = com, P.stab_task_lf = lf, P.stab_task_rf = rf;
+            P.stab_task_torso = tid("torso"), P.stab_task_momentum = tid("momentum");
+            P.stab_contact_lf = cid("contact_lfoot"), P.stab_contact_rf = cid("contact_rfoot");
+            P.stab_imu_frame = -1;
+            P.stab_talos = cs.controller_name == "talos-pos-tracker" ? 1 : 0;
+            if (P.stab_talos && model.exist_frame("imu_link")) // TalosPosTracker::update reads frameVelocity("imu_link")
+                P.stab_imu_frame = use_frame(cs, "imu_link");
+        }
+        else {
+            P.stab_task_com = P.stab_task_lf = P.stab_task_rf = P.stab_task_torso = P.stab_task_momentum = -1;
+            P.stab_contact_lf = P.stab_contact_rf = P.stab_imu_frame = -1;
         }
         // ---- Talos: limit the hip-roll range around the start posture (talos_pos_tracker.cpp:41-59)
         if (cs.controller_name == "talos-pos-tracker") {

@@ -39,11 +39,12 @@ import numpy as np
 import yaml
 
 # ------------------------------------------------------------------------------------------------ iwbc_problem.h mirror
-MAXJ, MAXNV, MAXF, MAXT, MAXC, MAXAV, MAXL0, MAXL1 = 56, 64, 48, 32, 4, 12, 16, 40
+MAXJ, MAXNV, MAXF, MAXT, MAXC, MAXAV, MAXL0, MAXL1, MAXWV = 56, 64, 48, 32, 4, 12, 16, 40, 4
 J_FREEFLYER, J_REVOLUTE, J_PRISMATIC = 0, 1, 2
 T_SE3, T_COM, T_POSTURE, T_MOMENTUM, T_SELFCOL, T_BOUNDS, T_ACTBOUNDS = range(7)
 B_BASEDYN, B_CONTACT_MOTION, B_CONTACT_FORCE, B_CONTACT_REG, B_TASK = range(5)
-REF_SE3, REF_COM, REF_MOM = 24, 9, 18
+REF_SE3, REF_COM, REF_MOM, REF_CONTACT = 24, 9, 18, 32
+BT_FIXED_BASE, BT_SINGLE_SUPPORT, BT_DOUBLE_SUPPORT = 0, 1, 2
 
 
 class TaskS(C.Structure):
@@ -63,6 +64,13 @@ class BlockS(C.Structure):
     _fields_ = [("kind", C.c_int), ("index", C.c_int)]
 
 
+class StabS(C.Structure):
+    _fields_ = [("filter_size", C.c_int), ("use_zmp", C.c_int), ("use_momentum", C.c_int), ("zmp_w_variant", C.c_int),
+                ("com_gains", C.c_double * 6), ("ankle_gains", C.c_double * 6), ("ffda_gains", C.c_double * 3), ("pad_", C.c_double),
+                ("zmp_p", C.c_double * 6), ("zmp_d", C.c_double * 6), ("zmp_w", C.c_double * 6), ("momentum_p", C.c_double * 6),
+                ("momentum_d", C.c_double * 6)]
+
+
 class ProblemS(C.Structure):
     _fields_ = [("magic", C.c_uint), ("version", C.c_uint), ("nj", C.c_int), ("nq", C.c_int), ("nv", C.c_int), ("na", C.c_int),
                 ("floating_base", C.c_int), ("nframes", C.c_int), ("ntasks", C.c_int), ("ncontacts", C.c_int), ("nl0", C.c_int),
@@ -75,7 +83,12 @@ class ProblemS(C.Structure):
                 ("q_lo", C.c_double * MAXNV), ("q_hi", C.c_double * MAXNV), ("v_max", C.c_double * MAXNV), ("tau_max", C.c_double * MAXNV),
                 ("fparent", C.c_int * MAXF), ("fplace", (C.c_double * 12) * MAXF),
                 ("tasks", TaskS * MAXT), ("contacts", ContactS * MAXC), ("l0", BlockS * MAXL0), ("l1", BlockS * MAXL1),
-                ("q0", C.c_double * (MAXNV + 1))]
+                ("q0", C.c_double * (MAXNV + 1)),
+                ("nwreg", C.c_int), ("pad2_", C.c_int), ("wreg_variants", (C.c_double * 6) * MAXWV),
+                ("stabilizer_activated", C.c_int), ("stab_present", C.c_int), ("stab_talos", C.c_int), ("stab_task_com", C.c_int),
+                ("stab_task_lf", C.c_int), ("stab_task_rf", C.c_int), ("stab_task_torso", C.c_int), ("stab_task_momentum", C.c_int),
+                ("stab_contact_lf", C.c_int), ("stab_contact_rf", C.c_int), ("stab_imu_frame", C.c_int), ("pad3_", C.c_int),
+                ("stab", StabS * 3)]
 
 
 class ConfigError(RuntimeError):
@@ -357,7 +370,7 @@ class OracleProblem:
         if str(_need(c, "solver", "CONTROLLER")) != "eiquadprog":
             raise ConfigError("solver in configuration file must be 'eiquadprog' on this path")
         S = self.S
-        S.magic, S.version = 0x43425749, 1
+        S.magic, S.version = 0x43425749, 2
         S.dt = float(_need(c, "dt", "CONTROLLER"))
         fb = _as_bool(_need(c, "floating_base", "CONTROLLER"))
         self.mimic_names = [str(x) for x in _need(c, "mimic_dof_names", "CONTROLLER")]
@@ -559,7 +572,7 @@ class OracleProblem:
                 ct.lb[:], ct.ub[:] = [-1e10] * 16 + [fmin], [0.0] * 16 + [fmax]
                 ct.wreg[:] = [1, 1, 1e-3, 2, 2, 2]
                 ct.w_forcereg = 1e-3  # cst::w_force_feet
-                ct.ref_off = alloc(REF_SE3, oMi[model.joint_id(jn)].sample24())
+                ct.ref_off = alloc(REF_CONTACT, oMi[model.joint_id(jn)].sample24())  # then f_ref = 0 and weight vector 0 (Contact6d's default)
                 for kind in (B_CONTACT_MOTION, B_CONTACT_FORCE):  # addRigidContact: motion + force at level 0, regularisation at level 1
                     S.l0[S.nl0].kind, S.l0[S.nl0].index = kind, cid
                     S.nl0 += 1
@@ -568,6 +581,8 @@ class OracleProblem:
             else:
                 raise ConfigError("task type '%s' (%s) is not on the path the oracle restates" % (ttype, name))
         S.nref = len(self.ref0)
+        S.nwreg = 1
+        S.wreg_variants[0][:] = [1, 1, 1e-3, 2, 2, 2]
 
         if "joint_range_reduction" in c:  # pos_tracker.cpp:115-148
             red = float(c["joint_range_reduction"]) / 180 * math.pi
@@ -593,6 +608,46 @@ class OracleProblem:
             if d > 0.01:
                 raise ConfigError("Wrong starting configuration: the CoM needs to be between the two feet with less than 1cm difference, but the distance is %g" % d)
             self.ref0[co:co + 2] = final
+            # HumanoidPosTracker::parse_stabilizer (humanoid_pos_tracker.cpp:81-114) with parse_stab_conf (stabilizer_conf.hpp:46-92)
+            sn = _need(c, "stabilizer", "CONTROLLER")
+            S.stabilizer_activated = int(_as_bool(_need(sn, "activated", "CONTROLLER.stabilizer")))
+            keys = ("params_fixed_base", "params_ss", "params_ds")  # behaviour types FIXED_BASE, SINGLE_SUPPORT, DOUBLE_SUPPORT
+            if all(k in sn for k in keys):
+                for bt, k in enumerate(keys):
+                    st = _load_yaml(os.path.join(base_path, str(sn[k])))
+                    sc = S.stab[bt]
+                    for key, field, n in (("com", "com_gains", 6), ("ankle", "ankle_gains", 6), ("ffda", "ffda_gains", 3), ("zmp_p", "zmp_p", 6),
+                                          ("zmp_d", "zmp_d", 6), ("zmp_w", "zmp_w", 6), ("momentum_p", "momentum_p", 6), ("momentum_d", "momentum_d", 6)):
+                        vals = [float(x) for x in _need(st, key, str(sn[k]))]
+                        if len(vals) != n:
+                            raise ConfigError("you need %d coefficient in %s" % (n, key))
+                        getattr(sc, field)[:] = vals
+                    sc.use_zmp = int(_as_bool(_need(st, "use_zmp", str(sn[k]))))
+                    sc.use_momentum = int(_as_bool(_need(st, "use_momentum", str(sn[k]))))
+                    sc.filter_size = int(_need(st, "filter_size", str(sn[k])))
+                    sc.zmp_w_variant = 0
+                    if sc.use_zmp:  # setRegularizationTaskWeightVector(zmp_w): one more weight vector the contacts may carry
+                        have = [list(S.wreg_variants[v]) for v in range(S.nwreg)]
+                        w = list(sc.zmp_w)
+                        if w not in have:
+                            if S.nwreg >= MAXWV:
+                                raise ConfigError("too many distinct zmp_w vectors")
+                            S.wreg_variants[S.nwreg][:] = w
+                            S.nwreg += 1
+                            have.append(w)
+                        sc.zmp_w_variant = have.index(w)
+                S.stab_present = 1
+            elif S.stabilizer_activated:
+                raise ConfigError("config error reading CONTROLLER.stabilizer.params_*")
+            tid = lambda n: self.task_names.index(n) if n in self.task_names else -1  # noqa: E731
+            S.stab_task_com, S.stab_task_lf, S.stab_task_rf = tid("com"), tid("lf"), tid("rf")
+            S.stab_task_torso, S.stab_task_momentum = tid("torso"), tid("momentum")
+            S.stab_contact_lf, S.stab_contact_rf = self.contact_names.index("contact_lfoot"), self.contact_names.index("contact_rfoot")
+            S.stab_talos = int(self.controller_name == "talos-pos-tracker")
+            S.stab_imu_frame = use_frame("imu_link") if S.stab_talos and model.frame_id("imu_link") >= 0 else -1
+        else:
+            S.stab_task_com = S.stab_task_lf = S.stab_task_rf = S.stab_task_torso = S.stab_task_momentum = -1
+            S.stab_contact_lf = S.stab_contact_rf = S.stab_imu_frame = -1
         if self.controller_name == "talos-pos-tracker":  # TalosPosTracker ctor
             roll = float(np.float32(_need(c, "torso_max_roll", "CONTROLLER")) / np.float32(180)) * math.pi
             names = model.actuated_names()
@@ -638,7 +693,7 @@ class OracleProblem:
             if t.ref_off >= 0:
                 return t.ref_off, {T_SE3: REF_SE3, T_COM: REF_COM, T_MOMENTUM: REF_MOM}.get(t.type, 3 * S.na)
         if name in self.contact_names:
-            return S.contacts[self.contact_names.index(name)].ref_off, REF_SE3
+            return S.contacts[self.contact_names.index(name)].ref_off, REF_CONTACT
         raise KeyError(name)
 
     def set_task_weight(self, name, w):

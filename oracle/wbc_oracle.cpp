@@ -1145,12 +1145,20 @@ void cycle(const iwbc_problem_t& P, const double* q, const double* v, const doub
             if (cidx[c] < 0)
                 continue;
             const iwbc_contact_t& C = P.contacts[c];
+            // Contact6d::updateForceRegularizationTask: matrix = diag(w) T, vector = diag(w) f_ref; the instance's reference row
+            // carries f_ref (Contact6d::setForceReference) and which weight vector is installed (setRegularizationTaskWeightVector:
+            // the stabilizer's zmp_w, src/controllers/humanoid_pos_tracker.cpp:220-223)
+            const double* fref = ref + C.ref_off + IWBC_REF_CONTACT_FREF;
+            int wv = (int)ref[C.ref_off + IWBC_REF_CONTACT_WREG];
+            if (wv < 0 || wv >= P.nwreg)
+                wv = 0;
+            const real_t* wreg = P.wreg_variants[wv];
             Mat A(6, n);
             double b[6];
             for (int r = 0; r < 6; ++r) {
                 for (int k = 0; k < 12; ++k)
-                    A(r, nv + cidx[c] + k) = C.wreg[r] * C.T[r * 12 + k];
-                b[r] = C.wreg[r] * C.fref[r];
+                    A(r, nv + cidx[c] + k) = wreg[r] * C.T[r * 12 + k];
+                b[r] = wreg[r] * fref[r];
             }
             add_cost(C.w_forcereg, A, b, 6);
             continue;

@@ -49,7 +49,7 @@ def test_joint_order_is_pinocchio_like(talos):
 
 def test_reference_slots_and_defaults(talos, franka):
     r = talos.default_refs()
-    assert r.shape == (talos.nref,) and talos.nref == 8 * 24 + 9 + 3 * 44 + 18 + 2 * 24
+    assert r.shape == (talos.nref,) and talos.nref == 8 * 24 + 9 + 3 * 44 + 18 + 2 * 32  # a contact block: SE3 sample (24) + f_ref (6) + weight-vector index + pad
     off, n = talos.ref_slot("com")
     assert n == 9
     lf, _ = talos.ref_slot("lf")

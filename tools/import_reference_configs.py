@@ -22,15 +22,18 @@ YAMLS = {
     "franka": ["pos_tracker.yaml", "tasks.yaml", "cartesian_line.yaml"],
     "talos": ["talos_pos_tracker.yaml", "tasks.yaml", "frames.yaml", "squat.yaml", "arm.yaml",
               "walk.yaml", "walk_on_spot.yaml", "move_com.yaml", "move_feet.yaml", "clapping.yaml", "align.yaml",
-              "collisions/talos_collisions_margin.yaml", "collisions/talos_collisions.yaml"],
-    "icub": ["humanoid_pos_tracker.yaml", "tasks.yaml", "frames.yaml", "squat.yaml", "arm.yaml", "walk.yaml", "walk_on_spot.yaml", "clapping.yaml"],
+              "collisions/talos_collisions_margin.yaml", "collisions/talos_collisions.yaml",
+              "stab_double_support.yaml", "stab_single_support.yaml", "stab_fixed_base.yaml", "collision_thresholds.yaml",
+              "talos_pos_tracker_real_robot.yaml"],
+    "icub": ["humanoid_pos_tracker.yaml", "tasks.yaml", "frames.yaml", "squat.yaml", "arm.yaml", "walk.yaml", "walk_on_spot.yaml", "clapping.yaml", "align.yaml",
+             "stab_double_support.yaml", "stab_single_support.yaml", "stab_fixed_base.yaml", "collision_thresholds.yaml"],
     "tiago": ["pos_tracker.yaml", "tasks.yaml", "frames.yaml", "cartesian_line.yaml", "collisions.yaml"],
 }
 SRDFS = {
     "franka": ["configurations.srdf"],
     "talos": ["configurations.srdf"],
     "icub": ["configurations.srdf"],
-    "tiago": ["configurations-elbow-down.srdf"],
+    "tiago": ["configurations-elbow-down.srdf", "configurations-elbow-up.srdf"],
 }
 
 
