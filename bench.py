@@ -35,17 +35,20 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+OPEN_LOOP = {"stabilizer": {"activated": False}, "collision_detection": {"activated": False}, "closed_loop": False}
 WORKLOADS = {
     # name: (controller yaml, overrides, per-GPU batch, recipe)
-    "talos_ds_16384": ("talos/talos_pos_tracker.yaml", None, 16384, "talos"),
+    # (stabilizer / torque collision detection off and open loop, as the reference's own controller-only test runs it:
+    # tests/test_determinism.cpp:66-69)
+    "talos_ds_16384": ("talos/talos_pos_tracker.yaml", OPEN_LOOP, 16384, "talos"),
     # config 3, fast-URDF variant (the reference's `-f` runs: nq = 39, QP n = 62, me = 18, mi = 196, 85 cost rows)
-    "talos_fast_ds_16384": ("talos/talos_pos_tracker.yaml", {"urdf": "talos/talos_fast.urdf"}, 16384, "talos"),
+    "talos_fast_ds_16384": ("talos/talos_pos_tracker.yaml", dict(OPEN_LOOP, urdf="talos/talos_fast.urdf"), 16384, "talos"),
     "franka_65536": ("franka/pos_tracker.yaml", None, 65536, "franka"),
     # config 5: Talos walking, a mix of double- and single-support shapes bucketed by contact mask
-    "talos_walk_131072": ("talos/talos_pos_tracker.yaml", None, 131072, "walk"),
+    "talos_walk_131072": ("talos/talos_pos_tracker.yaml", OPEN_LOOP, 131072, "walk"),
     # the same shapes from the CPU-only stand-in recipe (make_walk_masks): what the walking workload was before the device-side behaviour
-    "talos_walk_standin_131072": ("talos/talos_pos_tracker.yaml", None, 131072, "walk_standin"),
-    "icub_ds_16384": ("icub/humanoid_pos_tracker.yaml", {"stabilizer": {"activated": False}}, 16384, "talos"),
+    "talos_walk_standin_131072": ("talos/talos_pos_tracker.yaml", OPEN_LOOP, 131072, "walk_standin"),
+    "icub_ds_16384": ("icub/humanoid_pos_tracker.yaml", OPEN_LOOP, 16384, "talos"),
     "tiago_65536": ("tiago/pos_tracker.yaml", {"urdf": "tiago/tiago_steel_no_wheel.urdf"}, 65536, "arm"),
 }
 DEFAULT_WORKLOAD = "talos_ds_16384"

@@ -248,6 +248,36 @@ int iwbc_batch_safe_rollout_device(iwbc_batch* b, iwbc_collision* collision, int
 /* qp_step_back(): (q, v) <- (q_prev, v_prev) for the instances with select[i] != 0 (select == NULL: all) */
 int iwbc_batch_qp_step_back_device(iwbc_batch* b, int B, double* q, double* v, const iwbc_safety_t* safety, const int* select, void* stream);
 
+/* ------------------------------------------------------------------ stabilizer: the sensor-driven pre-step
+ * `HumanoidPosTracker::update(sensor_data)` with CONTROLLER.stabilizer.activated (src/controllers/humanoid_pos_tracker.cpp:134-302):
+ * CoP estimate from the feet's force / torque sensors (src/estimators/cop.cpp:10-96) through moving-average filters
+ * (include/inria_wbc/estimators/filtering.hpp:17-146), then the CoM / ZMP-distributor / ankle / foot-force-difference admittances
+ * (src/stabilizers/stabilizer.cpp:31-59, 277-311 + 340-429, 168-224, 226-275) rewrite the references of ONE solve; for
+ * talos-pos-tracker the IMU momentum admittance comes first (src/controllers/talos_pos_tracker.cpp:135-150).  The parameter sets are
+ * the reference's stab_*.yaml files named by CONTROLLER.stabilizer.params_{fixed_base,ss,ds}, read unchanged at load time.
+ * A controller loaded with stabilizer.activated = true REFUSES the plain update / roll-out entry points ("the stabilizer needs the
+ * LF force", :180) -- load it with `stabilizer: {activated: false}` for open-loop use, as tests/test_determinism.cpp:67 does.
+ *
+ * iwbc_stabilizer = the per-robot state that survives a tick, for the batch's max_batch robots: filter windows, normal forces of the
+ * last solve, the contacts' force references and installed regularisation weights, the state tsid's data was computed on.
+ *   sensors[B][15]        : lf_force(3) rf_force(3) lf_torque(3) rf_torque(3) imu_vel(3)   (SensorData keys of the same names)
+ *   contact_mask[B]       : activated contacts per robot (NULL: the default mask); both feet, left only or right only
+ *   behavior_type[B]      : iwbc_behavior_type per robot = Controller::set_behavior_type (NULL: behavior_type_all for everybody)
+ *   refs / refs_stride    : the behaviours' reference rows; they are NOT modified (the reference puts its references back after the
+ *                           solve, :291-301); refs_used[B][nref] (may be NULL) receives the rows the solve saw
+ */
+typedef struct iwbc_stabilizer iwbc_stabilizer;
+iwbc_stabilizer* iwbc_stabilizer_create(iwbc_batch* b);
+void iwbc_stabilizer_free(iwbc_stabilizer* s);
+int iwbc_stabilizer_reset(iwbc_stabilizer* s, void* stream); /* fresh controllers: empty windows, data state = (q0, 0) */
+/* DEVICE pointers, enqueued on `stream`, no synchronisation */
+int iwbc_batch_update_sensors_device(iwbc_batch* b, iwbc_stabilizer* s, int B, const double* q, const double* v, const double* refs, long refs_stride,
+    const unsigned* contact_mask, const int* behavior_type, int behavior_type_all, const double* sensors, const iwbc_results_t* out, double* refs_used,
+    void* stream);
+/* HOST pointers; synchronous */
+int iwbc_batch_update_sensors(iwbc_batch* b, iwbc_stabilizer* s, int B, const double* q, const double* v, const double* refs, long refs_stride,
+    const unsigned* contact_mask, const int* behavior_type, int behavior_type_all, const double* sensors, const iwbc_results_t* out, double* refs_used);
+
 /* ------------------------------------------------------------------ solver interface
  * Batched form of `tsid::solvers::SolverHQPBase::solve` for the EiquadprogFast backend
  * (src/controllers/pos_tracker.cpp:96,102; src/controllers/controller.cpp:247): B dense QPs of one

@@ -85,6 +85,11 @@ def lib():
         "iwbc_batch_check_collisions_device": (ci, [vp, vp, ci, vp, vp, vp, vp]),
         "iwbc_batch_safe_rollout_device": (ci, [vp, vp, ci, vp, vp, vp, cl, cu, ci, C.POINTER(_Safety), vp, vp]),
         "iwbc_batch_qp_step_back_device": (ci, [vp, ci, vp, vp, C.POINTER(_Safety), vp, vp]),
+        "iwbc_stabilizer_create": (vp, [vp]),
+        "iwbc_stabilizer_free": (None, [vp]),
+        "iwbc_stabilizer_reset": (ci, [vp, vp]),
+        "iwbc_batch_update_sensors_device": (ci, [vp, vp, ci, vp, vp, vp, cl, vp, vp, ci, vp, C.POINTER(_Results), vp, vp]),
+        "iwbc_batch_update_sensors": (ci, [vp, vp, ci, vp, vp, vp, cl, vp, vp, ci, vp, C.POINTER(_Results), vp]),
         "iwbc_behavior_load": (vp, [vp, cp, cp]),
         "iwbc_behavior_free": (None, [vp]),
         "iwbc_behavior_info": (ci, [vp, pi, pi, pi, pi, vp]),
@@ -263,6 +268,27 @@ class Behavior:
             raise IwbcError(_err(lib()))
 
 
+class Stabilizer:
+    def __init__(self, batch):
+        self.batch = batch
+        self._h = lib().iwbc_stabilizer_create(batch._h)
+        if not self._h:
+            raise IwbcError(_err(lib()))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.iwbc_stabilizer_free(self._h)
+            self._h = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def reset(self):
+        if lib().iwbc_stabilizer_reset(self._h, None) != 0:
+            raise IwbcError(_err(lib()))
+
+
 def _yaml_scalar(v):
     if isinstance(v, bool):
         return "true" if v else "false"
@@ -370,6 +396,32 @@ class Batch:
         rc = lib().iwbc_batch_check_collisions_device(self._h, collision_model.handle, B, q_ptr, colliding_ptr, pair_ptr, stream)
         if rc != 0:
             raise IwbcError(_err(lib()))
+
+    def stabilizer(self):
+        """Per-robot stabilizer state (filters, last normal forces, ...) for this batch: HumanoidPosTracker's sensor-driven pre-step."""
+        return Stabilizer(self)
+
+    def update_sensors(self, stab, q, v, sensors, refs=None, contact_mask=None, behavior_type=2, out=None, fields=Results.FIELDS, want_refs=False):
+        """`HumanoidPosTracker::update(sensor_data)` for B robots, host arrays.  sensors[B][15] = lf_force rf_force lf_torque rf_torque
+        imu_vel; behavior_type: int (everybody) or int array [B] (0 fixed base, 1 single support, 2 double support)."""
+        P = self.problem
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, P.nq)
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, P.nv)
+        B = q.shape[0]
+        sensors = np.ascontiguousarray(sensors, dtype=np.float64).reshape(B, 15)
+        refs = P.default_refs() if refs is None else np.ascontiguousarray(refs, dtype=np.float64)
+        stride = 0 if refs.ndim == 1 else P.nref
+        cm = None if contact_mask is None else np.ascontiguousarray(np.broadcast_to(np.asarray(contact_mask, dtype=np.uint32), (B,)))
+        bt_all, bt = (int(behavior_type), None) if np.isscalar(behavior_type) else (2, np.ascontiguousarray(behavior_type, dtype=np.int32))
+        if out is None:
+            out = Results(P, B, fields)
+        st = out.as_struct()
+        used = np.zeros((B, P.nref)) if want_refs else None
+        rc = lib().iwbc_batch_update_sensors(self._h, stab.handle, B, q.ctypes.data, v.ctypes.data, refs.ctypes.data, stride, _ptr(cm), _ptr(bt), bt_all,
+                                             sensors.ctypes.data, C.byref(st), _ptr(used))
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+        return (out, used) if want_refs else out
 
     SAFETY_FIELDS = ("send_cmd", "colliding", "q_prev", "v_prev", "q_solver", "q_cmd", "tau_cmd", "dq_cmd", "ddq_cmd")
 

@@ -394,6 +394,12 @@ int upload_constants(iwbc_batch* b, cudaStream_t st)
 // one pass of the cycle over io's instances (all of them, or io.list) with one contact mask; shared with behavior.cu
 int iwbc_run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t st)
 {
+    if (b->prob->cs.prob.stabilizer_activated && !b->sensor_call) {
+        // HumanoidPosTracker::update asserts its sensors when CONTROLLER.stabilizer.activated (humanoid_pos_tracker.cpp:180-184)
+        set_error("the stabilizer needs the LF force: this controller has CONTROLLER.stabilizer.activated = true, call iwbc_batch_update_sensors"
+                  " (or load it with stabilizer: {activated: false}, as the reference's open-loop tests do)");
+        return IWBC_ERR_ARG;
+    }
     int rc = prepare_shape(b, mask);
     if (rc)
         return rc;
@@ -497,7 +503,7 @@ void iwbc_batch_free(iwbc_batch* b)
     for (auto& m : b->mask_cache)
         if (m.d_fplan && m.d_fplan != b->d_fplan)
             cudaFree(m.d_fplan);
-    void* ptrs[] = {b->d_phase, b->d_cmask, b->d_scratch, b->d_slow_code, b->d_fplan, b->d_slow_list, b->d_slow_count, b->d_prof, b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
+    void* ptrs[] = {b->d_sensors, b->d_phase, b->d_cmask, b->d_scratch, b->d_slow_code, b->d_fplan, b->d_slow_list, b->d_slow_count, b->d_prof, b->d_prob, b->d_q, b->d_v, b->d_refs, b->d_tau, b->d_dv, b->d_f, b->d_qn, b->d_vn, b->d_qc, b->d_mom, b->d_status, b->d_iters, b->d_active};
     for (void* p : ptrs)
         if (p)
             cudaFree(p);

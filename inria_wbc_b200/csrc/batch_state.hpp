@@ -49,6 +49,8 @@ struct iwbc_batch {
     double *d_tau = nullptr, *d_dv = nullptr, *d_f = nullptr, *d_qn = nullptr, *d_vn = nullptr, *d_qc = nullptr, *d_mom = nullptr;
     int *d_status = nullptr, *d_iters = nullptr;
     unsigned* d_active = nullptr;
+    double* d_sensors = nullptr;  // iwbc_batch_update_sensors: [max_batch][15] staging (allocated on first use)
+    bool sensor_call = false;     // set while iwbc_batch_update_sensors_device drives the cycle (the plain entry points refuse an activated stabilizer)
     int* d_phase = nullptr;       // iwbc_batch_behavior_run: per-instance phase offsets, contact masks (allocated on first use)
     unsigned* d_cmask = nullptr;
     // bucketing scratch (host)

@@ -1744,6 +1744,32 @@ int oracle_frame(const iwbc_problem_t* P, const double* q, const double* v, int 
     return 0;
 }
 
+// What the stabilizer reads from tsid's data (src/controllers/humanoid_pos_tracker.cpp:170-176,205; talos_pos_tracker.cpp:142):
+// out21 = com(3) vcom(3) acom(3) [data.com[0], vcom[0], acom[0] after computeAllTerms + centerOfMass(q, v, 0)], the placements'
+// translations of the two contact joints (contact_lfoot, contact_rfoot), the angular velocity of imu_link in its own frame.
+int oracle_stab_model(const iwbc_problem_t* P, const double* q, const double* v, double* out21)
+{
+    Dyn D;
+    compute_all_terms(*P, q, v, D);
+    double t[21] = {D.com.x, D.com.y, D.com.z, D.vcom.x, D.vcom.y, D.vcom.z, D.acom.x, D.acom.y, D.acom.z};
+    for (int k = 9; k < 21; ++k)
+        t[k] = 0;
+    const int cs[2] = {P->stab_contact_lf, P->stab_contact_rf};
+    for (int s = 0; s < 2; ++s)
+        if (cs[s] >= 0) {
+            FrameKin K;
+            frame_kinematics(*P, D, P->contacts[cs[s]].frame, K);
+            t[9 + 3 * s] = K.oMf.p.x, t[10 + 3 * s] = K.oMf.p.y, t[11 + 3 * s] = K.oMf.p.z;
+        }
+    if (P->stab_imu_frame >= 0) {
+        FrameKin K;
+        frame_kinematics(*P, D, P->stab_imu_frame, K);
+        t[15] = K.v.ang.x, t[16] = K.v.ang.y, t[17] = K.v.ang.z;
+    }
+    std::copy(t, t + 21, out21);
+    return 0;
+}
+
 int oracle_problem_size(void) { return (int)sizeof(iwbc_problem_t); }
 
 } // extern "C"

@@ -31,14 +31,16 @@ def franka():
 @pytest.fixture(scope="session")
 def talos():
     import inria_wbc_b200 as iw
-    return iw.Problem("talos/talos_pos_tracker.yaml")
+    # stabilizer off, as the reference's open-loop tests run the controller (tests/test_determinism.cpp:67): with it activated the
+    # controller needs F/T + IMU sensor data for every update (tests/test_stabilizer.py)
+    return iw.Problem("talos/talos_pos_tracker.yaml", overrides={"stabilizer": {"activated": False}})
 
 
 @pytest.fixture(scope="session")
 def talos_fast():
     """Talos with the `talos_fast.urdf` model of the reference's `-f` runs (grippers reduced to their driven joint)."""
     import inria_wbc_b200 as iw
-    return iw.Problem("talos/talos_pos_tracker.yaml", overrides={"urdf": "talos/talos_fast.urdf"})
+    return iw.Problem("talos/talos_pos_tracker.yaml", overrides={"urdf": "talos/talos_fast.urdf", "stabilizer": {"activated": False}})
 
 
 @pytest.fixture(scope="session")

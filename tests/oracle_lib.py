@@ -121,6 +121,14 @@ def frame(problem, q, v, frame_id):
     return dict(oMf=oMf, vel=vel, acc=acc, J=J)
 
 
+def stab_model(problem, q, v):
+    """What the stabilizer reads from tsid's data: CoM sample (9), the two ankle (contact joint) positions, imu_link's angular velocity."""
+    out = np.zeros(21)
+    lib().oracle_stab_model(C.c_void_p(problem.data_ptr), _p(np.ascontiguousarray(q, dtype=np.float64)),
+                            _p(np.ascontiguousarray(v, dtype=np.float64)), _p(out))
+    return dict(com=out[0:9].copy(), lf_p=out[9:12].copy(), rf_p=out[12:15].copy(), imu_w=out[15:18].copy())
+
+
 # ----------------------------------------------------------------- CPU simulation of the device source (test tooling)
 _sim = None
 

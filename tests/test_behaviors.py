@@ -13,12 +13,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import behaviors_oracle as bo  # noqa: E402
 
+OFF = {"stabilizer": {"activated": False}}
 WALK = os.path.join(iw.ETC_PATH, "talos", "walk.yaml")
 
 
 @pytest.fixture(scope="module")
 def walk_problem():
-    P = iw.Problem("talos/talos_pos_tracker.yaml")
+    P = iw.Problem("talos/talos_pos_tracker.yaml", overrides=OFF)
     P.set_task_weight("momentum", 0.0)  # BEHAVIOR.customize_task_weights (etc/talos/walk.yaml:8-9; src/behaviors/behavior.cpp:7-22)
     return P
 
@@ -61,7 +62,7 @@ def test_walk_contact_schedule(walk_problem):
 
 def test_loading_a_behaviour_customizes_task_weights():
     """Behavior::_customize_tasks (src/behaviors/behavior.cpp:7-22): etc/talos/walk.yaml sets the momentum task's weight to 0."""
-    P = iw.Problem("talos/talos_pos_tracker.yaml")
+    P = iw.Problem("talos/talos_pos_tracker.yaml", overrides=OFF)
     k = P.names("tasks").index("momentum")
     assert P.struct().tasks[k].weight > 0
     iw.Behavior(P, "talos/walk.yaml")
@@ -241,7 +242,7 @@ def test_franka_known_answer_with_the_behaviour_on_the_device(franka):
 
 def test_walk_on_spot_table(talos):
     """humanoid::walk-on-spot (src/behaviors/humanoid/walk_on_spot.cpp): INIT once, then six states for ever."""
-    P = iw.Problem("talos/talos_pos_tracker.yaml")
+    P = iw.Problem("talos/talos_pos_tracker.yaml", overrides=OFF)
     beh = iw.Behavior(P, "talos/walk_on_spot.yaml")
     ora = bo.WalkOnSpot(P, os.path.join(iw.ETC_PATH, "talos", "walk_on_spot.yaml"))
     assert beh.total_ticks == 7000 and beh.nsegments == 7 and beh.nchannels == 3
@@ -260,7 +261,7 @@ def test_walk_on_spot_table(talos):
 @pytest.mark.gpu
 def test_walk_on_spot_on_device_loops_past_its_init_segment(talos):
     import torch
-    P = iw.Problem("talos/talos_pos_tracker.yaml")
+    P = iw.Problem("talos/talos_pos_tracker.yaml", overrides=OFF)
     beh = iw.Behavior(P, "talos/walk_on_spot.yaml")
     ora = bo.WalkOnSpot(P, os.path.join(iw.ETC_PATH, "talos", "walk_on_spot.yaml"))
     B = 7000 + 2 * 6000 + 17  # INIT + two and a bit loops
