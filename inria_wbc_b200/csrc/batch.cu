@@ -25,7 +25,7 @@ namespace dev {
     // (the warp-per-instance form is occupancy-bound by registers: three CTAs per SM need <= 168; without the bound ptxas drifts to
     // 216 and Franka drops from 38 M to 27 M updates/s)
     template <int G, int IPC>
-    __global__ void __launch_bounds__(G* IPC, (G <= 32 ? 3 : 1)) k_cycle(const iwbc_problem_t* __restrict__ gP, const __grid_constant__ Shape S, IO io)
+    __global__ void __launch_bounds__(G* IPC, (G <= 32 && G * IPC <= 128 ? 3 : 1)) k_cycle(const iwbc_problem_t* __restrict__ gP, const __grid_constant__ Shape S, IO io)
     {
         extern __shared__ double smem[];
         const int grp = threadIdx.x / G;
@@ -242,6 +242,12 @@ void choose_group(const iwbc_problem_t& P, int n, int& G, int& IPC)
     if (n <= 32 && P.nj * 16 <= 8 * 32) {
         G = 32;
         IPC = 4;
+        // IWBC_ARM_SHAPE="G,IPC": sub-warp groups for the small arms (tuning aid; instantiated shapes only)
+        if (const char* e = std::getenv("IWBC_ARM_SHAPE")) {
+            int g = 0, ipc = 0;
+            if (std::sscanf(e, "%d,%d", &g, &ipc) == 2 && ((g == 16 && (ipc == 8 || ipc == 12)) || (g == 8 && (ipc == 16 || ipc == 24)) || (g == 32 && ipc == 4)))
+                G = g, IPC = ipc;
+        }
     }
     else if (n <= 64 && P.nj * 16 <= 8 * 64) {
         G = 64;
@@ -408,6 +414,10 @@ int iwbc_run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t
         return rc;
     if (b->G == 32)
         return launch_cycle<32, 4>(b, io, st);
+    if (b->G == 16)
+        return b->IPC == 8 ? launch_cycle<16, 8>(b, io, st) : launch_cycle<16, 12>(b, io, st);
+    if (b->G == 8)
+        return b->IPC == 16 ? launch_cycle<8, 16>(b, io, st) : launch_cycle<8, 24>(b, io, st);
     if (b->G == 64)
         return launch_cycle<64, 1>(b, io, st);
     if (b->G == 96)

@@ -446,6 +446,10 @@ namespace dev {
             }
         }
         fsync<T>();
+        // per active-contact slot: the force-block factor of the weight vector this instance has installed (registers)
+        const double* const Uq0 = gF->Uff[(int)frv[6]][0];
+        const double* const Uq1 = F.nca > 1 ? gF->Uff[(int)frv[14]][1] : Uq0;
+        auto Usel = [&](int s) { return s == 0 ? Uq0 : (s == 1 ? Uq1 : gF->Uff[(int)frv[8 * s + 6]][s]); }; // (humanoids: two contacts)
         if (cyc && tid == 0)
             cyc[0] = clock64();
 
@@ -965,7 +969,7 @@ namespace dev {
                 else {
                     const int c = F.cact[s];
                     const double* Tm = gP->contacts[c].T;
-                    const double* U = gF->Uff[wvs][s];
+                    const double* U = Usel(s);
                     val = 0;
                     for (int i = 0; i <= k2; ++i) {
                         double npf = 0;
@@ -1425,7 +1429,7 @@ namespace dev {
             else {
                 for (int kk = tid - 32; kk < 12 * F.nca; kk += (T > 32 ? T - 32 : 1)) {
                     const int s = kk / 12, i = kk - 12 * s;
-                    const double* U = gF->Uff[(int)frv[8 * s + 6]][s] + i * 12;
+                    const double* U = Usel(s) + i * 12;
                     double a = 0;
                     for (int j = i; j < 12; ++j)
                         a += U[j] * wv[nv + 12 * s + j];
@@ -1435,7 +1439,7 @@ namespace dev {
             if (T == 1)
                 for (int kk = 0; kk < 12 * F.nca; ++kk) {
                     const int s = kk / 12, i = kk - 12 * s;
-                    const double* U = gF->Uff[(int)frv[8 * s + 6]][s] + i * 12;
+                    const double* U = Usel(s) + i * 12;
                     double a = 0;
                     for (int j = i; j < 12; ++j)
                         a += U[j] * wv[nv + 12 * s + j];
@@ -1513,6 +1517,9 @@ namespace dev {
         double* const tv = smem + F.o_tv;
         double* const il = smem + F.o_il;
         double* const frv = smem + F.o_fr;
+        const double* const Uq0 = gF->Uff[(int)frv[6]][0];
+        const double* const Uq1 = F.nca > 1 ? gF->Uff[(int)frv[14]][1] : Uq0;
+        auto Usel = [&](int s) { return s == 0 ? Uq0 : (s == 1 ? Uq1 : gF->Uff[(int)frv[8 * s + 6]][s]); }; // (humanoids: two contacts)
         Sizes z;
         z.nv = nv, z.nq = gP->nq, z.nj = gP->nj, z.nf = gP->nframes, z.nc = gP->ncontacts, z.n = n, z.mi = S.mi, z.rows_dense = S.rows_dense;
         z.nref = gP->nref, z.ldJ = ldJ, z.ldM = nv | 1;
@@ -1610,7 +1617,7 @@ namespace dev {
                     }
 #pragma unroll
                     for (int i2 = 0; i2 < 12; ++i2) {
-                        const double* U = gF->Uff[(int)frv[8 * sidx + 6]][sidx] + i2 * 12;
+                        const double* U = Usel(sidx) + i2 * 12;
                         double a0 = 0;
 #pragma unroll
                         for (int j2 = 0; j2 < 12; ++j2)
@@ -1656,7 +1663,7 @@ namespace dev {
                 }
                 else {
                     const int ii = j - nv, sidx = ii / 12, i2 = ii - 12 * sidx;
-                    const double* U = gF->Uff[(int)frv[8 * sidx + 6]][sidx] + i2 * 12;
+                    const double* U = Usel(sidx) + i2 * 12;
                     for (int j2 = i2; j2 < 12; ++j2)
                         sm.J[j + (nv + 12 * sidx + j2) * ldJ] = U[j2];
                 }
@@ -1743,7 +1750,7 @@ namespace dev {
                     }
     #pragma unroll
                     for (int i2 = 0; i2 < 12; ++i2) {
-                        const double* U = gF->Uff[(int)frv[8 * sidx + 6]][sidx] + i2 * 12;
+                        const double* U = Usel(sidx) + i2 * 12;
                         double a0 = 0;
     #pragma unroll
                         for (int j2 = 0; j2 < 12; ++j2)

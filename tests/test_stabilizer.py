@@ -104,7 +104,7 @@ def _streams(P, B, T, seed):
         share = rng.uniform(0.35, 0.65)
         lift = None
         if i >= B // 2:
-            t0 = int(rng.integers(8, T - 12))
+            t0 = int(rng.integers(8, max(9, T - 12)))
             lift = (t0, t0 + int(rng.integers(4, 10)), int(rng.integers(0, 2)))
         for t in range(T):
             lz, rz = share * Mg, (1 - share) * Mg
@@ -166,7 +166,8 @@ def test_batched_stabilizer_matches_the_restated_controllers(robot, talos_stab, 
     stab = bt.stabilizer()
     ctrl = [so.HumanoidController(ol, P) for _ in range(B)]
     q, v = np.tile(P.q0(), (B, 1)), np.zeros((B, P.nv))
-    worst = dict(refs=0.0, tau=0.0, dv=0.0, f=0.0)
+    from test_cpu_sim import active_sets_equivalent
+    worst = dict(refs=0.0, tau=0.0, dv=0.0, f=0.0, f_other_abs=0.0)
     same_sets = total = 0
     for t in range(T):
         out, used = bt.update_sensors(stab, q, v, sensors[t], refs, contact_mask=masks[t], behavior_type=btype[t], want_refs=True)
@@ -183,14 +184,21 @@ def test_batched_stabilizer_matches_the_restated_controllers(robot, talos_stab, 
             total += 1
             for k in ("tau", "dv", "f"):
                 err = np.abs(getattr(out, k)[i] - o[k][0]).max() / max(np.abs(o[k][0]).max(), 1e-9)
-                worst[k] = max(worst[k], float(err))
+                if k != "f" or same:
+                    worst[k] = max(worst[k], float(err))
+            if not same:
+                # another description of the same vertex, or an argmin tie inside eiquadprog's termination slack (tests/test_gpu_parity.py):
+                # the force split between corners may then differ by a fraction of a newton, nothing else does
+                worst["f_other_abs"] = max(worst["f_other_abs"], float(np.abs(out.f[i] - o["f"][0]).max()))
+                assert out.iters[i] == o["iters"][0] or active_sets_equivalent(P, q[i], v[i], r, o["active"][0], out.active[i], int(masks[t, i])), (t, i)
             qn[i], vn[i] = o["q_next"][0], o["v_next"][0]
         q, v = qn, vn  # closed loop on the restated controllers' state: both sides see identical inputs at every tick
-    print("stabilizer %s: %d robots x %d ticks, worst relative error refs %.2e tau %.2e dv %.2e f %.2e, identical active sets %d / %d"
-          % (robot, B, T, worst["refs"], worst["tau"], worst["dv"], worst["f"], same_sets, total))
-    assert worst["refs"] < 1e-9 and worst["tau"] < 1e-8 and worst["dv"] < 1e-8 and worst["f"] < 5e-7
+    print("stabilizer %s: %d robots x %d ticks, worst relative error refs %.2e tau %.2e dv %.2e f %.2e (identical active sets: %d / %d; the others: "
+          "max |df| %.3g N)" % (robot, B, T, worst["refs"], worst["tau"], worst["dv"], worst["f"], same_sets, total, worst["f_other_abs"]))
+    assert worst["refs"] < 1e-9 and worst["tau"] < 1e-8 and worst["dv"] < 1e-8 and worst["f"] < 5e-7 and worst["f_other_abs"] < 0.5
     assert same_sets > 0.9 * total
-    assert any(c.wreg_variant != 0 for c in ctrl)  # the ZMP distributor really ran
+    if robot == "talos":  # (the iCub parameter sets have use_zmp: false)
+        assert any(c.wreg_variant != 0 for c in ctrl)  # the ZMP distributor really ran
 
 
 @pytest.mark.gpu
