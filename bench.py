@@ -344,16 +344,268 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+MIXED = {"mixed_icub_tiago_16384": ("icub_ds_16384", "tiago_65536", 8192)}  # BASELINE config 4: 50 / 50 iCub + Tiago on one GPU
+SECONDARY = ("franka_65536", "tiago_65536", "icub_ds_16384", "mixed_icub_tiago_16384", "talos_walk_131072")
+
+
+class Part:
+    """One robot's share of a workload on this rank's GPU: its handle, synthetic states and device buffers."""
+
+    def __init__(self, iw, torch, workload, B, rank, local, dev):
+        yaml, ov, _, recipe = WORKLOADS[workload]
+        self.workload, self.yaml, self.recipe, self.B = workload, yaml, recipe, B
+        P = self.P = iw.Problem(yaml, overrides=ov)
+        bt = self.bt = iw.Batch(P, local, B)
+        self.n, self.me, self.mi, self.rows = P.qp_shape()
+        self.masks, self.beh = None, None
+        self.buckets = [(0, B, P.default_contact_mask)]
+        if recipe == "walk":
+            P.set_task_weight("momentum", 0.0)  # BEHAVIOR.customize_task_weights, etc/talos/walk.yaml:8-9
+            self.q, self.v, self.refs, self.masks, self.phase, self.beh = make_walk_workload(P, bt, B, 0xB200 + 5 + 1000 * rank, local)
+        else:
+            self.q, self.v, self.refs = make_inputs(P, B, recipe, 0xB200 + 3 + 1000 * rank)
+        if recipe == "walk_standin":
+            P.set_task_weight("momentum", 0.0)
+            self.masks = make_walk_masks(P, B, self.refs, 0xB200 + 5 + 1000 * rank)
+            self.buckets, first = [], 0
+            for m in (3, 2, 1):
+                cnt = int((self.masks == m).sum())
+                if cnt:
+                    self.buckets.append((first, cnt, m))
+                first += cnt
+        self.dq, self.dv, self.dr = (torch.from_numpy(x).to(dev) for x in (self.q, self.v, self.refs))
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.out = {"tau": torch.empty(B, P.na, **f64), "dv": torch.empty(B, P.nv, **f64), "f": torch.empty(B, max(12 * P.ncontacts, 1), **f64),
+                    "q_next": torch.empty(B, P.nq, **f64), "v_next": torch.empty(B, P.nv, **f64),
+                    "status": torch.empty(B, dtype=torch.int32, device=dev), "iters": torch.empty(B, dtype=torch.int32, device=dev)}
+        self.ptrs = {k: t.data_ptr() for k, t in self.out.items()}
+        self.esz = {"tau": 8 * P.na, "dv": 8 * P.nv, "f": 8 * max(12 * P.ncontacts, 1), "q_next": 8 * P.nq, "v_next": 8 * P.nv, "status": 4, "iters": 4}
+        self.stream = torch.cuda.Stream(device=dev)  # an explicit stream: the timing events must see the kernels
+        if self.beh is not None:
+            self.d_phase = torch.from_numpy(self.phase).to(dev)
+            self.d_maskbuf = torch.zeros(B, dtype=torch.int32, device=dev)
+            self.walk_tick = 0
+        # end-to-end arm: pinned host buffers and results
+        self.hq, self.hv, self.hr = (torch.from_numpy(x).pin_memory() for x in (self.q, self.v, self.refs))
+        self.res = iw.Results(P, B, fields=("tau", "dv", "f", "q_next", "v_next", "status"))
+        self.pinned = {}
+        for fld in ("tau", "dv", "f", "q_next", "v_next", "status"):
+            t = torch.from_numpy(getattr(self.res, fld)).pin_memory()
+            self.pinned[fld] = t
+            setattr(self.res, fld, t.numpy())
+
+    def step(self):
+        P, bt, B = self.P, self.bt, self.B
+        if self.beh is not None:
+            # closed device-side tick: behaviour -> refs + contact masks, device-side bucketing, one launch set per mask, state
+            # integrated in place (every timed step is the NEXT tick of every instance's walk)
+            bt.behavior_rollout_device(self.beh, B, self.dq.data_ptr(), self.dv.data_ptr(), self.dr.data_ptr(), self.d_phase.data_ptr(), self.walk_tick, 1,
+                                       init_refs=False, out_ptrs=self.ptrs, mask_ptr=self.d_maskbuf.data_ptr(), stream=self.stream.cuda_stream)
+            self.walk_tick += 1
+            return
+        for first, cnt, m in self.buckets:  # one shape-uniform launch set per contact-mask bucket (instances are ordered by mask)
+            bt.update_device(cnt, self.dq.data_ptr() + 8 * P.nq * first, self.dv.data_ptr() + 8 * P.nv * first, self.dr.data_ptr() + 8 * P.nref * first,
+                             P.nref, m, {k: p + self.esz[k] * first for k, p in self.ptrs.items()}, self.stream.cuda_stream)
+
+    def host_call(self):
+        self.bt.update(self.hq.numpy(), self.hv.numpy(), self.hr.numpy(), contact_mask=self.masks, out=self.res)  # synchronous
+
+    def io_bytes(self):
+        h2d = self.q.nbytes + self.v.nbytes + self.refs.nbytes
+        d2h = sum(getattr(self.res, f).nbytes for f in ("tau", "dv", "f", "q_next", "v_next", "status"))
+        return h2d, d2h
+
+
+def run_workload(ctx, workload, steps, warmup, batch=0, with_cpu=False, peak=None):
+    """One bench line (dict, on rank 0; None elsewhere) for `workload` on every rank's GPU."""
+    import torch
+    import inria_wbc_b200 as iw
+    rank, world, local, dev, dist = ctx["rank"], ctx["world"], ctx["local"], ctx["dev"], ctx["dist"]
+    if workload in MIXED:
+        a, b, each = MIXED[workload]
+        parts = [Part(iw, torch, a, batch // 2 if batch else each, rank, local, dev), Part(iw, torch, b, batch // 2 if batch else each, rank, local, dev)]
+    else:
+        parts = [Part(iw, torch, workload, batch or WORKLOADS[workload][2], rank, local, dev)]
+    B = sum(p.B for p in parts)
+    flush = ctx["flush"]
+    main = parts[0].stream
+    fork, joins = torch.cuda.Event(), [torch.cuda.Event() for _ in parts[1:]]
+
+    def step():
+        # the parts (robots) of a mixed batch run concurrently on their own streams, bracketed by the first part's stream
+        if len(parts) > 1:
+            fork.record(main)
+        parts[0].step()
+        for p, j in zip(parts[1:], joins):
+            p.stream.wait_event(fork)
+            p.step()
+            j.record(p.stream)
+            main.wait_event(j)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    launches0 = sum(p.bt.launch_count for p in parts)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    barrier()
+    for k in range(steps):
+        with torch.cuda.stream(main):
+            flush.fill_(float(k))  # L2 flush, outside the timed events
+            ev[k][0].record(main)
+            step()
+            ev[k][1].record(main)
+    barrier()
+    launches = sum(p.bt.launch_count for p in parts) - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(sum(step_ms))
+    clocks = sampler.stop() if rank == 0 else None
+    n_opt = sum(int((p.out["status"].cpu().numpy() == 0).sum()) for p in parts)
+    it_sum = [float(p.out["iters"].cpu().numpy().sum()) for p in parts]
+
+    # ---- end-to-end arm: pinned host buffers through the reference-facing call (H2D + kernels + D2H inside the timed region)
+    e2e_steps = max(3, steps)
+    for _ in range(3):
+        for p in parts:
+            p.host_call()
+    barrier()
+    e2e_lat = []
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        t1 = time.perf_counter()
+        for p in parts:
+            p.host_call()
+        e2e_lat.append(time.perf_counter() - t1)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = sum(p.io_bytes()[0] for p in parts)
+    d2h = sum(p.io_bytes()[1] for p in parts)
+
+    # ---- max over ranks
+    tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
+    agg = torch.tensor([float(n_opt)] + it_sum, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+    total_ms, e2e_s = tt.tolist()
+    agg = agg.tolist()
+    n_opt_all, it_all = agg[0], agg[1:]
+    if rank != 0:
+        return None
+    ms_per_step = total_ms / steps
+    value = B * world / (ms_per_step * 1e-3)
+    e2e_val = B * world / (e2e_s / e2e_steps)
+    kern_ms = float(np.mean(step_ms))
+    flops_step, fl_parts, io_step = 0.0, {}, 0
+    for p, its in zip(parts, it_all):
+        P = p.P
+        adds = max(its / (p.B * world) - 1.0, 0.0)
+        nj, nfr, nsc = problem_counts(P)
+        fl = algorithmic_flops(P.nv, P.na, p.n, p.me, p.mi, p.rows, adds, nj, nfr, nsc)
+        fl["source"] = "F_qp: SURVEY.md 8(d) reference-algorithm formula with the measured mean additions; F_dyn, F_asm: textbook estimate"
+        try:  # F_dyn / F_asm counted by the instrumented oracle (tools/count_flops.py, oracle/count_scalar.hpp)
+            counted = json.load(open(os.path.join(ROOT, "profiles", "flops_per_update.json"))).get(p.workload)
+            if counted:
+                fl["f_dyn"], fl["f_asm"] = counted["f_dyn"], counted["f_asm"]
+                fl["total"] = fl["f_qp"] + fl["f_dyn"] + fl["f_asm"]
+                fl["f_qp_executed_by_oracle"] = counted["f_qp_executed_by_oracle"]
+                fl["source"] = ("F_qp: SURVEY.md 8(d) reference-algorithm formula with the measured mean additions; F_dyn, F_asm: counted by the "
+                                "instrumented oracle (profiles/flops_per_update.json)")
+        except Exception:
+            pass
+        fl["mean_active_set_iterations"] = its / (p.B * world)
+        fl_parts[p.workload] = fl
+        flops_step += fl["total"] * p.B
+        io_step += (8 * (P.nq + P.nv + P.nref) + 8 * (P.na + 2 * P.nv + 12 * P.ncontacts + P.nq) + 8) * p.B
+    achieved = flops_step / (kern_ms * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload, {}).get("bytes_per_launch")
+    except Exception:
+        pass
+    p0 = parts[0]
+    line = {
+        "metric": "batched TSID control updates (QP solves) per second", "value": value, "unit": "updates/s", "n_gpus": world,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload, "controller": [p.yaml for p in parts] if len(parts) > 1 else p0.yaml, "per_gpu_batch": B,
+                   "qp": {"n": p0.n, "me": p0.me, "mi": p0.mi, "cost_rows": p0.rows} if len(parts) == 1 else
+                   {p.workload: {"n": p.n, "me": p.me, "mi": p.mi, "cost_rows": p.rows, "batch": p.B} for p in parts},
+                   "l2": "flushed (256 MB write) between timed steps", "optimal_fraction": n_opt_all / (B * world),
+                   "mean_active_set_iterations": sum(it_all) / (B * world), "p50_device_ms_per_batch": float(np.median(step_ms)),
+                   "p95_device_ms_per_batch": float(np.percentile(step_ms, 95)),
+                   "parallelism": "dp%d (independent shards, no collective)" % world,
+                   "states": ("random ticks of humanoid::walk (etc/talos/walk.yaml): a seed instance is walked on the device, instances are its "
+                              "snapshots + noise; every timed step is the next tick, references and contact masks generated on the device")
+                   if p0.beh is not None else "SURVEY.md 8(d) randomized-state recipe " + ", ".join("'%s'" % p.recipe for p in parts)},
+        "e2e": {"value": e2e_val, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
+                "p50_cycle_latency_ms": 1e3 * float(np.percentile(e2e_lat, 50)), "p95_cycle_latency_ms": 1e3 * float(np.percentile(e2e_lat, 95))},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp64", "bound_note": "FP64 FMA on CUDA cores + shared-memory bandwidth; neither hbm nor tensor bound (SURVEY.md 8(d))",
+                     "achieved": achieved, "peak": peak["measured_tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / peak["measured_tflops"] if peak["measured_tflops"] > 0 else None,
+                     "peak_source": "measured live (dependent-FMA probe, iwbc_measure_fp64_tflops); MEASURED_PEAKS.json holds no FP64 figure",
+                     "peak_probe": peak, "frac_of_clock_bound": achieved / peak["clock_bound_tflops"] if peak.get("clock_bound_tflops") else None,
+                     "flops_per_update": fl_parts[p0.workload] if len(parts) == 1 else fl_parts, "kernel_ms": kern_ms, "traffic": traffic,
+                     "hbm": {"achieved": io_step / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": io_step / (kern_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_update": io_step / B,
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+        "clocks": clocks,
+    }
+    if with_cpu and len(parts) == 1:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import problem_loader
+        Pc = problem_loader.load(p0.yaml, overrides=WORKLOADS[workload][1])  # the oracle's own reader of the same configuration
+        threads = os.cpu_count() or 1
+        ns = min(p0.B, 4096)
+        rate, done, el = oracle_rate(Pc, p0.q[:ns], p0.v[:ns], p0.refs[:ns], 10.0, threads)
+        rate1, done1, el1 = oracle_rate(Pc, p0.q[:256], p0.v[:256], p0.refs[:256], 2.0, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": "updates/s", "cores": threads, "kind": "port",
+                                "sample": "%d updates of the same workload in %.2f s on %d threads (oracle port)" % (done, el, threads),
+                                "single_thread": rate1,
+                                "reference_recorded": "0.0126 ms/cycle Franka, different unknown hardware (tests/ref_test_franka.yaml:11)"}
+    return line
+
+
+def fp64_peak(iw, local):
+    """The roofline denominator: a live dependent-FMA probe, with the clock record it was taken at and the bound from the SM count."""
+    sampler = ClockSampler(local)
+    sampler.start()
+    vals = [iw.measure_fp64_tflops(local) for _ in range(3)]
+    clk = sampler.stop()
+    import torch
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    mhz = clk.get("sm_max_mhz") or 1965.0
+    return {"measured_tflops": max(vals), "runs": vals, "clocks": clk, "sm_count": sms, "fp64_fma_lanes_per_sm": 64,
+            "clock_bound_tflops": sms * 64 * 2 * mhz * 1e6 / 1e12,
+            "how": "8 independent dependent-FMA chains per thread, 8 CTAs x 256 threads per SM, best of 4 launches, CUDA events"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + sorted(MIXED))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary BASELINE configs (Franka batch, Talos walking) appended at N = 1")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs appended to the default line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -377,208 +629,35 @@ def main():
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
     except Exception:
         pass
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-
-    yaml, ov, B, recipe = WORKLOADS[args.workload]
-    if args.batch:
-        B = args.batch
-    P = iw.Problem(yaml, overrides=ov)
-    bt = iw.Batch(P, local, B)
-    n, me, mi, rows = P.qp_shape()
-    mask = P.default_contact_mask
-    masks = None
-    beh = None
-    buckets = [(0, B, mask)]
-    if recipe == "walk":
-        P.set_task_weight("momentum", 0.0)  # BEHAVIOR.customize_task_weights, etc/talos/walk.yaml:8-9
-        q, v, refs, masks, phase, beh = make_walk_workload(P, bt, B, 0xB200 + 5 + 1000 * rank, local)
-    else:
-        q, v, refs = make_inputs(P, B, recipe, 0xB200 + 3 + 1000 * rank)
-    if recipe == "walk_standin":
-        P.set_task_weight("momentum", 0.0)
-        masks = make_walk_masks(P, B, refs, 0xB200 + 5 + 1000 * rank)
-        buckets, first = [], 0
-        for m in (3, 2, 1):
-            cnt = int((masks == m).sum())
-            if cnt:
-                buckets.append((first, cnt, m))
-            first += cnt
-
-    # ---- device-resident arm
-    dq, dv_, dr = (torch.from_numpy(x).to(dev) for x in (q, v, refs))
-    out = {"tau": torch.empty(B, P.na, dtype=torch.float64, device=dev), "dv": torch.empty(B, P.nv, dtype=torch.float64, device=dev),
-           "f": torch.empty(B, max(12 * P.ncontacts, 1), dtype=torch.float64, device=dev),
-           "q_next": torch.empty(B, P.nq, dtype=torch.float64, device=dev), "v_next": torch.empty(B, P.nv, dtype=torch.float64, device=dev),
-           "status": torch.empty(B, dtype=torch.int32, device=dev), "iters": torch.empty(B, dtype=torch.int32, device=dev)}
-    ptrs = {k: t.data_ptr() for k, t in out.items()}
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-    stream = torch.cuda.Stream(device=dev)  # an explicit stream: the events below must see the kernel
-    torch.cuda.synchronize()
-
-    esz = {"tau": 8 * P.na, "dv": 8 * P.nv, "f": 8 * max(12 * P.ncontacts, 1), "q_next": 8 * P.nq, "v_next": 8 * P.nv, "status": 4, "iters": 4}
-
-    if beh is not None:
-        d_phase = torch.from_numpy(phase).to(dev)
-        d_maskbuf = torch.zeros(B, dtype=torch.int32, device=dev)
-        walk_tick = [0]
-
-    def step():
-        if beh is not None:
-            # closed device-side tick: behaviour -> refs + contact masks, device-side bucketing, one launch set per mask, state
-            # integrated in place (every timed step is the NEXT tick of every instance's walk)
-            bt.behavior_rollout_device(beh, B, dq.data_ptr(), dv_.data_ptr(), dr.data_ptr(), d_phase.data_ptr(), walk_tick[0], 1,
-                                       init_refs=False, out_ptrs=ptrs, mask_ptr=d_maskbuf.data_ptr(), stream=stream.cuda_stream)
-            walk_tick[0] += 1
-            return
-        # one shape-uniform launch set per contact-mask bucket (instances are ordered by mask)
-        for first, cnt, m in buckets:
-            bt.update_device(cnt, dq.data_ptr() + 8 * P.nq * first, dv_.data_ptr() + 8 * P.nv * first, dr.data_ptr() + 8 * P.nref * first, P.nref, m,
-                             {k: p + esz[k] * first for k, p in ptrs.items()}, stream.cuda_stream)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    launches0 = bt.launch_count
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for k in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush.fill_(float(k))  # L2 flush, outside the timed events
-            ev[k][0].record(stream)
-            step()
-            ev[k][1].record(stream)
-    barrier()
-    launches = bt.launch_count - launches0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(sum(step_ms))
-    clocks = sampler.stop() if rank == 0 else None
-    status = out["status"].cpu().numpy()
-    iters = out["iters"].cpu().numpy()
-    n_opt = int((status == 0).sum())
-
-    # ---- end-to-end arm: pinned host buffers through the reference-facing call
-    hq, hv, hr = (torch.from_numpy(x).pin_memory() for x in (q, v, refs))
-    res = iw.Results(P, B, fields=("tau", "dv", "f", "q_next", "v_next", "status"))
-    pinned = {}
-    for fld in ("tau", "dv", "f", "q_next", "v_next", "status"):
-        t = torch.from_numpy(getattr(res, fld)).pin_memory()
-        pinned[fld] = t
-        setattr(res, fld, t.numpy())
-    e2e_steps = max(3, args.steps)
-    for _ in range(3):
-        bt.update(hq.numpy(), hv.numpy(), hr.numpy(), contact_mask=masks, out=res)
-    barrier()
-    e2e_lat = []
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        t1 = time.perf_counter()
-        bt.update(hq.numpy(), hv.numpy(), hr.numpy(), contact_mask=masks, out=res)  # synchronous: results are in host memory on return
-        e2e_lat.append(time.perf_counter() - t1)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    h2d = q.nbytes + v.nbytes + refs.nbytes
-    d2h = sum(getattr(res, f).nbytes for f in ("tau", "dv", "f", "q_next", "v_next", "status"))
-
-    # ---- max over ranks
-    tt = torch.tensor([total_ms, e2e_s], dtype=torch.float64, device=dev)
-    agg = torch.tensor([float(n_opt), float(iters.sum())], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    total_ms, e2e_s = tt.tolist()
-    n_opt_all, iters_all = agg.tolist()
-
-    if rank == 0:
-        ms_per_step = total_ms / args.steps
-        value = B * world / (ms_per_step * 1e-3)
-        e2e_val = B * world / (e2e_s / e2e_steps)
-        adds = max(iters_all / (B * world) - 1.0, 0.0)
-        nj, nfr, nsc = problem_counts(P)
-        fl = algorithmic_flops(P.nv, P.na, n, me, mi, rows, adds, nj, nfr, nsc)
-        fl["source"] = "F_qp: SURVEY.md 8(d) reference-algorithm formula with the measured mean additions; F_dyn, F_asm: textbook estimate"
-        try:  # F_dyn / F_asm counted by the instrumented oracle (tools/count_flops.py, oracle/count_scalar.hpp)
-            counted = json.load(open(os.path.join(ROOT, "profiles", "flops_per_update.json"))).get(args.workload)
-            if counted:
-                fl["f_dyn"], fl["f_asm"] = counted["f_dyn"], counted["f_asm"]
-                fl["total"] = fl["f_qp"] + fl["f_dyn"] + fl["f_asm"]
-                fl["f_qp_executed_by_oracle"] = counted["f_qp_executed_by_oracle"]
-                fl["source"] = ("F_qp: SURVEY.md 8(d) reference-algorithm formula with the measured mean additions; F_dyn, F_asm: counted by the "
-                                "instrumented oracle (profiles/flops_per_update.json)")
-        except Exception:
-            pass
-        kern_ms = float(np.mean(step_ms))
-        peak = iw.measure_fp64_tflops(local)
-        achieved = fl["total"] * B / (kern_ms * 1e-3) / 1e12
-        io_bytes = 8 * (P.nq + P.nv + P.nref) + 8 * (P.na + 2 * P.nv + 12 * P.ncontacts + P.nq) + 8
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get("bytes_per_launch")
-        except Exception:
-            pass
-        line = {
-            "metric": "batched TSID control updates (QP solves) per second", "value": value, "unit": "updates/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "controller": yaml, "per_gpu_batch": B, "qp": {"n": n, "me": me, "mi": mi, "cost_rows": rows},
-                       "l2": "flushed (256 MB write) between timed steps", "optimal_fraction": n_opt_all / (B * world),
-                       "mean_active_set_iterations": iters_all / (B * world), "p50_device_ms_per_batch": float(np.median(step_ms)), "p95_device_ms_per_batch": float(np.percentile(step_ms, 95)),
-                       "parallelism": "dp%d (independent shards, no collective)" % world,
-                       "states": ("random ticks of humanoid::walk (etc/talos/walk.yaml): a seed instance is walked on the device, instances are its "
-                                  "snapshots + noise; every timed step is the next tick, references and contact masks generated on the device")
-                       if beh is not None else "SURVEY.md 8(d) randomized-state recipe '%s'" % recipe},
-            "e2e": {"value": e2e_val, "unit": "updates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
-                    "p50_cycle_latency_ms": 1e3 * float(np.percentile(e2e_lat, 50)), "p95_cycle_latency_ms": 1e3 * float(np.percentile(e2e_lat, 95))},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "bound_note": "FP64 FMA on CUDA cores + shared-memory bandwidth; neither hbm nor tensor bound (SURVEY.md 8(d))", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak > 0 else None, "peak_source": "measured live (dependent-FMA probe, iwbc_measure_fp64_tflops)",
-                         "flops_per_update": fl, "kernel_ms": kern_ms, "traffic": traffic,
-                         "hbm": {"achieved": io_bytes * B / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": io_bytes * B / (kern_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_update": io_bytes,
-                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
-            "clocks": clocks,
-        }
-        if world == 1 and not args.no_cpu:
-            threads = os.cpu_count() or 1
-            ns = min(B, 4096)
-            rate, done, el = oracle_rate(P, q[:ns], v[:ns], refs[:ns], 10.0, threads)
-            rate1, done1, el1 = oracle_rate(P, q[:256], v[:256], refs[:256], 2.0, 1)
-            line["cpu_baseline"] = {"value": rate, "unit": "updates/s", "cores": threads, "kind": "port",
-                                    "sample": "%d updates of the same workload in %.2f s on %d threads (oracle port)" % (done, el, threads),
-                                    "single_thread": rate1,
-                                    "reference_recorded": "0.0126 ms/cycle Franka, different unknown hardware (tests/ref_test_franka.yaml:11)"}
-        if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_secondary and not args.batch:
-            # BASELINE.json's other single-GPU configs, measured by the same program right after (same GPU, sequentially): configs[1]
-            # (Franka batch 65 536) and one GPU's share of configs[4] (Talos walking, 131 072 states)
-            line["secondary"] = {}
-            for wl in ("franka_65536", "talos_walk_131072"):
-                try:
-                    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wl, "--steps", "10", "--warmup", "3", "--no-cpu",
-                                          "--no-secondary"], capture_output=True, text=True, timeout=240)
-                    d = json.loads(out.stdout.strip().splitlines()[-1])
-                    line["secondary"][wl] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "e2e": d["e2e"]["value"],
-                                             "p50_cycle_latency_ms": d["e2e"].get("p50_cycle_latency_ms"), "roofline_frac": d["roofline"]["frac"],
-                                             "gpu_launches": d["gpu_launches"], "per_gpu_batch": d["config"]["per_gpu_batch"]}
-                except Exception as e:  # the headline line must not depend on it
-                    line["secondary"][wl] = {"error": str(e)[:200]}
+    ctx = {"rank": rank, "world": world, "local": local, "dev": dev, "dist": dist,
+           "flush": torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)}  # > 126 MB L2
+    peak = fp64_peak(iw, local)
+    line = run_workload(ctx, args.workload, args.steps, args.warmup, batch=args.batch, with_cpu=(world == 1 and not args.no_cpu), peak=peak)
+    if args.workload == DEFAULT_WORKLOAD and not args.no_secondary and not args.batch:
+        # BASELINE.json's other configurations, measured by the same program right after on the same GPUs (every rank its own shard, at
+        # every N: configs[4] = Talos walking is 131 072 states per GPU, i.e. 1 M over 8): configs[1] Franka batch, configs[3] iCub /
+        # Tiago alone and as ONE mixed step, configs[4] walking
+        sec = {}
+        for wl in SECONDARY:
+            try:
+                d = run_workload(ctx, wl, 10, 3, peak=peak)
+                if d is not None:
+                    sec[wl] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "e2e": d["e2e"]["value"],
+                               "p50_cycle_latency_ms": d["e2e"].get("p50_cycle_latency_ms"), "roofline_frac": d["roofline"]["frac"],
+                               "gpu_launches": d["gpu_launches"], "per_gpu_batch": d["config"]["per_gpu_batch"], "n_gpus": d["n_gpus"],
+                               "optimal_fraction": d["config"]["optimal_fraction"]}
+            except Exception as e:  # the headline line must not depend on it
+                if rank == 0:
+                    sec[wl] = {"error": str(e)[:200]}
+            torch.cuda.empty_cache()
+        if line is not None:
+            line["secondary"] = sec
+    if line is not None:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -278,6 +278,24 @@ int iwbc_batch_update_sensors_device(iwbc_batch* b, iwbc_stabilizer* s, int B, c
 int iwbc_batch_update_sensors(iwbc_batch* b, iwbc_stabilizer* s, int B, const double* q, const double* v, const double* refs, long refs_stride,
     const unsigned* contact_mask, const int* behavior_type, int behavior_type_all, const double* sensors, const iwbc_results_t* out, double* refs_used);
 
+/* ------------------------------------------------------------------ one call, several GPUs (SURVEY.md 7 "shard/gather", 8(e))
+ * The batched form of `Controller::update` for a batch that spans the GPUs of one node: contiguous shards
+ * [g B / G, (g + 1) B / G), one iwbc_batch and one worker thread per device, every shard read from / written into its own slice
+ * of the caller's HOST arrays (the "host gather of torques and accelerations" of the north star); no collective.  Allocate the
+ * arrays with iwbc_host_alloc (pinned, portable) for the copies to run at PCIe speed on all devices at once.
+ *   devices: ndev device ordinals (NULL: 0 .. ndev-1; an ordinal may repeat: several shards on one GPU) */
+typedef struct iwbc_multi iwbc_multi;
+iwbc_multi* iwbc_multi_create(const iwbc_problem* p, int ndev, const int* devices, int max_batch_total);
+void iwbc_multi_free(iwbc_multi* m);
+int iwbc_multi_device_count(const iwbc_multi* m);
+int iwbc_multi_update(iwbc_multi* m, int B, const double* q, const double* v, const double* refs, long refs_stride,
+    const unsigned* contact_mask, const iwbc_results_t* out);
+long iwbc_multi_launch_count(const iwbc_multi* m);
+/* shard g of nshards of a batch of B: first instance and count (host only) */
+int iwbc_shard_range(int B, int nshards, int g, int* first, int* count);
+void* iwbc_host_alloc(size_t bytes);
+void iwbc_host_free(void* p);
+
 /* ------------------------------------------------------------------ solver interface
  * Batched form of `tsid::solvers::SolverHQPBase::solve` for the EiquadprogFast backend
  * (src/controllers/pos_tracker.cpp:96,102; src/controllers/controller.cpp:247): B dense QPs of one

@@ -90,6 +90,14 @@ def lib():
         "iwbc_stabilizer_reset": (ci, [vp, vp]),
         "iwbc_batch_update_sensors_device": (ci, [vp, vp, ci, vp, vp, vp, cl, vp, vp, ci, vp, C.POINTER(_Results), vp, vp]),
         "iwbc_batch_update_sensors": (ci, [vp, vp, ci, vp, vp, vp, cl, vp, vp, ci, vp, C.POINTER(_Results), vp]),
+        "iwbc_multi_create": (vp, [vp, ci, vp, ci]),
+        "iwbc_multi_free": (None, [vp]),
+        "iwbc_multi_device_count": (ci, [vp]),
+        "iwbc_multi_update": (ci, [vp, ci, vp, vp, vp, cl, vp, C.POINTER(_Results)]),
+        "iwbc_multi_launch_count": (cl, [vp]),
+        "iwbc_shard_range": (ci, [ci, ci, ci, pi, pi]),
+        "iwbc_host_alloc": (vp, [C.c_size_t]),
+        "iwbc_host_free": (None, [vp]),
         "iwbc_behavior_load": (vp, [vp, cp, cp]),
         "iwbc_behavior_free": (None, [vp]),
         "iwbc_behavior_info": (ci, [vp, pi, pi, pi, pi, vp]),
@@ -498,6 +506,51 @@ class Batch:
 
     def kernel_ms(self, reset=False):
         return lib().iwbc_batch_kernel_ms(self._h, 1 if reset else 0)
+
+
+class MultiBatch:
+    """One host call for a batch sharded over several GPUs of the node (contiguous shards, one worker thread per device)."""
+
+    def __init__(self, problem, devices, max_batch_total):
+        self.problem = problem
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        self._h = lib().iwbc_multi_create(problem.handle, len(devs), devs.ctypes.data, max_batch_total)
+        if not self._h:
+            raise IwbcError(_err(lib()))
+        self.ndev = len(devs)
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.iwbc_multi_free(self._h)
+            self._h = None
+
+    def update(self, q, v, refs=None, contact_mask=None, out=None, fields=Results.FIELDS):
+        P = self.problem
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, P.nq)
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1, P.nv)
+        B = q.shape[0]
+        refs = P.default_refs() if refs is None else np.ascontiguousarray(refs, dtype=np.float64)
+        stride = 0 if refs.ndim == 1 else P.nref
+        cm = None if contact_mask is None else np.ascontiguousarray(np.broadcast_to(np.asarray(contact_mask, dtype=np.uint32), (B,)))
+        if out is None:
+            out = Results(P, B, fields)
+        st = out.as_struct()
+        rc = lib().iwbc_multi_update(self._h, B, q.ctypes.data, v.ctypes.data, refs.ctypes.data, stride, _ptr(cm), C.byref(st))
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+        return out
+
+    @property
+    def launch_count(self):
+        return lib().iwbc_multi_launch_count(self._h)
+
+
+def shard_range(total, rank, world):
+    """Contiguous instance range [lo, hi) of shard `rank` of `world` (iwbc_shard_range: [g B / G, (g + 1) B / G))."""
+    a, n = C.c_int(), C.c_int()
+    if lib().iwbc_shard_range(total, world, rank, C.byref(a), C.byref(n)) != 0:
+        raise IwbcError("bad shard")
+    return a.value, a.value + n.value
 
 
 def measure_fp64_tflops(device=0):

@@ -24,8 +24,8 @@ namespace dev {
     // One group of G threads per instance, IPC instances per CTA, persistent over the batch.
     // (the warp-per-instance form is occupancy-bound by registers: three CTAs per SM need <= 168; without the bound ptxas drifts to
     // 216 and Franka drops from 38 M to 27 M updates/s)
-    template <int G, int IPC>
-    __global__ void __launch_bounds__(G* IPC, (G <= 32 && G * IPC <= 128 ? 3 : 1)) k_cycle(const iwbc_problem_t* __restrict__ gP, const __grid_constant__ Shape S, IO io)
+    template <int G, int IPC, int MINB = (G <= 32 && G * IPC <= 128 ? 3 : 1)>
+    __global__ void __launch_bounds__(G* IPC, MINB) k_cycle(const iwbc_problem_t* __restrict__ gP, const __grid_constant__ Shape S, IO io)
     {
         extern __shared__ double smem[];
         const int grp = threadIdx.x / G;
@@ -190,10 +190,10 @@ int launch_fast(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
     return iwbc_launch_fast_0_0(b, io, st);
 }
 
-template <int G, int IPC>
+template <int G, int IPC, int MINB = (G <= 32 && G * IPC <= 128 ? 3 : 1)>
 int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
 {
-    auto kern = dev::k_cycle<G, IPC>;
+    auto kern = dev::k_cycle<G, IPC, MINB>;
     static size_t smem_set[16];
     int rc0 = iwbc_raise_smem_limit((const void*)kern, b->device, b->smem_bytes, smem_set);
     if (rc0)
@@ -214,6 +214,8 @@ int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
         return launch_fast(b, io, st);
     if (io.in_list) // a behaviour's bucket: the generic kernel walks it as its instance list
         iop.list = io.in_list, iop.list_count = io.in_count;
+    if (b->profiling)
+        iop.prof = b->d_prof;
     if (!io.dbg_M && !io.dbg_cycles) {
         iop.work = b->d_slow_count + 2 * b->slot + 1;
         CUDA_TRY(cudaMemsetAsync(iop.work, 0, sizeof(int), st));
@@ -412,8 +414,16 @@ int iwbc_run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t
     rc = upload_constants(b, st);
     if (rc)
         return rc;
-    if (b->G == 32)
+    if (b->G == 32) {
+        static const int minb = [] { const char* e = std::getenv("IWBC_ARM_MINB"); return e ? std::atoi(e) : 3; }(); // tuning aid
+        if (minb == 4)
+            return launch_cycle<32, 4, 4>(b, io, st);
+        if (minb == 5)
+            return launch_cycle<32, 4, 5>(b, io, st);
+        if (minb == 6)
+            return launch_cycle<32, 4, 6>(b, io, st);
         return launch_cycle<32, 4>(b, io, st);
+    }
     if (b->G == 16)
         return b->IPC == 8 ? launch_cycle<16, 8>(b, io, st) : launch_cycle<16, 12>(b, io, st);
     if (b->G == 8)

@@ -302,11 +302,11 @@ namespace dev {
         F.o_Jft = take(P.ncontacts * 6 * nv);
         F.o_cb = take(12 * P.ncontacts);
         F.o_nle = take(nv);
-        F.o_lb = take(nv);
-        F.o_ub = take(nv);
+        F.o_lb = take(na); // (acceleration bounds and torques exist for the actuated joints only; every byte counts here: Talos double
+        F.o_ub = take(na); //  support sits 100 B under the two-CTAs-per-SM limit of the continuation kernel)
         F.o_x = take(n + 2);
         F.o_sc = take(48);
-        F.o_fr = take(8 * IWBC_MAXC); // per active-contact slot: the instance's f_ref (6), its weight-vector index, pad
+        F.o_fr = take(8 * F.nca); // per active-contact slot: the instance's f_ref (6), its weight-vector index, pad
         F.o_int = take((nv + 16) / 2 + 1);
         // arrays that are dead once J has been formed: the iteration vectors of the continuation alias them
         const int dead0 = o;
@@ -320,7 +320,7 @@ namespace dev {
         F.o_tv = take(3 * (F.me + 2) + 4);
         F.o_hd = take(nv);
         F.o_il = take(nv);
-        F.o_tau = take(nv);
+        F.o_tau = take(na);
         F.total = o;
         // continuation: R aliases the augmented matrix (dead after J), the vectors alias the dead block
         const int rsz = n * (n + 1) / 2;

@@ -3,11 +3,7 @@ no collective on the data path.  torch.distributed is only used
 for the max-over-ranks / sum-over-ranks of the timing and counters."""
 
 
-def shard_range(total, rank, world):
-    """Contiguous instance range [lo, hi) of `rank`: [g*B/G, (g+1)*B/G)."""
-    lo = (total * rank) // world
-    hi = (total * (rank + 1)) // world
-    return lo, hi
+from ._lib import shard_range  # noqa: F401  (the library's own shard arithmetic: iwbc_shard_range, the one iwbc_multi_update uses)
 
 
 def reduce_timing(dist, device, step_ms_total, counts):

@@ -167,3 +167,19 @@ extern "C" int sim_qp_solve(int n, int me, int mi, const double* H, const double
     }
     return 0;
 }
+
+// shared-memory footprints (bytes) of the fast pass / active-set continuation / generic kernel for a contact mask (T = 128 plan)
+extern "C" int sim_smem_bytes(const iwbc_problem_t* P, unsigned mask, long* out3)
+{
+    dev::Sizes z;
+    static dev::Shape S;
+    static dev::FShape F;
+    static dev::FPlan plan;
+    prepare(*P, mask, S, z);
+    out3[2] = (long)S.total * 8;
+    out3[0] = out3[1] = 0;
+    if (!dev::build_fast_plan(*P, S, 128, F, plan))
+        return -1;
+    out3[0] = (long)F.total * 8, out3[1] = (long)F.s_total * 8;
+    return 0;
+}

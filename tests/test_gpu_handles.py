@@ -61,3 +61,20 @@ def test_two_handles_driven_from_two_host_threads(icub, talos_fast, talos, tiago
             for a, b in zip(want, rep):
                 for k in ("tau", "dv", "f", "q_next", "v_next", "status", "iters", "active"):
                     assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_one_call_over_several_shards(talos, franka):
+    """iwbc_multi_update: one host call, contiguous shards, one worker thread per shard.  On a one-GPU box the shards sit on the same
+    device (ordinal repeated): results must be bit-identical to the single-handle call, in instance order, for mixed contact masks too."""
+    for P, B in ((talos, 3001), (franka, 5000)):
+        q, v = random_states(P, B, 17, base=P.nv > P.na)
+        mask = None if P.ncontacts == 0 else np.random.default_rng(2).choice(np.array([3, 1, 2], dtype=np.uint32), B)
+        one = iw.Batch(P, 0, B).update(q, v, contact_mask=mask)
+        for ndev in (1, 3):
+            mb = iw.MultiBatch(P, [0] * ndev, B)
+            got = mb.update(q, v, contact_mask=mask)
+            for k in ("tau", "dv", "f", "q_next", "v_next", "status", "iters", "active"):
+                assert np.array_equal(getattr(got, k), getattr(one, k)), (k, ndev)
+            assert mb.launch_count > 0
+        with pytest.raises(iw.IwbcError, match="capacity"):
+            iw.MultiBatch(P, [0, 0], 64).update(q, v)
