@@ -20,6 +20,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 extern "C" {
@@ -53,6 +54,8 @@ namespace inria_wbc {
         // HQP status codes surfaced at src/controllers/controller.cpp:287-304
         enum Status { UNKNOWN = -1, OPTIMAL = 0, INFEASIBLE = 1, UNBOUNDED = 2, MAX_ITER_REACHED = 3, ERROR = 4 };
 
+        // Stands in for the `YAML::Node` the reference hands to Factory::create (yaml-cpp is not a dependency of this library): the file
+        // the node was loaded from plus the keys the caller mutated afterwards.
         struct Config {
             std::string controller_yaml;      // what the reference loads with YAML::LoadFile before Factory::create
             std::string robots_path;          // where CONTROLLER.urdf is resolved (utheque's role, controller.cpp:71-79)
@@ -60,7 +63,13 @@ namespace inria_wbc {
             std::string overrides_yaml;       // CONTROLLER keys mutated after loading, as tests/test_determinism.cpp:66-70 does
             int batch = 1;
             int device = 0;
+            bool throw_on_failure = false;    // true: update() throws like Controller::_solve (controller.cpp:284-308) when a robot's QP is not OPTIMAL
         };
+
+        // controller.hpp:39 with instance-major matrices: key -> [batch][dim] row-major.  Keys read here: "positions" (na),
+        // "joint_velocities" (na), "floating_base_position" (7: xyz + quaternion xyzw), "floating_base_velocity" (6), and for a
+        // controller whose stabilizer is activated "lf_force", "rf_force", "lf_torque", "rf_torque", "imu_vel" (3 each).
+        using SensorData = std::unordered_map<std::string, std::vector<double>>;
 
         class BatchController {
         public:
@@ -89,11 +98,15 @@ namespace inria_wbc {
                 forces_.assign((size_t)B_ * 12 * (nc_ > 0 ? nc_ : 1), 0.0), momentum_.assign((size_t)B_ * 3, 0.0);
                 status_.assign(B_, UNKNOWN), iters_.assign(B_, 0);
                 qn_.resize(q_tsid_.size()), vn_.resize(v_tsid_.size());
+                btype_.assign(B_, IWBC_BT_FIXED_BASE); // humanoid_pos_tracker.cpp:39
+                closed_loop_ = iwbc_problem_closed_loop(prob_) != 0;
             }
             BatchController(const BatchController&) = delete; // controller.hpp:50-51
             BatchController& operator=(const BatchController&) = delete;
             virtual ~BatchController()
             {
+                if (stab_)
+                    iwbc_stabilizer_free(stab_);
                 if (batch_)
                     iwbc_batch_free(batch_);
                 if (prob_)
@@ -110,7 +123,66 @@ namespace inria_wbc {
             }
             // Controller::update() open loop (controller.cpp:163-170): the controller's own integrated state
             virtual void update() { solve(q_tsid_.data(), v_tsid_.data()); }
+            // Controller::update(const SensorData&) (controller.hpp:57, controller.cpp:161-206; HumanoidPosTracker::update,
+            // humanoid_pos_tracker.cpp:134-302): closed loop reads the state from the sensors, open loop the controller's own; an
+            // activated stabilizer needs the F/T and IMU keys ("the stabilizer needs the LF force", :180-184)
+            virtual void update(const SensorData& sensors)
+            {
+                const iwbc_problem_t* P = iwbc_problem_data(prob_);
+                const double *q = q_tsid_.data(), *dq = v_tsid_.data();
+                if (closed_loop_) {
+                    const auto& pos = need(sensors, "positions", "we need the joint positions in closed loop mode!");
+                    const auto& vel = need(sensors, "joint_velocities", "we need the joint velocities in closed loop mode!");
+                    IWBC_B200_ASSERT(pos.size() == (size_t)B_ * na_, "Joint positions do not have the correct size");
+                    IWBC_B200_ASSERT(vel.size() == (size_t)B_ * na_, "Joint velocities do not have the correct size");
+                    qs_.resize((size_t)B_ * nq_), vs_.resize((size_t)B_ * nv_);
+                    const std::vector<double>*fbp = nullptr, *fbv = nullptr;
+                    if (nv_ > na_) {
+                        fbp = &need(sensors, "floating_base_position", "we need the floating base position in closed loop mode!");
+                        fbv = &need(sensors, "floating_base_velocity", "we need the floating base velocity in closed loop mode!");
+                        IWBC_B200_ASSERT(fbp->size() == (size_t)B_ * 7 && fbv->size() == (size_t)B_ * 6, "floating base sensors do not have the correct size");
+                    }
+                    for (int i = 0; i < B_; ++i) {
+                        double* qi = &qs_[(size_t)i * nq_];
+                        double* vi = &vs_[(size_t)i * nv_];
+                        if (fbp) {
+                            std::copy(fbp->begin() + 7 * i, fbp->begin() + 7 * i + 7, qi);
+                            std::copy(fbv->begin() + 6 * i, fbv->begin() + 6 * i + 6, vi);
+                        }
+                        std::copy(pos.begin() + (size_t)i * na_, pos.begin() + (size_t)(i + 1) * na_, qi + (nq_ - na_));
+                        std::copy(vel.begin() + (size_t)i * na_, vel.begin() + (size_t)(i + 1) * na_, vi + (nv_ - na_));
+                    }
+                    q = qs_.data(), dq = vs_.data();
+                }
+                if (P->stabilizer_activated) {
+                    const char* keys[5] = {"lf_force", "rf_force", "lf_torque", "rf_torque", "imu_vel"};
+                    const char* msgs[5] = {"the stabilizer needs the LF force", "the stabilizer needs the RF force", "the stabilizer needs the LF torque",
+                        "the stabilizer needs the RF torque", "the stabilizer imu needs angular velocity"};
+                    sens_.resize((size_t)B_ * 15);
+                    for (int k = 0; k < 5; ++k) {
+                        const auto& sv = need(sensors, keys[k], msgs[k]);
+                        IWBC_B200_ASSERT(sv.size() == (size_t)B_ * 3, std::string(keys[k]) + " needs batch * 3 entries");
+                        for (int i = 0; i < B_; ++i)
+                            std::copy(sv.begin() + 3 * i, sv.begin() + 3 * i + 3, sens_.begin() + (size_t)i * 15 + 3 * k);
+                    }
+                    solve(q, dq, sens_.data());
+                }
+                else
+                    solve(q, dq);
+            }
+            // Controller::set_behavior_type (controller.cpp:436-443): selects the stabilizer parameter set (and filter windows) of a robot
+            void set_behavior_type(int i, int behavior_type)
+            {
+                IWBC_B200_ASSERT(behavior_type >= IWBC_BT_FIXED_BASE && behavior_type <= IWBC_BT_DOUBLE_SUPPORT,
+                    "behavior type is either behavior_types::FIXED_BASE , behavior_types::SINGLE_SUPPORT or behavior_types::DOUBLE_SUPPORT ");
+                btype_.at(i) = behavior_type;
+            }
 
+            // filter_mimics = true forms of the getters (controller.hpp:117-121, controller.cpp:372-400): the entries of non_mimic_indexes()
+            std::vector<double> q(bool filter_mimics) const { return filter_mimics ? slice(q_, nv_) : q_; }
+            std::vector<double> dq(bool filter_mimics) const { return filter_mimics ? slice(v_tsid_, nv_) : v_tsid_; }
+            std::vector<double> ddq(bool filter_mimics) const { return filter_mimics ? slice(a_tsid_, nv_) : a_tsid_; }
+            // (tau_ of the reference carries six leading zeros for a floating base: controller.cpp:268,275; here [B][na])
             // results, instance-major (controller.hpp:117-122, controller.cpp:250-282)
             const std::vector<double>& tau() const { return tau_; }             // [B][na]
             const std::vector<double>& ddq() const { return a_tsid_; }          // [B][nv]
@@ -209,25 +281,61 @@ namespace inria_wbc {
                         throw IWBC_B200_EXCEPTION(std::string("cannot create the GPU batch: ") + iwbc_last_error());
                 }
             }
-            void solve(const double* q, const double* dq)
+            void solve(const double* q, const double* dq, const double* sensors15 = nullptr)
             {
-                if (!batch_) {
-                    batch_ = iwbc_batch_create(prob_, config_.device, B_);
-                    if (!batch_)
-                        throw IWBC_B200_EXCEPTION(std::string("cannot create the GPU batch: ") + iwbc_last_error());
-                }
+                ensure_batch();
                 iwbc_results_t out = {tau_.data(), a_tsid_.data(), forces_.data(), qn_.data(), vn_.data(), q_.data(), momentum_.data(), status_.data(),
                     iters_.data(), nullptr};
-                if (iwbc_batch_update(batch_, B_, q, dq, refs_.data(), nref_, mask_.data(), &out) != IWBC_OK)
+                int rc;
+                if (sensors15) {
+                    if (!stab_) {
+                        stab_ = iwbc_stabilizer_create(batch_);
+                        if (!stab_)
+                            throw IWBC_B200_EXCEPTION(std::string("cannot create the stabilizer state: ") + iwbc_last_error());
+                    }
+                    rc = iwbc_batch_update_sensors(batch_, stab_, B_, q, dq, refs_.data(), nref_, mask_.data(), btype_.data(), 0, sensors15, &out, nullptr);
+                }
+                else
+                    rc = iwbc_batch_update(batch_, B_, q, dq, refs_.data(), nref_, mask_.data(), &out);
+                if (rc != IWBC_OK)
                     throw IWBC_B200_EXCEPTION(std::string("update failed: ") + iwbc_last_error());
+                if (config_.throw_on_failure)
+                    for (int i = 0; i < B_; ++i)
+                        if (status_[i] != OPTIMAL) { // the reference's message (controller.cpp:285-307), with the robot's index
+                            static const char* what[] = {" => Unknown", "", " => Infeasible ", " => Unbounded ", " => Max iter reached ", " => Error "};
+                            const int s = status_[i];
+                            throw IWBC_B200_EXCEPTION("Controller failed, can't solve problem. Status : " + std::to_string(s)
+                                + (s >= -1 && s <= 4 ? what[s + 1] : " => Uknown status") + " (t=" + std::to_string(t_) + ", robot " + std::to_string(i) + ")");
+                        }
                 q_tsid_.swap(qn_);
                 v_tsid_.swap(vn_);
                 t_ += dt_;
+            }
+            static const std::vector<double>& need(const SensorData& s, const char* key, const char* msg)
+            {
+                auto it = s.find(key);
+                if (it == s.end())
+                    throw IWBC_B200_EXCEPTION(msg);
+                return it->second;
+            }
+            std::vector<double> slice(const std::vector<double>& full, int width) const
+            {
+                const std::vector<int> idx = non_mimic_indexes();
+                std::vector<double> out;
+                out.reserve((size_t)B_ * idx.size());
+                for (int i = 0; i < B_; ++i)
+                    for (int k : idx)
+                        out.push_back(full[(size_t)i * width + k]);
+                return out;
             }
 
             Config config_;
             iwbc_problem* prob_ = nullptr;
             iwbc_batch* batch_ = nullptr;
+            iwbc_stabilizer* stab_ = nullptr;
+            bool closed_loop_ = false;
+            std::vector<double> qs_, vs_, sens_;
+            std::vector<int> btype_;
             int B_ = 0, nq_ = 0, nv_ = 0, na_ = 0, nc_ = 0, nref_ = 0;
             double t_ = 0.0, dt_ = 0.0;
             std::vector<double> q_tsid_, v_tsid_, a_tsid_, tau_, q_, forces_, momentum_, refs_, qn_, vn_;
@@ -335,6 +443,14 @@ namespace inria_wbc {
                 return f;
             }
             void register_creator(const std::string& name, creator_t c) { map_[name] = c; }
+            // AutoRegister (factory.hpp:66-76): `static Register<MyController> __my("my-controller");` in the plugin's translation unit
+            template <class T>
+            struct AutoRegister {
+                explicit AutoRegister(const std::string& name)
+                {
+                    Factory::instance().register_creator(name, [](const Config& c) { return std::static_pointer_cast<BatchController>(std::make_shared<T>(c)); });
+                }
+            };
             std::shared_ptr<BatchController> create(const std::string& name, const Config& c) const
             {
                 auto it = map_.find(name);
@@ -355,6 +471,8 @@ namespace inria_wbc {
             }
             std::map<std::string, creator_t> map_;
         };
+        template <class T>
+        using Register = Factory::AutoRegister<T>; // controller.hpp:236-237
     } // namespace controllers
 
     namespace behaviors {

@@ -74,6 +74,8 @@ int iwbc_problem_contact_index(const iwbc_problem* p, const char* contact);
 /* names: kind 0 = actuated dofs (Controller::controllable_dofs), 1 = tasks, 2 = contacts, 3 = mimic dofs.
  * Returns the count; name i is copied to buf (if buf != NULL). */
 int iwbc_problem_name(const iwbc_problem* p, int kind, int i, char* buf, int buflen);
+/* CONTROLLER.closed_loop (src/controllers/controller.cpp:86): 1 when the controller expects the state from the sensors */
+int iwbc_problem_closed_loop(const iwbc_problem* p);
 /* reference configuration q0 (nq doubles, pinocchio layout, quaternion normalised: pos_tracker.cpp:62-77) */
 int iwbc_problem_q0(const iwbc_problem* p, double* out);
 

@@ -59,6 +59,7 @@ def lib():
         "iwbc_problem_contact_index": (ci, [vp, cp]),
         "iwbc_problem_name": (ci, [vp, ci, ci, cp, ci]),
         "iwbc_problem_q0": (ci, [vp, vp]),
+        "iwbc_problem_closed_loop": (ci, [vp]),
         "iwbc_batch_create": (vp, [vp, ci, ci]),
         "iwbc_batch_free": (None, [vp]),
         "iwbc_batch_update": (ci, [vp, ci, vp, vp, vp, cl, vp, C.POINTER(_Results)]),

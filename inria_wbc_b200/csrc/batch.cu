@@ -244,12 +244,8 @@ void choose_group(const iwbc_problem_t& P, int n, int& G, int& IPC)
     if (n <= 32 && P.nj * 16 <= 8 * 32) {
         G = 32;
         IPC = 4;
-        // IWBC_ARM_SHAPE="G,IPC": sub-warp groups for the small arms (tuning aid; instantiated shapes only)
-        if (const char* e = std::getenv("IWBC_ARM_SHAPE")) {
-            int g = 0, ipc = 0;
-            if (std::sscanf(e, "%d,%d", &g, &ipc) == 2 && ((g == 16 && (ipc == 8 || ipc == 12)) || (g == 8 && (ipc == 16 || ipc == 24)) || (g == 32 && ipc == 4)))
-                G = g, IPC = ipc;
-        }
+        // (sub-warp groups -- 16 or 8 lanes per instance, 8 .. 24 instances per CTA -- were measured in round 2 with this generic code:
+        // Franka 44.6 M/s at (16, 8) against 39.8 M/s, every other shape and every Tiago shape slower: profiles/r02_arm_shapes.md)
     }
     else if (n <= 64 && P.nj * 16 <= 8 * 64) {
         G = 64;
@@ -415,19 +411,15 @@ int iwbc_run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t
     if (rc)
         return rc;
     if (b->G == 32) {
-        static const int minb = [] { const char* e = std::getenv("IWBC_ARM_MINB"); return e ? std::atoi(e) : 3; }(); // tuning aid
-        if (minb == 4)
+        // The warp-per-instance kernel is latency bound (dependent shared-memory load -> FP64 chains): resident warps are what it
+        // needs.  Four CTAs per SM (<= 128 registers, 16 warps) when the instance's shared memory allows it (Franka: 36 kB per CTA),
+        // three otherwise (Tiago: 60 kB).  Measured: Franka 29.0 -> 49.9 M/s from 3 to 4 CTAs, 38.3 at 5 (96 registers: spills).
+        static const int minb = [] { const char* e = std::getenv("IWBC_ARM_MINB"); return e ? std::atoi(e) : 0; }(); // tuning aid
+        const bool four = minb ? minb == 4 : 4 * (b->smem_bytes + 1024) <= 233472;
+        if (four)
             return launch_cycle<32, 4, 4>(b, io, st);
-        if (minb == 5)
-            return launch_cycle<32, 4, 5>(b, io, st);
-        if (minb == 6)
-            return launch_cycle<32, 4, 6>(b, io, st);
         return launch_cycle<32, 4>(b, io, st);
     }
-    if (b->G == 16)
-        return b->IPC == 8 ? launch_cycle<16, 8>(b, io, st) : launch_cycle<16, 12>(b, io, st);
-    if (b->G == 8)
-        return b->IPC == 16 ? launch_cycle<8, 16>(b, io, st) : launch_cycle<8, 24>(b, io, st);
     if (b->G == 64)
         return launch_cycle<64, 1>(b, io, st);
     if (b->G == 96)

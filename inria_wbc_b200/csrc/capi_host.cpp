@@ -213,6 +213,8 @@ int iwbc_problem_name(const iwbc_problem* p, int kind, int i, char* buf, int buf
     return (int)names.size();
 }
 
+int iwbc_problem_closed_loop(const iwbc_problem* p) { return p && p->cs.closed_loop ? 1 : 0; }
+
 int iwbc_problem_q0(const iwbc_problem* p, double* out)
 {
     if (!p || !out)

@@ -88,7 +88,7 @@ namespace dev {
         CeBlock ce[IWBC_MAXL0];
         CiBlock ci[IWBC_MAXL0];
         // shared-memory layout (offsets in doubles, per instance)
-        int o_J, o_R, o_M, o_Jft, o_cb, o_nle, o_vec, o_dyn, o_A, o_b, o_int, total;
+        int o_J, o_R, o_M, o_Jft, o_cb, o_nle, o_vec, o_ovl, o_dyn, o_A, o_b, o_int, total;
     };
 
     struct IO {
@@ -380,10 +380,20 @@ namespace dev {
         o += align2(z.nc * 12);
         S.o_nle = o;
         o += align2(z.nv);
+        // vectors alive from the assembly on: g, lb, ub, red, sc
         S.o_vec = o;
-        o += qp_vec_doubles(z);
-        S.o_dyn = o;
-        o += dyn_doubles(z);
+        o += vec_len(z) + 2 * align2(z.nv) + 32 + 96;
+        // overlay: the 13 vectors only the QP uses (x d z np r u x_old u_old gc gs gx Ldiag sub) and s share their bytes with the
+        // dynamics scratch that dies with the assembly (everything of dyn_doubles() but qs, vs): the warp-per-instance kernel is
+        // latency bound and its occupancy is set by shared memory per instance (Tiago: 60 kB -> 54 kB per CTA = 4 CTAs per SM)
+        S.o_ovl = o;
+        {
+            const int qp_only = 13 * vec_len(z) + align2(z.mi);
+            const int dyn_dead = dyn_doubles(z) - align2(z.nq) - align2(z.nv);
+            o += qp_only > dyn_dead ? qp_only : dyn_dead;
+        }
+        S.o_dyn = o; // qs, vs
+        o += align2(z.nq) + align2(z.nv);
         S.o_int = o;
         o += align2((int_count(z) + 1) / 2);
         S.total = o;
@@ -404,6 +414,11 @@ namespace dev {
         double* p = base + S.o_vec;
         const int L = vec_len(z);
         s.g = p, p += L;
+        s.lb = p, p += align2(z.nv);
+        s.ub = p, p += align2(z.nv);
+        s.red = p, p += 32;
+        s.sc = p, p += 96;
+        p = base + S.o_ovl; // QP-only vectors ...
         s.x = p, p += L;
         s.d = p, p += L;
         s.z = p, p += L;
@@ -418,11 +433,7 @@ namespace dev {
         s.Ldiag = p, p += L;
         s.sub = p, p += L;
         s.s = p, p += align2(z.mi);
-        s.lb = p, p += align2(z.nv);
-        s.ub = p, p += align2(z.nv);
-        s.red = p, p += 32;
-        s.sc = p, p += 96;
-        p = base + S.o_dyn;
+        p = base + S.o_ovl; // ... over the dynamics scratch that is dead once H, g and the constraint data are assembled
         s.oMi = p, p += 12 * z.nj;
         s.Sw = p, p += 6 * z.nv;
         s.vw = p, p += 6 * z.nj;
@@ -433,9 +444,10 @@ namespace dev {
         s.oMf = p, p += 12 * z.nf;
         s.vf = p, p += 6 * z.nf;
         s.af = p, p += 6 * z.nf;
+        s.ref = p, p += align2(z.nref);
+        p = base + S.o_dyn;
         s.qs = p, p += align2(z.nq);
         s.vs = p, p += align2(z.nv);
-        s.ref = p, p += align2(z.nref);
         int* ip = reinterpret_cast<int*>(base + S.o_int);
         s.act = ip, ip += z.n + 2;
         s.act_old = ip, ip += z.n + 2;
@@ -452,7 +464,7 @@ namespace dev {
 
     // =================================================================================== k_dyn
     template <int G>
-    __device__ void k_dyn(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, int tid, int& flip)
+    __device__ __forceinline__ void k_dyn(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, int tid, int& flip)
     {
         const int nj = z.nj, nv = z.nv;
         // ---- placements, world motion subspaces, velocities and drift accelerations, level by level
@@ -784,7 +796,7 @@ namespace dev {
     // Fills: Jft / cb (contacts), lb / ub (acceleration bounds), A / b (dense level-1 rows, scaled
     // by sqrt(w)), then H (lower triangle, in sm.J) and g.
     template <int G>
-    __device__ void k_asm(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, int tid, int& flip)
+    __device__ __forceinline__ void k_asm(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, int tid, int& flip)
     {
         const int nv = z.nv, n = z.n, na = z.P->na, nu = nv - na;
         const Shape& S = *z.S;
@@ -1442,7 +1454,7 @@ namespace dev {
     // Cholesky of the lower triangle held in sm.J (in place), then J <- L^-T (upper), c1 = trace(H), c2 = trace(J).
     // Returns false if H is not positive definite.
     template <int G>
-    __device__ bool factor_and_invert(const Sm& sm, int n, int ld, double& c1, double& c2, int tid, int& flip)
+    __device__ __forceinline__ bool factor_and_invert(const Sm& sm, int n, int ld, double& c1, double& c2, int tid, int& flip)
     {
         {
             double t[1] = {0};
@@ -1499,7 +1511,7 @@ namespace dev {
     // x = -H^-1 g using U = L^-T:  H^-1 = U U^T  (called before the strict lower triangle of J is cleared:
     // uses only the strict upper part and Ldiag)
     template <int G>
-    __device__ void unconstrained_min(const Sm& sm, int n, int ld, int tid)
+    __device__ __forceinline__ void unconstrained_min(const Sm& sm, int n, int ld, int tid)
     {
         // y = U^T g  (y_j = sum_{i <= j} U[i][j] g_i)
         for (int j = tid; j < n; j += G) {
@@ -1521,7 +1533,7 @@ namespace dev {
 
     // finish J: diagonal = 1 / Ldiag, strict lower = 0; returns trace(J)
     template <int G>
-    __device__ double finish_J(const Sm& sm, int n, int ld, int tid, int& flip)
+    __device__ __forceinline__ double finish_J(const Sm& sm, int n, int ld, int tid, int& flip)
     {
         for (int e = tid; e < n * n; e += G) {
             const int j = e / n, i = e - j * n;
@@ -1539,13 +1551,13 @@ namespace dev {
     }
 
     template <int G, class ROWS>
-    __device__ int gi_loop(const iwbc_problem_t* gP, const Sm& sm, const Sizes& z, const ROWS* dense, int me, int mi, int tid, int& flip,
+    __device__ __forceinline__ int gi_loop(const iwbc_problem_t* gP, const Sm& sm, const Sizes& z, const ROWS* dense, int me, int mi, int tid, int& flip,
         int& iter_out, int& iq_out, double c1, double c2, double R_norm);
 
     // The Goldfarb-Idnani loop.  ROWS provides the constraint rows.
     // Returns the eiquadprog status mapped to iwbc_status; iq_out = final active-set size.
     template <int G, class ROWS>
-    __device__ int gi_solve(const iwbc_problem_t* gP, const Sm& sm, const Sizes& z, const ROWS* dense, int me, int mi, int tid, int& flip,
+    __device__ __forceinline__ int gi_solve(const iwbc_problem_t* gP, const Sm& sm, const Sizes& z, const ROWS* dense, int me, int mi, int tid, int& flip,
         int& iter_out, int& iq_out, long long* cyc = nullptr)
     {
         const int n = z.n, ld = z.ldJ;
@@ -1607,7 +1619,7 @@ namespace dev {
     // The inequality iterations of Goldfarb-Idnani, started from the minimiser on the equality constraints:
     // J (n x n, J'HJ = I, first me columns span H^-1 N_eq), R (me x me), x, c1 = trace(H), c2 = trace(L^-T), R_norm given.
     template <int G, class ROWS>
-    __device__ int gi_loop(const iwbc_problem_t* gP, const Sm& sm, const Sizes& z, const ROWS* dense, int me, int mi, int tid, int& flip,
+    __device__ __forceinline__ int gi_loop(const iwbc_problem_t* gP, const Sm& sm, const Sizes& z, const ROWS* dense, int me, int mi, int tid, int& flip,
         int& iter_out, int& iq_out, double c1, double c2, double R_norm)
     {
         const int n = z.n, ld = z.ldJ;
@@ -2477,7 +2489,7 @@ namespace dev {
     // decode (controller.cpp:250-260) + integrate (:254-256) + command repack (:263-282) + result stores.
     // Scratch: sm.d (v+), sm.x_old (q+).  taut: precomputed M_a dv - J_a' f (or nullptr: evaluated here).
     template <int G>
-    __device__ void k_dec(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, const IO& io, int inst, int tid, int status, int iters,
+    __device__ __forceinline__ void k_dec(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, const IO& io, int inst, int tid, int status, int iters,
         int iq, const double* taut)
     {
         const int nv = z.nv, nq = z.nq, n = z.n, na = z.P->na, nu = nv - na;
@@ -2625,7 +2637,7 @@ namespace dev {
     // =================================================================================== one instance
     // load -> k_dyn -> k_asm -> k_qp -> k_dec for instance `inst`, executed by one group of G threads
     template <int G>
-    __device__ void cycle_instance(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, const IO& io, int inst, int tid, int& flip)
+    __device__ __forceinline__ void cycle_instance(const iwbc_problem_t* __restrict__ gP, const Sm& sm, const Sizes& z, const IO& io, int inst, int tid, int& flip)
     {
         const int nv = z.nv, nq = z.nq, n = z.n, na = z.P->na, nu = nv - na;
         // ---- load state and references (coalesced: the instance's q / v / refs are contiguous)

@@ -85,6 +85,59 @@ int main(int argc, char** argv)
     }
     catch (const inria_wbc::Exception&) {
     }
+    // Controller::update(const SensorData&): the reference's assertions, in its order, before anything touches the GPU
+    try { // the shipped Talos file has stabilizer.activated: true (humanoid_pos_tracker.cpp:180)
+        p->update(SensorData{});
+        CHECK(false);
+    }
+    catch (const inria_wbc::Exception& e) {
+        CHECK(std::strstr(e.what(), "the stabilizer needs the LF force") != nullptr);
+    }
+    try {
+        SensorData s;
+        s["lf_force"] = std::vector<double>(12, 0.0);
+        p->update(s);
+        CHECK(false);
+    }
+    catch (const inria_wbc::Exception& e) {
+        CHECK(std::strstr(e.what(), "the stabilizer needs the RF force") != nullptr);
+    }
+    {
+        Config cl = c;
+        cl.overrides_yaml = "closed_loop: true\nstabilizer: {activated: false}\n";
+        auto pc = Factory::instance().create("talos-pos-tracker", cl);
+        try { // controller.cpp:165-168
+            pc->update(SensorData{});
+            CHECK(false);
+        }
+        catch (const inria_wbc::Exception& e) {
+            CHECK(std::strstr(e.what(), "we need the joint positions in closed loop mode!") != nullptr);
+        }
+        try {
+            SensorData s;
+            s["positions"] = std::vector<double>(4 * 44, 0.0);
+            s["joint_velocities"] = std::vector<double>(4 * 44, 0.0);
+            pc->update(s);
+            CHECK(false);
+        }
+        catch (const inria_wbc::Exception& e) {
+            CHECK(std::strstr(e.what(), "we need the floating base position in closed loop mode!") != nullptr);
+        }
+        CHECK(pc->non_mimic_indexes().size() == 6 + 32);
+        CHECK(pc->q(true).size() == (size_t)4 * 38 && pc->q(false).size() == (size_t)4 * 50);
+        try {
+            pc->set_behavior_type(0, 7); // controller.cpp:438-439
+            CHECK(false);
+        }
+        catch (const inria_wbc::Exception&) {
+        }
+    }
+    // AutoRegister (factory.hpp:66-76): a plugin registers its controller under a new name with a static object
+    struct MyController : BatchPosTracker {
+        explicit MyController(const Config& cc) : BatchPosTracker(cc) {}
+    };
+    static Register<MyController> reg("my-controller");
+    CHECK(std::dynamic_pointer_cast<MyController>(Factory::instance().create("my-controller", c)).get() != nullptr);
     std::printf(failures ? "FAILED (%d)\n" : "OK\n", failures);
     return failures ? 1 : 0;
 }
