@@ -404,6 +404,14 @@ int iwbc_run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t
                   " (or load it with stabilizer: {activated: false}, as the reference's open-loop tests do)");
         return IWBC_ERR_ARG;
     }
+    if (b->prob->cs.torque_collision_detection) {
+        // TalosPosTracker::update asserts "joints_torque" when CONTROLLER.collision_detection.activated (talos_pos_tracker.cpp:127-129);
+        // the torque-discrepancy monitor is not part of the batched path
+        set_error("torque collision detection requires torque sensor data: this controller has CONTROLLER.collision_detection.activated = true;"
+                  " the monitor is outside the batched path -- load the controller with collision_detection: {activated: false}, as the reference's"
+                  " controller-only tests do (tests/test_determinism.cpp:68)");
+        return IWBC_ERR_UNSUPPORTED;
+    }
     int rc = prepare_shape(b, mask);
     if (rc)
         return rc;

@@ -48,6 +48,7 @@ namespace host {
         std::vector<std::string> mimic_dof_names;
         std::string controller_name;
         bool closed_loop = false;
+        bool torque_collision_detection = false; // CONTROLLER.collision_detection.activated (talos-pos-tracker)
     };
 
     namespace detail {
@@ -615,6 +616,14 @@ namespace host {
             }
             if (bounds_task < 0)
                 throw ConfigError("talos-pos-tracker needs a 'bounds' task");
+            // parse_torque_safety (talos_pos_tracker.cpp:62-108): the torque-discrepancy monitor itself is outside the batched path
+            // (SURVEY.md 2.1 row 10); an activated one makes every update demand "joints_torque" sensor data, so it is remembered
+            const yaml::Node& cd = c["collision_detection"];
+            if (!cd.is_map())
+                throw ConfigError("config error reading CONTROLLER.collision_detection");
+            cs.torque_collision_detection = IWBC_HCHECK(cd["activated"].as<bool>(), "CONTROLLER.collision_detection.activated");
+            (void)IWBC_HCHECK(cd["filter_size"].as<int>(), "CONTROLLER.collision_detection.filter_size");
+            (void)IWBC_HCHECK(cd["max_invalid"].as<int>(), "CONTROLLER.collision_detection.max_invalid");
         }
         (void)nv;
         return cs;

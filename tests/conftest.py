@@ -8,6 +8,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+# the reference's controller-only tests switch these off (tests/test_determinism.cpp:67-69); activated, they demand sensor data
+OPEN_LOOP = {"stabilizer": {"activated": False}, "collision_detection": {"activated": False}, "closed_loop": False}
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
@@ -33,14 +37,14 @@ def talos():
     import inria_wbc_b200 as iw
     # stabilizer off, as the reference's open-loop tests run the controller (tests/test_determinism.cpp:67): with it activated the
     # controller needs F/T + IMU sensor data for every update (tests/test_stabilizer.py)
-    return iw.Problem("talos/talos_pos_tracker.yaml", overrides={"stabilizer": {"activated": False}})
+    return iw.Problem("talos/talos_pos_tracker.yaml", overrides=OPEN_LOOP)
 
 
 @pytest.fixture(scope="session")
 def talos_fast():
     """Talos with the `talos_fast.urdf` model of the reference's `-f` runs (grippers reduced to their driven joint)."""
     import inria_wbc_b200 as iw
-    return iw.Problem("talos/talos_pos_tracker.yaml", overrides={"urdf": "talos/talos_fast.urdf", "stabilizer": {"activated": False}})
+    return iw.Problem("talos/talos_pos_tracker.yaml", overrides=dict(OPEN_LOOP, urdf="talos/talos_fast.urdf"))
 
 
 @pytest.fixture(scope="session")
@@ -52,7 +56,7 @@ def tiago():
 @pytest.fixture(scope="session")
 def icub():
     import inria_wbc_b200 as iw
-    return iw.Problem("icub/humanoid_pos_tracker.yaml", overrides={"stabilizer": {"activated": False}})
+    return iw.Problem("icub/humanoid_pos_tracker.yaml", overrides=OPEN_LOOP)
 
 
 def random_states(P, B, seed, qn=0.02, vn=0.05, base=False):

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import behaviors_oracle as bo  # noqa: E402
 
-OFF = {"stabilizer": {"activated": False}}
+OFF = {"stabilizer": {"activated": False}, "collision_detection": {"activated": False}}
 WALK = os.path.join(iw.ETC_PATH, "talos", "walk.yaml")
 
 
@@ -374,7 +374,7 @@ def test_icub_walk_rollout_on_device(icub):
     same number of iterations."""
     import torch
     import oracle_lib as ol
-    P = iw.Problem("icub/humanoid_pos_tracker.yaml", overrides={"stabilizer": {"activated": False}})
+    P = iw.Problem("icub/humanoid_pos_tracker.yaml", overrides=OFF)
     beh = iw.Behavior(P, "icub/walk.yaml", overrides={"num_of_cycles": 1})
     ora = bo.Walk(P, os.path.join(iw.ETC_PATH, "icub", "walk.yaml"), num_of_cycles=1)
     assert beh.total_ticks == ora.total_ticks == 5500

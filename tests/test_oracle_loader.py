@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import problem_loader as pl  # noqa: E402
 
-OFF = {"stabilizer": {"activated": False}}
+OFF = {"stabilizer": {"activated": False}, "collision_detection": {"activated": False}}
 CASES = [("franka/pos_tracker.yaml", None),
          ("tiago/pos_tracker.yaml", {"urdf": "tiago/tiago_steel_no_wheel.urdf"}),
          ("icub/humanoid_pos_tracker.yaml", OFF),

@@ -18,7 +18,7 @@ import oracle_lib as ol  # noqa: E402
 from conftest import random_states  # noqa: E402
 from test_cpu_sim import active_sets_equivalent  # noqa: E402
 
-OFF = {"stabilizer": {"activated": False}}
+OFF = {"stabilizer": {"activated": False}, "collision_detection": {"activated": False}}
 
 
 def rel(a, b):
