@@ -423,8 +423,13 @@ int iwbc_run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t
         // needs.  Four CTAs per SM (<= 128 registers, 16 warps) when the instance's shared memory allows it (Franka: 36 kB per CTA),
         // three otherwise (Tiago: 60 kB).  Measured: Franka 29.0 -> 49.9 M/s from 3 to 4 CTAs, 38.3 at 5 (96 registers: spills).
         static const int minb = [] { const char* e = std::getenv("IWBC_ARM_MINB"); return e ? std::atoi(e) : 0; }(); // tuning aid
-        const bool four = minb ? minb == 4 : 4 * (b->smem_bytes + 1024) <= 233472;
-        if (four)
+        const int fit = (int)(233472 / (b->smem_bytes + 1024));
+        const int want = minb ? minb : (fit >= 4 ? 4 : 3);
+        if (want >= 6 && fit >= 6)
+            return launch_cycle<32, 4, 6>(b, io, st);
+        if (want == 5 && fit >= 5)
+            return launch_cycle<32, 4, 5>(b, io, st);
+        if (want >= 4 && fit >= 4)
             return launch_cycle<32, 4, 4>(b, io, st);
         return launch_cycle<32, 4>(b, io, st);
     }

@@ -36,6 +36,7 @@
 #include <type_traits>
 #define __device__
 #define __host__
+#define __noinline__
 #define __forceinline__ inline
 #define __constant__
 #define __grid_constant__
