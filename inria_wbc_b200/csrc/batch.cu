@@ -423,12 +423,10 @@ int iwbc_run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t
         // needs.  Four CTAs per SM (<= 128 registers, 16 warps) when the instance's shared memory allows it (Franka: 36 kB per CTA),
         // three otherwise (Tiago: 60 kB).  Measured: Franka 29.0 -> 49.9 M/s from 3 to 4 CTAs, 38.3 at 5 (96 registers: spills).
         static const int minb = [] { const char* e = std::getenv("IWBC_ARM_MINB"); return e ? std::atoi(e) : 0; }(); // tuning aid
+        // (five / six CTAs per SM -- 96 / 80 registers -- change nothing any more once the phases are inlined: Franka 50.8 / 48.7 M/s
+        // against 49.6, Tiago 6.13 / 6.14 against 6.14: profiles/README.md)
         const int fit = (int)(233472 / (b->smem_bytes + 1024));
         const int want = minb ? minb : (fit >= 4 ? 4 : 3);
-        if (want >= 6 && fit >= 6)
-            return launch_cycle<32, 4, 6>(b, io, st);
-        if (want == 5 && fit >= 5)
-            return launch_cycle<32, 4, 5>(b, io, st);
         if (want >= 4 && fit >= 4)
             return launch_cycle<32, 4, 4>(b, io, st);
         return launch_cycle<32, 4>(b, io, st);
