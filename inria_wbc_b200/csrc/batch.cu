@@ -20,137 +20,6 @@
 namespace iwbc {
 namespace dev {
 
-    // ------------------------------------------------------------------------------ the kernel
-    // One group of G threads per instance, IPC instances per CTA, persistent over the batch.
-    // (the warp-per-instance form is occupancy-bound by registers: three CTAs per SM need <= 168; without the bound ptxas drifts to
-    // 216 and Franka drops from 38 M to 27 M updates/s)
-    template <int G, int IPC, int MINB = (G <= 32 && G * IPC <= 128 ? 3 : 1)>
-    __global__ void __launch_bounds__(G* IPC, MINB) k_cycle(const iwbc_problem_t* __restrict__ gP, const __grid_constant__ Shape S, IO io)
-    {
-        extern __shared__ double smem[];
-        const int grp = threadIdx.x / G;
-        const int tid = threadIdx.x - grp * G;
-        Sizes z;
-        z.nv = gP->nv;
-        z.nq = gP->nq;
-        z.nj = gP->nj;
-        z.nf = gP->nframes;
-        z.nc = gP->ncontacts;
-        z.n = S.n;
-        z.mi = S.mi;
-        z.rows_dense = S.rows_dense;
-        z.nref = gP->nref;
-        z.ldJ = S.ldJ;
-        z.ldM = S.ldM;
-        z.S = &S;
-        z.P = gP;
-        const Sm sm = make_sm(smem + (size_t)grp * S.total, z);
-        int flip = 0;
-
-        // dof -> joint table
-        for (int j = tid; j < z.nj; j += G) {
-            const int c0 = gP->idx_v[j], cn = gP->jtype[j] == IWBC_J_FREEFLYER ? 6 : 1;
-            for (int k = 0; k < cn; ++k)
-                sm.dofj[c0 + k] = j;
-        }
-        const int ngroups = gridDim.x * IPC;
-        const int count = io.list ? *io.list_count : io.B;
-        if (io.work) {
-            // dynamic hand-out: instances differ in active-set iterations (Tiago: 1 .. 30), a static stride leaves groups idle at the end
-            __shared__ int s_next[IPC];
-            for (;;) {
-                int idx;
-                if (G <= 32) {
-                    idx = 0;
-                    if (tid == 0)
-                        idx = atomicAdd(io.work, 1);
-                    idx = __shfl_sync(Grp<G>::mask(), idx, (threadIdx.x & 31) / G * G);
-                }
-                else {
-                    if (tid == 0)
-                        s_next[grp] = atomicAdd(io.work, 1);
-                    __syncthreads();
-                    idx = s_next[grp];
-                }
-                if (idx >= count)
-                    break;
-                const int inst = io.list ? io.list[idx] : idx;
-                cycle_instance<G>(gP, sm, z, io, inst, tid, flip);
-                Grp<G>::sync();
-            }
-            return;
-        }
-        for (int idx = blockIdx.x * IPC + grp; idx < count; idx += ngroups) {
-            const int inst = io.list ? io.list[idx] : idx;
-            cycle_instance<G>(gP, sm, z, io, inst, tid, flip);
-            Grp<G>::sync();
-        }
-    }
-
-    // ---- dense QP kernel: the SolverHQPBase-shaped entry point.  H[B][n][n] etc. in global memory.
-    struct QpIO {
-        int B, n, me, mi;
-        const double *H, *g, *CE, *ce0, *CI, *ci0;
-        double* x;
-        int* status;
-        int* iters;
-        unsigned* active;
-    };
-    template <int G, int IPC>
-    __global__ void __launch_bounds__(G* IPC) k_qp_dense(const __grid_constant__ Shape S, QpIO io)
-    {
-        extern __shared__ double smem[];
-        const int grp = threadIdx.x / G;
-        const int tid = threadIdx.x - grp * G;
-        Sizes z;
-        z.nv = 0, z.nq = 0, z.nj = 0, z.nf = 0, z.nc = 0, z.nref = 0, z.rows_dense = 0;
-        z.n = io.n;
-        z.mi = io.mi;
-        z.ldJ = S.ldJ;
-        z.ldM = 1;
-        z.S = &S;
-        z.P = nullptr;
-        const Sm sm = make_sm(smem + (size_t)grp * S.total, z);
-        const int n = io.n;
-        int flip = 0;
-        const int ngroups = gridDim.x * IPC;
-        for (int inst = blockIdx.x * IPC + grp; inst < io.B; inst += ngroups) {
-            const double* H = io.H + (size_t)inst * n * n;
-            for (int e = tid; e < n * n; e += G) {
-                const int i = e / n, j = e - i * n;
-                if (i >= j)
-                    sm.J[i + j * z.ldJ] = H[e];
-            }
-            for (int k = tid; k < n; k += G)
-                sm.g[k] = io.g[(size_t)inst * n + k];
-            Grp<G>::sync();
-            DenseRows rows;
-            rows.CE = io.CE + (size_t)inst * io.me * n;
-            rows.ce0 = io.ce0 + (size_t)inst * io.me;
-            rows.CI = io.CI + (size_t)inst * io.mi * n;
-            rows.ci0 = io.ci0 + (size_t)inst * io.mi;
-            rows.n = n, rows.me = io.me, rows.mi = io.mi;
-            int iters = 0, iq = 0;
-            const int status = gi_solve<G, DenseRows>(nullptr, sm, z, &rows, io.me, io.mi, tid, flip, iters, iq);
-            Grp<G>::sync();
-            for (int k = tid; k < n; k += G)
-                io.x[(size_t)inst * n + k] = sm.x[k];
-            if (tid == 0) {
-                io.status[inst] = status;
-                io.iters[inst] = iters;
-                unsigned* a = io.active + (size_t)inst * IWBC_ACTIVE_WORDS;
-                for (int k = 0; k < IWBC_ACTIVE_WORDS; ++k)
-                    a[k] = 0;
-                for (int k = io.me; k < iq; ++k) {
-                    const int r = sm.act[k];
-                    if (r >= 0 && r < 32 * IWBC_ACTIVE_WORDS)
-                        a[r >> 5] |= 1u << (r & 31);
-                }
-            }
-            Grp<G>::sync();
-        }
-    }
-
     // FP64 FMA peak probe: 8 independent dependent-FMA chains per thread (the roofline denominator of this
     // path is FP64 CUDA-core throughput, which MEASURED_PEAKS.json does not hold: SURVEY.md 8(d))
     __global__ void k_fp64_peak(double* out, int iters, double a, double b)
@@ -190,50 +59,19 @@ int launch_fast(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
     return iwbc_launch_fast_0_0(b, io, st);
 }
 
-template <int G, int IPC, int MINB = (G <= 32 && G * IPC <= 128 ? 3 : 1)>
-int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st)
+// generic kernel (or, for the humanoids, the fast pair): the kernels of each group width live in their own translation unit (cycle_tu.cuh)
+int launch_cycle(iwbc_batch* b, const dev::IO& io, cudaStream_t st, int minb = 0)
 {
-    auto kern = dev::k_cycle<G, IPC, MINB>;
-    static size_t smem_set[16];
-    int rc0 = iwbc_raise_smem_limit((const void*)kern, b->device, b->smem_bytes, smem_set);
-    if (rc0)
-        return rc0;
-    if (b->grid == 0) {
-        int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G * IPC, b->smem_bytes));
-        if (per_sm < 1) {
-            set_error("cycle kernel does not fit on an SM (shared memory " + std::to_string(b->smem_bytes) + " B)");
-            return IWBC_ERR_CUDA;
-        }
-        b->grid = b->sm_count * per_sm;
-    }
-    int grid = std::min(b->grid, (io.B + IPC - 1) / IPC);
-    dev::IO iop = io;
-    const bool use_fast = b->fast_ok && b->fast_enabled && G > 32 && !io.dbg_M && !io.dbg_cycles;
+    const bool use_fast = b->fast_ok && b->fast_enabled && b->G > 32 && !io.dbg_M && !io.dbg_cycles;
     if (use_fast)
         return launch_fast(b, io, st);
-    if (io.in_list) // a behaviour's bucket: the generic kernel walks it as its instance list
-        iop.list = io.in_list, iop.list_count = io.in_count;
-    if (b->profiling)
-        iop.prof = b->d_prof;
-    if (!io.dbg_M && !io.dbg_cycles) {
-        iop.work = b->d_slow_count + 2 * b->slot + 1;
-        CUDA_TRY(cudaMemsetAsync(iop.work, 0, sizeof(int), st));
-    }
-    if (b->timing && !use_fast)
-        cudaEventRecord(b->ev0, st);
-    kern<<<grid, G * IPC, b->smem_bytes, st>>>(b->d_prob, b->shape, iop);
-    if (b->timing) {
-        cudaEventRecord(b->ev1, st);
-        cudaEventSynchronize(b->ev1);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, b->ev0, b->ev1);
-        b->ms_sum += ms;
-        b->ms_n++;
-    }
-    b->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return IWBC_OK;
+    if (b->G == 32)
+        return minb == 4 ? iwbc_launch_cycle_32_4_4(b, io, st) : iwbc_launch_cycle_32_4_3(b, io, st);
+    if (b->G == 64)
+        return iwbc_launch_cycle_64(b, io, st);
+    if (b->G == 96)
+        return iwbc_launch_cycle_96(b, io, st);
+    return iwbc_launch_cycle_128(b, io, st);
 }
 
 // choose the thread-group width for this problem shape
@@ -418,6 +256,21 @@ int iwbc_run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t
     rc = upload_constants(b, st);
     if (rc)
         return rc;
+    if (b->G == 32 && !io.dbg_M && !io.dbg_cycles && b->shape.total <= 1792) {
+        // Large arm batches run one THREAD per instance (k_cycle_tpi): a warp instruction advances 32 instances, lane efficiency
+        // 27 / 32 instead of 9 / 32.  Measured (profiles/r02_tpi_*.txt): Franka 49.6 -> 141 M/s, Tiago 6.1 -> 40 M/s at 65 536 states,
+        // four CTAs of 128 threads per SM (128 registers; 3 CTAs: 105 / 30 M/s, 5: 136 / 39, 6: 134 / 38).  A thread is ~30x slower
+        // than a warp on one instance, so small batches (latency, debugging) stay on the warp-per-instance kernel below (measured
+        // crossover, profiles/r02_tpi_crossover.txt: Franka ~9 k states, Tiago ~11 k).
+        static const int tpi_min = [] { const char* e = std::getenv("IWBC_ARM_TPI_MIN_BATCH"); return e ? std::atoi(e) : 12288; }();
+        if (io.B >= tpi_min) {
+            dev::IO iop = io;
+            if (io.in_list)
+                iop.list = io.in_list, iop.list_count = io.in_count;
+            const int grid = std::min(b->sm_count * 4, (io.B + 127) / 128);
+            return b->shape.total <= 1024 ? iwbc_launch_cycle_tpi_1024(b, iop, grid, st) : iwbc_launch_cycle_tpi_1792(b, iop, grid, st);
+        }
+    }
     if (b->G == 32) {
         // The warp-per-instance kernel is latency bound (dependent shared-memory load -> FP64 chains): resident warps are what it
         // needs.  Four CTAs per SM (<= 128 registers, 16 warps) when the instance's shared memory allows it (Franka: 36 kB per CTA),
@@ -427,15 +280,9 @@ int iwbc_run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t
         // against 49.6, Tiago 6.13 / 6.14 against 6.14: profiles/README.md)
         const int fit = (int)(233472 / (b->smem_bytes + 1024));
         const int want = minb ? minb : (fit >= 4 ? 4 : 3);
-        if (want >= 4 && fit >= 4)
-            return launch_cycle<32, 4, 4>(b, io, st);
-        return launch_cycle<32, 4>(b, io, st);
+        return launch_cycle(b, io, st, want >= 4 && fit >= 4 ? 4 : 3);
     }
-    if (b->G == 64)
-        return launch_cycle<64, 1>(b, io, st);
-    if (b->G == 96)
-        return launch_cycle<96, 1>(b, io, st);
-    return launch_cycle<128, 1>(b, io, st);
+    return launch_cycle(b, io, st);
 }
 
 namespace {
@@ -733,7 +580,9 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
                 CUDA_TRY(cudaStreamWaitEvent(b->s_in, b->ev_const, 0)); // (the previous call's kernels are done: the call synchronises before returning)
             // Chunk plan: sizes are multiples of the persistent grid's instance capacity (no partially filled last round), a short
             // first chunk (its upload is the pipeline's fill: nothing overlaps it) and whatever is left at the end.
-            const int unit = b->fast_ok && b->fast_grid > 0 ? b->fast_grid : (b->grid > 0 ? b->grid * b->IPC : 4 * b->sm_count);
+            // (thread-per-instance arms: a chunk needs tens of thousands of instances to fill the GPU -- 32 instances per warp)
+            const bool tpi_arm = b->G == 32 && b->shape.total <= 1792;
+            const int unit = tpi_arm ? 32 * b->sm_count : b->fast_ok && b->fast_grid > 0 ? b->fast_grid : (b->grid > 0 ? b->grid * b->IPC : 4 * b->sm_count);
             int u_first = 4, u_mid = 10; // (IWBC_PIPE="first,mid" in units of the grid capacity: tuning aid)
             if (const char* e = std::getenv("IWBC_PIPE"))
                 std::sscanf(e, "%d,%d", &u_first, &u_mid);
@@ -1102,31 +951,14 @@ int iwbc_qp_solve_batch(int device, int B, int n, int me, int mi, const double* 
     }
     dev::QpIO io = {B, n, me, mi, dH, dg, dCE, dce, dCI, dci, dx, dst, dit, dact};
     int rc = IWBC_OK;
-    auto launch = [&](auto kern, int G, int IPC) -> int {
-        size_t smem = (size_t)S.total * 8 * IPC;
-        {
-            std::lock_guard<std::mutex> lock(g_attr_mutex); // (the attribute is per function and device; concurrent callers may differ in n)
-            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        }
-        int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, G * IPC, smem));
-        if (per_sm < 1) {
-            set_error("QP kernel does not fit in shared memory");
-            return IWBC_ERR_CUDA;
-        }
-        int grid = std::min(prop.multiProcessorCount * per_sm, (B + IPC - 1) / IPC);
-        kern<<<grid, G * IPC, smem>>>(S, io);
-        CUDA_TRY(cudaGetLastError());
-        return IWBC_OK;
-    };
     if (n <= 32)
-        rc = launch(dev::k_qp_dense<32, 4>, 32, 4);
+        rc = iwbc_launch_qp_dense_32(S, io, device, prop.multiProcessorCount);
     else if (n <= 64)
-        rc = launch(dev::k_qp_dense<64, 1>, 64, 1);
+        rc = iwbc_launch_qp_dense_64(S, io, device, prop.multiProcessorCount);
     else if (n <= 96)
-        rc = launch(dev::k_qp_dense<96, 1>, 96, 1);
+        rc = iwbc_launch_qp_dense_96(S, io, device, prop.multiProcessorCount);
     else
-        rc = launch(dev::k_qp_dense<128, 1>, 128, 1);
+        rc = iwbc_launch_qp_dense_128(S, io, device, prop.multiProcessorCount);
     if (rc == IWBC_OK) {
         CUDA_TRY(cudaMemcpy(x, dx, Bz * n * 8, cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(status, dst, Bz * 4, cudaMemcpyDeviceToHost));

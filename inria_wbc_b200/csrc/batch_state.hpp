@@ -106,6 +106,31 @@ int iwbc_launch_fast_38_18(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t 
 int iwbc_launch_fast_38_12(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
 int iwbc_launch_fast_0_0(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
 
+// generic cycle kernel per group width, its thread-per-instance form per working-set size, the dense-QP kernel (cycle_tu.cuh)
+namespace iwbc {
+namespace dev {
+    struct QpIO { // H[B][n][n] etc. in global memory: the SolverHQPBase-shaped entry point
+        int B, n, me, mi;
+        const double *H, *g, *CE, *ce0, *CI, *ci0;
+        double* x;
+        int* status;
+        int* iters;
+        unsigned* active;
+    };
+}
+}
+int iwbc_launch_cycle_32_4_3(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
+int iwbc_launch_cycle_32_4_4(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
+int iwbc_launch_cycle_64(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
+int iwbc_launch_cycle_96(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
+int iwbc_launch_cycle_128(iwbc_batch* b, const iwbc::dev::IO& io, cudaStream_t st);
+int iwbc_launch_cycle_tpi_1024(iwbc_batch* b, const iwbc::dev::IO& io, int grid, cudaStream_t st);
+int iwbc_launch_cycle_tpi_1792(iwbc_batch* b, const iwbc::dev::IO& io, int grid, cudaStream_t st);
+int iwbc_launch_qp_dense_32(const iwbc::dev::Shape& S, const iwbc::dev::QpIO& io, int device, int sm_count);
+int iwbc_launch_qp_dense_64(const iwbc::dev::Shape& S, const iwbc::dev::QpIO& io, int device, int sm_count);
+int iwbc_launch_qp_dense_96(const iwbc::dev::Shape& S, const iwbc::dev::QpIO& io, int device, int sm_count);
+int iwbc_launch_qp_dense_128(const iwbc::dev::Shape& S, const iwbc::dev::QpIO& io, int device, int sm_count);
+
 // one pass of the control cycle over io's instances (io.list / io.list_count: optional device-side instance list) with one
 // contact mask: prepares the shape, refreshes constants, launches (batch.cu)
 int iwbc_run_cycle(iwbc_batch* b, const iwbc::dev::IO& io, unsigned mask, cudaStream_t st);

@@ -329,7 +329,8 @@ namespace dev {
     struct Sm {
         double* J;    // n x ldJ column-major: H (lower) -> L -> J = L^-T
         double* R;    // packed upper triangular, column-major: R(i,j) at j(j+1)/2 + i
-        double* M;    // nv x ldM (symmetric, both halves)
+        double* M;    // nv x ldM (symmetric, both halves); the fast pass / continuation keep one half only: mass_at()
+        double* Md;   // diagonal of M when Sizes::msym == 1
         double* Jft;  // [ncontacts][6][nv] local contact-frame Jacobians
         double* cb;   // [ncontacts][6] contact motion right-hand sides; then wrench scratch [ncontacts][6]
         double* nle;  // nv
@@ -346,6 +347,7 @@ namespace dev {
     // The layout is computed on the host (fills Shape::o_* and total) and replayed on the device.
     struct Sizes {
         int nv, nq, nj, nf, nc, n, mi, rows_dense, nref, ldJ, ldM;
+        int msym = 0; // storage of the mass matrix: see mass_at()
         // per-launch tables: the QP shape of this launch's contact mask (a __grid_constant__ kernel parameter) and the problem
         // (the handle's own global-memory copy, read through the read-only path).  No process-global __constant__ state: two
         // handles, or two contact masks of one handle, never share anything on the device.
@@ -1052,6 +1054,19 @@ namespace dev {
     }
 
     // =================================================================================== k_qp
+    // M(r, k).  msym 0: full nv x ldM.  1: strict lower triangle only, row r at M + r ldM (k < r), diagonal in Md -- the fast pass keeps
+    // M in the unused upper triangle of its column-major augmented matrix (ldM = that matrix's leading dimension).  2: packed lower
+    // triangle, row r at M + r (r + 1) / 2 (k <= r) -- the continuation's own copy (its R overwrites the augmented matrix).
+    __device__ __forceinline__ double mass_at(const Sm& sm, const Sizes& z, int r, int k)
+    {
+        if (z.msym == 0)
+            return sm.M[r * z.ldM + k];
+        const int hi = r > k ? r : k, lo = r > k ? k : r;
+        if (z.msym == 1)
+            return hi == lo ? sm.Md[hi] : sm.M[hi * z.ldM + lo];
+        return sm.M[hi * (hi + 1) / 2 + lo];
+    }
+
     // Implicit constraint rows of the fused problem.
     struct FusedRows {
         // np <- CE.row(i) ; returns ce0_i
@@ -1068,7 +1083,7 @@ namespace dev {
                 for (int k = tid; k < n; k += G) {
                     double val;
                     if (k < nv)
-                        val = sm.M[r * z.ldM + k];
+                        val = mass_at(sm, z, r, k);
                     else {
                         // -(T^T Jft_c)[kk][r]
                         int c = 0;
@@ -1115,17 +1130,50 @@ namespace dev {
         {
             const Shape& S = *z.S;
             const int nv = z.nv, nu = nv - z.P->na;
-            const double* Mr = sm.M + (nu + i) * z.ldM;
             double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            int k = 0;
-            for (; k + 3 < nv; k += 4) {
-                s0 += Mr[k] * sm.x[k];
-                s1 += Mr[k + 1] * sm.x[k + 1];
-                s2 += Mr[k + 2] * sm.x[k + 2];
-                s3 += Mr[k + 3] * sm.x[k + 3];
+            if (z.msym == 0) {
+                const double* Mr = sm.M + (nu + i) * z.ldM;
+                int k = 0;
+                for (; k + 3 < nv; k += 4) {
+                    s0 += Mr[k] * sm.x[k];
+                    s1 += Mr[k + 1] * sm.x[k + 1];
+                    s2 += Mr[k + 2] * sm.x[k + 2];
+                    s3 += Mr[k + 3] * sm.x[k + 3];
+                }
+                for (; k < nv; ++k)
+                    s0 += Mr[k] * sm.x[k];
             }
-            for (; k < nv; ++k)
-                s0 += Mr[k] * sm.x[k];
+            else {
+                // one stored half: the row's own part (k < r, contiguous), the diagonal, then column r of the rows below
+                const int r = nu + i;
+                const double* Mr = z.msym == 1 ? sm.M + r * z.ldM : sm.M + r * (r + 1) / 2;
+                int k = 0;
+                for (; k + 3 < r; k += 4) {
+                    s0 += Mr[k] * sm.x[k];
+                    s1 += Mr[k + 1] * sm.x[k + 1];
+                    s2 += Mr[k + 2] * sm.x[k + 2];
+                    s3 += Mr[k + 3] * sm.x[k + 3];
+                }
+                for (; k < r; ++k)
+                    s0 += Mr[k] * sm.x[k];
+                s1 += (z.msym == 1 ? sm.Md[r] : Mr[r]) * sm.x[r];
+                if (z.msym == 1) {
+                    for (k = r + 1; k + 1 < nv; k += 2) {
+                        s2 += sm.M[k * z.ldM + r] * sm.x[k];
+                        s3 += sm.M[(k + 1) * z.ldM + r] * sm.x[k + 1];
+                    }
+                    if (k < nv)
+                        s2 += sm.M[k * z.ldM + r] * sm.x[k];
+                }
+                else {
+                    for (k = r + 1; k + 1 < nv; k += 2) {
+                        s2 += sm.M[k * (k + 1) / 2 + r] * sm.x[k];
+                        s3 += sm.M[(k + 1) * (k + 2) / 2 + r] * sm.x[k + 1];
+                    }
+                    if (k < nv)
+                        s2 += sm.M[k * (k + 1) / 2 + r] * sm.x[k];
+                }
+            }
             double s = (s0 + s1) + (s2 + s3);
             for (int c = 0; c < z.P->ncontacts; ++c) {
                 if (S.cidx[c] < 0)
@@ -1215,7 +1263,7 @@ namespace dev {
                     val = (k == nu + r) ? 1.0 : 0.0;
                 else if (B.kind == 1) {
                     if (k < nv)
-                        val = sm.M[(nu + r) * z.ldM + k];
+                        val = mass_at(sm, z, nu + r, k);
                     else {
                         int c = 0;
                         for (int cc = 0; cc < z.P->ncontacts; ++cc)
@@ -2119,7 +2167,7 @@ namespace dev {
                             val = (k == nu + r) ? 1.0 : 0.0;
                         else if (B.kind == 1) {
                             if (k < nv)
-                                val = sm.M[(nu + r) * z.ldM + k];
+                                val = mass_at(sm, z, nu + r, k);
                             else {
                                 int c = 0;
                                 for (int cc = 0; cc < ncon; ++cc)

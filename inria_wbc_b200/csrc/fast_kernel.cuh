@@ -40,6 +40,7 @@ namespace dev {
 #define IWBC_FMAXBLK 40
 #define IWBC_FMAXROWS 96
 #define IWBC_FMAXME 24
+#define IWBC_FMAXCHUNK 3 /* row chunks of the Hessian assembly */
 #define IWBC_FMAXPAIRS ((IWBC_FMAXME + 1) * (IWBC_FMAXME + 2) / 2)
 
     enum { FJ_SE3 = 0, FJ_CONTACT = 1, FJ_SELFCOL = 2, FJ_COM = 3, FJ_MOM = 4 };
@@ -84,10 +85,14 @@ namespace dev {
         int ci_bounds, ci_act; // index of the bounds / actuation-bounds block in Shape::ci (-1: none)
         int posture[4];
         // shared-memory offsets (doubles)
-        int o_qs, o_vs, o_X, o_Y, o_Z, o_Jft, o_cb, o_nle, o_lb, o_ub, o_g, o_x, o_w, o_sc, o_fr, o_rhs, o_sc4, o_P, o_Rm, o_tv, o_hd, o_il, o_tau, o_int, total;
+        int o_qs, o_vs, o_X, o_Y, o_Z, o_Jft, o_cb, o_nle, o_lb, o_ub, o_g, o_x, o_w, o_sc, o_fr, o_rhs, o_sc4, o_P, o_Rm, o_tv, o_hd, o_il, o_tau, o_int, o_Md, total;
         int d_liMi, d_oMi, d_Sw, d_vw, d_aw, d_Yw, d_fw, d_Fc, d_oMf, d_vf, d_af;
         int z_Bf, z_G;
-        int s_J, s_R, s_vec, s_int, s_total; // extra regions of the active-set continuation (k_slow)
+        int s_J, s_R, s_vec, s_int, s_M, s_total; // extra regions of the active-set continuation (k_slow)
+        // The dense level-1 rows are formed and folded into H in chunks of whole row blocks (the row buffer is what decides whether
+        // four CTAs fit on an SM): chunk c = blocks [ch_b0, ch_b1), rows [ch_r0, ch_r0 + ch_nr); crows = the largest chunk.
+        int nchunk, crows;
+        int ch_b0[IWBC_FMAXCHUNK], ch_b1[IWBC_FMAXCHUNK], ch_r0[IWBC_FMAXCHUNK], ch_nr[IWBC_FMAXCHUNK];
     };
 
 
@@ -186,6 +191,49 @@ namespace dev {
             B.kind = FB_CONTACT, B.index = (short)F.cact[s], B.row0 = 0, B.nrows = 6, B.slot0 = 0;
         }
         F.nslots = nslots;
+        // ---- row chunks: the smallest capacity that packs the row blocks (in order) into at most IWBC_FMAXCHUNK chunks; the contact
+        // blocks (no rows of A: they fill Jft) ride in the last chunk
+        {
+            const int ntask = F.nblocks - F.nca;
+            for (int cap = 1; cap <= IWBC_FMAXROWS; ++cap) {
+                int nch = 0, used = 0;
+                bool fits = true;
+                for (int bi = 0; bi < ntask && fits; ++bi) {
+                    const int nr = pl.blocks[bi].nrows;
+                    if (nr > cap)
+                        fits = false;
+                    else if (nch == 0 || used + nr > cap) {
+                        if (nch == IWBC_FMAXCHUNK)
+                            fits = false;
+                        else {
+                            F.ch_b0[nch] = bi, F.ch_r0[nch] = pl.blocks[bi].row0, F.ch_nr[nch] = 0;
+                            ++nch;
+                            used = 0;
+                        }
+                    }
+                    if (fits) {
+                        used += nr;
+                        F.ch_nr[nch - 1] = used;
+                        F.ch_b1[nch - 1] = bi + 1;
+                    }
+                }
+                if (fits) {
+                    if (nch == 0) {
+                        F.ch_b0[0] = F.ch_b1[0] = 0, F.ch_r0[0] = F.ch_nr[0] = 0;
+                        nch = 1;
+                    }
+                    F.nchunk = nch;
+                    F.crows = cap;
+                    break;
+                }
+            }
+            if (F.nchunk == 0)
+                return false;
+            F.ch_b1[F.nchunk - 1] = F.nblocks;
+            F.crows = 0;
+            for (int c = 0; c < F.nchunk; ++c)
+                F.crows = std::max(F.crows, F.ch_nr[c]);
+        }
         F.ci_bounds = F.ci_act = -1;
         for (int b = 0; b < S.nci; ++b) {
             if (S.ci[b].kind == 0) {
@@ -280,8 +328,7 @@ namespace dev {
         };
         F.o_qs = take(nq);
         F.o_vs = take(nv);
-        const int xa = S.rows_dense * F.nvp + align2(S.rows_dense), xm = nv * S.ldM;
-        F.o_X = take(xa > xm ? xa : xm);
+        F.o_X = take(F.crows * F.nvp + align2(F.crows)); // one chunk of A and its right-hand side
         int d = 0;
         auto dt = [&](int cnt) {
             int r = d;
@@ -308,6 +355,7 @@ namespace dev {
         F.o_sc = take(48);
         F.o_fr = take(8 * F.nca); // per active-contact slot: the instance's f_ref (6), its weight-vector index, pad
         F.o_int = take((nv + 16) / 2 + 1);
+        F.o_Md = take(nv); // diagonal of the mass matrix (its strict lower triangle sits in the upper triangle of the augmented matrix)
         // arrays that are dead once J has been formed: the iteration vectors of the continuation alias them
         const int dead0 = o;
         F.o_Z = take(P.nref > zq ? P.nref : zq);
@@ -332,12 +380,16 @@ namespace dev {
         o = dead0 + (vsz > F.total - dead0 ? vsz : F.total - dead0);
         F.s_int = take((2 * (n + 2) + S.mi + 1) / 2 + 1);
         F.s_J = take(n * S.ldJ);
+        F.s_M = take(nv * (nv + 1) / 2); // packed lower triangle of M: R is about to overwrite the augmented matrix that held it
         F.s_total = o;
         F.ok = 1;
         return true;
     }
 
     // ------------------------------------------------------------------------------------------ device
+#ifndef IWBC_FAST_MINB
+#define IWBC_FAST_MINB 4 // CTAs of k_fast per SM the register budget is compiled for
+#endif
     template <int T>
     struct FT {
         static constexpr int PAIR = T >= 64 ? 2 : 1;                   // threads per row in the Cholesky
@@ -382,15 +434,15 @@ namespace dev {
     {
         const int nv = NV_ ? NV_ : gP->nv, me = ME_ ? ME_ : F.me, NC = me + 1;
         const int nq = gP->nq, nj = gP->nj, nu = 6, na = nv - nu, nfr = gP->nframes, n = ME_ ? nv + 2 * (me - 6) : S.n;
-        const int ld = (nv + me + 2) & ~1, nvp = (nv + 3) & ~3, ldM = nv | 1; // = F.ldh, F.nvp, S.ldM
+        const int ld = (nv + me + 2) & ~1, nvp = (nv + 3) & ~3; // = F.ldh, F.nvp
         double* const qs = smem + F.o_qs;
         double* const vs = smem + F.o_vs;
         double* const X = smem + F.o_X;
         double* const Y = smem + F.o_Y;
         double* const Z = smem + F.o_Z;
         double* const A = X;
-        double* const bvec = X + F.nrows * nvp;
-        double* const M = X;
+        double* const bvec = X + F.crows * nvp;
+        double* const Md = smem + F.o_Md;
         double* const Hs = Y;
         double* const liMi = Y + F.d_liMi;
         double* const vJ = Y + F.d_oMf; // scratch until the frames are computed
@@ -416,7 +468,7 @@ namespace dev {
         sm.qs = qs, sm.vs = vs, sm.ref = Z;
         sm.oMi = Y + F.d_oMi, sm.Sw = Y + F.d_Sw, sm.vw = Y + F.d_vw, sm.aw = Y + F.d_aw, sm.Yw = Y + F.d_Yw, sm.fw = Y + F.d_fw, sm.Fc = Y + F.d_Fc;
         sm.oMf = Y + F.d_oMf, sm.vf = Y + F.d_vf, sm.af = Y + F.d_af;
-        sm.M = M, sm.Jft = smem + F.o_Jft, sm.cb = smem + F.o_cb, sm.nle = smem + F.o_nle, sm.lb = smem + F.o_lb, sm.ub = smem + F.o_ub;
+        sm.M = Hs, sm.Md = Md, sm.Jft = smem + F.o_Jft, sm.cb = smem + F.o_cb, sm.nle = smem + F.o_nle, sm.lb = smem + F.o_lb, sm.ub = smem + F.o_ub;
         sm.x = xv, sm.g = gvec, sm.sc = sc;
         sm.dofj = reinterpret_cast<int*>(smem + F.o_int);
 
@@ -776,14 +828,26 @@ namespace dev {
             }
         }
         fsync<T>();
-        // ---------------------------------------------------------------- rows: A (dense level-1 rows, scaled by sqrt(w)), b, contact Jacobians
-        {
+        // ---------------------------------------------------------------- rows: A (dense level-1 rows, scaled by sqrt(w)), b, contact Jacobians;
+        // H = A'A in 4 x 4 register tiles (lower triangle), g = -A'b - posture.  The rows are formed and folded in F.nchunk chunks of
+        // whole row blocks (the accumulators stay in registers across the chunks; summation order = row order, as before).
+        double hacc[FT<T>::NTPT][16];
+#pragma unroll 1
+        for (int tt = 0; tt < FT<T>::NTPT; ++tt)
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                hacc[tt][e] = 0;
+        for (int k = (T - 1 - tid); k < nv; k += T)
+            gvec[k] = 0.0;
+#pragma unroll 1
+        for (int ch = 0; ch < F.nchunk; ++ch) {
+            const int b0 = F.ch_b0[ch], b1 = F.ch_b1[ch], r0 = F.ch_r0[ch], R = F.ch_nr[ch];
             const int NH = (T / nv) > 0 ? (T / nv) : 1;
             for (int item = tid; item < nv * NH; item += T) {
                 const int hh = item / nv, k = item - hh * nv;
                 const int jk = gF->dofj[k];
                 const V3 sl = ld3(sm.Sw + 6 * k), sa = ld3(sm.Sw + 6 * k + 3);
-                for (int bi = hh; bi < F.nblocks; bi += NH) {
+                for (int bi = b0 + hh; bi < b1; bi += NH) {
                     const FBlock Bk = gF->blocks[bi];
                     if (Bk.kind == FB_CONTACT) {
                         const int c = Bk.index;
@@ -795,6 +859,7 @@ namespace dev {
                     }
                     const iwbc_task_t& Tk = gP->tasks[Bk.index];
                     const double sw = sqrt(Tk.weight);
+                    double* const Ab = A + (Bk.row0 - r0) * nvp + k;
                     if (Bk.kind == FB_SE3) {
                         V3 l, a;
                         frame_jac_col(gP, sm, Tk.frame, k, l, a);
@@ -803,14 +868,14 @@ namespace dev {
 #pragma unroll
                         for (int i = 0; i < 6; ++i)
                             if (Tk.mask[i])
-                                A[(Bk.row0 + idx++) * nvp + k] = sw * col[i];
+                                Ab[(idx++) * nvp] = sw * col[i];
                     }
                     else if (Bk.kind == FB_COM) {
                         const double imt = 1.0 / sc[0];
                         int idx = 0;
                         for (int i = 0; i < 3; ++i)
                             if (Tk.mask[i])
-                                A[(Bk.row0 + idx++) * nvp + k] = sw * imt * sm.Fc[6 * k + i];
+                                Ab[(idx++) * nvp] = sw * imt * sm.Fc[6 * k + i];
                     }
                     else if (Bk.kind == FB_MOM) {
                         const V3 com = ld3(sc + 22);
@@ -820,7 +885,7 @@ namespace dev {
 #pragma unroll
                         for (int i = 0; i < 6; ++i)
                             if (Tk.mask[i])
-                                A[(Bk.row0 + idx++) * nvp + k] = sw * col[i];
+                                Ab[(idx++) * nvp] = sw * col[i];
                     }
                     else { // FB_SELFCOL
                         const int lwa = !gP->sc_jacobian_world;
@@ -834,12 +899,12 @@ namespace dev {
                         double acc = 0;
                         for (int a = 0; a < Tk.nav; ++a)
                             acc += dot(ld3(sc4 + 4 * (Bk.slot0 + a)), c0 - col(Tk.av_frame[a]));
-                        A[Bk.row0 * nvp + k] = sw * acc;
+                        Ab[0] = sw * acc;
                     }
                 }
             }
-            for (int r = tid; r < F.nrows; r += T) {
-                const FRow Rw = gF->rows[r];
+            for (int r = tid; r < R; r += T) {
+                const FRow Rw = gF->rows[r0 + r];
                 const iwbc_task_t& Tk = gP->tasks[Rw.task];
                 const double sw = sqrt(Tk.weight);
                 double val;
@@ -854,22 +919,11 @@ namespace dev {
                 for (int k = nv; k < nvp; ++k) // zero padding of the row
                     A[r * nvp + k] = 0.0;
             }
-        }
-        fsync<T>();
-        if (cyc && tid == 0)
-            cyc[2] = clock64();
-
-        // ---------------------------------------------------------------- H = A'A in 4 x 4 register tiles (lower triangle), g = -A'b - posture
-        double hacc[FT<T>::NTPT][16];
-        {
-            const int R = F.nrows;
+            fsync<T>();
 #pragma unroll 1
             for (int tt = 0; tt < FT<T>::NTPT; ++tt) {
                 const int tile = tt * T + tid;
                 double* h = hacc[tt];
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                    h[e] = 0;
                 if (tile < F.ntiles) {
                     const double* Ai = A + 4 * gF->tile_i[tile];
                     const double* Aj = A + 4 * gF->tile_j[tile];
@@ -883,37 +937,52 @@ namespace dev {
                     }
                 }
             }
-            // g: threads from the top end (the tile owners sit at the bottom end)
+            // g: threads from the top end (the tile owners sit at the bottom end); thread-owned accumulator in shared memory
             for (int k = (T - 1 - tid); k < nv; k += T) {
                 double s = 0;
                 for (int r = 0; r < R; ++r)
                     s += A[r * nvp + k] * bvec[r];
-                s = -s;
-                if (k >= nu) {
-                    const int i = k - nu;
-                    for (int pt = 0; pt < F.nposture; ++pt) {
-                        const iwbc_task_t& Tk = gP->tasks[F.posture[pt]];
-                        if (!Tk.mask[i])
-                            continue;
-                        const double* r = Z + Tk.ref_off;
-                        const double a_des = -Tk.kp[0] * (qs[nq - na + i] - r[i]) - Tk.kd[0] * (vs[nv - na + i] - r[na + i]) + r[2 * na + i];
-                        s -= Tk.weight * a_des;
-                    }
+                gvec[k] -= s;
+            }
+            fsync<T>(); // this chunk of A is dead
+        }
+        for (int k = (T - 1 - tid); k < nv; k += T) {
+            if (k >= nu) {
+                double s = gvec[k];
+                const int i = k - nu;
+                for (int pt = 0; pt < F.nposture; ++pt) {
+                    const iwbc_task_t& Tk = gP->tasks[F.posture[pt]];
+                    if (!Tk.mask[i])
+                        continue;
+                    const double* r = Z + Tk.ref_off;
+                    const double a_des = -Tk.kp[0] * (qs[nq - na + i] - r[i]) - Tk.kd[0] * (vs[nv - na + i] - r[na + i]) + r[2 * na + i];
+                    s -= Tk.weight * a_des;
                 }
                 gvec[k] = s;
             }
         }
-        fsync<T>(); // A is dead
-        // ---------------------------------------------------------------- mass matrix M[r][c] = S_lo . F_hi when joint(lo) supports joint(hi)
-        for (int e = tid; e < nv * nv; e += T) {
-            const int r = e / nv, c = e - r * nv;
-            if (c > r)
-                continue;
-            double m = 0;
-            if (supports(gP, gF->dofj[c], gF->dofj[r]))
-                m = dot(ld3(sm.Sw + 6 * c), ld3(sm.Fc + 6 * r)) + dot(ld3(sm.Sw + 6 * c + 3), ld3(sm.Fc + 6 * r + 3));
-            M[r * ldM + c] = m;
-            M[c * ldM + r] = m;
+        if (cyc && tid == 0)
+            cyc[2] = clock64();
+        // ---------------------------------------------------------------- mass matrix M[r][c] = S_lo . F_hi when joint(lo) supports joint(hi): one half,
+        // held in registers until the dynamics scratch it is computed from is dead (its home is the upper triangle of the augmented
+        // matrix, which overlays that scratch)
+        constexpr int MNV = NV_ > 0 ? NV_ : 60; // (the tile table bounds nv to 60)
+        constexpr int MPT = (MNV * (MNV + 1) / 2 + T - 1) / T;
+        double mreg[MPT];
+#pragma unroll
+        for (int m = 0; m < MPT; ++m) {
+            const int e = m * T + tid;
+            mreg[m] = 0.0;
+            if (e < nv * (nv + 1) / 2) {
+                int r = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
+                while (r * (r + 1) / 2 > e)
+                    --r;
+                while ((r + 1) * (r + 2) / 2 <= e)
+                    ++r;
+                const int c = e - r * (r + 1) / 2;
+                if (supports(gP, gF->dofj[c], gF->dofj[r]))
+                    mreg[m] = dot(ld3(sm.Sw + 6 * c), ld3(sm.Fc + 6 * r)) + dot(ld3(sm.Sw + 6 * c + 3), ld3(sm.Fc + 6 * r + 3));
+            }
         }
         fsync<T>(); // the dynamics scratch is dead
         // ---------------------------------------------------------------- augmented matrix: [H ; N' ; g'] (column-major, ld = ldh)
@@ -940,14 +1009,37 @@ namespace dev {
                         }
                 }
             }
-            // constraint normals (dv part) as rows nv .. nv+me-1, the gradient as row nv+me
-            for (int e = tid; e < (me + 1) * nv; e += T) {
-                const int c = e / nv, k = e - c * nv;
+            // the mass matrix: strict lower triangle into the (unused) upper triangle of the augmented matrix -- M(r, c), r > c, at
+            // Hs[c + r ld] --, its diagonal into Md; its first nu rows are the base-dynamics normals (rows nv+cb0 .. nv+me-1)
+#pragma unroll
+            for (int m = 0; m < MPT; ++m) {
+                const int e = m * T + tid;
+                if (e < nv * (nv + 1) / 2) {
+                    int r = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
+                    while (r * (r + 1) / 2 > e)
+                        --r;
+                    while ((r + 1) * (r + 2) / 2 <= e)
+                        ++r;
+                    const int c = e - r * (r + 1) / 2;
+                    const double val = mreg[m];
+                    if (r == c)
+                        Md[r] = val;
+                    else
+                        Hs[c + r * ld] = val;
+                    if (c < nu) {
+                        Hs[(nv + F.cb0 + c) + r * ld] = val;
+                        if (r < nu && r != c)
+                            Hs[(nv + F.cb0 + r) + c * ld] = val;
+                    }
+                }
+            }
+            // constraint normals (dv part) of the contacts as rows nv .. nv+cb0-1, the gradient as row nv+me
+            for (int e = tid; e < (F.cb0 + 1) * nv; e += T) {
+                const int c0 = e / nv, k = e - c0 * nv;
+                const int c = c0 < F.cb0 ? c0 : me;
                 double val;
                 if (c < F.cb0)
                     val = sm.Jft[(F.cact[c / 6] * 6 + (c % 6)) * nv + k];
-                else if (c < me)
-                    val = M[(c - F.cb0) * ldM + k];
                 else
                     val = gvec[k];
                 Hs[(nv + c) + k * ld] = val;
@@ -1015,12 +1107,12 @@ namespace dev {
                     if (act && sub == 0) {
                         double* Ri = Hs + i + cb * ld;
                         const double v0 = Ri[0] - a0, v1 = pw > 1 ? Ri[ld] - a1 : 0.0, v2 = pw > 2 ? Ri[2 * ld] - a2 : 0.0, v3 = pw > 3 ? Ri[3 * ld] - a3 : 0.0;
-                        Ri[0] = v0;
-                        if (pw > 1)
+                        Ri[0] = v0; // (lower triangle only: the upper triangle of the dv block holds the mass matrix)
+                        if (pw > 1 && i > cb)
                             Ri[ld] = v1;
-                        if (pw > 2)
+                        if (pw > 2 && i > cb + 1)
                             Ri[2 * ld] = v2;
-                        if (pw > 3)
+                        if (pw > 3 && i > cb + 2)
                             Ri[3 * ld] = v3;
                         if (i < cb + 4) {
                             double* dr = Db + 4 * (i - cb);
@@ -1453,7 +1545,7 @@ namespace dev {
         // ---------------------------------------------------------------- s = CI x + ci0: eiquadprog's termination test at x_eq
         Sizes z;
         z.nv = nv, z.nq = nq, z.nj = nj, z.nf = nfr, z.nc = gP->ncontacts, z.n = n, z.mi = S.mi, z.rows_dense = S.rows_dense, z.nref = gP->nref;
-        z.ldJ = S.ldJ, z.ldM = ldM;
+        z.ldJ = S.ldJ, z.ldM = ld, z.msym = 1;
         z.S = &S, z.P = gP;
         FusedRows::wrenches<T>(sm, z, tid);
         fsync<T>();
@@ -1522,11 +1614,11 @@ namespace dev {
         auto Usel = [&](int s) { return s == 0 ? Uq0 : (s == 1 ? Uq1 : gF->Uff[(int)frv[8 * s + 6]][s]); }; // (humanoids: two contacts)
         Sizes z;
         z.nv = nv, z.nq = gP->nq, z.nj = gP->nj, z.nf = gP->nframes, z.nc = gP->ncontacts, z.n = n, z.mi = S.mi, z.rows_dense = S.rows_dense;
-        z.nref = gP->nref, z.ldJ = ldJ, z.ldM = nv | 1;
+        z.nref = gP->nref, z.ldJ = ldJ, z.ldM = 0, z.msym = 2;
         z.S = &S, z.P = gP;
         Sm sm;
         sm.qs = smem + F.o_qs, sm.vs = smem + F.o_vs, sm.ref = Z;
-        sm.M = smem + F.o_X, sm.Jft = smem + F.o_Jft, sm.cb = smem + F.o_cb, sm.nle = smem + F.o_nle, sm.lb = smem + F.o_lb, sm.ub = smem + F.o_ub;
+        sm.M = smem + F.s_M, sm.Md = nullptr, sm.Jft = smem + F.o_Jft, sm.cb = smem + F.o_cb, sm.nle = smem + F.o_nle, sm.lb = smem + F.o_lb, sm.ub = smem + F.o_ub;
         sm.x = smem + F.o_x, sm.g = smem + F.o_g, sm.sc = smem + F.o_sc;
         sm.dofj = reinterpret_cast<int*>(smem + F.o_int);
         sm.J = smem + F.s_J;
@@ -1551,6 +1643,21 @@ namespace dev {
             sm.act = ip, ip += n + 2;
             sm.act_old = ip, ip += n + 2;
             sm.iai = ip;
+        }
+        // The mass matrix leaves the augmented matrix (fast_instance kept its strict lower triangle in that matrix's upper triangle, which
+        // R and the J construction overwrite): packed lower triangle in the continuation's own region.  (Readers and overwriters are
+        // all behind at least one barrier.)
+        {
+            const double* Md = smem + F.o_Md;
+            for (int e = tid; e < nv * (nv + 1) / 2; e += T) {
+                int r = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
+                while (r * (r + 1) / 2 > e)
+                    --r;
+                while ((r + 1) * (r + 2) / 2 <= e)
+                    ++r;
+                const int c = e - r * (r + 1) / 2;
+                sm.M[e] = r == c ? Md[r] : Hs[c + r * ld];
+            }
         }
         if (code < 0) { // Cholesky failed: eiquadprog cannot start (gi_solve's convention)
             for (int k = tid; k < n; k += T)
@@ -1796,7 +1903,7 @@ namespace dev {
     // One CTA of T threads per instance, persistent over the batch.  Instances that need the active-set iteration are
     // appended to io.slow_list (order is arbitrary; every instance's results are independent of it).
     template <int T, int NV_, int ME_>
-    __global__ void __launch_bounds__(T, 3)
+    __global__ void __launch_bounds__(T, IWBC_FAST_MINB)
         k_fast(const iwbc_problem_t* __restrict__ gP, const FPlan* __restrict__ gF, const __grid_constant__ Shape S, const __grid_constant__ FShape F, IO io)
     {
         extern __shared__ double smem[];
