@@ -562,6 +562,11 @@ def run_workload(ctx, workload, steps, warmup, batch=0, with_cpu=False, peak=Non
                      "peak_source": "measured live (dependent-FMA probe, iwbc_measure_fp64_tflops); MEASURED_PEAKS.json holds no FP64 figure",
                      "peak_probe": peak, "frac_of_clock_bound": achieved / peak["clock_bound_tflops"] if peak.get("clock_bound_tflops") else None,
                      "flops_per_update": fl_parts[p0.workload] if len(parts) == 1 else fl_parts, "kernel_ms": kern_ms, "traffic": traffic,
+                     # measured DRAM bytes per launch (ncu, profiles/traffic.json) over this run's kernel time: what the kernel really asks of
+                     # HBM -- for the thread-per-instance arm kernel (local-memory working set) this, not FP64, is the nearer roof
+                     "traffic_hbm": ({"achieved": traffic * (B / WORKLOADS[workload][2] if workload in WORKLOADS else 1.0) / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak,
+                                      "unit": "GB/s", "frac": traffic * (B / WORKLOADS[workload][2] if workload in WORKLOADS else 1.0) / (kern_ms * 1e-3) / 1e9 / hbm_peak}
+                                     if traffic else None),
                      "hbm": {"achieved": io_step / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": io_step / (kern_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_update": io_step / B,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
@@ -649,6 +654,7 @@ def main():
                 if d is not None:
                     sec[wl] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "e2e": d["e2e"]["value"],
                                "p50_cycle_latency_ms": d["e2e"].get("p50_cycle_latency_ms"), "roofline_frac": d["roofline"]["frac"],
+                               "traffic_hbm_frac": (d["roofline"].get("traffic_hbm") or {}).get("frac"),
                                "gpu_launches": d["gpu_launches"], "per_gpu_batch": d["config"]["per_gpu_batch"], "n_gpus": d["n_gpus"],
                                "optimal_fraction": d["config"]["optimal_fraction"]}
             except Exception as e:  # the headline line must not depend on it

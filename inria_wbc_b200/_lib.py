@@ -16,7 +16,8 @@ class IwbcError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libiwbc_b200.so")
+    # (IWBC_B200_LIB: another build of the same library, for A/B measurements of compile-time variants)
+    return os.environ.get("IWBC_B200_LIB") or os.path.join(_HERE, "libiwbc_b200.so")
 
 
 _lib = None

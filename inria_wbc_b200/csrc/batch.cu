@@ -267,7 +267,8 @@ int iwbc_run_cycle(iwbc_batch* b, const dev::IO& io, unsigned mask, cudaStream_t
             dev::IO iop = io;
             if (io.in_list)
                 iop.list = io.in_list, iop.list_count = io.in_count;
-            const int grid = std::min(b->sm_count * 4, (io.B + 127) / 128);
+            static const int tpi_ctas = [] { const char* e = std::getenv("IWBC_TPI_CTAS"); return e ? std::atoi(e) : 4; }(); // CTAs per SM (tuning aid)
+            const int grid = std::min(b->sm_count * tpi_ctas, (io.B + 127) / 128);
             return b->shape.total <= 1024 ? iwbc_launch_cycle_tpi_1024(b, iop, grid, st) : iwbc_launch_cycle_tpi_1792(b, iop, grid, st);
         }
     }

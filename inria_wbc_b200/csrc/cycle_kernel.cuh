@@ -53,6 +53,7 @@ inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
 inline int atomicAdd(int* p, int v) { const int o = *p; *p += v; return o; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 struct double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline double __longlong_as_double(long long v) { double d; std::memcpy(&d, &v, 8); return d; }
 inline long long clock64() { return 0; }
 inline void sincos(double x, double* s, double* c) { *s = std::sin(x); *c = std::cos(x); }

@@ -81,7 +81,7 @@ namespace dev {
     // (interleaved across the warp by the hardware: lane-adjacent instances touch adjacent words).  A warp instruction then
     // advances 32 instances instead of one.
     template <int MAXD, int MINB>
-    __global__ void __launch_bounds__(128, MINB) k_cycle_tpi(const iwbc_problem_t* __restrict__ gP, const __grid_constant__ Shape S, IO io)
+    __global__ void __launch_bounds__(128, MINB) k_cycle_tpi(const iwbc_problem_t* __restrict__ gP, const __grid_constant__ Shape S, IO io, int first, int last)
     {
         double buf[MAXD];
         Sizes z;
@@ -95,11 +95,11 @@ namespace dev {
                 sm.dofj[c0 + k] = j;
         }
         int flip = 0;
-        const int count = io.list ? *io.list_count : io.B;
-        // (warp-uniform trip count and a reconvergence point per pass: lanes that finish their active-set iteration early must not
-        // run ahead into their next instance, or the warp degenerates into 32 serial threads)
+        // positions [first, last) of the batch / list: the host launches one pass per kernel (below)
+        const int total = io.list ? *io.list_count : io.B;
+        const int count = last < total ? last : total;
         const int lane = threadIdx.x & 31;
-        for (int base = blockIdx.x * blockDim.x + (threadIdx.x - lane); base < count; base += gridDim.x * blockDim.x) {
+        for (int base = first + blockIdx.x * blockDim.x + (threadIdx.x - lane); base < count; base += gridDim.x * blockDim.x) {
             const int idx = base + lane;
             if (idx < count) {
                 const int inst = io.list ? io.list[idx] : idx;
@@ -242,8 +242,17 @@ int launch_qp_dense(const dev::Shape& S, const dev::QpIO& io, int device, int sm
 #ifdef IWBC_CYC_TPI
 int launch_tpi(iwbc_batch* b, const dev::IO& iop, int grid, cudaStream_t st)
 {
-    dev::k_cycle_tpi<IWBC_CYC_TPI, 4><<<grid, 128, 0, st>>>(b->d_prob, b->shape, iop);
-    b->launches++;
+    // One pass per launch: the warps of a pass walk the (large) kernel in near lock-step and share the instruction cache; in a
+    // grid-stride loop they drift apart pass by pass and the cache thrashes (measured, Tiago: 40 M/s in one pass of 65 536 states,
+    // 33 / 22 M/s with two / four passes in one launch -- at one CTA per SM the effect is absent).  Equal passes, each at most the
+    // resident capacity.
+    const int cap = grid * 128, passes = (iop.B + cap - 1) / cap;
+    const int per = (((iop.B + passes - 1) / passes) + 127) & ~127;
+    for (int first = 0; first < iop.B; first += per) {
+        const int last = std::min(iop.B, first + per);
+        dev::k_cycle_tpi<IWBC_CYC_TPI, 4><<<(last - first + 127) / 128, 128, 0, st>>>(b->d_prob, b->shape, iop, first, last);
+        b->launches++;
+    }
     CUDA_TRY(cudaGetLastError());
     return IWBC_OK;
 }

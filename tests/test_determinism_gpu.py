@@ -70,13 +70,15 @@ def test_gpu_rollouts_match_the_oracle_over_50000_ticks():
                 # position bound then returns 1e6 (its `q == qmin` branch) and the QP is infeasible: the reference throws there, the
                 # oracle roll-out stops, the batched path reports the status and keeps the state.  Whether the limit is hit exactly
                 # in one squat cycle or the next is decided by the last bit of the state, so the two sides may disagree on WHEN
-                # (measured: 30 122 vs 34 024).  Required: agreement to 1e-8 on every tick before the first of the two events, and
-                # at that tick the oracle, evaluated on the GPU's own state, reports the same status after the same iterations.
+                # (measured: 30 122 vs 34 024, and after a change of summation order in the kernel the other way round).  Required:
+                # agreement to 1e-8 on every tick before the first of the two events, and at that tick the oracle, evaluated on the
+                # GPU's own state, reports the same status after the same iterations as the GPU (non-optimal when the event is the
+                # GPU's; optimal when it is the oracle's, whose own state differs in the last bit).
                 assert status != 0 or failed_at is not None
                 bad = np.where(err_t > 1e-8)[0]
                 td = int(bad[0]) if len(bad) else n
                 assert td > 20000 and err_t[:td].max() < 1e-8, (beh, urdf, td)
-                if status != 0 and td < TICKS:
+                if td < TICKS:
                     P = _fresh(urdf)
                     b2, bt2 = iw.Behavior(P, "talos/%s.yaml" % beh), iw.Batch(P, 0, 1)
                     q, v = P.q0()[None].copy(), np.zeros((1, P.nv))
@@ -87,7 +89,8 @@ def test_gpu_rollouts_match_the_oracle_over_50000_ticks():
                     host = behaviors.Cartesian(P, cfg) if beh == "arm" else behaviors.MoveCom(P, cfg)
                     ref = host.table(b2.total_ticks)[td % b2.total_ticks]
                     oc = ol.cycle_batch(P, qb, vb, ref)
-                    assert o.status[0] != 0 and o.status[0] == oc["status"][0] and o.iters[0] == oc["iters"][0], (beh, urdf, td)
+                    assert o.status[0] == oc["status"][0] and o.iters[0] == oc["iters"][0], (beh, urdf, td)
+                    assert o.status[0] != 0 or failed_at == td, (beh, urdf, td, failed_at)
                 note = " (first non-optimal QP: GPU tick %d, oracle tick %s -- the joint limit is met exactly, see the test)" % (td, failed_at)
                 n = td
             err = err_t[:n].max()

@@ -31,6 +31,26 @@ for r in rows[2:]:
     for k in KEYS:
         if k in d:
             print("  %-82s %s %s" % (k, d[k], u[k]))
+    # every other stall reason above 0.05 warps per issue, and the pipe utilisations
+    for k in sorted(d):
+        if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio") and k not in KEYS:
+            try:
+                if float(d[k]) > 0.05:
+                    print("  %-82s %s %s" % (k, d[k], u[k]))
+            except ValueError:
+                pass
+    for k in sorted(d):
+        if (k.startswith("sm__inst_executed_pipe_") or k.startswith("sm__pipe_")) and k.endswith("pct_of_peak_sustained_active") and k not in KEYS:
+            try:
+                if float(d[k]) > 2.0:
+                    print("  %-82s %s %s" % (k, d[k], u[k]))
+            except ValueError:
+                pass
+    for k in ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed",
+              "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__cycles_elapsed.max", "smsp__warps_eligible.avg.per_cycle_active",
+              "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed"):
+        if k in d:
+            print("  %-82s %s %s" % (k, d[k], u[k]))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 kern, cur, data = None, None, {}
@@ -61,3 +81,14 @@ for kern, files in data.items():
             ii = sum(v[1] for l, v in d.items() if a <= l < b)
             if s * 200 > tot or ii * 200 > toti:
                 print("  %-22s %5d-%5d %-72s samples %5.1f%%  inst %5.1f%%" % (os.path.basename(f), a, b, nm, 100.0 * s / tot, 100.0 * ii / toti))
+    # the hottest source lines (stall samples), with their share of executed warp instructions
+    flat = [(v[0], v[1], f, l) for f, d in files.items() if "csrc" in f for l, v in d.items()]
+    flat.sort(reverse=True)
+    print("\n## hottest source lines of", kern, "(samples %, inst %, file:line, text)")
+    for smp, ins, f, l in flat[:45]:
+        local = f.replace("/root/repo", ROOT)
+        text = ""
+        if os.path.exists(local):
+            ls = open(local).read().split("\n")
+            text = ls[l - 1].strip()[:110] if l - 1 < len(ls) else ""
+        print("  %5.2f%% %5.2f%%  %s:%d  %s" % (100.0 * smp / tot, 100.0 * ins / toti, os.path.basename(f), l, text))
