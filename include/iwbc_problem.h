@@ -38,7 +38,11 @@ enum iwbc_task_type {
     IWBC_T_MOMENTUM = 3,  /* TaskMEquality (src/tsid/task-momentum-equality.cpp:144-174) */
     IWBC_T_SELFCOL = 4,   /* TaskSelfCollision (src/tsid/task-self-collision.cpp:84-204) */
     IWBC_T_BOUNDS = 5,    /* TaskJointPosVelAccBounds */
-    IWBC_T_ACTBOUNDS = 6  /* TaskActuationBounds */
+    IWBC_T_ACTBOUNDS = 6, /* TaskActuationBounds */
+    IWBC_T_TORQUE = 7     /* TaskActuationEquality through addActuationTask (tasks.cpp:227-271): level-1 cost on the joint torques
+                             tau = M_a dv + h_a - J_a^T f; reference block = [tau_ref (na) ; weight vector (na)] (setReference /
+                             setWeightVector); mask: na entries.  Upstream TSID source is not in the reference tree: restated
+                             from the published task-actuation-equality.cpp / inverse-dynamics-formulation-acc-force.cpp. */
 };
 
 /* kinds of level-0 / level-1 blocks, in HQPData insertion order */

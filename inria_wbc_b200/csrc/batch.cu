@@ -181,7 +181,7 @@ int prepare_shape(iwbc_batch* b, unsigned mask)
     }
     S.rows_dense = 0;
     for (int k = 0; k < P.nl1; ++k)
-        if (P.l1[k].kind == IWBC_B_TASK && P.tasks[P.l1[k].index].type != IWBC_T_POSTURE)
+        if (P.l1[k].kind == IWBC_B_TASK && P.tasks[P.l1[k].index].type != IWBC_T_POSTURE && P.tasks[P.l1[k].index].type != IWBC_T_TORQUE)
             S.rows_dense += P.tasks[P.l1[k].index].nrows;
     S.maxdepth = 0;
     for (int j = 0; j < P.nj; ++j)

@@ -797,6 +797,19 @@ namespace dev {
     }
 
     // =================================================================================== k_asm
+    // M(r, k).  msym 0: full nv x ldM.  1: strict lower triangle only, row r at M + r ldM (k < r), diagonal in Md -- the fast pass keeps
+    // M in the unused upper triangle of its column-major augmented matrix (ldM = that matrix's leading dimension).  2: packed lower
+    // triangle, row r at M + r (r + 1) / 2 (k <= r) -- the continuation's own copy (its R overwrites the augmented matrix).
+    __device__ __forceinline__ double mass_at(const Sm& sm, const Sizes& z, int r, int k)
+    {
+        if (z.msym == 0)
+            return sm.M[r * z.ldM + k];
+        const int hi = r > k ? r : k, lo = r > k ? k : r;
+        if (z.msym == 1)
+            return hi == lo ? sm.Md[hi] : sm.M[hi * z.ldM + lo];
+        return sm.M[hi * (hi + 1) / 2 + lo];
+    }
+
     // Fills: Jft / cb (contacts), lb / ub (acceleration bounds), A / b (dense level-1 rows, scaled
     // by sqrt(w)), then H (lower triangle, in sm.J) and g.
     template <int G>
@@ -1033,6 +1046,48 @@ namespace dev {
                     sm.g[o + k] -= C.w_forcereg * s;
                 }
             }
+            else if (z.P->tasks[Bk.index].type == IWBC_T_TORQUE) {
+                // TaskActuationEquality as a level-1 cost (tasks.cpp:227-271): w || diag(s) S (M_a dv - J_a^T f + h_a - tau_ref) ||^2.
+                // Row i over [dv ; f]: D(i, k) = M(nu + i, k) for k < nv, -(T_c^T Jft_c)[k'][nu + i] for the force columns; it couples
+                // dv and f, so the fast path (block-diagonal H) never takes a problem with this task.
+                const iwbc_task_t& T = z.P->tasks[Bk.index];
+                const double* r = sm.ref + T.ref_off; // tau_ref (na), weight vector (na)
+                auto Dik = [&](int i, int k) -> double {
+                    if (k < nv)
+                        return mass_at(sm, z, nu + i, k);
+                    int c = 0;
+                    for (int cc = 0; cc < z.P->ncontacts; ++cc)
+                        if (S.cidx[cc] >= 0 && k - nv >= S.cidx[cc] && k - nv < S.cidx[cc] + 12)
+                            c = cc;
+                    const int kk = k - nv - S.cidx[c];
+                    const double* Tm = z.P->contacts[c].T;
+                    double s = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+                        s += Tm[a * 12 + kk] * sm.Jft[(c * 6 + a) * nv + nu + i];
+                    return -s;
+                };
+                for (int e = tid; e < n * (n + 1) / 2; e += G) {
+                    int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+                    while (a * (a + 1) / 2 > e)
+                        --a;
+                    while ((a + 1) * (a + 2) / 2 <= e)
+                        ++a;
+                    const int b = e - a * (a + 1) / 2;
+                    double s = 0;
+                    for (int i = 0; i < na; ++i)
+                        if (T.mask[i])
+                            s += (r[na + i] * Dik(i, a)) * (r[na + i] * Dik(i, b));
+                    sm.J[a + b * ld] += T.weight * s;
+                }
+                for (int k = tid; k < n; k += G) {
+                    double s = 0;
+                    for (int i = 0; i < na; ++i)
+                        if (T.mask[i])
+                            s += (r[na + i] * Dik(i, k)) * (r[na + i] * (r[i] - sm.nle[nu + i]));
+                    sm.g[k] -= T.weight * s;
+                }
+            }
             else {
                 const iwbc_task_t& T = z.P->tasks[Bk.index];
                 if (T.type != IWBC_T_POSTURE)
@@ -1055,19 +1110,6 @@ namespace dev {
     }
 
     // =================================================================================== k_qp
-    // M(r, k).  msym 0: full nv x ldM.  1: strict lower triangle only, row r at M + r ldM (k < r), diagonal in Md -- the fast pass keeps
-    // M in the unused upper triangle of its column-major augmented matrix (ldM = that matrix's leading dimension).  2: packed lower
-    // triangle, row r at M + r (r + 1) / 2 (k <= r) -- the continuation's own copy (its R overwrites the augmented matrix).
-    __device__ __forceinline__ double mass_at(const Sm& sm, const Sizes& z, int r, int k)
-    {
-        if (z.msym == 0)
-            return sm.M[r * z.ldM + k];
-        const int hi = r > k ? r : k, lo = r > k ? k : r;
-        if (z.msym == 1)
-            return hi == lo ? sm.Md[hi] : sm.M[hi * z.ldM + lo];
-        return sm.M[hi * (hi + 1) / 2 + lo];
-    }
-
     // Implicit constraint rows of the fused problem.
     struct FusedRows {
         // np <- CE.row(i) ; returns ce0_i

@@ -468,8 +468,36 @@ namespace host {
                 P.l0[P.nl0++] = {IWBC_B_CONTACT_FORCE, cid};
                 P.l1[P.nl1++] = {IWBC_B_CONTACT_REG, cid};
             }
-            else if (type == "cop" || type == "torque")
-                throw ConfigError("task type '" + type + "' (" + name + ") is not supported by the batched path yet (SURVEY §8 f-2)");
+            else if (type == "torque") {
+                // make_torque (tasks.cpp:227-271): TaskActuationEquality, mask over the actuated joints (default all), optional
+                // per-joint `scaling` (setWeightVector), zero reference, addActuationTask(task, weight, 1)
+                double weight = IWBC_HCHECK(node["weight"].as<double>(), name + ".weight");
+                iwbc_task_t& t = new_task(IWBC_T_TORQUE, 1);
+                t.weight = weight;
+                if (node["mask"]) {
+                    std::string mask = IWBC_HCHECK(node["mask"].as<std::string>(), name + ".mask");
+                    if ((int)mask.size() != na)
+                        throw ConfigError("wrong size in torque mask, expected:" + std::to_string(na) + " got:" + std::to_string(mask.size()));
+                    parse_mask(mask, (size_t)na, t.mask, t.nrows, "torque");
+                }
+                else {
+                    for (int i = 0; i < na; ++i)
+                        t.mask[i] = 1;
+                    t.nrows = na;
+                }
+                t.ref_off = alloc_ref(cs, 2 * na); // tau_ref = 0, then the weight vector (TaskActuationEquality's default: ones)
+                for (int i = 0; i < na; ++i)
+                    cs.ref0[t.ref_off + na + i] = 1.0;
+                if (node["scaling"]) {
+                    auto scaling = IWBC_HCHECK(node["scaling"].as<std::vector<double>>(), name + ".scaling");
+                    if ((int)scaling.size() != na)
+                        throw ConfigError("wrong size in torque scaling, expected:" + std::to_string(na) + " got:" + std::to_string(scaling.size()));
+                    for (int i = 0; i < na; ++i)
+                        cs.ref0[t.ref_off + na + i] = scaling[i];
+                }
+            }
+            else if (type == "cop")
+                throw ConfigError("task type '" + type + "' (" + name + ") is not supported by the batched path (TaskCopEquality: DESIGN.md 8)");
             else
                 throw ConfigError("unknown task type '" + type + "' for task " + name);
         }

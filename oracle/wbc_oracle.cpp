@@ -1210,6 +1210,28 @@ void cycle(const iwbc_problem_t& P, const double* q, const double* v, const doub
             }
             add_cost(T.weight, A, b.data(), T.nrows);
         }
+        else if (T.type == IWBC_T_TORQUE) {
+            // tsid::tasks::TaskActuationEquality added with addActuationTask(task, w, 1) (tasks.cpp:227-271).  Upstream TSID is not in
+            // the reference tree; restated from its published source: the task's own constraint is row i = w_i e_i', vector
+            // w_i tau_ref_i over the masked actuated joints (task-actuation-equality.cpp: compute()), and
+            // InverseDynamicsFormulationAccForce::computeProblemData turns an actuation constraint A_tau tau = b into rows over
+            // [dv ; f] with tau = M_a dv + h_a - J_a^T f:  [A_tau M_a | -A_tau J_a^T] x = b - A_tau h_a.
+            const double* r = ref + T.ref_off; // tau_ref (na), weight vector (na)
+            Mat A(T.nrows, n);
+            Vec b(T.nrows);
+            int idx = 0;
+            for (int i = 0; i < na; ++i) {
+                if (!T.mask[i])
+                    continue;
+                const double s = r[na + i];
+                for (int k = 0; k < nv; ++k)
+                    A(idx, k) = s * D.M(nu + i, k);
+                for (int k = 0; k < nk; ++k)
+                    A(idx, nv + k) = -s * Jc(k, nu + i);
+                b[idx++] = s * (r[i] - D.nle[nu + i]);
+            }
+            add_cost(T.weight, A, b.data(), T.nrows);
+        }
         else if (T.type == IWBC_T_MOMENTUM) {
             const double* r = ref + T.ref_off;
             double L[6], drift[6] = {D.dhg.lin.x, D.dhg.lin.y, D.dhg.lin.z, D.dhg.ang.x, D.dhg.ang.y, D.dhg.ang.z};
