@@ -62,6 +62,7 @@ namespace dev {
         unsigned char dofj[IWBC_MAXNV];
         unsigned char tile_i[136], tile_j[136];
         unsigned char pair_i[IWBC_FMAXPAIRS], pair_k[IWBC_FMAXPAIRS];
+        unsigned char tri_r[1830], tri_c[1830]; // packed lower triangle (nv <= 60): entry e = r (r + 1) / 2 + c -> (r, c)
         FJob jobs[IWBC_FMAXJOBS];
         FBlock blocks[IWBC_FMAXBLK];
         FRow rows[IWBC_FMAXROWS];
@@ -258,6 +259,9 @@ namespace dev {
             }
         if (T > 1 && F.ntiles > T)
             return false;
+        for (int r = 0, e = 0; r < nv && r < 60; ++r)
+            for (int c = 0; c <= r; ++c, ++e)
+                pl.tri_r[e] = (unsigned char)r, pl.tri_c[e] = (unsigned char)c;
         for (int k = 0; k <= F.me; ++k) // k == me: the transformed right-hand side t
             for (int i = 0; i < k && i < F.me; ++i) {
                 pl.pair_i[F.npairs] = (unsigned char)i, pl.pair_k[F.npairs] = (unsigned char)k;
@@ -387,6 +391,15 @@ namespace dev {
     }
 
     // ------------------------------------------------------------------------------------------ device
+#ifndef IWBC_OPT_QR
+#define IWBC_OPT_QR 1   // Householder steps fully unrolled (static dead rows)
+#endif
+#ifndef IWBC_OPT_MTAB
+#define IWBC_OPT_MTAB 1 // (row, column) of the packed mass-matrix entries from a table instead of a square root
+#endif
+#ifndef IWBC_OPT_CHOL
+#define IWBC_OPT_CHOL 1 // 16-byte loads of the row buffer in the H tiles
+#endif
 #ifndef IWBC_FAST_MINB
 #define IWBC_FAST_MINB 4 // CTAs of k_fast per SM the register budget is compiled for
 #endif
@@ -928,8 +941,15 @@ namespace dev {
                     const double* Ai = A + 4 * gF->tile_i[tile];
                     const double* Aj = A + 4 * gF->tile_j[tile];
                     for (int r = 0; r < R; ++r) {
+#if IWBC_OPT_CHOL
+                        // (tile columns are multiples of 4 and nvp % 4 == 0: 16-byte loads)
+                        const double2 a01 = *reinterpret_cast<const double2*>(Ai + r * nvp), a23 = *reinterpret_cast<const double2*>(Ai + r * nvp + 2);
+                        const double2 b01 = *reinterpret_cast<const double2*>(Aj + r * nvp), b23 = *reinterpret_cast<const double2*>(Aj + r * nvp + 2);
+                        const double a0 = a01.x, a1 = a01.y, a2 = a23.x, a3 = a23.y, b0 = b01.x, b1 = b01.y, b2 = b23.x, b3 = b23.y;
+#else
                         const double a0 = Ai[r * nvp], a1 = Ai[r * nvp + 1], a2 = Ai[r * nvp + 2], a3 = Ai[r * nvp + 3];
                         const double b0 = Aj[r * nvp], b1 = Aj[r * nvp + 1], b2 = Aj[r * nvp + 2], b3 = Aj[r * nvp + 3];
+#endif
                         h[0] += a0 * b0, h[1] += a0 * b1, h[2] += a0 * b2, h[3] += a0 * b3;
                         h[4] += a1 * b0, h[5] += a1 * b1, h[6] += a1 * b2, h[7] += a1 * b3;
                         h[8] += a2 * b0, h[9] += a2 * b1, h[10] += a2 * b2, h[11] += a2 * b3;
@@ -974,12 +994,16 @@ namespace dev {
             const int e = m * T + tid;
             mreg[m] = 0.0;
             if (e < nv * (nv + 1) / 2) {
+#if IWBC_OPT_MTAB
+                const int r = gF->tri_r[e], c = gF->tri_c[e];
+#else
                 int r = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
                 while (r * (r + 1) / 2 > e)
                     --r;
                 while ((r + 1) * (r + 2) / 2 <= e)
                     ++r;
                 const int c = e - r * (r + 1) / 2;
+#endif
                 if (supports(gP, gF->dofj[c], gF->dofj[r]))
                     mreg[m] = dot(ld3(sm.Sw + 6 * c), ld3(sm.Fc + 6 * r)) + dot(ld3(sm.Sw + 6 * c + 3), ld3(sm.Fc + 6 * r + 3));
             }
@@ -1015,12 +1039,16 @@ namespace dev {
             for (int m = 0; m < MPT; ++m) {
                 const int e = m * T + tid;
                 if (e < nv * (nv + 1) / 2) {
+#if IWBC_OPT_MTAB
+                    const int r = gF->tri_r[e], c = gF->tri_c[e];
+#else
                     int r = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
                     while (r * (r + 1) / 2 > e)
                         --r;
                     while ((r + 1) * (r + 2) / 2 <= e)
                         ++r;
                     const int c = e - r * (r + 1) / 2;
+#endif
                     const double val = mreg[m];
                     if (r == c)
                         Md[r] = val;
@@ -1215,7 +1243,14 @@ namespace dev {
                     rowbuf[c] = cc[0];
             }
             fsync<T>();
-            for (int k = 0; k < me; ++k) {
+            // (k is a compile-time constant after unrolling: rows j = seg0 + SEG m <= k of every segment are statically dead -- on
+            // average half of the dot / update work --, and the next pivot row sits in a statically known register)
+#if IWBC_OPT_QR
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+            for (int k = 0; k < ME_; ++k) {
                 const bool frc = k >= cb0;
                 const double* rb = rowbuf + (k & 1) * NC;
                 double* rbn = rowbuf + ((k + 1) & 1) * NC;
@@ -1223,15 +1258,19 @@ namespace dev {
                     double sacc = 0;
 #pragma unroll
                     for (int m = 0; m < MR; ++m) {
+                        if (SEG * (m + 1) - 1 <= k) // dead for every segment
+                            continue;
                         const int j = seg0 + SEG * m;
                         ck[m] = (j > k && j < nv) ? colbuf[j] : 0.0;
                         sacc += ck[m] * cc[m];
                     }
+                    if (frc) {
 #pragma unroll
-                    for (int m = 0; m < MF; ++m) {
-                        const int jj = seg0 + SEG * m;
-                        ckf[m] = (frc && jj < nfrc) ? colbuf[nv + jj] : 0.0;
-                        sacc += ckf[m] * cf[m];
+                        for (int m = 0; m < MF; ++m) {
+                            const int jj = seg0 + SEG * m;
+                            ckf[m] = jj < nfrc ? colbuf[nv + jj] : 0.0;
+                            sacc += ckf[m] * cf[m];
+                        }
                     }
                     Pp[seg0 * NC + c] = sacc;
                 }
@@ -1241,7 +1280,7 @@ namespace dev {
                 for (int sg = 0; sg < SEG; ++sg)
                     sigma += Pp[sg * NC + k];
                 const double alpha = rb[k];
-                double beta = alpha, tau = 0, scale = 0, ibeta = 1.0 / alpha;
+                double beta = alpha, tau = 0, scale = 0, ibeta = 0;
                 if (sigma != 0.0) {
                     const double nn = alpha * alpha + sigma;
                     const double inr = rsqrt(nn), nr = nn * inr;
@@ -1256,7 +1295,7 @@ namespace dev {
                             Rm[k * NC + k] = beta;
                             tauv[k] = tau;
                             scalev[k] = scale;
-                            invb[k] = ibeta;
+                            invb[k] = sigma != 0.0 ? ibeta : 1.0 / alpha; // (the division only where it is needed: one thread, off the others' path)
                         }
                     }
                     else {
@@ -1276,27 +1315,33 @@ namespace dev {
                             const double cs = coef * scale;
 #pragma unroll
                             for (int m = 0; m < MR; ++m)
-                                cc[m] -= cs * ck[m];
+                                if (SEG * (m + 1) - 1 > k)
+                                    cc[m] -= cs * ck[m];
+                            if (frc) {
 #pragma unroll
-                            for (int m = 0; m < MF; ++m)
-                                cf[m] -= cs * ckf[m];
+                                for (int m = 0; m < MF; ++m)
+                                    cf[m] -= cs * ckf[m];
+                            }
                         }
                     }
                     // publish the next pivot column and pivot row
                     if (c == k + 1) {
 #pragma unroll
                         for (int m = 0; m < MR; ++m)
-                            if (seg0 + SEG * m < nv)
+                            if (SEG * (m + 1) - 1 > k && seg0 + SEG * m < nv) // (rows <= k + 1 of the next column are never read)
                                 colbuf[seg0 + SEG * m] = cc[m];
+                        if (k + 1 >= cb0) {
 #pragma unroll
-                        for (int m = 0; m < MF; ++m)
-                            if (seg0 + SEG * m < nfrc)
-                                colbuf[nv + seg0 + SEG * m] = cf[m];
+                            for (int m = 0; m < MF; ++m)
+                                if (seg0 + SEG * m < nfrc)
+                                    colbuf[nv + seg0 + SEG * m] = cf[m];
+                        }
                     }
-#pragma unroll
-                    for (int m = 0; m < MR; ++m)
-                        if (seg0 + SEG * m == k + 1)
-                            rbn[c] = cc[m];
+                    {
+                        const int m1 = (k + 1) / SEG; // the row k + 1 lives in segment (k + 1) % SEG, register m1
+                        if (m1 < MR && seg0 == (k + 1) - SEG * m1)
+                            rbn[c] = cc[m1];
+                    }
                 }
                 fsync<T>();
             }
@@ -1650,12 +1695,16 @@ namespace dev {
         {
             const double* Md = smem + F.o_Md;
             for (int e = tid; e < nv * (nv + 1) / 2; e += T) {
+#if IWBC_OPT_MTAB
+                const int r = gF->tri_r[e], c = gF->tri_c[e];
+#else
                 int r = (int)((sqrtf(8.f * e + 1.f) - 1.f) * 0.5f);
                 while (r * (r + 1) / 2 > e)
                     --r;
                 while ((r + 1) * (r + 2) / 2 <= e)
                     ++r;
                 const int c = e - r * (r + 1) / 2;
+#endif
                 sm.M[e] = r == c ? Md[r] : Hs[c + r * ld];
             }
         }
