@@ -584,7 +584,9 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
             // (thread-per-instance arms: a chunk needs tens of thousands of instances to fill the GPU -- 32 instances per warp)
             const bool tpi_arm = b->G == 32 && b->shape.total <= 1792;
             const int unit = tpi_arm ? 32 * b->sm_count : b->fast_ok && b->fast_grid > 0 ? b->fast_grid : (b->grid > 0 ? b->grid * b->IPC : 4 * b->sm_count);
-            int u_first = 4, u_mid = 10; // (IWBC_PIPE="first,mid" in units of the grid capacity: tuning aid)
+            // (IWBC_PIPE="first,mid" in units of the grid capacity: tuning aid.  Humanoids at 4 CTAs / SM -- unit 592 -- measured on
+            // Talos double support, 16 384 states: 4,10 -> 4.32 M/s, 2,10 -> 4.14, 3,8 -> 4.31, 1,6 -> 4.40, 2,4 -> 4.42, 2,6 -> 4.52)
+            int u_first = tpi_arm ? 4 : 2, u_mid = tpi_arm ? 10 : 6;
             if (const char* e = std::getenv("IWBC_PIPE"))
                 std::sscanf(e, "%d,%d", &u_first, &u_mid);
             const int budget = std::max(1, (15 - c) / (int)(runs.size() - ri)); // chunks this run may use

@@ -67,11 +67,13 @@ namespace dev {
         FBlock blocks[IWBC_FMAXBLK];
         FRow rows[IWBC_FMAXROWS];
         double hdiag[IWBC_MAXNV];   // posture weights on the diagonal of H + the 1e-8 regularisation
+        double blk_sw[IWBC_FMAXBLK], row_sw[IWBC_FMAXROWS]; // sqrt(task weight) per row block / per row
         // Force blocks of H, one per (regularisation weight vector, active-contact slot): H_ff = w T' W^2 T + 1e-8 I depends on the
         // problem and on WHICH weight vector W the instance has installed (iwbc_problem_t::wreg_variants: Contact6d's default or a
         // stabilizer's zmp_w), so it is factorised on the host for every variant and the kernel picks by the instance's index.
         double Uff[IWBC_MAXWV][IWBC_MAXC][144]; // L_ff^-T (upper triangular, row-major)
         double Gf[IWBC_MAXWV][IWBC_MAXC][72];   // L_ff^-1 g_f = Gf f_ref (12 x 6, row-major): g_f = -w T' W^2 f_ref is per instance
+        double UT[IWBC_MAXWV][IWBC_MAXC][72];   // U_ff' T' (12 x 6, row-major): (U_ff' N_f)[k][r] = -sum_a UT[k][a] Jft[a][r]
         double c1v[IWBC_MAXWV][IWBC_MAXC], c2v[IWBC_MAXWV][IWBC_MAXC]; // trace(H_ff), trace(L_ff^-T)
     };
 
@@ -192,6 +194,10 @@ namespace dev {
             B.kind = FB_CONTACT, B.index = (short)F.cact[s], B.row0 = 0, B.nrows = 6, B.slot0 = 0;
         }
         F.nslots = nslots;
+        for (int bi = 0; bi < F.nblocks; ++bi)
+            pl.blk_sw[bi] = pl.blocks[bi].kind == FB_CONTACT ? 1.0 : std::sqrt(P.tasks[pl.blocks[bi].index].weight);
+        for (int r = 0; r < F.nrows; ++r)
+            pl.row_sw[r] = std::sqrt(P.tasks[pl.rows[r].task].weight);
         // ---- row chunks: the smallest capacity that packs the row blocks (in order) into at most IWBC_FMAXCHUNK chunks; the contact
         // blocks (no rows of A: they fill Jft) ride in the last chunk
         {
@@ -308,6 +314,13 @@ namespace dev {
                         a -= L[i * 12 + j] * Li[j * 12 + c];
                     Li[i * 12 + c] = a / L[i * 12 + i];
                 }
+            for (int k2 = 0; k2 < 12; ++k2)
+                for (int a = 0; a < 6; ++a) {
+                    double w = 0;
+                    for (int i = 0; i <= k2; ++i)
+                        w += Li[k2 * 12 + i] * C.T[a * 12 + i]; // U[i][k2] = Li[k2][i]
+                    pl.UT[wv][s][k2 * 6 + a] = w;
+                }
             for (int i = 0; i < 12; ++i) {
                 for (int j = 0; j < 12; ++j)
                     pl.Uff[wv][s][i * 12 + j] = Li[j * 12 + i];
@@ -396,6 +409,15 @@ namespace dev {
 #endif
 #ifndef IWBC_OPT_MTAB
 #define IWBC_OPT_MTAB 1 // (row, column) of the packed mass-matrix entries from a table instead of a square root
+#endif
+#ifndef IWBC_OPT_BF
+#define IWBC_OPT_BF 1   // constants of the problem folded on the host: U_ff' T' for the force rows of B, sqrt(task weights)
+#endif
+#ifndef IWBC_OPT_PREFETCH
+#define IWBC_OPT_PREFETCH 1 // L2 prefetch of the next instance's inputs
+#endif
+#ifndef IWBC_OPT_XBS
+#define IWBC_OPT_XBS 1  // back-substitution x = L^-T w unrolled over its 50 / 38 steps
 #endif
 #ifndef IWBC_OPT_CHOL
 #define IWBC_OPT_CHOL 1 // 16-byte loads of the row buffer in the H tiles
@@ -871,7 +893,11 @@ namespace dev {
                         continue;
                     }
                     const iwbc_task_t& Tk = gP->tasks[Bk.index];
+#if IWBC_OPT_BF
+                    const double sw = gF->blk_sw[bi];
+#else
                     const double sw = sqrt(Tk.weight);
+#endif
                     double* const Ab = A + (Bk.row0 - r0) * nvp + k;
                     if (Bk.kind == FB_SE3) {
                         V3 l, a;
@@ -919,7 +945,11 @@ namespace dev {
             for (int r = tid; r < R; r += T) {
                 const FRow Rw = gF->rows[r0 + r];
                 const iwbc_task_t& Tk = gP->tasks[Rw.task];
+#if IWBC_OPT_BF
+                const double sw = gF->row_sw[r0 + r];
+#else
                 const double sw = sqrt(Tk.weight);
+#endif
                 double val;
                 if (Rw.kind == FB_SELFCOL) {
                     val = 0;
@@ -1088,6 +1118,14 @@ namespace dev {
                 }
                 else {
                     const int c = F.cact[s];
+#if IWBC_OPT_BF
+                    // (U_ff' T' is a constant of the problem: six products per entry instead of up to 84)
+                    const double* W6 = gF->UT[wvs][s] + k2 * 6;
+                    val = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+                        val -= W6[a] * sm.Jft[(c * 6 + a) * nv + r];
+#else
                     const double* Tm = gP->contacts[c].T;
                     const double* U = Usel(s);
                     val = 0;
@@ -1098,6 +1136,7 @@ namespace dev {
                             npf += Tm[a * 12 + i] * sm.Jft[(c * 6 + a) * nv + r];
                         val -= U[i * 12 + k2] * npf;
                     }
+#endif
                 }
                 Bf[kk * F.nf + r] = val;
             }
@@ -1148,31 +1187,36 @@ namespace dev {
                         }
                     }
                 }
-                fsync<T>();
-                // (2) factor the diagonal block (every thread, redundantly, from the copy) and solve the panel rows
-                {
+                // (2) factor the diagonal block (every thread, redundantly, from the copy) and solve the panel rows.  (Measured and
+                // dropped: ONE thread factorising it before the barrier and publishing the ten numbers -- 5 % fewer instructions, but
+                // the factorisation then sits on warp 0's path to the barrier instead of overlapping across the warps: 4.89 -> 4.79 M/s.)
+                auto factor4 = [&](double& l10, double& l20, double& l30, double& l21, double& l31, double& l32, double& i0, double& i1, double& i2,
+                                   double& i3) {
                     const double d00 = Db[0], d10 = Db[4], d20 = pw > 2 ? Db[8] : 0.0, d30 = pw > 3 ? Db[12] : 0.0;
                     const double d11 = pw > 1 ? Db[5] : 1.0, d21 = pw > 2 ? Db[9] : 0.0, d31 = pw > 3 ? Db[13] : 0.0;
                     const double d22 = pw > 2 ? Db[10] : 1.0, d32 = pw > 3 ? Db[14] : 0.0, d33 = pw > 3 ? Db[15] : 1.0;
                     const double d10u = pw > 1 ? d10 : 0.0;
-                    if (!(d00 > 0.0))
-                        spd = false;
-                    const double i0 = rsqrt(d00 > 0.0 ? d00 : 1.0);
-                    const double l10 = d10u * i0, l20 = d20 * i0, l30 = d30 * i0;
+                    bool ok = d00 > 0.0;
+                    i0 = rsqrt(d00 > 0.0 ? d00 : 1.0);
+                    l10 = d10u * i0, l20 = d20 * i0, l30 = d30 * i0;
                     const double t1 = d11 - l10 * l10;
-                    if (!(t1 > 0.0))
-                        spd = false;
-                    const double i1 = rsqrt(t1 > 0.0 ? t1 : 1.0);
-                    const double l21 = (d21 - l20 * l10) * i1, l31 = (d31 - l30 * l10) * i1;
+                    ok = ok && t1 > 0.0;
+                    i1 = rsqrt(t1 > 0.0 ? t1 : 1.0);
+                    l21 = (d21 - l20 * l10) * i1, l31 = (d31 - l30 * l10) * i1;
                     const double t2 = d22 - l20 * l20 - l21 * l21;
-                    if (!(t2 > 0.0))
-                        spd = false;
-                    const double i2 = rsqrt(t2 > 0.0 ? t2 : 1.0);
-                    const double l32 = (d32 - l30 * l20 - l31 * l21) * i2;
+                    ok = ok && t2 > 0.0;
+                    i2 = rsqrt(t2 > 0.0 ? t2 : 1.0);
+                    l32 = (d32 - l30 * l20 - l31 * l21) * i2;
                     const double t3 = d33 - l30 * l30 - l31 * l31 - l32 * l32;
-                    if (!(t3 > 0.0))
+                    ok = ok && t3 > 0.0;
+                    i3 = rsqrt(t3 > 0.0 ? t3 : 1.0);
+                    return ok;
+                };
+                fsync<T>();
+                {
+                    double l10, l20, l30, l21, l31, l32, i0, i1, i2, i3;
+                    if (!factor4(l10, l20, l30, l21, l31, l32, i0, i1, i2, i3))
                         spd = false;
-                    const double i3 = rsqrt(t3 > 0.0 ? t3 : 1.0);
                     if (tid == 0) {
                         il[cb] = i0;
                         if (pw > 1)
@@ -1551,7 +1595,7 @@ namespace dev {
             else if (tid < 32) {
                 // lane l owns rows l and l + 32 (nv <= 64)
                 double w0 = tid < nv ? wv[tid] : 0.0, w1 = tid + 32 < nv ? wv[tid + 32] : 0.0;
-                for (int k = nv - 1; k >= 0; --k) {
+                auto step = [&](int k) {
                     const double mine = (k >= 32) ? w1 : w0;
                     const double xk = __shfl_sync(0xffffffffu, mine, k & 31) * il[k];
                     if (tid == (k & 31))
@@ -1559,8 +1603,19 @@ namespace dev {
                     // w_i -= L[k][i] x_k for i < k
                     if (tid < k)
                         w0 -= Hs[k + tid * ld] * xk;
-                    if (tid + 32 < k)
+                    if (k > 32 && tid + 32 < k)
                         w1 -= Hs[k + (tid + 32) * ld] * xk;
+                };
+                if constexpr (NV_ > 0 && IWBC_OPT_XBS) {
+                    // (compile-time k: the operand loads of later steps are hoisted above the shuffle chain, the upper half is
+                    // skipped once k <= 32)
+#pragma unroll
+                    for (int k = NV_ - 1; k >= 0; --k)
+                        step(k);
+                }
+                else {
+                    for (int k = nv - 1; k >= 0; --k)
+                        step(k);
                 }
             }
             else {
@@ -1967,6 +2022,21 @@ namespace dev {
         const int count = io.in_list ? *io.in_count : io.B;
         for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
             const int inst = io.in_list ? io.in_list[idx] : idx;
+#if IWBC_OPT_PREFETCH
+            // the next instance's state and reference rows towards L2 while this one computes (the inputs are larger than L2 and
+            // the load phase of an instance otherwise waits on DRAM with nothing to overlap inside the CTA)
+            if (idx + (int)gridDim.x < count) {
+                const int nxt = io.in_list ? io.in_list[idx + gridDim.x] : idx + (int)gridDim.x;
+                const int nq_ = gP->nq, nv_ = gP->nv, nr_ = gP->nref;
+                const int lq = (nq_ * 8 + 127) / 128, lv = (nv_ * 8 + 127) / 128, lr = (nr_ * 8 + 127) / 128;
+                for (int l = tid; l < lq + lv + lr; l += T) {
+                    const char* pbase = l < lq ? reinterpret_cast<const char*>(io.q + (size_t)nxt * nq_) + 128 * l
+                        : l < lq + lv    ? reinterpret_cast<const char*>(io.v + (size_t)nxt * nv_) + 128 * (l - lq)
+                                         : reinterpret_cast<const char*>(io.refs + (size_t)nxt * io.refs_stride) + 128 * (l - lq - lv);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pbase));
+                }
+            }
+#endif
             long long stamps[8];
             long long* cyc = io.prof ? stamps : nullptr;
             const int code = fast_instance<T, NV_, ME_>(gP, gF, S, F, smem, io, inst, tid, cyc);

@@ -367,18 +367,20 @@ def test_recorded_trajectory_replay_on_device(talos, tmp_path):
 
 @pytest.mark.gpu
 def test_icub_walk_rollout_on_device(icub):
-    """iCub walking (etc/icub/walk.yaml: 1 s CoM shifts, 0.25 s foot trajectories) as one closed device-side roll-out of 900 ticks against
-    900 oracle ticks driven by the restated behaviour.  Towards the end of the first CoM shift the stand-in iCub model takes the QP to
-    the edge of feasibility, where eiquadprog's outcome flips under a 1e-14 perturbation of the state (ticks 928 .. 994 depending on
-    rounding): status is data -- on the GPU's OWN state at its first non-optimal tick the oracle must report the same status after the
-    same number of iterations."""
+    """iCub walking (etc/icub/walk.yaml: 1 s CoM shifts, 0.25 s foot trajectories) as one closed device-side roll-out of 600 ticks against
+    600 oracle ticks driven by the restated behaviour, then tick by tick.  From tick ~690 on the stand-in iCub model walks along the
+    edge of feasibility (20+ active-set iterations per tick): the oracle's outcome flips there under a 1e-13 perturbation of the state
+    (measured first non-optimal tick on the GPU: 744 .. 994 depending on the summation orders inside the kernel; the oracle on its own
+    trajectory: ~930), so beyond tick 600 the comparison is state-wise -- at EVERY tick the oracle, evaluated on the GPU's own state,
+    must report the same status, and either the same iteration count or the same next state to 1e-8 (two eiquadprog paths to one
+    vertex) -- up to and including the GPU's first non-optimal tick."""
     import torch
     import oracle_lib as ol
     P = iw.Problem("icub/humanoid_pos_tracker.yaml", overrides=OFF)
     beh = iw.Behavior(P, "icub/walk.yaml", overrides={"num_of_cycles": 1})
     ora = bo.Walk(P, os.path.join(iw.ETC_PATH, "icub", "walk.yaml"), num_of_cycles=1)
     assert beh.total_ticks == ora.total_ticks == 5500
-    T = 900
+    T = 600
     q, v = P.q0().copy(), np.zeros(P.nv)
     for t in range(T):
         r, m = ora.tick(t)
@@ -395,13 +397,18 @@ def test_icub_walk_rollout_on_device(icub):
     torch.cuda.synchronize()
     assert int(st[0]) == 0
     assert np.abs(dq.cpu().numpy()[0] - q).max() < 1e-8 and np.abs(dv_.cpu().numpy()[0] - v).max() < 1e-6
-    for t in range(T, 1100):
+    hard = 0
+    for t in range(T, 1500):
         pq, pv = dq.cpu().numpy().copy(), dv_.cpu().numpy().copy()
         bt.behavior_rollout_device(beh, 1, dq.data_ptr(), dv_.data_ptr(), d_refs.data_ptr(), None, t, 1, init_refs=False,
                                    out_ptrs={"status": st.data_ptr(), "iters": it.data_ptr()})
         torch.cuda.synchronize()
+        o = ol.cycle_batch(P, pq, pv, d_refs.cpu().numpy(), contact_mask=ora.tick(t)[1])
+        assert o["status"][0] == int(st[0]), t
+        hard += int(it[0]) > 10
         if int(st[0]) != 0:
+            assert o["iters"][0] == int(it[0]), t
             break
-    assert int(st[0]) != 0 and 900 < t < 1100, t  # (measured: 928 .. 994 depending on the summation orders inside the kernel)
-    o = ol.cycle_batch(P, pq, pv, d_refs.cpu().numpy(), contact_mask=ora.tick(t)[1])
-    assert o["status"][0] == int(st[0]) and o["iters"][0] == int(it[0])
+        assert o["iters"][0] == int(it[0]) or np.abs(o["q_next"][0] - dq.cpu().numpy()[0]).max() < 1e-8, t
+        assert np.abs(o["q_next"][0] - dq.cpu().numpy()[0]).max() < 1e-8, t
+    assert int(st[0]) != 0 and t > 650 and hard >= 2, (t, hard)  # (ticks with more than ten active-set iterations on the way)
