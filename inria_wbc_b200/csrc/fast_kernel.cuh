@@ -50,7 +50,11 @@ namespace dev {
         short kind, task, a, slot; // slot: rhs slot (SE3 / COM / MOM) or pair slot (SELFCOL)
     };
     struct FBlock {
-        short kind, index, row0, nrows, slot0, pad;
+        short kind, index, row0, nrows, slot0;
+        // flattened from the task / contact record so that the row loop reads ONE record per block instead of a chain of dependent
+        // global loads (block -> task -> frame -> parent joint): frame and its parent joint (-1: none), component mask bits, and for
+        // a self-collision block the number of avoided frames (their frames / parent joints: FPlan::pair_frame / pair_pj by pair slot)
+        short frame, pj, maskbits, nav, pad0, pad1, pad2;
     };
     struct FRow {
         short kind, task, comp, slot; // kind: FB_*; comp: component of the 6-/3-vector; slot: rhs slot (or first pair slot)
@@ -63,11 +67,13 @@ namespace dev {
         unsigned char tile_i[136], tile_j[136];
         unsigned char pair_i[IWBC_FMAXPAIRS], pair_k[IWBC_FMAXPAIRS];
         unsigned char tri_r[1830], tri_c[1830]; // packed lower triangle (nv <= 60): entry e = r (r + 1) / 2 + c -> (r, c)
+        unsigned char tri_sup[1830];            // ... and whether joint(c) supports joint(r), i.e. M(r, c) is structurally non-zero
         FJob jobs[IWBC_FMAXJOBS];
         FBlock blocks[IWBC_FMAXBLK];
         FRow rows[IWBC_FMAXROWS];
         double hdiag[IWBC_MAXNV];   // posture weights on the diagonal of H + the 1e-8 regularisation
         double blk_sw[IWBC_FMAXBLK], row_sw[IWBC_FMAXROWS]; // sqrt(task weight) per row block / per row
+        short pair_frame[IWBC_FMAXJOBS], pair_pj[IWBC_FMAXJOBS]; // self-collision pair slot -> avoided frame, its parent joint
         // Force blocks of H, one per (regularisation weight vector, active-contact slot): H_ff = w T' W^2 T + 1e-8 I depends on the
         // problem and on WHICH weight vector W the instance has installed (iwbc_problem_t::wreg_variants: Contact6d's default or a
         // stabilizer's zmp_w), so it is factorised on the host for every variant and the kernel picks by the instance's index.
@@ -194,8 +200,30 @@ namespace dev {
             B.kind = FB_CONTACT, B.index = (short)F.cact[s], B.row0 = 0, B.nrows = 6, B.slot0 = 0;
         }
         F.nslots = nslots;
-        for (int bi = 0; bi < F.nblocks; ++bi)
-            pl.blk_sw[bi] = pl.blocks[bi].kind == FB_CONTACT ? 1.0 : std::sqrt(P.tasks[pl.blocks[bi].index].weight);
+        for (int bi = 0; bi < F.nblocks; ++bi) {
+            FBlock& B = pl.blocks[bi];
+            pl.blk_sw[bi] = B.kind == FB_CONTACT ? 1.0 : std::sqrt(P.tasks[B.index].weight);
+            B.frame = B.pj = -1, B.maskbits = 0, B.nav = 0;
+            if (B.kind == FB_CONTACT)
+                B.frame = (short)P.contacts[B.index].frame;
+            else {
+                const iwbc_task_t& Tk = P.tasks[B.index];
+                if (B.kind == FB_SE3 || B.kind == FB_SELFCOL)
+                    B.frame = (short)Tk.frame;
+                for (int i = 0; i < 6; ++i)
+                    if ((B.kind == FB_SE3 || B.kind == FB_MOM || (B.kind == FB_COM && i < 3)) && Tk.mask[i])
+                        B.maskbits |= (short)(1 << i);
+                if (B.kind == FB_SELFCOL) {
+                    B.nav = (short)Tk.nav;
+                    for (int a = 0; a < Tk.nav; ++a) {
+                        pl.pair_frame[B.slot0 + a] = (short)Tk.av_frame[a];
+                        pl.pair_pj[B.slot0 + a] = (short)P.fparent[Tk.av_frame[a]];
+                    }
+                }
+            }
+            if (B.frame >= 0)
+                B.pj = (short)P.fparent[B.frame];
+        }
         for (int r = 0; r < F.nrows; ++r)
             pl.row_sw[r] = std::sqrt(P.tasks[pl.rows[r].task].weight);
         // ---- row chunks: the smallest capacity that packs the row blocks (in order) into at most IWBC_FMAXCHUNK chunks; the contact
@@ -266,8 +294,11 @@ namespace dev {
         if (T > 1 && F.ntiles > T)
             return false;
         for (int r = 0, e = 0; r < nv && r < 60; ++r)
-            for (int c = 0; c <= r; ++c, ++e)
+            for (int c = 0; c <= r; ++c, ++e) {
                 pl.tri_r[e] = (unsigned char)r, pl.tri_c[e] = (unsigned char)c;
+                const int jc = pl.dofj[c], jr = pl.dofj[r];
+                pl.tri_sup[e] = (unsigned char)(jc <= jr && jr <= P.last_desc[jc]);
+            }
         for (int k = 0; k <= F.me; ++k) // k == me: the transformed right-hand side t
             for (int i = 0; i < k && i < F.me; ++i) {
                 pl.pair_i[F.npairs] = (unsigned char)i, pl.pair_k[F.npairs] = (unsigned char)k;
@@ -874,46 +905,53 @@ namespace dev {
                 hacc[tt][e] = 0;
         for (int k = (T - 1 - tid); k < nv; k += T)
             gvec[k] = 0.0;
+        // (this thread's tile: read from the plan once, not once per chunk)
+        const int tile0_i = (T > 1 && tid < F.ntiles) ? 4 * gF->tile_i[tid] : 0, tile0_j = (T > 1 && tid < F.ntiles) ? 4 * gF->tile_j[tid] : 0;
 #pragma unroll 1
         for (int ch = 0; ch < F.nchunk; ++ch) {
             const int b0 = F.ch_b0[ch], b1 = F.ch_b1[ch], r0 = F.ch_r0[ch], R = F.ch_nr[ch];
             const int NH = (T / nv) > 0 ? (T / nv) : 1;
             for (int item = tid; item < nv * NH; item += T) {
                 const int hh = item / nv, k = item - hh * nv;
-                const int jk = gF->dofj[k];
+                const int jk = gF->dofj[k], jk_last = gP->last_desc[jk]; // joint jk supports joint j iff jk <= j <= jk_last
                 const V3 sl = ld3(sm.Sw + 6 * k), sa = ld3(sm.Sw + 6 * k + 3);
+                // local-frame Jacobian column of a frame whose parent joint is pj (frame_jac_col with the chain of lookups folded)
+                auto jac_col = [&](int f, int pj, V3& lin, V3& ang) {
+                    lin = mk(0, 0, 0);
+                    ang = mk(0, 0, 0);
+                    if (pj < 0 || pj < jk || pj > jk_last)
+                        return;
+                    const double* o = sm.oMf + 12 * f;
+                    ang = rtmul(o, sa);
+                    lin = rtmul(o, sl - cross(ld3(o + 9), sa));
+                };
                 for (int bi = b0 + hh; bi < b1; bi += NH) {
                     const FBlock Bk = gF->blocks[bi];
                     if (Bk.kind == FB_CONTACT) {
                         const int c = Bk.index;
                         V3 l, a;
-                        frame_jac_col(gP, sm, gP->contacts[c].frame, k, l, a);
+                        jac_col(Bk.frame, Bk.pj, l, a);
                         double* Jc = sm.Jft + (c * 6) * nv + k;
                         Jc[0] = l.x, Jc[nv] = l.y, Jc[2 * nv] = l.z, Jc[3 * nv] = a.x, Jc[4 * nv] = a.y, Jc[5 * nv] = a.z;
                         continue;
                     }
-                    const iwbc_task_t& Tk = gP->tasks[Bk.index];
-#if IWBC_OPT_BF
                     const double sw = gF->blk_sw[bi];
-#else
-                    const double sw = sqrt(Tk.weight);
-#endif
                     double* const Ab = A + (Bk.row0 - r0) * nvp + k;
                     if (Bk.kind == FB_SE3) {
                         V3 l, a;
-                        frame_jac_col(gP, sm, Tk.frame, k, l, a);
+                        jac_col(Bk.frame, Bk.pj, l, a);
                         const double col[6] = {l.x, l.y, l.z, a.x, a.y, a.z};
                         int idx = 0;
 #pragma unroll
                         for (int i = 0; i < 6; ++i)
-                            if (Tk.mask[i])
+                            if (Bk.maskbits >> i & 1)
                                 Ab[(idx++) * nvp] = sw * col[i];
                     }
                     else if (Bk.kind == FB_COM) {
                         const double imt = 1.0 / sc[0];
                         int idx = 0;
                         for (int i = 0; i < 3; ++i)
-                            if (Tk.mask[i])
+                            if (Bk.maskbits >> i & 1)
                                 Ab[(idx++) * nvp] = sw * imt * sm.Fc[6 * k + i];
                     }
                     else if (Bk.kind == FB_MOM) {
@@ -923,21 +961,20 @@ namespace dev {
                         int idx = 0;
 #pragma unroll
                         for (int i = 0; i < 6; ++i)
-                            if (Tk.mask[i])
+                            if (Bk.maskbits >> i & 1)
                                 Ab[(idx++) * nvp] = sw * col[i];
                     }
                     else { // FB_SELFCOL
                         const int lwa = !gP->sc_jacobian_world;
-                        auto col = [&](int f) {
-                            int pj = gP->fparent[f];
-                            if (pj < 0 || !supports(gP, jk, pj))
+                        auto col = [&](int f, int pj) {
+                            if (pj < 0 || pj < jk || pj > jk_last)
                                 return mk(0, 0, 0);
                             return lwa ? sl + cross(sa, ld3(sm.oMf + 12 * f + 9)) : sl;
                         };
-                        const V3 c0 = col(Tk.frame);
+                        const V3 c0 = col(Bk.frame, Bk.pj);
                         double acc = 0;
-                        for (int a = 0; a < Tk.nav; ++a)
-                            acc += dot(ld3(sc4 + 4 * (Bk.slot0 + a)), c0 - col(Tk.av_frame[a]));
+                        for (int a = 0; a < Bk.nav; ++a)
+                            acc += dot(ld3(sc4 + 4 * (Bk.slot0 + a)), c0 - col(gF->pair_frame[Bk.slot0 + a], gF->pair_pj[Bk.slot0 + a]));
                         Ab[0] = sw * acc;
                     }
                 }
@@ -968,8 +1005,8 @@ namespace dev {
                 const int tile = tt * T + tid;
                 double* h = hacc[tt];
                 if (tile < F.ntiles) {
-                    const double* Ai = A + 4 * gF->tile_i[tile];
-                    const double* Aj = A + 4 * gF->tile_j[tile];
+                    const double* Ai = A + (T > 1 ? tile0_i : 4 * gF->tile_i[tile]);
+                    const double* Aj = A + (T > 1 ? tile0_j : 4 * gF->tile_j[tile]);
                     for (int r = 0; r < R; ++r) {
 #if IWBC_OPT_CHOL
                         // (tile columns are multiples of 4 and nvp % 4 == 0: 16-byte loads)
@@ -1034,7 +1071,11 @@ namespace dev {
                     ++r;
                 const int c = e - r * (r + 1) / 2;
 #endif
+#if IWBC_OPT_MTAB
+                if (gF->tri_sup[e])
+#else
                 if (supports(gP, gF->dofj[c], gF->dofj[r]))
+#endif
                     mreg[m] = dot(ld3(sm.Sw + 6 * c), ld3(sm.Fc + 6 * r)) + dot(ld3(sm.Sw + 6 * c + 3), ld3(sm.Fc + 6 * r + 3));
             }
         }
