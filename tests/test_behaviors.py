@@ -240,6 +240,29 @@ def test_franka_known_answer_with_the_behaviour_on_the_device(franka):
     assert r["rc"] == 0 and dq_max < 1e-8, dq_max  # tests/test_determinism.cpp:51,63 tolerance after 10 000 ticks
 
 
+@pytest.mark.gpu
+def test_arm_behaviour_rollout_takes_the_thread_per_instance_kernel(franka):
+    """A behaviour roll-out of a LARGE arm batch runs the thread-per-instance kernel over the behaviour's per-mask instance list, in
+    several passes per launch when the batch exceeds the resident capacity (cycle_tu.cuh: launch_tpi); the same robots in a small
+    batch run the warp-per-instance kernel.  Same instances, same phases: the two must agree to rounding after 40 closed ticks."""
+    B, n = 98304, 96  # > 75 776 resident threads: two passes
+    rng = np.random.default_rng(5)
+    beh = iw.Behavior(franka, "franka/cartesian_line.yaml")
+    q = np.tile(franka.q0(), (B, 1)) + 0.05 * rng.standard_normal((B, franka.nq))
+    v = 0.05 * rng.standard_normal((B, franka.nv))
+    phase = rng.integers(0, beh.total_ticks, B).astype(np.int32)
+    pick = np.concatenate([np.arange(n // 2), B - 1 - np.arange(n // 2)])  # instances of the first and of the last pass
+    qs, vs = q[pick].copy(), v[pick].copy()
+    big, small = iw.Batch(franka, 0, B), iw.Batch(franka, 0, n)
+    l0 = big.launch_count
+    rb = big.behavior_run(beh, q, v, 40, phase=phase, fields=("tau", "status"))
+    assert big.launch_count - l0 >= 40 * 2  # (behaviour kernel + cycle passes per tick)
+    rs = small.behavior_run(beh, qs, vs, 40, phase=phase[pick], fields=("tau", "status"))
+    assert (rb.status == 0).all() and (rs.status == 0).all()
+    assert np.abs(q[pick] - qs).max() < 1e-10 and np.abs(v[pick] - vs).max() < 1e-8
+    assert np.abs(rb.tau[pick] - rs.tau).max() < 1e-8 * max(1.0, np.abs(rs.tau).max())
+
+
 def test_walk_on_spot_table(talos):
     """humanoid::walk-on-spot (src/behaviors/humanoid/walk_on_spot.cpp): INIT once, then six states for ever."""
     P = iw.Problem("talos/talos_pos_tracker.yaml", overrides=OFF)
