@@ -586,7 +586,9 @@ int iwbc_batch_update(iwbc_batch* b, int B, const double* q, const double* v, co
             const int unit = tpi_arm ? 32 * b->sm_count : b->fast_ok && b->fast_grid > 0 ? b->fast_grid : (b->grid > 0 ? b->grid * b->IPC : 4 * b->sm_count);
             // (IWBC_PIPE="first,mid" in units of the grid capacity: tuning aid.  Humanoids at 4 CTAs / SM -- unit 592 -- measured on
             // Talos double support, 16 384 states: 4,10 -> 4.32 M/s, 2,10 -> 4.14, 3,8 -> 4.31, 1,6 -> 4.40, 2,4 -> 4.42, 2,6 -> 4.52)
-            int u_first = tpi_arm ? 4 : 2, u_mid = tpi_arm ? 10 : 6;
+            // Thread-per-instance arms -- unit 4 736 -- at 65 536 states (profiles/r02d_pipe_arms.txt): Franka 4,10 -> 48.0 M/s, 3,4 -> 59.1,
+            // 3,6 -> 54.7; Tiago 4,10 -> 23.3, 3,4 -> 23.0, 3,6 -> 23.8 (its kernel needs larger chunks to fill the GPU).
+            int u_first = tpi_arm ? 3 : 2, u_mid = tpi_arm ? (b->shape.total <= 1024 ? 4 : 6) : 6;
             if (const char* e = std::getenv("IWBC_PIPE"))
                 std::sscanf(e, "%d,%d", &u_first, &u_mid);
             const int budget = std::max(1, (15 - c) / (int)(runs.size() - ri)); // chunks this run may use

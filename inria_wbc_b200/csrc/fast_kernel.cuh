@@ -444,6 +444,9 @@ namespace dev {
 #ifndef IWBC_OPT_BF
 #define IWBC_OPT_BF 1   // constants of the problem folded on the host: U_ff' T' for the force rows of B, sqrt(task weights)
 #endif
+#ifndef IWBC_OPT_SIGMA
+#define IWBC_OPT_SIGMA 1 // QR: the next pivot column's norm is computed by its owners one step ahead
+#endif
 #ifndef IWBC_OPT_PREFETCH
 #define IWBC_OPT_PREFETCH 1 // L2 prefetch of the next instance's inputs
 #endif
@@ -1304,6 +1307,10 @@ namespace dev {
             constexpr int MR = (NV_ + SEG - 1) / SEG, MF = (2 * (ME_ - 6) + SEG - 1) / SEG;
             double* const colbuf = wv;   // B(:, k)
             double* const rowbuf = gvec; // B(k, :), double-buffered: [2][NC]
+            // |B(k+1:, k)|^2 of the NEXT pivot column, per row segment, double-buffered: its owners compute it right after they have
+            // updated the column, so that the sigma -> rsqrt -> reciprocal chain of a step starts at the top of the step and overlaps
+            // the dot products and the first barrier instead of following them (tv is free until the QR is done)
+            double* const Sg = tv;
             const bool qact = seg0 < SEG;
             const int c = qc0;
             double cc[MR], cf[MF], ck[MR], ckf[MF];
@@ -1323,6 +1330,14 @@ namespace dev {
                     for (int m = 0; m < MR; ++m)
                         if (seg0 + SEG * m < nv)
                             colbuf[seg0 + SEG * m] = cc[m];
+#if IWBC_OPT_SIGMA
+                    double sg0 = 0;
+#pragma unroll
+                    for (int m = 0; m < MR; ++m)
+                        if (seg0 + SEG * m > 0 && seg0 + SEG * m < nv)
+                            sg0 += cc[m] * cc[m];
+                    Sg[seg0] = sg0; // (column 0 has no force rows)
+#endif
                 }
                 if (seg0 == 0)
                     rowbuf[c] = cc[0];
@@ -1359,11 +1374,13 @@ namespace dev {
                     }
                     Pp[seg0 * NC + c] = sacc;
                 }
+#if !IWBC_OPT_SIGMA
                 fsync<T>();
+#endif
                 double sigma = 0;
 #pragma unroll
                 for (int sg = 0; sg < SEG; ++sg)
-                    sigma += Pp[sg * NC + k];
+                    sigma += IWBC_OPT_SIGMA ? Sg[(k & 1) * SEG + sg] : Pp[sg * NC + k];
                 const double alpha = rb[k];
                 double beta = alpha, tau = 0, scale = 0, ibeta = 0;
                 if (sigma != 0.0) {
@@ -1374,6 +1391,9 @@ namespace dev {
                     tau = 1.0 + fabs(alpha) * inr; // (beta - alpha) / beta
                     scale = 1.0 / (alpha - beta);
                 }
+#if IWBC_OPT_SIGMA
+                fsync<T>();
+#endif
                 if (qact) {
                     if (c == k) {
                         if (seg0 == 0) {
@@ -1421,6 +1441,20 @@ namespace dev {
                                 if (seg0 + SEG * m < nfrc)
                                     colbuf[nv + seg0 + SEG * m] = cf[m];
                         }
+#if IWBC_OPT_SIGMA
+                        double sgn = 0; // same terms in the same order as the pivot column's own dot product of the next step
+#pragma unroll
+                        for (int m = 0; m < MR; ++m)
+                            if (SEG * (m + 1) - 1 > k + 1 && seg0 + SEG * m > k + 1 && seg0 + SEG * m < nv)
+                                sgn += cc[m] * cc[m];
+                        if (k + 1 >= cb0) {
+#pragma unroll
+                            for (int m = 0; m < MF; ++m)
+                                if (seg0 + SEG * m < nfrc)
+                                    sgn += cf[m] * cf[m];
+                        }
+                        Sg[((k + 1) & 1) * SEG + seg0] = sgn;
+#endif
                     }
                     {
                         const int m1 = (k + 1) / SEG; // the row k + 1 lives in segment (k + 1) % SEG, register m1
