@@ -191,6 +191,29 @@ namespace inria_wbc {
             const std::vector<double>& q_tsid() const { return q_tsid_; }       // [B][nq]
             const std::vector<double>& activated_contacts_forces() const { return forces_; } // [B][12 * ncontacts]
             const std::vector<double>& momentum() const { return momentum_; }   // [B][3]
+            // Controller::cost(task_name) (controller.hpp:148-153, pos_tracker.hpp:43) and PosTracker::objective_value()
+            // (pos_tracker.hpp:44) of robot i at its last solve.  Logging getters in the reference (src/robot_dart/talos.cpp:502-505):
+            // re-evaluated on demand from a stage dump of that ONE robot at the state and references its QP was solved at (the
+            // arrays given to update(q, dq) must still hold that state; update() keeps its own).
+            double cost(const std::string& task_name, int i = 0) const
+            {
+                IWBC_B200_ASSERT(solved_q_ && i >= 0 && i < B_, "cost(): no solve yet, or robot index out of range");
+                double c = 0;
+                if (iwbc_batch_task_cost(batch_, solved_q_ + (size_t)i * nq_, solved_v_ + (size_t)i * nv_, refs_.data() + (size_t)i * nref_, mask_[i],
+                        task_name.c_str(), a_tsid_.data() + (size_t)i * nv_, tau_.data() + (size_t)i * na_, &c)
+                    != IWBC_OK)
+                    throw IWBC_B200_EXCEPTION(std::string("cost(") + task_name + "): " + iwbc_last_error());
+                return c;
+            }
+            double objective_value(int i = 0) const
+            {
+                IWBC_B200_ASSERT(solved_q_ && i >= 0 && i < B_, "objective_value(): no solve yet, or robot index out of range");
+                double f = 0;
+                if (iwbc_batch_objective_value(batch_, solved_q_ + (size_t)i * nq_, solved_v_ + (size_t)i * nv_, refs_.data() + (size_t)i * nref_, mask_[i], &f)
+                    != IWBC_OK)
+                    throw IWBC_B200_EXCEPTION(std::string("objective_value(): ") + iwbc_last_error());
+                return f;
+            }
             const std::vector<int>& status() const { return status_; }          // per-instance HQP status (data, not an exception)
             const std::vector<int>& solver_iterations() const { return iters_; }
             bool all_optimal() const
@@ -307,6 +330,7 @@ namespace inria_wbc {
                             throw IWBC_B200_EXCEPTION("Controller failed, can't solve problem. Status : " + std::to_string(s)
                                 + (s >= -1 && s <= 4 ? what[s + 1] : " => Uknown status") + " (t=" + std::to_string(t_) + ", robot " + std::to_string(i) + ")");
                         }
+                solved_q_ = q, solved_v_ = dq; // (update(): these are the buffers that become qn_ / vn_ below and keep the solved state)
                 q_tsid_.swap(qn_);
                 v_tsid_.swap(vn_);
                 t_ += dt_;
@@ -341,6 +365,7 @@ namespace inria_wbc {
             std::vector<double> q_tsid_, v_tsid_, a_tsid_, tau_, q_, forces_, momentum_, refs_, qn_, vn_;
             std::vector<int> status_, iters_;
             std::vector<unsigned> mask_;
+            const double *solved_q_ = nullptr, *solved_v_ = nullptr; // state of the last solve (cost / objective_value)
         };
 
         // PosTracker's reference setters, per instance (pos_tracker.hpp:52-67, pos_tracker.cpp:220-260)

@@ -151,6 +151,15 @@ double iwbc_measure_fp64_tflops(int device);
 
 /* stage dump of ONE instance for parity tests (device results copied to host; any pointer may be NULL):
  * M[nv*nv] nle[nv] H[n*n] g[n] x[n], all row-major */
+/* Controller::cost(task) (controller.hpp:148-152: norm of the task's own constraint residual A ddq - b at the accelerations `ddq`,
+ * usually the last solution) and PosTracker::objective_value() (pos_tracker.hpp:44: eiquadprog's objective x'Hx/2 + g'x at the
+ * solution) of ONE robot: logging getters of the reference, re-evaluated on demand from a stage dump of that robot at the state the
+ * QP was solved at (the batched cycle does not carry H or the task rows off the SM).  `task`: a level-1 task name (se3, com,
+ * momentum, self-collision, posture; `torque`: tau[na] of that solve must be passed, NULL otherwise); either output may be NULL. */
+int iwbc_batch_task_cost(iwbc_batch* b, const double* q, const double* v, const double* ref, unsigned contact_mask, const char* task,
+    const double* ddq, const double* tau, double* cost);
+int iwbc_batch_objective_value(iwbc_batch* b, const double* q, const double* v, const double* ref, unsigned contact_mask, double* objective);
+
 int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, const double* ref, unsigned contact_mask,
     double* M, double* nle, double* H, double* g, double* x);
 

@@ -70,6 +70,8 @@ def lib():
         "iwbc_batch_kernel_ms": (cd, [vp, ci]),
         "iwbc_batch_enable_timing": (ci, [vp, ci]),
         "iwbc_batch_debug_instance": (ci, [vp, vp, vp, vp, cu, vp, vp, vp, vp, vp]),
+        "iwbc_batch_task_cost": (ci, [vp, vp, vp, vp, cu, C.c_char_p, vp, vp, vp]),
+        "iwbc_batch_objective_value": (ci, [vp, vp, vp, vp, cu, vp]),
         "iwbc_measure_fp64_tflops": (cd, [ci]),
         "iwbc_batch_debug_cycles": (ci, [vp, vp]),
         "iwbc_batch_phase_profile": (ci, [vp, ci, vp]),
@@ -462,6 +464,31 @@ class Batch:
         if rc != 0:
             raise IwbcError(_err(lib()))
         return dict(M=M, nle=nle, H=H, g=g, x=x)
+
+    def objective_value(self, q, v, ref=None, contact_mask=None):
+        """PosTracker::objective_value() of one robot: eiquadprog's objective x'Hx/2 + g'x at the solution of the QP at (q, v, ref)."""
+        P = self.problem
+        ref = P.default_refs() if ref is None else np.ascontiguousarray(ref, dtype=np.float64)
+        q, v = np.ascontiguousarray(q, dtype=np.float64), np.ascontiguousarray(v, dtype=np.float64)
+        m = P.default_contact_mask if contact_mask is None else contact_mask
+        out = C.c_double(0.0)
+        if lib().iwbc_batch_objective_value(self._h, q.ctypes.data, v.ctypes.data, ref.ctypes.data, m, C.byref(out)) != 0:
+            raise IwbcError(_err(lib()))
+        return out.value
+
+    def task_cost(self, task, q, v, ddq, ref=None, contact_mask=None, tau=None):
+        """Controller::cost(task) of one robot: norm of the task's own constraint residual at the accelerations ddq."""
+        P = self.problem
+        ref = P.default_refs() if ref is None else np.ascontiguousarray(ref, dtype=np.float64)
+        q, v, ddq = (np.ascontiguousarray(a, dtype=np.float64) for a in (q, v, ddq))
+        tau = None if tau is None else np.ascontiguousarray(tau, dtype=np.float64)
+        m = P.default_contact_mask if contact_mask is None else contact_mask
+        out = C.c_double(0.0)
+        rc = lib().iwbc_batch_task_cost(self._h, q.ctypes.data, v.ctypes.data, ref.ctypes.data, m, task.encode(), ddq.ctypes.data,
+                                        None if tau is None else tau.ctypes.data, C.byref(out))
+        if rc != 0:
+            raise IwbcError(_err(lib()))
+        return out.value
 
     def debug_cycles(self):
         """Phase durations (SM cycles) of the last debug_instance call: dyn, asm, factor, equalities, active-set loop, decode."""

@@ -851,8 +851,9 @@ double iwbc_batch_kernel_ms(iwbc_batch* b, int reset)
     return r;
 }
 
-int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, const double* ref, unsigned contact_mask, double* M, double* nle,
-    double* H, double* g, double* x)
+// stage dump of one instance through the generic kernel (any output may be NULL); A / bvec: the dense level-1 rows and right-hand sides
+static int debug_dump(iwbc_batch* b, const double* q, const double* v, const double* ref, unsigned contact_mask, double* M, double* nle,
+    double* H, double* g, double* x, double* A, double* bvec)
 {
     if (!b || !q || !v || !ref) {
         set_error("iwbc_batch_debug_instance: bad argument");
@@ -862,12 +863,20 @@ int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, c
     const iwbc_problem_t& P = b->prob->cs.prob;
     host::QPShape qs = host::qp_shape(P, contact_mask);
     const size_t nv = P.nv, n = qs.n;
-    double *dM, *dn, *dH, *dg, *dx;
+    size_t rows = 0;
+    for (int k = 0; k < P.nl1; ++k)
+        if (P.l1[k].kind == IWBC_B_TASK && P.tasks[P.l1[k].index].type != IWBC_T_POSTURE && P.tasks[P.l1[k].index].type != IWBC_T_TORQUE)
+            rows += P.tasks[P.l1[k].index].nrows;
+    double *dM, *dn, *dH, *dg, *dx, *dA = nullptr, *db = nullptr;
     CUDA_TRY(cudaMalloc(&dM, nv * nv * 8));
     CUDA_TRY(cudaMalloc(&dn, nv * 8));
     CUDA_TRY(cudaMalloc(&dH, n * n * 8));
     CUDA_TRY(cudaMalloc(&dg, n * 8));
     CUDA_TRY(cudaMalloc(&dx, n * 8));
+    if (A) {
+        CUDA_TRY(cudaMalloc(&dA, std::max<size_t>(rows * nv, 1) * 8));
+        CUDA_TRY(cudaMalloc(&db, std::max<size_t>(rows, 1) * 8));
+    }
     cudaStream_t st = b->stream;
     CUDA_TRY(cudaMemcpyAsync(b->d_q, q, P.nq * 8, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->d_v, v, nv * 8, cudaMemcpyHostToDevice, st));
@@ -876,7 +885,7 @@ int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, c
     std::memset(&io, 0, sizeof(io));
     io.B = 1;
     io.q = b->d_q, io.v = b->d_v, io.refs = b->d_refs, io.refs_stride = 0;
-    io.dbg_M = dM, io.dbg_nle = dn, io.dbg_H = dH, io.dbg_g = dg, io.dbg_x = dx;
+    io.dbg_M = dM, io.dbg_nle = dn, io.dbg_H = dH, io.dbg_g = dg, io.dbg_x = dx, io.dbg_A = dA, io.dbg_b = db;
     long long* dcyc = nullptr;
     CUDA_TRY(cudaMalloc(&dcyc, 8 * sizeof(long long)));
     CUDA_TRY(cudaMemsetAsync(dcyc, 0, 8 * sizeof(long long), st));
@@ -893,6 +902,10 @@ int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, c
             cudaMemcpyAsync(g, dg, n * 8, cudaMemcpyDeviceToHost, st);
         if (x)
             cudaMemcpyAsync(x, dx, n * 8, cudaMemcpyDeviceToHost, st);
+        if (A && rows) {
+            cudaMemcpyAsync(A, dA, rows * nv * 8, cudaMemcpyDeviceToHost, st);
+            cudaMemcpyAsync(bvec, db, rows * 8, cudaMemcpyDeviceToHost, st);
+        }
         cudaMemcpyAsync(b->last_cycles, dcyc, 8 * sizeof(long long), cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) {
@@ -900,8 +913,105 @@ int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, c
             rc = IWBC_ERR_CUDA;
         }
     }
-    cudaFree(dM), cudaFree(dn), cudaFree(dH), cudaFree(dg), cudaFree(dx), cudaFree(dcyc);
+    cudaFree(dM), cudaFree(dn), cudaFree(dH), cudaFree(dg), cudaFree(dx), cudaFree(dcyc), cudaFree(dA), cudaFree(db);
     return rc;
+}
+
+int iwbc_batch_debug_instance(iwbc_batch* b, const double* q, const double* v, const double* ref, unsigned contact_mask, double* M, double* nle,
+    double* H, double* g, double* x)
+{
+    return debug_dump(b, q, v, ref, contact_mask, M, nle, H, g, x, nullptr, nullptr);
+}
+
+int iwbc_batch_objective_value(iwbc_batch* b, const double* q, const double* v, const double* ref, unsigned contact_mask, double* objective)
+{
+    if (!b || !objective) {
+        set_error("iwbc_batch_objective_value: bad argument");
+        return IWBC_ERR_ARG;
+    }
+    const size_t n = host::qp_shape(b->prob->cs.prob, contact_mask).n;
+    std::vector<double> H(n * n), g(n), x(n);
+    int rc = debug_dump(b, q, v, ref, contact_mask, nullptr, nullptr, H.data(), g.data(), x.data(), nullptr, nullptr);
+    if (rc)
+        return rc;
+    double f = 0; // eiquadprog's f_value at the solution: x'Hx/2 + g'x
+    for (size_t i = 0; i < n; ++i) {
+        double hx = 0;
+        for (size_t j = 0; j < n; ++j)
+            hx += H[i * n + j] * x[j];
+        f += x[i] * (0.5 * hx + g[i]);
+    }
+    *objective = f;
+    return IWBC_OK;
+}
+
+int iwbc_batch_task_cost(iwbc_batch* b, const double* q, const double* v, const double* ref, unsigned contact_mask, const char* task,
+    const double* ddq, const double* tau, double* cost)
+{
+    if (!b || !q || !v || !ref || !task || !ddq || !cost) {
+        set_error("iwbc_batch_task_cost: bad argument");
+        return IWBC_ERR_ARG;
+    }
+    const iwbc_problem_t& P = b->prob->cs.prob;
+    int t = -1;
+    for (size_t i = 0; i < b->prob->cs.task_names.size(); ++i)
+        if (b->prob->cs.task_names[i] == task)
+            t = (int)i;
+    if (t < 0 || P.tasks[t].level != 1) {
+        set_error(std::string("iwbc_batch_task_cost: '") + task + "' is not a level-1 task of this controller");
+        return IWBC_ERR_ARG;
+    }
+    const iwbc_task_t& T = P.tasks[t];
+    const int nv = P.nv, na = P.na, nu = nv - na;
+    double s2 = 0;
+    if (T.type == IWBC_T_POSTURE) { // TaskJointPosture: S (ddq_a - a_des)
+        const double* r = ref + T.ref_off;
+        for (int i = 0; i < na; ++i)
+            if (T.mask[i]) {
+                const double a_des = -T.kp[0] * (q[P.nq - na + i] - r[i]) - T.kd[0] * (v[nv - na + i] - r[na + i]) + r[2 * na + i];
+                s2 += (ddq[nu + i] - a_des) * (ddq[nu + i] - a_des);
+            }
+    }
+    else if (T.type == IWBC_T_TORQUE) { // TaskActuationEquality: diag(w) S (tau - tau_ref)
+        if (!tau) {
+            set_error("iwbc_batch_task_cost: a torque task needs the joint torques of that solve");
+            return IWBC_ERR_ARG;
+        }
+        const double* r = ref + T.ref_off;
+        for (int i = 0; i < na; ++i)
+            if (T.mask[i])
+                s2 += r[na + i] * (tau[i] - r[i]) * r[na + i] * (tau[i] - r[i]);
+    }
+    else {
+        if (!(T.weight > 0)) {
+            set_error(std::string("iwbc_batch_task_cost: task '") + task + "' has weight 0: its rows are not formed");
+            return IWBC_ERR_UNSUPPORTED;
+        }
+        int row0 = 0, rows = 0;
+        for (int k = 0; k < P.nl1; ++k) {
+            if (P.l1[k].kind != IWBC_B_TASK)
+                continue;
+            const iwbc_task_t& Tk = P.tasks[P.l1[k].index];
+            if (Tk.type == IWBC_T_POSTURE || Tk.type == IWBC_T_TORQUE)
+                continue;
+            if (P.l1[k].index == t)
+                row0 = rows;
+            rows += Tk.nrows;
+        }
+        std::vector<double> A((size_t)std::max(rows, 1) * nv), bv(std::max(rows, 1));
+        int rc = debug_dump(b, q, v, ref, contact_mask, nullptr, nullptr, nullptr, nullptr, nullptr, A.data(), bv.data());
+        if (rc)
+            return rc;
+        const double sw = std::sqrt(T.weight); // (the rows are stored scaled by sqrt(weight); the reference's constraint is not)
+        for (int r = row0; r < row0 + T.nrows; ++r) {
+            double a = -bv[r];
+            for (int k = 0; k < nv; ++k)
+                a += A[(size_t)r * nv + k] * ddq[k];
+            s2 += (a / sw) * (a / sw);
+        }
+    }
+    *cost = std::sqrt(s2);
+    return IWBC_OK;
 }
 
 int iwbc_qp_solve_batch(int device, int B, int n, int me, int mi, const double* H, const double* g, const double* CE, const double* ce0,

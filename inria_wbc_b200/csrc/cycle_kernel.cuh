@@ -119,6 +119,8 @@ namespace dev {
         double* dbg_H;
         double* dbg_g;
         double* dbg_x;
+        double* dbg_A;         // optional: the dense level-1 rows [rows_dense][nv] (scaled by sqrt(weight)) and their right-hand sides
+        double* dbg_b;
         long long* dbg_cycles; // phase timestamps (clock64) of instance 0: load, dyn, asm, factor, eq, ineq, decode
         const int* list;       // optional: instance indices to process (active-set continuation of the fast path)
         const int* list_count; // device-side length of `list`
@@ -2766,6 +2768,12 @@ namespace dev {
             }
             for (int k = tid; k < n; k += G)
                 io.dbg_g[k] = sm.g[k];
+            if (io.dbg_A) {
+                for (int e = tid; e < z.rows_dense * nv; e += G)
+                    io.dbg_A[e] = sm.A[e];
+                for (int k = tid; k < z.rows_dense; k += G)
+                    io.dbg_b[k] = sm.b[k];
+            }
             Grp<G>::sync();
         }
 

@@ -83,6 +83,31 @@ int main(int argc, char** argv)
             std::printf("FAILED: unknown behaviour did not throw\n");
             return 1;
         }
+        // cost(task) / objective_value() (controller.hpp:148-153, pos_tracker.hpp:43-44): after one open-loop update, of every robot;
+        // identical robots give identical numbers, the posture cost equals the norm built from ddq and the gains by hand
+        {
+            controllers::Config cc;
+            cc.controller_yaml = std::string(argv[1]) + "/talos/talos_pos_tracker.yaml";
+            cc.robots_path = argv[2];
+            cc.etc_path = argv[1];
+            cc.overrides_yaml = "stabilizer: {activated: false}\ncollision_detection: {activated: false}\nclosed_loop: false\n";
+            cc.batch = 2;
+            auto ctl = controllers::Factory::instance().create("talos-pos-tracker", cc);
+            ctl->update();
+            const double f0 = ctl->objective_value(0), f1 = ctl->objective_value(1);
+            const double c_com = ctl->cost("com", 0), c_lh = ctl->cost("lh", 1), c_post = ctl->cost("posture", 0);
+            // at the start pose the posture task asks for zero acceleration: its cost is the norm of the actuated accelerations
+            double want = 0;
+            const std::vector<double>& a = ctl->ddq();
+            const size_t nv1 = a.size() / 2;
+            for (size_t k = 6; k < nv1; ++k)
+                want += a[k] * a[k];
+            want = std::sqrt(want);
+            if (!(f0 == f1) || !std::isfinite(f0) || !(c_com >= 0) || !(c_lh >= 0) || std::fabs(c_post - want) > 1e-9 * std::fmax(1.0, want)) {
+                std::printf("FAILED getters: objective %g %g cost com %g lh %g posture %g (want %g)\n", f0, f1, c_com, c_lh, c_post, want);
+                return 1;
+            }
+        }
         std::printf("OK run-to-run %g chunked-vs-ticks %g\n", e_ab, e_ac);
         return 0;
     }

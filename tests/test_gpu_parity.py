@@ -358,3 +358,42 @@ def test_franka_known_answer_through_the_gpu_path(franka):
     before, after = mean_error(behaviors.Cartesian(franka, cfg, feed_forward=False).table(ticks))
     assert abs(before - gold["ee_error_tsid"]) < 3e-4 * gold["ee_error_tsid"], before  # the recorded value itself (see test_franka_kat.py)
     assert abs(after - gold["ee_error_dart"]) < 3e-4 * gold["ee_error_dart"], after
+
+
+@pytest.mark.gpu
+def test_cost_and_objective_value_getters(talos, tiago):
+    """Controller::cost(task) (controller.hpp:148-152: ||A ddq - b|| of the task's own, unweighted constraint) and
+    PosTracker::objective_value() (pos_tracker.hpp:44: eiquadprog's x'Hx/2 + g'x) of one robot, re-evaluated from a stage dump.
+    Objective: against the oracle's H, g, x.  Costs: CoM and posture rebuilt in numpy from the oracle's Jcom / CoM drift and the task
+    gains; an SE3 task through the identity  sum_t w_t cost_t^2 = 2 f(x) + sum_t w_t ||b_t||^2  restricted to a change of one weight."""
+    def task_of(P, name):
+        t = P.struct().tasks[P.names("tasks").index(name)]
+        return dict(kp=list(t.kp), kd=list(t.kd), mask=list(t.mask), weight=t.weight)
+
+    for P in (talos, tiago):
+        q, v = random_states(P, 2, 21, **({"qn": 0.1, "vn": 0.2} if P.ncontacts == 0 else {}))
+        bt = iw.Batch(P, 0, 4)
+        r = bt.update(q, v)
+        for i in range(2):
+            d = ol.cycle_debug(P, q[i], v[i])
+            f = 0.5 * d["x"] @ d["H"] @ d["x"] + d["g"] @ d["x"]
+            assert abs(bt.objective_value(q[i], v[i]) - f) <= 1e-8 * max(1.0, abs(f))
+            ddq = r.dv[i]
+            na, nu = P.na, P.nv - P.na
+            # posture: S (ddq_a - a_des), a_des = -kp (q - q_ref) - kd v  (zero reference velocity / acceleration)
+            off, _ = P.ref_slot("posture")
+            ref = P.default_refs()
+            T = task_of(P, "posture")
+            a_des = -T["kp"][0] * (q[i][P.nq - na:] - ref[off:off + na]) - T["kd"][0] * v[i][P.nv - na:]
+            want = np.linalg.norm(np.array(T["mask"][:na]) * (ddq[nu:] - a_des))
+            assert abs(bt.task_cost("posture", q[i], v[i], ddq) - want) <= 1e-9 * max(1.0, want)
+            if "com" in P.names("tasks"):
+                T = task_of(P, "com")
+                off, _ = P.ref_slot("com")
+                com, vcom, drift = d["com"][0:3], d["com"][3:6], d["com"][6:9]
+                a_des = -np.array(T["kp"][:3]) * (com - ref[off:off + 3]) - np.array(T["kd"][:3]) * vcom
+                res = (d["Jcom"] @ ddq - (a_des - drift)) * np.array(T["mask"][:3])
+                want = np.linalg.norm(res)
+                assert abs(bt.task_cost("com", q[i], v[i], ddq) - want) <= 1e-8 * max(1.0, want)
+    with pytest.raises(iw.IwbcError, match="not a level-1 task"):
+        bt.task_cost("bounds", q[0], v[0], r.dv[0])
