@@ -39,6 +39,12 @@ enum iwbc_task_type {
     IWBC_T_SELFCOL = 4,   /* TaskSelfCollision (src/tsid/task-self-collision.cpp:84-204) */
     IWBC_T_BOUNDS = 5,    /* TaskJointPosVelAccBounds */
     IWBC_T_ACTBOUNDS = 6, /* TaskActuationBounds */
+    IWBC_T_COP = 8,       /* TaskCopEquality through addForceTask (tasks.cpp:156-178): level-1 cost on the contact forces,
+                             sum over the active contacts' points j of (p_j - cop_ref) (n' f_j) = 0 (p_j: world position of the contact
+                             point, f_j: its 3 force coefficients); reference block = [cop_ref (3) ; normal (3)] (setReference /
+                             setContactNormal; the reference's factory sets (0,0,0), TSID's default normal is (0,0,1)).  Upstream TSID
+                             is not in the reference tree: restated from the published task-cop-equality.cpp and the m_taskContactForces
+                             loop of inverse-dynamics-formulation-acc-force.cpp ("by default associated to all contact forces"). */
     IWBC_T_TORQUE = 7     /* TaskActuationEquality through addActuationTask (tasks.cpp:227-271): level-1 cost on the joint torques
                              tau = M_a dv + h_a - J_a^T f; reference block = [tau_ref (na) ; weight vector (na)] (setReference /
                              setWeightVector); mask: na entries.  Upstream TSID source is not in the reference tree: restated

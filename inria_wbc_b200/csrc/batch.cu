@@ -181,7 +181,7 @@ int prepare_shape(iwbc_batch* b, unsigned mask)
     }
     S.rows_dense = 0;
     for (int k = 0; k < P.nl1; ++k)
-        if (P.l1[k].kind == IWBC_B_TASK && P.tasks[P.l1[k].index].type != IWBC_T_POSTURE && P.tasks[P.l1[k].index].type != IWBC_T_TORQUE)
+        if (P.l1[k].kind == IWBC_B_TASK && P.tasks[P.l1[k].index].type != IWBC_T_POSTURE && P.tasks[P.l1[k].index].type != IWBC_T_TORQUE && P.tasks[P.l1[k].index].type != IWBC_T_COP)
             S.rows_dense += P.tasks[P.l1[k].index].nrows;
     S.maxdepth = 0;
     for (int j = 0; j < P.nj; ++j)
@@ -865,7 +865,7 @@ static int debug_dump(iwbc_batch* b, const double* q, const double* v, const dou
     const size_t nv = P.nv, n = qs.n;
     size_t rows = 0;
     for (int k = 0; k < P.nl1; ++k)
-        if (P.l1[k].kind == IWBC_B_TASK && P.tasks[P.l1[k].index].type != IWBC_T_POSTURE && P.tasks[P.l1[k].index].type != IWBC_T_TORQUE)
+        if (P.l1[k].kind == IWBC_B_TASK && P.tasks[P.l1[k].index].type != IWBC_T_POSTURE && P.tasks[P.l1[k].index].type != IWBC_T_TORQUE && P.tasks[P.l1[k].index].type != IWBC_T_COP)
             rows += P.tasks[P.l1[k].index].nrows;
     double *dM, *dn, *dH, *dg, *dx, *dA = nullptr, *db = nullptr;
     CUDA_TRY(cudaMalloc(&dM, nv * nv * 8));
@@ -982,6 +982,10 @@ int iwbc_batch_task_cost(iwbc_batch* b, const double* q, const double* v, const 
             if (T.mask[i])
                 s2 += r[na + i] * (tau[i] - r[i]) * r[na + i] * (tau[i] - r[i]);
     }
+    else if (T.type == IWBC_T_COP) {
+        set_error("iwbc_batch_task_cost: the cop task is a cost on the contact forces (the reference's cost() multiplies task matrices by ddq: not defined for it)");
+        return IWBC_ERR_UNSUPPORTED;
+    }
     else {
         if (!(T.weight > 0)) {
             set_error(std::string("iwbc_batch_task_cost: task '") + task + "' has weight 0: its rows are not formed");
@@ -992,7 +996,7 @@ int iwbc_batch_task_cost(iwbc_batch* b, const double* q, const double* v, const 
             if (P.l1[k].kind != IWBC_B_TASK)
                 continue;
             const iwbc_task_t& Tk = P.tasks[P.l1[k].index];
-            if (Tk.type == IWBC_T_POSTURE || Tk.type == IWBC_T_TORQUE)
+            if (Tk.type == IWBC_T_POSTURE || Tk.type == IWBC_T_TORQUE || Tk.type == IWBC_T_COP)
                 continue;
             if (P.l1[k].index == t)
                 row0 = rows;

@@ -141,6 +141,7 @@ int iwbc_problem_ref_slot(const iwbc_problem* p, const char* name, int* offset, 
             int len = t.type == IWBC_T_SE3 ? IWBC_REF_SE3 : t.type == IWBC_T_COM ? IWBC_REF_COM
                 : t.type == IWBC_T_MOMENTUM                                      ? IWBC_REF_MOM
                 : t.type == IWBC_T_TORQUE                                        ? 2 * P.na
+                : t.type == IWBC_T_COP                                           ? 6
                                                                                  : 3 * P.na;
             if (offset)
                 *offset = t.ref_off;

@@ -1048,6 +1048,42 @@ namespace dev {
                     sm.g[o + k] -= C.w_forcereg * s;
                 }
             }
+            else if (z.P->tasks[Bk.index].type == IWBC_T_COP) {
+                // TaskCopEquality as a level-1 cost (tasks.cpp:156-178): w || sum_c sum_j (p_cj - cop_ref) (n' f_cj) ||^2 over the ACTIVE
+                // contacts' four points (p_cj: world position of contact point j of contact c, f_cj: its three force coefficients).
+                // Force columns only, zero right-hand side: it makes the force block of H depend on the state, so the fast path
+                // (constant force-block factor) never takes a problem with this task.
+                const iwbc_task_t& T = z.P->tasks[Bk.index];
+                const double* r = sm.ref + T.ref_off; // cop reference (3), contact normal (3)
+                // entry (row d, force column kf of the QP) of the task matrix: (p - ref)[d] * normal[kf % 3]
+                auto Adk = [&](int d, int kf) -> double {
+                    int c = 0;
+                    for (int cc = 0; cc < z.P->ncontacts; ++cc)
+                        if (S.cidx[cc] >= 0 && kf >= S.cidx[cc] && kf < S.cidx[cc] + 12)
+                            c = cc;
+                    const int kk = kf - S.cidx[c], j = kk / 3, a = kk - 3 * j;
+                    const iwbc_contact_t& C = z.P->contacts[c];
+                    // contact point j in the contact frame, read back from the force generator T = [I ; skew(P_j)] (rows 3..5)
+                    const V3 Pl = mk(C.T[5 * 12 + 3 * j + 1], C.T[3 * 12 + 3 * j + 2], C.T[4 * 12 + 3 * j + 0]);
+                    const double* o = sm.oMf + 12 * C.frame;
+                    const V3 pw = rmul(o, Pl) + ld3(o + 9);
+                    const double pd = d == 0 ? pw.x - r[0] : (d == 1 ? pw.y - r[1] : pw.z - r[2]);
+                    return pd * r[3 + a];
+                };
+                const int nk = n - nv;
+                for (int e = tid; e < nk * (nk + 1) / 2; e += G) {
+                    int a = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+                    while (a * (a + 1) / 2 > e)
+                        --a;
+                    while ((a + 1) * (a + 2) / 2 <= e)
+                        ++a;
+                    const int b = e - a * (a + 1) / 2;
+                    double s = 0;
+                    for (int d = 0; d < 3; ++d)
+                        s += Adk(d, a) * Adk(d, b);
+                    sm.J[(nv + a) + (nv + b) * ld] += T.weight * s;
+                }
+            }
             else if (z.P->tasks[Bk.index].type == IWBC_T_TORQUE) {
                 // TaskActuationEquality as a level-1 cost (tasks.cpp:227-271): w || diag(s) S (M_a dv - J_a^T f + h_a - tau_ref) ||^2.
                 // Row i over [dv ; f]: D(i, k) = M(nu + i, k) for k < nv, -(T_c^T Jft_c)[k'][nu + i] for the force columns; it couples

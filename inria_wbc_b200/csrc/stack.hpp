@@ -496,8 +496,15 @@ namespace host {
                         cs.ref0[t.ref_off + na + i] = scaling[i];
                 }
             }
-            else if (type == "cop")
-                throw ConfigError("task type '" + type + "' (" + name + ") is not supported by the batched path (TaskCopEquality: DESIGN.md 8)");
+            else if (type == "cop") {
+                // make_cop (tasks.cpp:156-178): TaskCopEquality, reference (0, 0, 0), addForceTask(task, weight, 1)
+                double weight = IWBC_HCHECK(node["weight"].as<double>(), name + ".weight");
+                iwbc_task_t& t = new_task(IWBC_T_COP, 1);
+                t.weight = weight;
+                t.nrows = 3;
+                t.ref_off = alloc_ref(cs, 6); // cop reference (0, 0, 0), contact normal (TaskCopEquality's default (0, 0, 1))
+                cs.ref0[t.ref_off + 5] = 1.0;
+            }
             else
                 throw ConfigError("unknown task type '" + type + "' for task " + name);
         }

@@ -41,7 +41,7 @@ import yaml
 # ------------------------------------------------------------------------------------------------ iwbc_problem.h mirror
 MAXJ, MAXNV, MAXF, MAXT, MAXC, MAXAV, MAXL0, MAXL1, MAXWV = 56, 64, 48, 32, 4, 12, 16, 40, 4
 J_FREEFLYER, J_REVOLUTE, J_PRISMATIC = 0, 1, 2
-T_SE3, T_COM, T_POSTURE, T_MOMENTUM, T_SELFCOL, T_BOUNDS, T_ACTBOUNDS, T_TORQUE = range(8)
+T_SE3, T_COM, T_POSTURE, T_MOMENTUM, T_SELFCOL, T_BOUNDS, T_ACTBOUNDS, T_TORQUE, T_COP = range(9)
 B_BASEDYN, B_CONTACT_MOTION, B_CONTACT_FORCE, B_CONTACT_REG, B_TASK = range(5)
 REF_SE3, REF_COM, REF_MOM, REF_CONTACT = 24, 9, 18, 32
 BT_FIXED_BASE, BT_SINGLE_SUPPORT, BT_DOUBLE_SUPPORT = 0, 1, 2
@@ -514,6 +514,10 @@ class OracleProblem:
                 t = new_task(name, T_BOUNDS, 0)
                 t.weight, t.nrows = float(_need(node, "weight", name)), na
                 bounds_task = S.ntasks - 1
+            elif ttype == "cop":  # make_cop, tasks.cpp:156-178
+                t = new_task(name, T_COP, 1)
+                t.weight, t.nrows = float(_need(node, "weight", name)), 3
+                t.ref_off = alloc(6, [0.0, 0.0, 0.0, 0.0, 0.0, 1.0])  # cop reference, contact normal
             elif ttype == "torque":  # make_torque, tasks.cpp:227-271
                 t = new_task(name, T_TORQUE, 1)
                 t.weight = float(_need(node, "weight", name))
@@ -707,7 +711,7 @@ class OracleProblem:
         if name in self.task_names:
             t = S.tasks[self.task_names.index(name)]
             if t.ref_off >= 0:
-                return t.ref_off, {T_SE3: REF_SE3, T_COM: REF_COM, T_MOMENTUM: REF_MOM, T_TORQUE: 2 * S.na}.get(t.type, 3 * S.na)
+                return t.ref_off, {T_SE3: REF_SE3, T_COM: REF_COM, T_MOMENTUM: REF_MOM, T_TORQUE: 2 * S.na, T_COP: 6}.get(t.type, 3 * S.na)
         if name in self.contact_names:
             return S.contacts[self.contact_names.index(name)].ref_off, REF_CONTACT
         raise KeyError(name)

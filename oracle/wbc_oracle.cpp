@@ -1210,6 +1210,34 @@ void cycle(const iwbc_problem_t& P, const double* q, const double* v, const doub
             }
             add_cost(T.weight, A, b.data(), T.nrows);
         }
+        else if (T.type == IWBC_T_COP) {
+            // tsid::tasks::TaskCopEquality added with addForceTask(task, w, 1) (tasks.cpp:156-178).  Upstream TSID is not in the reference
+            // tree; restated from its published source: for every contact of the formulation's (active) contact list and every contact
+            // point j, the three columns of the point's force coefficients get (p_world_j - cop_ref) * normal' (task-cop-equality.cpp:
+            // compute()), the vector stays zero, and InverseDynamicsFormulationAccForce::computeProblemData writes that matrix into the
+            // force columns of a level-1 constraint (m_taskContactForces loop: "by default the task is associated to all contact forces").
+            const double* r = ref + T.ref_off; // cop reference (3), contact normal (3)
+            Mat A(3, n);
+            double b[3] = {0, 0, 0};
+            for (int c = 0; c < P.ncontacts; ++c) {
+                if (cidx[c] < 0)
+                    continue;
+                const iwbc_contact_t& C = P.contacts[c];
+                FrameKin K;
+                frame_kinematics(P, D, C.frame, K);
+                const SE3& oMf = K.oMf; // Contact6d's motion-task frame: robot.framePosition(data, frame_id)
+                for (int j = 0; j < 4; ++j) {
+                    // contact point j in the contact frame (tasks.cpp:353-356), read back from T = [I ; skew(P_j)]
+                    V3 Pl = {C.T[5 * 12 + 3 * j + 1], C.T[3 * 12 + 3 * j + 2], C.T[4 * 12 + 3 * j + 0]};
+                    V3 pw = oMf.R * Pl + oMf.p;
+                    const double pd[3] = {pw.x - r[0], pw.y - r[1], pw.z - r[2]};
+                    for (int d = 0; d < 3; ++d)
+                        for (int a = 0; a < 3; ++a)
+                            A(d, nv + cidx[c] + 3 * j + a) = pd[d] * r[3 + a];
+                }
+            }
+            add_cost(T.weight, A, b, 3);
+        }
         else if (T.type == IWBC_T_TORQUE) {
             // tsid::tasks::TaskActuationEquality added with addActuationTask(task, w, 1) (tasks.cpp:227-271).  Upstream TSID is not in
             // the reference tree; restated from its published source: the task's own constraint is row i = w_i e_i', vector

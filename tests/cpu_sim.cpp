@@ -56,7 +56,7 @@ static void prepare(const iwbc_problem_t& P, unsigned mask, dev::Shape& S, dev::
         }
     }
     for (int k = 0; k < P.nl1; ++k)
-        if (P.l1[k].kind == IWBC_B_TASK && P.tasks[P.l1[k].index].type != IWBC_T_POSTURE && P.tasks[P.l1[k].index].type != IWBC_T_TORQUE)
+        if (P.l1[k].kind == IWBC_B_TASK && P.tasks[P.l1[k].index].type != IWBC_T_POSTURE && P.tasks[P.l1[k].index].type != IWBC_T_TORQUE && P.tasks[P.l1[k].index].type != IWBC_T_COP)
             S.rows_dense += P.tasks[P.l1[k].index].nrows;
     for (int j = 0; j < P.nj; ++j)
         S.maxdepth = std::max(S.maxdepth, P.depth[j]);
