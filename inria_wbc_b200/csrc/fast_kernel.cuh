@@ -444,6 +444,9 @@ namespace dev {
 #ifndef IWBC_OPT_BF
 #define IWBC_OPT_BF 1   // constants of the problem folded on the host: U_ff' T' for the force rows of B, sqrt(task weights)
 #endif
+#ifndef IWBC_OPT_RELOAD
+#define IWBC_OPT_RELOAD 1 // QR: pivot column double-buffered and re-read in the update instead of held in registers
+#endif
 #ifndef IWBC_OPT_SIGMA
 #define IWBC_OPT_SIGMA 1 // QR: the next pivot column's norm is computed by its owners one step ahead
 #endif
@@ -1305,7 +1308,8 @@ namespace dev {
             // Register-resident variant: thread (seg0, c) owns rows j = seg0 + SEG m of column c for the whole factorisation;
             // only the pivot column and the pivot row are published through shared memory (wv / gvec are free here).
             constexpr int MR = (NV_ + SEG - 1) / SEG, MF = (2 * (ME_ - 6) + SEG - 1) / SEG;
-            double* const colbuf = wv;   // B(:, k)
+            double* const colbuf = wv;   // B(:, k); IWBC_OPT_RELOAD: double-buffered with xv (free until the solve), so that the update can
+                                         // read the pivot column again instead of holding it in 26 registers across the barrier
             double* const rowbuf = gvec; // B(k, :), double-buffered: [2][NC]
             // |B(k+1:, k)|^2 of the NEXT pivot column, per row segment, double-buffered: its owners compute it right after they have
             // updated the column, so that the sigma -> rsqrt -> reciprocal chain of a step starts at the top of the step and overlaps
@@ -1354,6 +1358,8 @@ namespace dev {
                 const bool frc = k >= cb0;
                 const double* rb = rowbuf + (k & 1) * NC;
                 double* rbn = rowbuf + ((k + 1) & 1) * NC;
+                const double* const cbk = (IWBC_OPT_RELOAD && (k & 1)) ? xv : colbuf;  // this step's pivot column
+                double* const cbn = (IWBC_OPT_RELOAD && !(k & 1)) ? xv : colbuf;       // where the next one is published
                 if (qact) {
                     double sacc = 0;
 #pragma unroll
@@ -1361,14 +1367,14 @@ namespace dev {
                         if (SEG * (m + 1) - 1 <= k) // dead for every segment
                             continue;
                         const int j = seg0 + SEG * m;
-                        ck[m] = (j > k && j < nv) ? colbuf[j] : 0.0;
+                        ck[m] = (j > k && j < nv) ? cbk[j] : 0.0;
                         sacc += ck[m] * cc[m];
                     }
                     if (frc) {
 #pragma unroll
                         for (int m = 0; m < MF; ++m) {
                             const int jj = seg0 + SEG * m;
-                            ckf[m] = jj < nfrc ? colbuf[nv + jj] : 0.0;
+                            ckf[m] = jj < nfrc ? cbk[nv + jj] : 0.0;
                             sacc += ckf[m] * cf[m];
                         }
                     }
@@ -1418,6 +1424,19 @@ namespace dev {
                             if (seg0 == 0)
                                 Rm[k * NC + c] = bkc - coef;
                             const double cs = coef * scale;
+#if IWBC_OPT_RELOAD
+#pragma unroll
+                            for (int m = 0; m < MR; ++m)
+                                if (SEG * (m + 1) - 1 > k) {
+                                    const int j = seg0 + SEG * m;
+                                    cc[m] -= cs * ((j > k && j < nv) ? cbk[j] : 0.0);
+                                }
+                            if (frc) {
+#pragma unroll
+                                for (int m = 0; m < MF; ++m)
+                                    cf[m] -= cs * (seg0 + SEG * m < nfrc ? cbk[nv + seg0 + SEG * m] : 0.0);
+                            }
+#else
 #pragma unroll
                             for (int m = 0; m < MR; ++m)
                                 if (SEG * (m + 1) - 1 > k)
@@ -1427,6 +1446,7 @@ namespace dev {
                                 for (int m = 0; m < MF; ++m)
                                     cf[m] -= cs * ckf[m];
                             }
+#endif
                         }
                     }
                     // publish the next pivot column and pivot row
@@ -1434,12 +1454,12 @@ namespace dev {
 #pragma unroll
                         for (int m = 0; m < MR; ++m)
                             if (SEG * (m + 1) - 1 > k && seg0 + SEG * m < nv) // (rows <= k + 1 of the next column are never read)
-                                colbuf[seg0 + SEG * m] = cc[m];
+                                cbn[seg0 + SEG * m] = cc[m];
                         if (k + 1 >= cb0) {
 #pragma unroll
                             for (int m = 0; m < MF; ++m)
                                 if (seg0 + SEG * m < nfrc)
-                                    colbuf[nv + seg0 + SEG * m] = cf[m];
+                                    cbn[nv + seg0 + SEG * m] = cf[m];
                         }
 #if IWBC_OPT_SIGMA
                         double sgn = 0; // same terms in the same order as the pivot column's own dot product of the next step
