@@ -444,6 +444,9 @@ namespace dev {
 #ifndef IWBC_OPT_BF
 #define IWBC_OPT_BF 1   // constants of the problem folded on the host: U_ff' T' for the force rows of B, sqrt(task weights)
 #endif
+#ifndef IWBC_OPT_BS2
+#define IWBC_OPT_BS2 1    // continuation: back-substitution of J's columns two rows per step (16-byte loads of L)
+#endif
 #ifndef IWBC_OPT_RELOAD
 #define IWBC_OPT_RELOAD 1 // QR: pivot column double-buffered and re-read in the update instead of held in registers
 #endif
@@ -1933,6 +1936,24 @@ namespace dev {
                     }
                 }
                 // y = L^-T r (right-looking): y_i = r_i / L_ii, then r_k -= L[i][k] y_i for k < i
+#if IWBC_OPT_BS2
+                // two rows per step: L[i-1][k] and L[i][k] are neighbours in the column-major factor, one 16-byte load feeds two FMAs
+                static_assert(NV_ % 2 == 0, "paired back-substitution");
+#pragma unroll
+                for (int i = NV_ - 1; i >= 1; i -= 2) {
+                    const double yi = r[i] * il[i];
+                    col[i] = yi;
+                    r[i - 1] -= Hs[i + (i - 1) * ld] * yi;
+                    const double yj = r[i - 1] * il[i - 1];
+                    col[i - 1] = yj;
+                    const double* Lp = Hs + (i - 1); // (L[i-1][k], L[i][k]) = Lp[k ld .. k ld + 1]; i - 1 and ld are even
+#pragma unroll
+                    for (int k = 0; k < i - 1; ++k) {
+                        const double2 l2 = *reinterpret_cast<const double2*>(Lp + k * ld);
+                        r[k] -= l2.y * yi + l2.x * yj;
+                    }
+                }
+#else
 #pragma unroll
                 for (int i = NV_ - 1; i >= 0; --i) {
                     const double yi = r[i] * il[i];
@@ -1942,6 +1963,7 @@ namespace dev {
                     for (int k = 0; k < i; ++k)
                         r[k] -= Li[k * ld] * yi;
                 }
+#endif
             }
         }
         else {
