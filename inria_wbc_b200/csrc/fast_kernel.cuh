@@ -444,9 +444,6 @@ namespace dev {
 #ifndef IWBC_OPT_BF
 #define IWBC_OPT_BF 1   // constants of the problem folded on the host: U_ff' T' for the force rows of B, sqrt(task weights)
 #endif
-#ifndef IWBC_OPT_BS2
-#define IWBC_OPT_BS2 1    // continuation: back-substitution of J's columns two rows per step (16-byte loads of L)
-#endif
 #ifndef IWBC_OPT_RELOAD
 #define IWBC_OPT_RELOAD 1 // QR: pivot column double-buffered and re-read in the update instead of held in registers
 #endif
@@ -728,12 +725,27 @@ namespace dev {
                 if (it < items) {
                     const int j = it >> 4, k = it & 15;
                     const int last = gP->last_desc[j];
-                    if (k < 10)
-                        for (int jj = j; jj <= last; ++jj)
+                    // (two chains per item: the root's items sum over every joint)
+                    double s1 = 0;
+                    if (k < 10) {
+                        int jj = j;
+                        for (; jj + 1 <= last; jj += 2) {
                             s += sm.Yw[10 * jj + k];
-                    else
-                        for (int jj = j; jj <= last; ++jj)
+                            s1 += sm.Yw[10 * (jj + 1) + k];
+                        }
+                        if (jj <= last)
+                            s += sm.Yw[10 * jj + k];
+                    }
+                    else {
+                        int jj = j;
+                        for (; jj + 1 <= last; jj += 2) {
                             s += sm.fw[6 * jj + (k - 10)];
+                            s1 += sm.fw[6 * (jj + 1) + (k - 10)];
+                        }
+                        if (jj <= last)
+                            s += sm.fw[6 * jj + (k - 10)];
+                    }
+                    s += s1;
                 }
                 acc[c8] = s;
             }
@@ -1215,6 +1227,7 @@ namespace dev {
                         const double2 p23 = *reinterpret_cast<const double2*>(Lp + j * ld + 2);
                         a0 += li * p01.x, a1 += li * p01.y, a2 += li * p23.x, a3 += li * p23.y;
                     }
+                    // (measured and dropped: two columns per trip into two accumulator sets -- neutral)
                     if (PAIR == 2) {
                         a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
                         a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
@@ -1364,24 +1377,27 @@ namespace dev {
                 const double* const cbk = (IWBC_OPT_RELOAD && (k & 1)) ? xv : colbuf;  // this step's pivot column
                 double* const cbn = (IWBC_OPT_RELOAD && !(k & 1)) ? xv : colbuf;       // where the next one is published
                 if (qact) {
-                    double sacc = 0;
+                    double sacc = 0, sacc1 = 0, sacc2 = 0; // (three chains: a single accumulator is 13 dependent FMAs per step)
 #pragma unroll
                     for (int m = 0; m < MR; ++m) {
                         if (SEG * (m + 1) - 1 <= k) // dead for every segment
                             continue;
                         const int j = seg0 + SEG * m;
                         ck[m] = (j > k && j < nv) ? cbk[j] : 0.0;
-                        sacc += ck[m] * cc[m];
+                        if (m & 1)
+                            sacc1 += ck[m] * cc[m];
+                        else
+                            sacc += ck[m] * cc[m];
                     }
                     if (frc) {
 #pragma unroll
                         for (int m = 0; m < MF; ++m) {
                             const int jj = seg0 + SEG * m;
                             ckf[m] = jj < nfrc ? cbk[nv + jj] : 0.0;
-                            sacc += ckf[m] * cf[m];
+                            sacc2 += ckf[m] * cf[m];
                         }
                     }
-                    Pp[seg0 * NC + c] = sacc;
+                    Pp[seg0 * NC + c] = (sacc + sacc1) + sacc2;
                 }
 #if !IWBC_OPT_SIGMA
                 fsync<T>();
@@ -1465,18 +1481,22 @@ namespace dev {
                                     cbn[nv + seg0 + SEG * m] = cf[m];
                         }
 #if IWBC_OPT_SIGMA
-                        double sgn = 0; // same terms in the same order as the pivot column's own dot product of the next step
+                        double sgn = 0, sgn1 = 0, sgn2 = 0; // (three chains, like the dot products)
 #pragma unroll
                         for (int m = 0; m < MR; ++m)
-                            if (SEG * (m + 1) - 1 > k + 1 && seg0 + SEG * m > k + 1 && seg0 + SEG * m < nv)
-                                sgn += cc[m] * cc[m];
+                            if (SEG * (m + 1) - 1 > k + 1 && seg0 + SEG * m > k + 1 && seg0 + SEG * m < nv) {
+                                if (m & 1)
+                                    sgn1 += cc[m] * cc[m];
+                                else
+                                    sgn += cc[m] * cc[m];
+                            }
                         if (k + 1 >= cb0) {
 #pragma unroll
                             for (int m = 0; m < MF; ++m)
                                 if (seg0 + SEG * m < nfrc)
-                                    sgn += cf[m] * cf[m];
+                                    sgn2 += cf[m] * cf[m];
                         }
-                        Sg[((k + 1) & 1) * SEG + seg0] = sgn;
+                        Sg[((k + 1) & 1) * SEG + seg0] = (sgn + sgn1) + sgn2;
 #endif
                     }
                     {
@@ -1936,24 +1956,6 @@ namespace dev {
                     }
                 }
                 // y = L^-T r (right-looking): y_i = r_i / L_ii, then r_k -= L[i][k] y_i for k < i
-#if IWBC_OPT_BS2
-                // two rows per step: L[i-1][k] and L[i][k] are neighbours in the column-major factor, one 16-byte load feeds two FMAs
-                static_assert(NV_ % 2 == 0, "paired back-substitution");
-#pragma unroll
-                for (int i = NV_ - 1; i >= 1; i -= 2) {
-                    const double yi = r[i] * il[i];
-                    col[i] = yi;
-                    r[i - 1] -= Hs[i + (i - 1) * ld] * yi;
-                    const double yj = r[i - 1] * il[i - 1];
-                    col[i - 1] = yj;
-                    const double* Lp = Hs + (i - 1); // (L[i-1][k], L[i][k]) = Lp[k ld .. k ld + 1]; i - 1 and ld are even
-#pragma unroll
-                    for (int k = 0; k < i - 1; ++k) {
-                        const double2 l2 = *reinterpret_cast<const double2*>(Lp + k * ld);
-                        r[k] -= l2.y * yi + l2.x * yj;
-                    }
-                }
-#else
 #pragma unroll
                 for (int i = NV_ - 1; i >= 0; --i) {
                     const double yi = r[i] * il[i];
@@ -1963,7 +1965,7 @@ namespace dev {
                     for (int k = 0; k < i; ++k)
                         r[k] -= Li[k * ld] * yi;
                 }
-#endif
+                // (measured and dropped: two rows per step with one 16-byte load of (L[i-1][k], L[i][k]) feeding two FMAs -- neutral)
             }
         }
         else {
