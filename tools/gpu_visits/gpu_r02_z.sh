@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, final visit (r02e): what the driver runs at round end -- smoke(), the default bench line, the reference arm -- plus the final ncu evidence
-tag=r02e
+tag=r02f
 mkdir -p gpurun_out /tmp/ncu
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
 timeout 900 python bench.py > gpurun_out/${tag}_bench_default.json 2> gpurun_out/${tag}_bench_default.err; tail -c 300 gpurun_out/${tag}_bench_default.json; echo
